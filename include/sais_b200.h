@@ -1,0 +1,189 @@
+/*
+ * sais_b200 — C ABI of the B200 (sm_100a) implementation of SAIS's inference hot path.
+ *
+ * The reference (danikiyasseh/SAIS) is pure Python and has no FFI; the interfaces each entry point
+ * replaces are therefore Python call sites, cited per function below (paths relative to the reference
+ * repo root).  All pointers are DEVICE pointers unless a parameter says "host".  Every function
+ * returns 0 on success or a negative error code (sais_last_error() gives the text), never throws,
+ * never allocates device memory (workspaces are caller-provided) and enqueues its work on `stream`
+ * (a cudaStream_t passed as void*).  There is no CPU fallback: without an sm_100 device the calls fail.
+ */
+#ifndef SAIS_B200_H_
+#define SAIS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAIS_OK 0
+#define SAIS_ERR_INVALID_ARG (-1)
+#define SAIS_ERR_SHAPE (-2)
+#define SAIS_ERR_CUDA (-3)
+#define SAIS_ERR_WORKSPACE (-4)
+#define SAIS_ERR_DRIVER (-5)
+
+#define SAIS_ACT_NONE 0
+#define SAIS_ACT_GELU_ERF 1 /* nn.GELU() default (erf form), vision_transformer.py:50 */
+#define SAIS_ACT_RELU 2     /* nn.TransformerEncoderLayer default activation */
+
+#define SAIS_VIT_DIM 384
+#define SAIS_VIT_DEPTH 12
+#define SAIS_VIT_HEADS 6
+#define SAIS_VIT_TOKENS 197
+#define SAIS_VIT_PATCHES 196
+#define SAIS_VIT_PATCH_K 768
+#define SAIS_VIT_HIDDEN 1536
+#define SAIS_TMP_LAYERS 4
+#define SAIS_TMP_HEADS 4
+#define SAIS_TMP_FF 2048
+#define SAIS_TMP_OUT 256
+
+typedef void* sais_stream_t; /* cudaStream_t */
+typedef uint16_t sais_bf16;  /* raw bfloat16 bits */
+
+int sais_version(void);
+const char* sais_last_error(void);
+/* number of kernels this library has launched since load (for bench.py's gpu_launches) */
+int64_t sais_launch_count(void);
+
+/* Optional per-kernel-class CUDA-event profiler (bench.py's roofline leg).  Between begin and end every
+ * launch is bracketed by events on its stream; end synchronises the device and returns, per class
+ * (0 GEMM, 1 ViT attention, 2 LayerNorm, 3 patchify, 4 temporal attention, 5 misc): summed milliseconds,
+ * summed algorithmic work (flops for classes 0-1, bytes otherwise) and launch counts.  All arrays are HOST. */
+#define SAIS_NUM_KERNEL_CLASSES 6
+void sais_profile_begin(void);
+int sais_profile_end(double* ms_per_class, double* work_per_class, int64_t* launches_per_class, int32_t n_classes);
+
+/* ---------------------------------------------------------------------------------------------
+ * GEMM  out = act(A · Wᵀ + bias) [+ residual]           (tcgen05 / TMEM / TMA kernel)
+ * replaces nn.Linear / nn.Conv2d-as-GEMM call sites: vision_transformer.py:60-63 (fc1, fc2),
+ * :82 (qkv), :90 (proj), :126-130 (patch embed); torch MultiheadAttention in/out projections and
+ * TransformerEncoderLayer.linear1/linear2 reached through prepare_model.py:213.
+ * A: bf16 [M,K] (row pitch lda), W: bf16 [N,K] (nn.Linear layout, row pitch ldw); fp32 accumulate.
+ * N must be a multiple of 128, K a multiple of 64.  out_f32 and/or out_bf16 may be given.
+ * Patch-embed row remap: if remap_group > 0, GEMM row r = g*remap_group + p is written to output
+ * row g*(remap_group+1) + 1 + p and row_add[p, :] (fp32 [remap_group, N]) is added (pos_embed).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const sais_bf16* a;
+  const sais_bf16* w;
+  const float* bias;     /* [N] or NULL */
+  const float* residual; /* fp32 [M,N] pitch ldr or NULL; added after the activation */
+  float* out_f32;        /* pitch ldo32, or NULL */
+  sais_bf16* out_bf16;   /* pitch ldo16, or NULL */
+  const float* row_add;  /* see remap_group */
+  int64_t M, N, K;
+  int64_t lda, ldw, ldr, ldo32, ldo16;
+  int32_t act;
+  int32_t remap_group;
+} SaisGemmArgs;
+int sais_gemm_bias_act(const SaisGemmArgs* args, sais_stream_t stream);
+
+/* LayerNorm over the last dim (cols == 384) — nn.LayerNorm at vision_transformer.py:99,103,156
+ * (eps 1e-6) and TransformerEncoderLayer.norm1/norm2 (eps 1e-5).  x: fp32, row pitch in_pitch
+ * elements; writes fp32 and/or bf16 (dense [rows,384]). */
+int sais_layernorm(const float* x, int64_t in_pitch, const float* gamma, const float* beta, float eps,
+                   int64_t rows, int32_t cols, float* out_f32, sais_bf16* out_bf16, sais_stream_t stream);
+
+/* Frame normalisation + patch layout.  u8 variant replaces ToTensor+Normalize
+ * (extract_representations.py:158-162): frames u8 [B,224,224,3] -> patches bf16 [B*196,768],
+ * k = c*256 + ky*16 + kx, value = (u8/255 - mean[c]) / std[c].  f32 variant takes the already
+ * normalised fp32 [B,3,224,224] tensor the reference model is called with (:370). */
+int sais_normalize_patchify_u8(const uint8_t* frames, int32_t B, const float* mean3_host, const float* std3_host,
+                               sais_bf16* patches, sais_stream_t stream);
+int sais_patchify_f32(const float* frames_chw, int32_t B, sais_bf16* patches, sais_stream_t stream);
+
+/* ViT self-attention for one block: qkv bf16 [B*197,1152] (q|k|v, head-major inside each third,
+ * vision_transformer.py:82-89) -> out bf16 [B*197,384].  probs (optional) receives the softmax
+ * probabilities fp32 [B,6,197,197] (get_last_selfattention, :216-223). */
+int sais_vit_attention(const sais_bf16* qkv, int32_t B, sais_bf16* out, float* probs, sais_stream_t stream);
+
+/* Whole ViT-S/16 backbone. */
+typedef struct {
+  const float* ln1_w; const float* ln1_b;
+  const sais_bf16* qkv_w; const float* qkv_b;   /* [1152,384], [1152] */
+  const sais_bf16* proj_w; const float* proj_b; /* [384,384], [384] */
+  const float* ln2_w; const float* ln2_b;
+  const sais_bf16* fc1_w; const float* fc1_b;   /* [1536,384], [1536] */
+  const sais_bf16* fc2_w; const float* fc2_b;   /* [384,1536], [384] */
+} SaisVitBlockWeights;
+typedef struct {
+  const sais_bf16* patch_w; /* [384,768] = patch_embed.proj.weight.view(384,-1) */
+  const float* patch_b;     /* [384] */
+  const float* cls_pos0;    /* [384] = cls_token + pos_embed[0] */
+  const float* pos_patch;   /* [196,384] = pos_embed[1:] + patch_b is NOT folded; plain pos_embed[1:] */
+  SaisVitBlockWeights blocks[SAIS_VIT_DEPTH];
+  const float* norm_w; const float* norm_b;
+} SaisVitWeights;
+
+#define SAIS_INPUT_F32_CHW 0 /* normalised fp32 [B,3,224,224] */
+#define SAIS_INPUT_U8_HWC 1  /* raw u8 [B,224,224,3], normalised with ImageNet mean/std */
+size_t sais_vit_workspace_bytes(int32_t chunk_frames);
+/* VisionTransformer.forward (vision_transformer.py:209-214): out_cls fp32 [B,384].
+ * If out_probs != NULL also writes block 12's attention probabilities fp32 [B,6,197,197]
+ * (get_last_selfattention).  Frames are processed in chunks of `chunk_frames` (workspace sized for it).
+ * out_tokens (optional) receives the final-LayerNorm'd tokens fp32 [B,197,384] (get_intermediate_layers n=1). */
+int sais_vit_forward(const SaisVitWeights* w_host, const void* input, int32_t input_kind, int32_t B,
+                     int32_t chunk_frames, void* workspace, size_t workspace_bytes, float* out_cls,
+                     float* out_probs, float* out_tokens, sais_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * SAIS temporal head (prepare_model.py:179-221 + README-patched nn.TransformerEncoder).
+ * Sequences are PACKED: sequence i owns tokens [seq_offsets[i], seq_offsets[i+1]) with S_i = T_i+1
+ * (token 0 = frame_cls, token t+1 = frame t + frame_pos_embeddings[t]); x_frames holds the T_i frame
+ * embeddings of all sequences back to back (fp32 [total_tokens - nseq, 384]).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const sais_bf16* in_w; const float* in_b;   /* [1152,384], [1152] */
+  const sais_bf16* out_w; const float* out_b; /* [384,384], [384] */
+  const float* n1_w; const float* n1_b;
+  const sais_bf16* ff1_w; const float* ff1_b; /* [2048,384], [2048] */
+  const sais_bf16* ff2_w; const float* ff2_b; /* [384,2048], [384] */
+  const float* n2_w; const float* n2_b;
+} SaisTemporalLayerWeights;
+typedef struct {
+  const float* frame_cls; /* [384] */
+  const float* frame_pos; /* [2000,384] stacked frame_pos_embeddings['0'..'1999'] */
+  int32_t n_pos;
+  SaisTemporalLayerWeights layers[SAIS_TMP_LAYERS];
+} SaisTemporalWeights;
+
+/* +pos-emb, prepend CLS (prepare_model.py:189-194): writes fp32 and bf16 token matrices [total_tokens,384]. */
+int sais_temporal_prep(const float* x_frames, const int32_t* seq_offsets, int32_t nseq, int32_t total_tokens,
+                       const float* frame_cls, const float* frame_pos, int32_t n_pos, float* tok_f32,
+                       sais_bf16* tok_bf16, sais_stream_t stream);
+
+/* Multi-head attention core of one temporal layer: qkv bf16 [total_tokens,1152] -> out bf16
+ * [total_tokens,384]; 4 heads x 96, scale 96^-0.5, key_pad (u8 [total_tokens], 1 = padded key) adds -inf.
+ * If attn_out != NULL, sequence i with attn_offsets[i] >= 0 gets its head-averaged probabilities
+ * fp32 [S_i,S_i] written at attn_out + attn_offsets[i] (need_weights=True semantics). */
+int sais_temporal_attention(const sais_bf16* qkv, const int32_t* seq_offsets, const uint8_t* key_pad,
+                            const int64_t* attn_offsets, int32_t nseq, int32_t max_S, sais_bf16* out,
+                            float* attn_out, sais_stream_t stream);
+
+size_t sais_temporal_workspace_bytes(int32_t total_tokens);
+/* 4-layer post-norm encoder over packed sequences.  out_cls fp32 [nseq,384] = relu(out[CLS])
+ * (prepare_model.py:215-220); out_tokens (optional) = raw encoder output fp32 [total_tokens,384];
+ * attention map of the LAST layer as in sais_temporal_attention. */
+int sais_temporal_forward(const SaisTemporalWeights* w_host, const float* x_frames, const int32_t* seq_offsets,
+                          const uint8_t* key_pad, const int64_t* attn_offsets, int32_t nseq, int32_t total_tokens,
+                          int32_t max_S, void* workspace, size_t workspace_bytes, float* out_cls, float* out_tokens,
+                          float* attn_out, sais_stream_t stream);
+
+/* Clip head (prepare_model.py:378-382,405-409): out[b] = W · relu(mean_s cls_a[b,s] + mean_s cls_b[b,s]) + bias.
+ * cls_a/cls_b fp32 [B*nsnip,384] (cls_b may be NULL for single-modality); W fp32 [256,384]. */
+int sais_clip_head(const float* cls_a, const float* cls_b, int32_t B, int32_t nsnip, const float* lin_w,
+                   const float* lin_b, float* out, sais_stream_t stream);
+
+/* Prototype scoring (prepare_miscellaneous.py:102-125, process_inference_results.py:76-91):
+ * probs = softmax-free exp(cos)/sum exp(cos); pred = argmax.  reps fp32 [B,D], protos fp32 [P,D], P <= 64. */
+int sais_prototype_score(const float* reps, const float* protos, int32_t B, int32_t P, int32_t D, float* probs,
+                         float* sims, int32_t* pred, sais_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAIS_B200_H_ */

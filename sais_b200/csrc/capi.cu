@@ -1,0 +1,408 @@
+// extern "C" surface of libsais_b200.so (declared in include/sais_b200.h) plus the host-side glue:
+// error text, launch counter, TMA descriptor encoding through the driver entry point, and the two
+// composed forwards (ViT-S/16 backbone, SAIS temporal encoder) that sequence the kernels on one stream.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <atomic>
+#include <mutex>
+
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sais {
+
+namespace {
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+}  // namespace
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return kOk;
+  set_last_error("%s: %s", what, cudaGetErrorString(e));
+  return kErrCuda;
+}
+
+// ---- launch counter + optional CUDA-event profiler ------------------------------------------------------
+namespace {
+constexpr int kMaxProfSlots = 8192;
+struct Prof {
+  bool on = false;
+  int used = 0;
+  cudaEvent_t ev[kMaxProfSlots][2];
+  int cls[kMaxProfSlots];
+  int created = 0;
+  double work[kNumClasses] = {0};
+  int64_t launches[kNumClasses] = {0};
+} g_prof;
+std::atomic<int64_t> g_cls_launches[kNumClasses];
+}  // namespace
+
+LaunchScope::LaunchScope(int cls, cudaStream_t stream, double work) : cls_(cls), stream_(stream), slot_(-1) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  g_cls_launches[cls].fetch_add(1, std::memory_order_relaxed);
+  if (g_prof.on && g_prof.used < kMaxProfSlots) {
+    slot_ = g_prof.used++;
+    if (slot_ >= g_prof.created) {
+      cudaEventCreate(&g_prof.ev[slot_][0]);
+      cudaEventCreate(&g_prof.ev[slot_][1]);
+      g_prof.created = slot_ + 1;
+    }
+    g_prof.cls[slot_] = cls;
+    g_prof.work[cls] += work;
+    g_prof.launches[cls] += 1;
+    cudaEventRecord(g_prof.ev[slot_][0], stream);
+  }
+}
+LaunchScope::~LaunchScope() {
+  if (slot_ >= 0) cudaEventRecord(g_prof.ev[slot_][1], stream_);
+}
+
+int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;
+  }
+  return sms;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_rows, uint32_t box_cols) {
+  static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  });
+  if (!encode) {
+    set_last_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+    return kErrDriver;
+  }
+  const cuuint64_t gdim[2] = {cols, rows};
+  const cuuint64_t gstride[1] = {ld * 2};
+  const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box,
+                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box=%ux%u", int(r),
+                   (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, box_cols);
+    return kErrDriver;
+  }
+  return kOk;
+}
+
+namespace {
+
+// bump allocator over the caller's workspace, 256-byte aligned slices
+struct Arena {
+  uint8_t* p;
+  size_t left;
+  bool ok = true;
+  void* take(size_t bytes) {
+    const size_t need = (bytes + 255) & ~size_t(255);
+    if (need > left) {
+      ok = false;
+      return nullptr;
+    }
+    void* r = p;
+    p += need;
+    left -= need;
+    return r;
+  }
+};
+
+inline size_t a256(size_t b) { return (b + 255) & ~size_t(255); }
+
+const float kMean[3] = {0.485f, 0.456f, 0.406f};  // extract_representations.py:161
+const float kStd[3] = {0.229f, 0.224f, 0.225f};
+
+}  // namespace
+}  // namespace sais
+
+using namespace sais;
+
+extern "C" {
+
+int sais_version(void) { return 100; }
+const char* sais_last_error(void) { return g_err; }
+int64_t sais_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+void sais_profile_begin(void) {
+  g_prof.on = true;
+  g_prof.used = 0;
+  for (int c = 0; c < kNumClasses; ++c) g_prof.work[c] = 0, g_prof.launches[c] = 0;
+}
+
+int sais_profile_end(double* ms_per_class, double* work_per_class, int64_t* launches_per_class, int32_t n_classes) {
+  g_prof.on = false;
+  if (n_classes < kNumClasses) {
+    set_last_error("profile_end: need room for %d classes", int(kNumClasses));
+    return kErrInvalidArg;
+  }
+  int rc = check_cuda(cudaDeviceSynchronize(), "profile_end sync");
+  if (rc) return rc;
+  for (int c = 0; c < n_classes; ++c) ms_per_class[c] = 0, work_per_class[c] = 0, launches_per_class[c] = 0;
+  for (int i = 0; i < g_prof.used; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_prof.ev[i][0], g_prof.ev[i][1]) == cudaSuccess) ms_per_class[g_prof.cls[i]] += ms;
+  }
+  for (int c = 0; c < kNumClasses; ++c) work_per_class[c] = g_prof.work[c], launches_per_class[c] = g_prof.launches[c];
+  return kOk;
+}
+
+int sais_gemm_bias_act(const SaisGemmArgs* args, sais_stream_t stream) {
+  if (!args) {
+    set_last_error("gemm: null args");
+    return kErrInvalidArg;
+  }
+  return gemm_bias_act(*args, static_cast<cudaStream_t>(stream));
+}
+
+int sais_layernorm(const float* x, int64_t in_pitch, const float* gamma, const float* beta, float eps,
+                   int64_t rows, int32_t cols, float* out_f32, sais_bf16* out_bf16, sais_stream_t stream) {
+  if (cols != SAIS_VIT_DIM) {
+    set_last_error("layernorm: cols must be 384 (got %d)", cols);
+    return kErrShape;
+  }
+  return layernorm(x, in_pitch, gamma, beta, eps, rows, out_f32, out_bf16, static_cast<cudaStream_t>(stream));
+}
+
+int sais_normalize_patchify_u8(const uint8_t* frames, int32_t B, const float* mean3_host, const float* std3_host,
+                               sais_bf16* patches, sais_stream_t stream) {
+  return normalize_patchify_u8(frames, B, mean3_host ? mean3_host : kMean, std3_host ? std3_host : kStd, patches,
+                               static_cast<cudaStream_t>(stream));
+}
+
+int sais_patchify_f32(const float* frames_chw, int32_t B, sais_bf16* patches, sais_stream_t stream) {
+  return patchify_f32(frames_chw, B, patches, static_cast<cudaStream_t>(stream));
+}
+
+int sais_vit_attention(const sais_bf16* qkv, int32_t B, sais_bf16* out, float* probs, sais_stream_t stream) {
+  return vit_attention(qkv, B, out, probs, static_cast<cudaStream_t>(stream));
+}
+
+size_t sais_vit_workspace_bytes(int32_t chunk_frames) {
+  if (chunk_frames <= 0) return 0;
+  const size_t tok = size_t(chunk_frames) * SAIS_VIT_TOKENS;
+  return a256(tok * SAIS_VIT_DIM * 4)         // x   fp32 residual stream
+         + a256(tok * SAIS_VIT_DIM * 2)       // xn  bf16 LayerNorm output / attention output
+         + a256(tok * 3 * SAIS_VIT_DIM * 2)   // qkv bf16
+         + a256(tok * SAIS_VIT_DIM * 2)       // attention output bf16
+         + a256(tok * SAIS_VIT_HIDDEN * 2);   // MLP hidden bf16 (aliased by the patch matrix)
+}
+
+int sais_vit_forward(const SaisVitWeights* w, const void* input, int32_t input_kind, int32_t B,
+                     int32_t chunk_frames, void* workspace, size_t workspace_bytes, float* out_cls,
+                     float* out_probs, float* out_tokens, sais_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!w || !input || !workspace || !out_cls || B < 0 || chunk_frames <= 0 ||
+      (input_kind != SAIS_INPUT_F32_CHW && input_kind != SAIS_INPUT_U8_HWC)) {
+    set_last_error("vit_forward: bad arguments");
+    return kErrInvalidArg;
+  }
+  if (workspace_bytes < sais_vit_workspace_bytes(chunk_frames)) {
+    set_last_error("vit_forward: workspace too small (%zu < %zu)", workspace_bytes,
+                   sais_vit_workspace_bytes(chunk_frames));
+    return kErrWorkspace;
+  }
+  constexpr int Dm = SAIS_VIT_DIM, Tk = SAIS_VIT_TOKENS, Hid = SAIS_VIT_HIDDEN;
+  for (int b0 = 0; b0 < B; b0 += chunk_frames) {
+    const int Bc = (B - b0 < chunk_frames) ? (B - b0) : chunk_frames;
+    const int64_t tok = int64_t(Bc) * Tk;
+    Arena ar{static_cast<uint8_t*>(workspace), workspace_bytes};
+    float* x = static_cast<float*>(ar.take(size_t(chunk_frames) * Tk * Dm * 4));
+    sais_bf16* xn = static_cast<sais_bf16*>(ar.take(size_t(chunk_frames) * Tk * Dm * 2));
+    sais_bf16* qkv = static_cast<sais_bf16*>(ar.take(size_t(chunk_frames) * Tk * 3 * Dm * 2));
+    sais_bf16* ao = static_cast<sais_bf16*>(ar.take(size_t(chunk_frames) * Tk * Dm * 2));
+    sais_bf16* hid = static_cast<sais_bf16*>(ar.take(size_t(chunk_frames) * Tk * Hid * 2));
+    sais_bf16* patches = hid;  // [Bc*196, 768] <= [Bc*197, 1536]
+    if (!ar.ok) {
+      set_last_error("vit_forward: workspace carve failed");
+      return kErrWorkspace;
+    }
+    int rc;
+    // K0: frame normalisation + patch layout
+    if (input_kind == SAIS_INPUT_U8_HWC)
+      rc = normalize_patchify_u8(static_cast<const uint8_t*>(input) + size_t(b0) * 224 * 224 * 3, Bc, kMean, kStd,
+                                 patches, stream);
+    else
+      rc = patchify_f32(static_cast<const float*>(input) + size_t(b0) * 3 * 224 * 224, Bc, patches, stream);
+    if (rc) return rc;
+    // K1: patch-embed GEMM, epilogue adds bias + pos_embed[1+p] and scatters to token row b*197+1+p
+    SaisGemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.a = patches; g.w = w->patch_w; g.bias = w->patch_b; g.out_f32 = x; g.row_add = w->pos_patch;
+    g.M = int64_t(Bc) * SAIS_VIT_PATCHES; g.N = Dm; g.K = SAIS_VIT_PATCH_K;
+    g.lda = SAIS_VIT_PATCH_K; g.ldw = SAIS_VIT_PATCH_K; g.ldo32 = Dm; g.remap_group = SAIS_VIT_PATCHES;
+    if ((rc = gemm_bias_act(g, stream))) return rc;
+    if ((rc = write_cls_rows(w->cls_pos0, Bc, x, stream))) return rc;
+
+    for (int l = 0; l < SAIS_VIT_DEPTH; ++l) {
+      const SaisVitBlockWeights& bw = w->blocks[l];
+      const bool last = (l == SAIS_VIT_DEPTH - 1);
+      // norm1
+      if ((rc = layernorm(x, Dm, bw.ln1_w, bw.ln1_b, 1e-6f, tok, nullptr, xn, stream))) return rc;
+      // qkv
+      memset(&g, 0, sizeof(g));
+      g.a = xn; g.w = bw.qkv_w; g.bias = bw.qkv_b; g.out_bf16 = qkv;
+      g.M = tok; g.N = 3 * Dm; g.K = Dm; g.lda = Dm; g.ldw = Dm; g.ldo16 = 3 * Dm;
+      if ((rc = gemm_bias_act(g, stream))) return rc;
+      // attention (+ probabilities of the last block on request)
+      float* probs = (last && out_probs) ? out_probs + size_t(b0) * SAIS_VIT_HEADS * Tk * Tk : nullptr;
+      if ((rc = vit_attention(qkv, Bc, ao, probs, stream))) return rc;
+      // proj + residual
+      memset(&g, 0, sizeof(g));
+      g.a = ao; g.w = bw.proj_w; g.bias = bw.proj_b; g.residual = x; g.out_f32 = x;
+      g.M = tok; g.N = Dm; g.K = Dm; g.lda = Dm; g.ldw = Dm; g.ldr = Dm; g.ldo32 = Dm;
+      if ((rc = gemm_bias_act(g, stream))) return rc;
+      // norm2
+      if ((rc = layernorm(x, Dm, bw.ln2_w, bw.ln2_b, 1e-6f, tok, nullptr, xn, stream))) return rc;
+      // fc1 + GELU
+      memset(&g, 0, sizeof(g));
+      g.a = xn; g.w = bw.fc1_w; g.bias = bw.fc1_b; g.out_bf16 = hid; g.act = SAIS_ACT_GELU_ERF;
+      g.M = tok; g.N = Hid; g.K = Dm; g.lda = Dm; g.ldw = Dm; g.ldo16 = Hid;
+      if ((rc = gemm_bias_act(g, stream))) return rc;
+      // fc2 + residual
+      memset(&g, 0, sizeof(g));
+      g.a = hid; g.w = bw.fc2_w; g.bias = bw.fc2_b; g.residual = x; g.out_f32 = x;
+      g.M = tok; g.N = Dm; g.K = Hid; g.lda = Hid; g.ldw = Hid; g.ldr = Dm; g.ldo32 = Dm;
+      if ((rc = gemm_bias_act(g, stream))) return rc;
+    }
+    // final norm: only the CLS rows are consumed (vision_transformer.py:213-214)
+    if ((rc = layernorm(x, int64_t(Tk) * Dm, w->norm_w, w->norm_b, 1e-6f, Bc, out_cls + size_t(b0) * Dm, nullptr,
+                        stream)))
+      return rc;
+    if (out_tokens) {
+      if ((rc = layernorm(x, Dm, w->norm_w, w->norm_b, 1e-6f, tok, out_tokens + size_t(b0) * Tk * Dm, nullptr,
+                          stream)))
+        return rc;
+    }
+  }
+  return kOk;
+}
+
+int sais_temporal_prep(const float* x_frames, const int32_t* seq_offsets, int32_t nseq, int32_t total_tokens,
+                       const float* frame_cls, const float* frame_pos, int32_t n_pos, float* tok_f32,
+                       sais_bf16* tok_bf16, sais_stream_t stream) {
+  return temporal_prep(x_frames, seq_offsets, nseq, total_tokens, frame_cls, frame_pos, n_pos, tok_f32, tok_bf16,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int sais_temporal_attention(const sais_bf16* qkv, const int32_t* seq_offsets, const uint8_t* key_pad,
+                            const int64_t* attn_offsets, int32_t nseq, int32_t max_S, sais_bf16* out,
+                            float* attn_out, sais_stream_t stream) {
+  return temporal_attention(qkv, seq_offsets, key_pad, attn_offsets, nseq, max_S, out, attn_out,
+                            static_cast<cudaStream_t>(stream));
+}
+
+size_t sais_temporal_workspace_bytes(int32_t total_tokens) {
+  if (total_tokens <= 0) return 0;
+  const size_t t = size_t(total_tokens);
+  return a256(t * SAIS_VIT_DIM * 4) * 2     // x fp32, y fp32 (pre-norm sum)
+         + a256(t * SAIS_VIT_DIM * 2) * 2   // x bf16, attention output bf16
+         + a256(t * 3 * SAIS_VIT_DIM * 2)   // qkv bf16
+         + a256(t * SAIS_TMP_FF * 2);       // FF hidden bf16
+}
+
+int sais_temporal_forward(const SaisTemporalWeights* w, const float* x_frames, const int32_t* seq_offsets,
+                          const uint8_t* key_pad, const int64_t* attn_offsets, int32_t nseq, int32_t total_tokens,
+                          int32_t max_S, void* workspace, size_t workspace_bytes, float* out_cls, float* out_tokens,
+                          float* attn_out, sais_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (nseq == 0) return kOk;
+  if (!w || !seq_offsets || !workspace || nseq < 0 || total_tokens < nseq || max_S <= 0 ||
+      (!x_frames && total_tokens > nseq)) {
+    set_last_error("temporal_forward: bad arguments");
+    return kErrInvalidArg;
+  }
+  if (max_S - 1 > w->n_pos) {
+    set_last_error("temporal_forward: %d frames exceed the %d positional embeddings", max_S - 1, w->n_pos);
+    return kErrShape;
+  }
+  if (workspace_bytes < sais_temporal_workspace_bytes(total_tokens)) {
+    set_last_error("temporal_forward: workspace too small (%zu < %zu)", workspace_bytes,
+                   sais_temporal_workspace_bytes(total_tokens));
+    return kErrWorkspace;
+  }
+  constexpr int Dm = SAIS_VIT_DIM, FF = SAIS_TMP_FF;
+  const size_t t = size_t(total_tokens);
+  Arena ar{static_cast<uint8_t*>(workspace), workspace_bytes};
+  float* x = static_cast<float*>(ar.take(t * Dm * 4));
+  float* y = static_cast<float*>(ar.take(t * Dm * 4));
+  sais_bf16* xb = static_cast<sais_bf16*>(ar.take(t * Dm * 2));
+  sais_bf16* ao = static_cast<sais_bf16*>(ar.take(t * Dm * 2));
+  sais_bf16* qkv = static_cast<sais_bf16*>(ar.take(t * 3 * Dm * 2));
+  sais_bf16* hid = static_cast<sais_bf16*>(ar.take(t * FF * 2));
+  if (!ar.ok) {
+    set_last_error("temporal_forward: workspace carve failed");
+    return kErrWorkspace;
+  }
+  int rc;
+  if ((rc = temporal_prep(x_frames, seq_offsets, nseq, total_tokens, w->frame_cls, w->frame_pos, w->n_pos, x, xb,
+                          stream)))
+    return rc;
+  SaisGemmArgs g;
+  for (int l = 0; l < SAIS_TMP_LAYERS; ++l) {
+    const SaisTemporalLayerWeights& lw = w->layers[l];
+    const bool last = (l == SAIS_TMP_LAYERS - 1);
+    // in-proj
+    memset(&g, 0, sizeof(g));
+    g.a = xb; g.w = lw.in_w; g.bias = lw.in_b; g.out_bf16 = qkv;
+    g.M = total_tokens; g.N = 3 * Dm; g.K = Dm; g.lda = Dm; g.ldw = Dm; g.ldo16 = 3 * Dm;
+    if ((rc = gemm_bias_act(g, stream))) return rc;
+    // attention; only the last layer's head-mean map is returned (README-patched encoder keeps the last)
+    if ((rc = temporal_attention(qkv, seq_offsets, key_pad, last ? attn_offsets : nullptr, nseq, max_S, ao,
+                                 last ? attn_out : nullptr, stream)))
+      return rc;
+    // out-proj + residual -> y ; x = LN1(y)
+    memset(&g, 0, sizeof(g));
+    g.a = ao; g.w = lw.out_w; g.bias = lw.out_b; g.residual = x; g.out_f32 = y;
+    g.M = total_tokens; g.N = Dm; g.K = Dm; g.lda = Dm; g.ldw = Dm; g.ldr = Dm; g.ldo32 = Dm;
+    if ((rc = gemm_bias_act(g, stream))) return rc;
+    if ((rc = layernorm(y, Dm, lw.n1_w, lw.n1_b, 1e-5f, total_tokens, x, xb, stream))) return rc;
+    // FF: linear1 + ReLU, linear2 + residual -> y ; x = LN2(y)
+    memset(&g, 0, sizeof(g));
+    g.a = xb; g.w = lw.ff1_w; g.bias = lw.ff1_b; g.out_bf16 = hid; g.act = SAIS_ACT_RELU;
+    g.M = total_tokens; g.N = FF; g.K = Dm; g.lda = Dm; g.ldw = Dm; g.ldo16 = FF;
+    if ((rc = gemm_bias_act(g, stream))) return rc;
+    memset(&g, 0, sizeof(g));
+    g.a = hid; g.w = lw.ff2_w; g.bias = lw.ff2_b; g.residual = x; g.out_f32 = y;
+    g.M = total_tokens; g.N = Dm; g.K = FF; g.lda = FF; g.ldw = FF; g.ldr = Dm; g.ldo32 = Dm;
+    if ((rc = gemm_bias_act(g, stream))) return rc;
+    float* xo = (last && out_tokens) ? out_tokens : x;
+    if ((rc = layernorm(y, Dm, lw.n2_w, lw.n2_b, 1e-5f, total_tokens, xo, last ? nullptr : xb, stream))) return rc;
+    if (last && out_cls) {
+      if ((rc = gather_cls_relu(xo, seq_offsets, nseq, out_cls, stream))) return rc;
+    }
+  }
+  return kOk;
+}
+
+int sais_clip_head(const float* cls_a, const float* cls_b, int32_t B, int32_t nsnip, const float* lin_w,
+                   const float* lin_b, float* out, sais_stream_t stream) {
+  return clip_head(cls_a, cls_b, B, nsnip, lin_w, lin_b, out, static_cast<cudaStream_t>(stream));
+}
+
+int sais_prototype_score(const float* reps, const float* protos, int32_t B, int32_t P, int32_t D, float* probs,
+                         float* sims, int32_t* pred, sais_stream_t stream) {
+  return prototype_score(reps, protos, B, P, D, probs, sims, pred, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,395 @@
+// Memory-bound kernels of the SAIS hot path: LayerNorm, frame normalisation + patch layout,
+// CLS/positional-embedding assembly, clip head and prototype scoring.  All are HBM/L2-bound:
+// 16-byte vector accesses, warp-shuffle reductions, no shared-memory staging where there is no reuse.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sais {
+
+namespace {
+
+constexpr int D = 384;
+
+// ----------------------------------------------------------------------------------------------
+// LayerNorm(384): one warp per row, the row lives in registers (12 floats per lane), two-pass
+// statistics in fp32 (matches torch's mean / biased variance).
+// Reference: nn.LayerNorm in vision_transformer.py:99,103,156 (eps 1e-6) and
+// nn.TransformerEncoderLayer.norm1/norm2 (eps 1e-5).
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) layernorm384_kernel(const float* __restrict__ x, int64_t in_pitch,
+                                                           const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float eps, int64_t rows,
+                                                           float* __restrict__ out_f32,
+                                                           __nv_bfloat16* __restrict__ out_bf16) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * in_pitch;
+  float4 v[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) v[i] = *reinterpret_cast<const float4*>(xr + i * 128 + lane * 4);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) * (1.0f / D);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    ss += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(ss) * (1.0f / D) + eps);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int c = i * 128 + lane * 4;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+    float4 y;
+    y.x = (v[i].x - mean) * rstd * g.x + b.x;
+    y.y = (v[i].y - mean) * rstd * g.y + b.y;
+    y.z = (v[i].z - mean) * rstd * g.z + b.z;
+    y.w = (v[i].w - mean) * rstd * g.w + b.w;
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * D + c) = y;
+    if (out_bf16) {
+      uint2 o;
+      o.x = pack_bf16x2(y.x, y.y);
+      o.y = pack_bf16x2(y.z, y.w);
+      *reinterpret_cast<uint2*>(out_bf16 + row * D + c) = o;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Frame normalisation fused with the patch layout the patch-embed GEMM consumes.
+// One thread = one (frame, image row y, patch column px): reads 16 pixels x 3 channels (48 bytes,
+// contiguous) and writes three 32-byte runs, one per channel, at k = c*256 + (y%16)*16.
+// Reference: ToTensor + Normalize, extract_representations.py:158-162; PatchEmbed conv weight
+// layout [384,3,16,16], vision_transformer.py:126.
+// ----------------------------------------------------------------------------------------------
+struct NormConsts {
+  float scale[3];  // 1 / (255 * std)
+  float shift[3];  // -mean / std
+};
+
+__global__ void __launch_bounds__(256) normalize_patchify_u8_kernel(const uint8_t* __restrict__ frames, int B,
+                                                                    NormConsts nc,
+                                                                    __nv_bfloat16* __restrict__ patches) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t total = int64_t(B) * 224 * 14;
+  if (t >= total) return;
+  const int px = int(t % 14);
+  const int y = int((t / 14) % 224);
+  const int64_t b = t / (14 * 224);
+  const uint8_t* src = frames + ((b * 224 + y) * 224 + px * 16) * 3;
+  uint32_t w[12];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src) + i);
+    w[4 * i] = u.x; w[4 * i + 1] = u.y; w[4 * i + 2] = u.z; w[4 * i + 3] = u.w;
+  }
+  const int py = y >> 4, ky = y & 15;
+  __nv_bfloat16* dst = patches + (b * 196 + py * 14 + px) * 768 + ky * 16;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    uint32_t o[8];
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+      const int i0 = j * 3 + c, i1 = (j + 1) * 3 + c;
+      const float f0 = float((w[i0 >> 2] >> ((i0 & 3) * 8)) & 0xff);
+      const float f1 = float((w[i1 >> 2] >> ((i1 & 3) * 8)) & 0xff);
+      o[j >> 1] = pack_bf16x2(fmaf(f0, nc.scale[c], nc.shift[c]), fmaf(f1, nc.scale[c], nc.shift[c]));
+    }
+    uint4* d4 = reinterpret_cast<uint4*>(dst + c * 256);
+    d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  }
+}
+
+// fp32 NCHW (already normalised, what the reference model is called with) -> bf16 patch matrix.
+__global__ void __launch_bounds__(256) patchify_f32_kernel(const float* __restrict__ frames, int B,
+                                                           __nv_bfloat16* __restrict__ patches) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t total = int64_t(B) * 3 * 224 * 14;
+  if (t >= total) return;
+  const int px = int(t % 14);
+  const int y = int((t / 14) % 224);
+  const int c = int((t / (14 * 224)) % 3);
+  const int64_t b = t / (14 * 224 * 3);
+  const float4* src = reinterpret_cast<const float4*>(frames + ((b * 3 + c) * 224 + y) * 224 + px * 16);
+  const int py = y >> 4, ky = y & 15;
+  uint32_t o[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 f = __ldg(src + i);
+    o[2 * i] = pack_bf16x2(f.x, f.y);
+    o[2 * i + 1] = pack_bf16x2(f.z, f.w);
+  }
+  uint4* d4 = reinterpret_cast<uint4*>(patches + (b * 196 + py * 14 + px) * 768 + c * 256 + ky * 16);
+  d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
+  d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
+// x[b, 0, :] = cls_token + pos_embed[0]   (vision_transformer.py:201-205)
+__global__ void write_cls_rows_kernel(const float* __restrict__ cls_pos0, int B, float* __restrict__ x) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * (D / 4)) return;
+  const int b = t / (D / 4), c = (t % (D / 4)) * 4;
+  *reinterpret_cast<float4*>(x + int64_t(b) * 197 * D + c) = __ldg(reinterpret_cast<const float4*>(cls_pos0 + c));
+}
+
+// ----------------------------------------------------------------------------------------------
+// Temporal token assembly (prepare_model.py:189-194): token 0 = frame_cls, token s = frame[s-1] + pos[s-1].
+// One block per packed sequence.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) temporal_prep_kernel(const float* __restrict__ x_frames,
+                                                            const int32_t* __restrict__ seq_offsets,
+                                                            const float* __restrict__ frame_cls,
+                                                            const float* __restrict__ frame_pos,
+                                                            float* __restrict__ tok_f32,
+                                                            __nv_bfloat16* __restrict__ tok_bf16) {
+  const int i = blockIdx.x;
+  const int t0 = seq_offsets[i];
+  const int S = seq_offsets[i + 1] - t0;
+  const float* xf = x_frames + int64_t(t0 - i) * D;
+  for (int e = threadIdx.x; e < S * (D / 4); e += blockDim.x) {
+    const int s = e / (D / 4), c = (e % (D / 4)) * 4;
+    float4 v;
+    if (s == 0) {
+      v = __ldg(reinterpret_cast<const float4*>(frame_cls + c));
+    } else {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(xf + int64_t(s - 1) * D + c));
+      const float4 p = __ldg(reinterpret_cast<const float4*>(frame_pos + int64_t(s - 1) * D + c));
+      v = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+    }
+    const int64_t o = int64_t(t0 + s) * D + c;
+    *reinterpret_cast<float4*>(tok_f32 + o) = v;
+    uint2 b;
+    b.x = pack_bf16x2(v.x, v.y);
+    b.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(tok_bf16 + o) = b;
+  }
+}
+
+// out_cls[i] = relu(tokens[seq_offsets[i]])   (prepare_model.py:215,220)
+__global__ void gather_cls_relu_kernel(const float* __restrict__ tok, const int32_t* __restrict__ seq_offsets,
+                                       int nseq, float* __restrict__ out_cls) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nseq * (D / 4)) return;
+  const int i = t / (D / 4), c = (t % (D / 4)) * 4;
+  float4 v = *reinterpret_cast<const float4*>(tok + int64_t(seq_offsets[i]) * D + c);
+  v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+  *reinterpret_cast<float4*>(out_cls + int64_t(i) * D + c) = v;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Clip head (prepare_model.py:378-382, 405, 409): v = relu(mean_s a[b,s] + mean_s f[b,s]); out = W v + bias.
+// fp32 throughout.  4 clips per block so each W row is read once per 4 clips; warp per output row.
+// ----------------------------------------------------------------------------------------------
+constexpr int kClipsPerBlock = 4;
+constexpr int kOut = 256;
+
+__global__ void __launch_bounds__(256) clip_head_kernel(const float* __restrict__ cls_a,
+                                                        const float* __restrict__ cls_b, int B, int nsnip,
+                                                        const float* __restrict__ W, const float* __restrict__ bias,
+                                                        float* __restrict__ out) {
+  __shared__ float v[kClipsPerBlock][D];
+  const int b0 = blockIdx.x * kClipsPerBlock;
+  const float inv = 1.0f / float(nsnip);
+  for (int e = threadIdx.x; e < kClipsPerBlock * D; e += blockDim.x) {
+    const int cb = e / D, k = e % D;
+    const int b = b0 + cb;
+    float acc = 0.f;
+    if (b < B) {
+      float sa = 0.f, sb = 0.f;
+      for (int s = 0; s < nsnip; ++s) {
+        sa += cls_a[(int64_t(b) * nsnip + s) * D + k];
+        if (cls_b) sb += cls_b[(int64_t(b) * nsnip + s) * D + k];
+      }
+      // torch.mean(...) per modality, then the sum of the two modalities, then ReLU
+      acc = sa * inv + (cls_b ? sb * inv : 0.f);
+      acc = fmaxf(acc, 0.f);
+    }
+    v[cb][k] = acc;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int o = warp; o < kOut; o += 8) {
+    float w[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) w[i] = __ldg(W + int64_t(o) * D + i * 32 + lane);
+    const float bo = bias ? __ldg(bias + o) : 0.f;
+#pragma unroll
+    for (int cb = 0; cb < kClipsPerBlock; ++cb) {
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 12; ++i) acc = fmaf(w[i], v[cb][i * 32 + lane], acc);
+      acc = warp_sum(acc);
+      if (lane == 0 && b0 + cb < B) out[int64_t(b0 + cb) * kOut + o] = acc + bo;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Prototype scoring (prepare_miscellaneous.py:102-125; process_inference_results.py:76-91):
+// s_n = s/||s||, p_n = p/||p||, sim = s_n·p_n, probs = exp(sim)/sum exp(sim), pred = argmax.
+// One warp per clip; prototypes (P <= 64) are re-normalised per warp from L1/L2.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) prototype_score_kernel(const float* __restrict__ reps,
+                                                              const float* __restrict__ protos, int B, int P, int Dd,
+                                                              float* __restrict__ probs, float* __restrict__ sims,
+                                                              int32_t* __restrict__ pred) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const float* s = reps + int64_t(b) * Dd;
+  float ss = 0.f;
+  for (int k = lane; k < Dd; k += 32) ss = fmaf(s[k], s[k], ss);
+  const float sn = sqrtf(warp_sum(ss));
+  float my_e = 0.f, my_sim = 0.f;  // lane p%32 keeps prototype p (and p+32 in the second slot)
+  float my_e2 = 0.f, my_sim2 = 0.f;
+  float esum = 0.f;
+  for (int p = 0; p < P; ++p) {
+    const float* pr = protos + int64_t(p) * Dd;
+    float pp = 0.f;
+    for (int k = lane; k < Dd; k += 32) pp = fmaf(pr[k], pr[k], pp);
+    const float pn = sqrtf(warp_sum(pp));
+    float dot = 0.f;
+    for (int k = lane; k < Dd; k += 32) dot = fmaf(s[k] / sn, pr[k] / pn, dot);
+    dot = warp_sum(dot);
+    const float e = expf(dot);
+    esum += e;
+    if ((p & 31) == lane) {
+      if (p < 32) { my_e = e; my_sim = dot; } else { my_e2 = e; my_sim2 = dot; }
+    }
+  }
+  // argmax over probabilities (first maximal index, like torch.argmax)
+  float best = -1.f;
+  int best_i = 0x7fffffff;
+  if (lane < P) { best = my_e / esum; best_i = lane; }
+  if (lane + 32 < P) {
+    const float pv = my_e2 / esum;
+    if (pv > best) { best = pv; best_i = lane + 32; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+  }
+  if (lane < P) {
+    probs[int64_t(b) * P + lane] = my_e / esum;
+    if (sims) sims[int64_t(b) * P + lane] = my_sim;
+  }
+  if (lane + 32 < P) {
+    probs[int64_t(b) * P + lane + 32] = my_e2 / esum;
+    if (sims) sims[int64_t(b) * P + lane + 32] = my_sim2;
+  }
+  if (lane == 0 && pred) pred[b] = best_i;
+}
+
+}  // namespace
+
+int layernorm(const float* x, int64_t in_pitch, const float* gamma, const float* beta, float eps, int64_t rows,
+              float* out_f32, sais_bf16* out_bf16, cudaStream_t stream) {
+  if (rows == 0) return kOk;
+  if (!x || !gamma || !beta || (!out_f32 && !out_bf16) || rows < 0 || in_pitch % 4) {
+    set_last_error("layernorm: bad arguments");
+    return kErrInvalidArg;
+  }
+  const int64_t blocks = (rows + 7) / 8;
+  LaunchScope ls(kClsLayerNorm, stream, double(rows) * D * (4 + (out_f32 ? 4 : 0) + (out_bf16 ? 2 : 0)));
+  layernorm384_kernel<<<unsigned(blocks), 256, 0, stream>>>(x, in_pitch, gamma, beta, eps, rows, out_f32,
+                                                            reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  return check_cuda(cudaGetLastError(), "layernorm launch");
+}
+
+int normalize_patchify_u8(const uint8_t* frames, int B, const float* mean3, const float* std3, sais_bf16* patches,
+                          cudaStream_t stream) {
+  if (B == 0) return kOk;
+  if (!frames || !patches || !mean3 || !std3 || B < 0) {
+    set_last_error("normalize_patchify_u8: bad arguments");
+    return kErrInvalidArg;
+  }
+  NormConsts nc;
+  for (int c = 0; c < 3; ++c) {
+    nc.scale[c] = 1.0f / (255.0f * std3[c]);
+    nc.shift[c] = -mean3[c] / std3[c];
+  }
+  const int64_t total = int64_t(B) * 224 * 14;
+  LaunchScope ls(kClsPatchify, stream, double(B) * 224 * 224 * 3 * 3);
+  normalize_patchify_u8_kernel<<<unsigned((total + 255) / 256), 256, 0, stream>>>(
+      frames, B, nc, reinterpret_cast<__nv_bfloat16*>(patches));
+  return check_cuda(cudaGetLastError(), "normalize_patchify_u8 launch");
+}
+
+int patchify_f32(const float* frames, int B, sais_bf16* patches, cudaStream_t stream) {
+  if (B == 0) return kOk;
+  if (!frames || !patches || B < 0) {
+    set_last_error("patchify_f32: bad arguments");
+    return kErrInvalidArg;
+  }
+  const int64_t total = int64_t(B) * 3 * 224 * 14;
+  LaunchScope ls(kClsPatchify, stream, double(B) * 224 * 224 * 3 * 6);
+  patchify_f32_kernel<<<unsigned((total + 255) / 256), 256, 0, stream>>>(frames, B,
+                                                                         reinterpret_cast<__nv_bfloat16*>(patches));
+  return check_cuda(cudaGetLastError(), "patchify_f32 launch");
+}
+
+int write_cls_rows(const float* cls_pos0, int B, float* x, cudaStream_t stream) {
+  if (B == 0) return kOk;
+  const int total = B * (D / 4);
+  LaunchScope ls(kClsMisc, stream, double(B) * D * 8);
+  write_cls_rows_kernel<<<(total + 255) / 256, 256, 0, stream>>>(cls_pos0, B, x);
+  return check_cuda(cudaGetLastError(), "write_cls_rows launch");
+}
+
+int temporal_prep(const float* x_frames, const int32_t* seq_offsets, int nseq, int total_tokens,
+                  const float* frame_cls, const float* frame_pos, int n_pos, float* tok_f32, sais_bf16* tok_bf16,
+                  cudaStream_t stream) {
+  (void)n_pos;
+  if (nseq == 0) return kOk;
+  if (!seq_offsets || !frame_cls || !frame_pos || !tok_f32 || !tok_bf16 || nseq < 0) {
+    set_last_error("temporal_prep: bad arguments");
+    return kErrInvalidArg;
+  }
+  LaunchScope ls(kClsMisc, stream, double(total_tokens) * D * 14);
+  temporal_prep_kernel<<<nseq, 128, 0, stream>>>(x_frames, seq_offsets, frame_cls, frame_pos, tok_f32,
+                                                 reinterpret_cast<__nv_bfloat16*>(tok_bf16));
+  return check_cuda(cudaGetLastError(), "temporal_prep launch");
+}
+
+int gather_cls_relu(const float* tok_f32, const int32_t* seq_offsets, int nseq, float* out_cls,
+                    cudaStream_t stream) {
+  if (nseq == 0) return kOk;
+  const int total = nseq * (D / 4);
+  LaunchScope ls(kClsMisc, stream, double(nseq) * D * 8);
+  gather_cls_relu_kernel<<<(total + 255) / 256, 256, 0, stream>>>(tok_f32, seq_offsets, nseq, out_cls);
+  return check_cuda(cudaGetLastError(), "gather_cls_relu launch");
+}
+
+int clip_head(const float* cls_a, const float* cls_b, int B, int nsnip, const float* lin_w, const float* lin_b,
+              float* out, cudaStream_t stream) {
+  if (B == 0) return kOk;
+  if (!cls_a || !lin_w || !out || B < 0 || nsnip <= 0) {
+    set_last_error("clip_head: bad arguments");
+    return kErrInvalidArg;
+  }
+  LaunchScope ls(kClsMisc, stream, double(B) * (nsnip * D * 8 + 1024));
+  clip_head_kernel<<<(B + kClipsPerBlock - 1) / kClipsPerBlock, 256, 0, stream>>>(cls_a, cls_b, B, nsnip, lin_w,
+                                                                                 lin_b, out);
+  return check_cuda(cudaGetLastError(), "clip_head launch");
+}
+
+int prototype_score(const float* reps, const float* protos, int B, int P, int Dd, float* probs, float* sims,
+                    int32_t* pred, cudaStream_t stream) {
+  if (B == 0) return kOk;
+  if (!reps || !protos || !probs || B < 0 || P <= 0 || P > 64 || Dd <= 0) {
+    set_last_error("prototype_score: bad arguments (need 1 <= P <= 64)");
+    return kErrInvalidArg;
+  }
+  LaunchScope ls(kClsMisc, stream, double(B) * (Dd * 4 + P * 8));
+  prototype_score_kernel<<<(B + 3) / 4, 128, 0, stream>>>(reps, protos, B, P, Dd, probs, sims, pred);
+  return check_cuda(cudaGetLastError(), "prototype_score launch");
+}
+
+}  // namespace sais

@@ -1,0 +1,52 @@
+// Internal launcher declarations shared by the .cu files (the public surface is include/sais_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sais_b200.h"
+
+namespace sais {
+
+// kernel classes for the launch counter / optional CUDA-event profiler (sais_profile_*)
+enum LaunchClass : int { kClsGemm = 0, kClsVitAttn, kClsLayerNorm, kClsPatchify, kClsTemporalAttn, kClsMisc, kNumClasses };
+
+// RAII around one kernel launch: counts it and, when profiling is on, brackets it with CUDA events on `stream`
+// and books `work` (flops for GEMM/attention classes, algorithmic bytes for the memory-bound ones).
+struct LaunchScope {
+  LaunchScope(int cls, cudaStream_t stream, double work = 0.0);
+  ~LaunchScope();
+  int cls_;
+  cudaStream_t stream_;
+  int slot_;
+};
+
+// gemm_tcgen05.cu
+int gemm_bias_act(const SaisGemmArgs& a, cudaStream_t stream, int force_block_n = 0);
+int pick_block_n(int64_t M, int64_t N);
+
+// elementwise.cu
+int layernorm(const float* x, int64_t in_pitch, const float* gamma, const float* beta, float eps, int64_t rows,
+              float* out_f32, sais_bf16* out_bf16, cudaStream_t stream);
+int normalize_patchify_u8(const uint8_t* frames, int B, const float* mean3, const float* std3, sais_bf16* patches,
+                          cudaStream_t stream);
+int patchify_f32(const float* frames, int B, sais_bf16* patches, cudaStream_t stream);
+int write_cls_rows(const float* cls_pos0, int B, float* x, cudaStream_t stream);
+int temporal_prep(const float* x_frames, const int32_t* seq_offsets, int nseq, int total_tokens,
+                  const float* frame_cls, const float* frame_pos, int n_pos, float* tok_f32, sais_bf16* tok_bf16,
+                  cudaStream_t stream);
+int gather_cls_relu(const float* tok_f32, const int32_t* seq_offsets, int nseq, float* out_cls, cudaStream_t stream);
+int clip_head(const float* cls_a, const float* cls_b, int B, int nsnip, const float* lin_w, const float* lin_b,
+              float* out, cudaStream_t stream);
+int prototype_score(const float* reps, const float* protos, int B, int P, int D, float* probs, float* sims,
+                    int32_t* pred, cudaStream_t stream);
+
+// vit_attention.cu
+int vit_attention(const sais_bf16* qkv, int B, sais_bf16* out, float* probs, cudaStream_t stream);
+
+// temporal_attention.cu
+int temporal_attention(const sais_bf16* qkv, const int32_t* seq_offsets, const uint8_t* key_pad,
+                       const int64_t* attn_offsets, int nseq, int max_S, sais_bf16* out, float* attn_out,
+                       cudaStream_t stream);
+
+}  // namespace sais

@@ -1,0 +1,124 @@
+"""Thin Python wrappers over the individual C-ABI kernels (used by the parity tests and by callers that want a
+single op).  Each wrapper allocates outputs with torch, passes raw device pointers and the current stream, and
+raises :class:`sais_b200._lib.SaisError` on any non-zero return code.  No CPU fallbacks."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import SaisGemmArgs, check, current_stream, lib, ptr, require_cuda
+
+_IMAGENET_MEAN = (0.485, 0.456, 0.406)  # extract_representations.py:161
+_IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def gemm_bias_act(a, w, bias=None, act=_lib.ACT_NONE, residual=None, out_dtype=torch.bfloat16, out=None,
+                  row_add=None, remap_group=0):
+    """out = act(a @ w.T + bias) [+ residual].  a: bf16 [M,K]; w: bf16 [N,K]; bias/residual fp32."""
+    require_cuda(a, "a")
+    require_cuda(w, "w")
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    assert a.stride(-1) == 1 and w.stride(-1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    rows_out = M if remap_group == 0 else (M // remap_group) * (remap_group + 1)
+    if out is None:
+        out = torch.empty((rows_out, N), device=a.device, dtype=out_dtype)
+    g = SaisGemmArgs()
+    g.a, g.w, g.bias = ptr(a), ptr(w), ptr(bias)
+    g.residual = ptr(residual)
+    g.row_add = ptr(row_add)
+    if out.dtype == torch.float32:
+        g.out_f32, g.ldo32 = ptr(out), out.stride(0)
+    else:
+        g.out_bf16, g.ldo16 = ptr(out), out.stride(0)
+    g.M, g.N, g.K = M, N, K
+    g.lda, g.ldw = a.stride(0), w.stride(0)
+    g.ldr = residual.stride(0) if residual is not None else 0
+    g.act, g.remap_group = act, remap_group
+    check(lib().sais_gemm_bias_act(C.byref(g), current_stream()), "sais_gemm_bias_act")
+    return out
+
+
+def layernorm(x, gamma, beta, eps, out_f32=False, out_bf16=True, in_pitch=None, rows=None):
+    require_cuda(x, "x")
+    assert x.dtype == torch.float32
+    if in_pitch is None:
+        x2 = x.reshape(-1, x.shape[-1])
+        in_pitch, rows = x2.stride(0), x2.shape[0]
+    cols = gamma.numel()
+    of = torch.empty((rows, cols), device=x.device, dtype=torch.float32) if out_f32 else None
+    ob = torch.empty((rows, cols), device=x.device, dtype=torch.bfloat16) if out_bf16 else None
+    check(lib().sais_layernorm(ptr(x), in_pitch, ptr(gamma), ptr(beta), float(eps), rows, cols, ptr(of), ptr(ob),
+                               current_stream()), "sais_layernorm")
+    return of, ob
+
+
+def normalize_patchify_u8(frames):
+    """u8 [B,224,224,3] -> bf16 patches [B*196,768] with ImageNet normalisation."""
+    require_cuda(frames, "frames")
+    assert frames.dtype == torch.uint8 and frames.is_contiguous() and tuple(frames.shape[1:]) == (224, 224, 3)
+    B = frames.shape[0]
+    out = torch.empty((B * 196, 768), device=frames.device, dtype=torch.bfloat16)
+    mean = (C.c_float * 3)(*_IMAGENET_MEAN)
+    std = (C.c_float * 3)(*_IMAGENET_STD)
+    check(lib().sais_normalize_patchify_u8(ptr(frames), B, C.cast(mean, C.c_void_p), C.cast(std, C.c_void_p),
+                                           ptr(out), current_stream()), "sais_normalize_patchify_u8")
+    return out
+
+
+def patchify_f32(frames):
+    """fp32 [B,3,224,224] (already normalised) -> bf16 patches [B*196,768]."""
+    require_cuda(frames, "frames")
+    assert frames.dtype == torch.float32 and frames.is_contiguous() and tuple(frames.shape[1:]) == (3, 224, 224)
+    B = frames.shape[0]
+    out = torch.empty((B * 196, 768), device=frames.device, dtype=torch.bfloat16)
+    check(lib().sais_patchify_f32(ptr(frames), B, ptr(out), current_stream()), "sais_patchify_f32")
+    return out
+
+
+def vit_attention(qkv, B, emit_probs=False):
+    """qkv bf16 [B*197,1152] -> (out bf16 [B*197,384], probs fp32 [B,6,197,197] or None)."""
+    require_cuda(qkv, "qkv")
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and qkv.shape == (B * 197, 1152)
+    out = torch.empty((B * 197, 384), device=qkv.device, dtype=torch.bfloat16)
+    probs = torch.empty((B, 6, 197, 197), device=qkv.device, dtype=torch.float32) if emit_probs else None
+    check(lib().sais_vit_attention(ptr(qkv), B, ptr(out), ptr(probs), current_stream()), "sais_vit_attention")
+    return out, probs
+
+
+def temporal_attention(qkv, seq_offsets, key_pad=None, attn_offsets=None, max_S=None, attn_numel=0):
+    """qkv bf16 [tokens,1152]; seq_offsets int32 [nseq+1] (device); returns (out bf16 [tokens,384], attn flat)."""
+    require_cuda(qkv, "qkv")
+    nseq = seq_offsets.numel() - 1
+    out = torch.empty((qkv.shape[0], 384), device=qkv.device, dtype=torch.bfloat16)
+    attn = torch.zeros(attn_numel, device=qkv.device, dtype=torch.float32) if attn_numel else None
+    check(lib().sais_temporal_attention(ptr(qkv), ptr(seq_offsets), ptr(key_pad), ptr(attn_offsets), nseq,
+                                        int(max_S), ptr(out), ptr(attn), current_stream()),
+          "sais_temporal_attention")
+    return out, attn
+
+
+def clip_head(cls_a, cls_b, B, nsnip, lin_w, lin_b):
+    require_cuda(cls_a, "cls_a")
+    out = torch.empty((B, 256), device=cls_a.device, dtype=torch.float32)
+    check(lib().sais_clip_head(ptr(cls_a), ptr(cls_b), B, nsnip, ptr(lin_w), ptr(lin_b), ptr(out),
+                               current_stream()), "sais_clip_head")
+    return out
+
+
+def prototype_score(reps, protos, want_sims=False):
+    """reps fp32 [B,D], protos fp32 [P,D] -> (probs [B,P], sims or None, pred int32 [B])."""
+    require_cuda(reps, "reps")
+    reps = reps.contiguous().float()
+    protos = protos.contiguous().float().to(reps.device)
+    B, D = reps.shape
+    P = protos.shape[0]
+    probs = torch.empty((B, P), device=reps.device, dtype=torch.float32)
+    sims = torch.empty((B, P), device=reps.device, dtype=torch.float32) if want_sims else None
+    pred = torch.empty((B,), device=reps.device, dtype=torch.int32)
+    check(lib().sais_prototype_score(ptr(reps), ptr(protos), B, P, D, ptr(probs), ptr(sims), ptr(pred),
+                                     current_stream()), "sais_prototype_score")
+    return probs, sims, pred

@@ -1,0 +1,226 @@
+"""DINO ViT-S/16 feature extractor — drop-in for ``SAIS/scripts/dino-main/vision_transformer.py``.
+
+Same factory (``vit_small(patch_size=16, **kw)``), same ``state_dict`` keys (``cls_token``, ``pos_embed``,
+``patch_embed.proj.*``, ``blocks.{i}.{norm1,attn.qkv,attn.proj,norm2,mlp.fc1,mlp.fc2}.*``, ``norm.*`` —
+reference :68-165), same ``forward`` / ``get_last_selfattention`` / ``get_intermediate_layers`` contracts
+(:209-233).  The modules below only HOLD the fp32 parameters; all arithmetic happens in
+``libsais_b200.so`` (``sais_vit_forward``): tcgen05 GEMMs with fused bias/GELU/residual/pos-embed epilogues,
+fused attention and warp-shuffle LayerNorm, bf16 operands with fp32 accumulation, residual stream and
+LayerNorm statistics.  Inference only; 224x224 inputs only (197 tokens); no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from functools import partial
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import SaisVitWeights, check, current_stream, lib, ptr, require_cuda
+
+IMG = 224
+TOKENS = 197
+DIM = 384
+HEADS = 6
+DEPTH = 12
+
+
+class Mlp(nn.Module):
+    """Parameter holder for fc1 -> GELU(erf) -> fc2 (reference :49-65)."""
+
+    def __init__(self, in_features, hidden_features):
+        super().__init__()
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.fc2 = nn.Linear(hidden_features, in_features)
+
+
+class Attention(nn.Module):
+    """Parameter holder for qkv / proj (reference :68-92); softmax scale is head_dim**-0.5."""
+
+    def __init__(self, dim, num_heads, qkv_bias):
+        super().__init__()
+        self.num_heads = num_heads
+        self.scale = (dim // num_heads) ** -0.5
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.proj = nn.Linear(dim, dim)
+
+
+class Block(nn.Module):
+    """Pre-norm transformer block parameters (reference :95-113)."""
+
+    def __init__(self, dim, num_heads, mlp_ratio, qkv_bias, norm_layer):
+        super().__init__()
+        self.norm1 = norm_layer(dim)
+        self.attn = Attention(dim, num_heads, qkv_bias)
+        self.norm2 = norm_layer(dim)
+        self.mlp = Mlp(dim, int(dim * mlp_ratio))
+
+
+class PatchEmbed(nn.Module):
+    """16x16/16 conv == GEMM over [B*196, 768] patches (reference :116-131)."""
+
+    def __init__(self, img_size, patch_size, in_chans, embed_dim):
+        super().__init__()
+        self.img_size = img_size
+        self.patch_size = patch_size
+        self.num_patches = (img_size // patch_size) ** 2
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size)
+
+
+class VisionTransformer(nn.Module):
+    """ViT whose forward runs entirely in the sm_100a library."""
+
+    def __init__(self, img_size=(224,), patch_size=16, in_chans=3, num_classes=0, embed_dim=384, depth=12,
+                 num_heads=6, mlp_ratio=4.0, qkv_bias=True, qk_scale=None, drop_rate=0.0, attn_drop_rate=0.0,
+                 drop_path_rate=0.0, norm_layer=None, chunk_frames=96, **kwargs):
+        super().__init__()
+        img = img_size[0] if isinstance(img_size, (list, tuple)) else img_size
+        if (img, patch_size, in_chans, embed_dim, depth, num_heads, mlp_ratio, qkv_bias) != (
+                IMG, 16, 3, DIM, DEPTH, HEADS, 4.0, True) or qk_scale is not None or num_classes != 0:
+            raise NotImplementedError(
+                "sais_b200 implements the SAIS hot path only: ViT-S/16 at 224x224 (dim 384, depth 12, 6 heads)")
+        norm_layer = norm_layer or partial(nn.LayerNorm, eps=1e-6)
+        self.num_features = self.embed_dim = embed_dim
+        self.patch_embed = PatchEmbed(img, patch_size, in_chans, embed_dim)
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.pos_embed = nn.Parameter(torch.zeros(1, self.patch_embed.num_patches + 1, embed_dim))
+        self.blocks = nn.ModuleList(
+            [Block(embed_dim, num_heads, mlp_ratio, qkv_bias, norm_layer) for _ in range(depth)])
+        self.norm = norm_layer(embed_dim)
+        self.head = nn.Identity()
+        self.chunk_frames = int(chunk_frames)
+        # same initial distribution as the reference (:161-172): trunc-normal(0.02), zero bias, unit LN
+        nn.init.trunc_normal_(self.pos_embed, std=0.02)
+        nn.init.trunc_normal_(self.cls_token, std=0.02)
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.trunc_normal_(m.weight, std=0.02)
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+            elif isinstance(m, nn.LayerNorm):
+                nn.init.ones_(m.weight)
+                nn.init.zeros_(m.bias)
+        self._packed = None
+        self._packed_key = None
+        self._ws = None
+        self.eval()
+
+    # ------------------------------------------------------------------ weight packing
+    def _pack_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def pack_weights(self, force=False):
+        """fp32 parameters -> device buffers in the kernel layouts (bf16 GEMM operands, fp32 vectors)."""
+        key = self._pack_key()
+        if not force and self._packed is not None and self._packed_key == key:
+            return self._packed
+        dev = self.cls_token.device
+        if dev.type != "cuda":
+            raise _lib.SaisError("VisionTransformer parameters must live on a CUDA device (no CPU path)")
+        keep = []
+
+        def f32(t):
+            t = t.detach().to(dev, torch.float32).contiguous()
+            keep.append(t)
+            return t
+
+        def bf(t):
+            t = t.detach().to(dev, torch.float32).contiguous().to(torch.bfloat16)
+            keep.append(t)
+            return t
+
+        w = SaisVitWeights()
+        w.patch_w = ptr(bf(self.patch_embed.proj.weight.reshape(DIM, -1)))
+        w.patch_b = ptr(f32(self.patch_embed.proj.bias))
+        w.cls_pos0 = ptr(f32(self.cls_token[0, 0] + self.pos_embed[0, 0]))
+        w.pos_patch = ptr(f32(self.pos_embed[0, 1:]))
+        for i, blk in enumerate(self.blocks):
+            b = w.blocks[i]
+            b.ln1_w, b.ln1_b = ptr(f32(blk.norm1.weight)), ptr(f32(blk.norm1.bias))
+            b.qkv_w, b.qkv_b = ptr(bf(blk.attn.qkv.weight)), ptr(f32(blk.attn.qkv.bias))
+            b.proj_w, b.proj_b = ptr(bf(blk.attn.proj.weight)), ptr(f32(blk.attn.proj.bias))
+            b.ln2_w, b.ln2_b = ptr(f32(blk.norm2.weight)), ptr(f32(blk.norm2.bias))
+            b.fc1_w, b.fc1_b = ptr(bf(blk.mlp.fc1.weight)), ptr(f32(blk.mlp.fc1.bias))
+            b.fc2_w, b.fc2_b = ptr(bf(blk.mlp.fc2.weight)), ptr(f32(blk.mlp.fc2.bias))
+        w.norm_w, w.norm_b = ptr(f32(self.norm.weight)), ptr(f32(self.norm.bias))
+        self._packed = (w, keep)
+        self._packed_key = key
+        return self._packed
+
+    def _workspace(self, chunk, device):
+        need = lib().sais_vit_workspace_bytes(chunk)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=device)
+        return self._ws, need
+
+    # ------------------------------------------------------------------ forward paths
+    def _run(self, x, kind, want_probs=False, want_tokens=False):
+        if self.training:
+            raise _lib.SaisError("sais_b200.VisionTransformer is inference-only; call .eval()")
+        require_cuda(x, "input")
+        x = x.contiguous()
+        B = x.shape[0]
+        if B == 0:
+            return (torch.empty((0, DIM), device=x.device),
+                    torch.empty((0, HEADS, TOKENS, TOKENS), device=x.device) if want_probs else None,
+                    torch.empty((0, TOKENS, DIM), device=x.device) if want_tokens else None)
+        w, _ = self.pack_weights()
+        chunk = max(1, min(self.chunk_frames, B))
+        ws, need = self._workspace(chunk, x.device)
+        out = torch.empty((B, DIM), device=x.device, dtype=torch.float32)
+        probs = torch.empty((B, HEADS, TOKENS, TOKENS), device=x.device, dtype=torch.float32) if want_probs else None
+        toks = torch.empty((B, TOKENS, DIM), device=x.device, dtype=torch.float32) if want_tokens else None
+        with torch.cuda.device(x.device):
+            check(lib().sais_vit_forward(C.byref(w), ptr(x), kind, B, chunk, ptr(ws), need, ptr(out), ptr(probs),
+                                         ptr(toks), current_stream()), "sais_vit_forward")
+        return out, probs, toks
+
+    @staticmethod
+    def _check_f32(x):
+        if x.dim() != 4 or tuple(x.shape[1:]) != (3, IMG, IMG):
+            raise NotImplementedError(f"only [B,3,224,224] inputs are supported (got {tuple(x.shape)})")
+        return x.float()
+
+    @torch.no_grad()
+    def forward(self, x):
+        """``model(inputs[B,3,224,224] fp32, normalised) -> reps[B,384]`` (extract_representations.py:370)."""
+        return self._run(self._check_f32(x), _lib.INPUT_F32_CHW)[0]
+
+    @torch.no_grad()
+    def forward_u8(self, frames):
+        """Raw ``uint8 [B,224,224,3]`` frames; ToTensor+Normalize(ImageNet) is fused into the patch kernel."""
+        if frames.dtype != torch.uint8 or tuple(frames.shape[1:]) != (IMG, IMG, 3):
+            raise NotImplementedError(f"forward_u8 expects uint8 [B,224,224,3] (got {frames.dtype} {tuple(frames.shape)})")
+        return self._run(frames, _lib.INPUT_U8_HWC)[0]
+
+    @torch.no_grad()
+    def get_last_selfattention(self, x):
+        """Softmax probabilities of the last block, ``[B,6,197,197]`` (reference :216-223)."""
+        return self._run(self._check_f32(x), _lib.INPUT_F32_CHW, want_probs=True)[1]
+
+    @torch.no_grad()
+    def get_intermediate_layers(self, x, n=1):
+        """Final-norm'd tokens of the last block (reference :225-233); only ``n == 1`` is on the hot path."""
+        if n != 1:
+            raise NotImplementedError("get_intermediate_layers is implemented for n=1 only")
+        return [self._run(self._check_f32(x), _lib.INPUT_F32_CHW, want_tokens=True)[2]]
+
+    def train(self, mode=True):
+        if mode:
+            raise _lib.SaisError("sais_b200.VisionTransformer is inference-only")
+        return super().train(False)
+
+
+def vit_small(patch_size=16, **kwargs):
+    """``vits.__dict__['vit_small'](patch_size=16, drop_path_rate=...)`` (extract_representations.py:201)."""
+    return VisionTransformer(patch_size=patch_size, embed_dim=384, depth=12, num_heads=6, mlp_ratio=4.0,
+                             qkv_bias=True, norm_layer=partial(nn.LayerNorm, eps=1e-6), **kwargs)
+
+
+def vit_tiny(patch_size=16, **kwargs):
+    raise NotImplementedError("sais_b200 covers the SAIS hot path (ViT-S/16) only")
+
+
+def vit_base(patch_size=16, **kwargs):
+    raise NotImplementedError("sais_b200 covers the SAIS hot path (ViT-S/16) only")

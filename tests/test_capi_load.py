@@ -1,0 +1,64 @@
+"""CPU: the C-ABI library builds/loads without a GPU and exports exactly what include/sais_b200.h declares."""
+import re
+import subprocess
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+HEADER = ROOT / "include" / "sais_b200.h"
+
+
+def _declared():
+    text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    return sorted(set(re.findall(r"\b(sais_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_entry_points():
+    names = _declared()
+    for must in ("sais_gemm_bias_act", "sais_layernorm", "sais_vit_attention", "sais_normalize_patchify_u8",
+                 "sais_temporal_prep", "sais_temporal_attention", "sais_clip_head", "sais_prototype_score",
+                 "sais_vit_forward", "sais_temporal_forward", "sais_version", "sais_last_error"):
+        assert must in names
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from sais_b200 import _lib
+    handle = _lib.lib()  # builds in-tree if missing; raises if it cannot
+    declared = _declared()
+    assert sorted(_lib.SIGNATURES) == declared, "ctypes table and header disagree"
+    for name in declared:
+        assert hasattr(handle, name), f"{name} not exported"
+    out = subprocess.run(["nm", "-D", "--defined-only", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\bT (sais_[a-z0-9_]+)\b", out))
+    assert exported == set(declared)
+    assert handle.sais_version() >= 100
+    assert handle.sais_launch_count() == 0 or handle.sais_launch_count() > 0  # callable without a device
+
+
+def test_struct_layouts_match_header_sizes():
+    """ctypes mirrors of the header structs: pointer-count bookkeeping catches a forgotten field."""
+    import ctypes as C
+    from sais_b200 import _lib
+    assert C.sizeof(_lib.SaisVitBlockWeights) == 12 * 8
+    assert C.sizeof(_lib.SaisVitWeights) == (4 + 12 * 12 + 2) * 8
+    assert C.sizeof(_lib.SaisTemporalLayerWeights) == 12 * 8
+    assert C.sizeof(_lib.SaisTemporalWeights) == 2 * 8 + 8 + 4 * 12 * 8  # n_pos int32 padded to 8
+    assert C.sizeof(_lib.SaisGemmArgs) == 7 * 8 + 8 * 8 + 2 * 4
+
+
+def test_no_cpu_fallback():
+    """product modules refuse CPU tensors instead of silently computing on the host."""
+    import torch
+    from sais_b200 import SaisError, ops
+    with pytest.raises(SaisError):
+        ops.layernorm(torch.zeros(4, 384), torch.ones(384), torch.zeros(384), 1e-6)
+    with pytest.raises(SaisError):
+        ops.prototype_score(torch.zeros(2, 256), torch.zeros(2, 256))
+
+
+def test_product_never_imports_oracle():
+    for py in (ROOT / "sais_b200").rglob("*.py"):
+        assert "oracle" not in py.read_text(), f"{py} references the oracle"
+    for cu in (ROOT / "sais_b200" / "csrc").glob("*.cu*"):
+        assert "oracle" not in cu.read_text()

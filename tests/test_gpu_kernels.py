@@ -1,0 +1,281 @@
+"""GPU parity tests, one per C-ABI kernel, against plain fp32 CPU restatements on the same seeded inputs.
+Operands that the kernels consume as bf16 are rounded to bf16 on the CPU side too, so the comparison isolates the
+kernel arithmetic (fp32 accumulation) from the format conversion; tolerances are written next to each check."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import sais_oracle as O  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+def rnd(*shape, seed=0, std=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * std
+
+
+# ------------------------------------------------------------------------------------------------ layernorm
+@pytest.mark.parametrize("rows", [1, 7, 8, 197 * 3, 4099])
+@pytest.mark.parametrize("eps", [1e-6, 1e-5])
+def test_layernorm(dev, rows, eps):
+    from sais_b200 import ops
+    x = rnd(rows, 384, seed=rows) * 3 + 0.5
+    w, b = 1 + 0.1 * rnd(384, seed=1), 0.1 * rnd(384, seed=2)
+    of, ob = ops.layernorm(x.to(dev), w.to(dev), b.to(dev), eps, out_f32=True, out_bf16=True)
+    ref = O.layer_norm(x, w, b, eps)
+    assert torch.allclose(of.cpu(), ref, atol=2e-5, rtol=1e-5)
+    assert torch.equal(ob.cpu().float(), bf(of.cpu()))  # bf16 output is the rounding of the fp32 one
+
+
+def test_layernorm_strided_rows(dev):
+    """final norm reads only the CLS rows: row pitch 197*384."""
+    from sais_b200 import ops
+    x = rnd(5, 197, 384, seed=3)
+    w, b = 1 + 0.1 * rnd(384, seed=1), 0.1 * rnd(384, seed=2)
+    of, _ = ops.layernorm(x.to(dev), w.to(dev), b.to(dev), 1e-6, out_f32=True, out_bf16=False,
+                          in_pitch=197 * 384, rows=5)
+    assert torch.allclose(of.cpu(), O.layer_norm(x[:, 0], w, b, 1e-6), atol=2e-5, rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ patchify
+def _patches_ref(x):  # x fp32 [B,3,224,224] -> [B*196,768], k = c*256 + ky*16 + kx
+    B = x.shape[0]
+    return x.reshape(B, 3, 14, 16, 14, 16).permute(0, 2, 4, 1, 3, 5).reshape(B * 196, 768)
+
+
+@pytest.mark.parametrize("B", [1, 3])
+def test_patchify_f32(dev, B):
+    from sais_b200 import ops
+    x = rnd(B, 3, 224, 224, seed=B)
+    got = ops.patchify_f32(x.to(dev)).cpu().float()
+    assert torch.equal(got, bf(_patches_ref(x)))  # pure layout + round-to-nearest-even: bit exact
+
+
+@pytest.mark.parametrize("B", [1, 5])
+def test_normalize_patchify_u8(dev, B):
+    from sais_b200 import ops
+    fr = O.make_frames_u8(B, seed=B)
+    fr[0, 0, 0] = torch.tensor([0, 255, 128], dtype=torch.uint8)
+    got = ops.normalize_patchify_u8(fr.to(dev)).cpu().float()
+    ref = _patches_ref(O.normalize_frames(fr))
+    # fused (u8*scale + shift) vs ((u8/255 - mean)/std): <= 1 bf16 ulp (2^-8 relative) from double rounding
+    assert torch.allclose(got, ref, atol=1e-2, rtol=2 ** -7)
+    assert (got - bf(ref)).abs().max() <= 2 ** -6  # values are < 2.7 in magnitude: at most one ulp apart
+    assert ((got - bf(ref)) != 0).float().mean() < 0.02
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+def _gemm_ref(a, w, bias, act, residual):
+    y = bf(a).double() @ bf(w).double().t()
+    if bias is not None:
+        y = y + bias.double()
+    if act == 1:
+        y = 0.5 * y * (1 + torch.erf(y / math.sqrt(2)))
+    elif act == 2:
+        y = torch.relu(y)
+    if residual is not None:
+        y = y + residual.double()
+    return y.float()
+
+
+GEMM_CASES = [
+    # M, N, K, act, residual, out fp32?
+    (300, 384, 384, 0, False, False),
+    (1000, 1152, 384, 0, False, False),    # qkv
+    (257, 1536, 384, 1, False, False),     # fc1 + GELU(erf)
+    (777, 384, 1536, 0, True, True),       # fc2 + residual
+    (50, 2048, 384, 2, False, False),      # temporal FF1 + ReLU
+    (333, 384, 2048, 0, True, True),       # temporal FF2 + residual
+    (11, 1152, 384, 0, False, False),      # C1-sized temporal in-proj (single partial tile)
+    (128, 256, 384, 0, False, True),
+    (197 * 96, 384, 384, 0, True, True),   # one full wave of 148 m-tiles x 2-3 n-tiles
+    (5000, 1536, 384, 1, False, False),    # multi-tile persistent loop with the GELU epilogue
+]
+
+
+@pytest.mark.parametrize("M,N,K,act,use_res,f32_out", GEMM_CASES)
+def test_gemm_bias_act(dev, M, N, K, act, use_res, f32_out):
+    from sais_b200 import ops
+    a = rnd(M, K, seed=M + N)
+    w = rnd(N, K, seed=K, std=1 / math.sqrt(K))
+    bias = rnd(N, seed=7, std=0.5)
+    res = rnd(M, N, seed=9) if use_res else None
+    out = ops.gemm_bias_act(a.to(dev).bfloat16(), w.to(dev).bfloat16(), bias.to(dev), act=act,
+                            residual=None if res is None else res.to(dev),
+                            out_dtype=torch.float32 if f32_out else torch.bfloat16)
+    ref = _gemm_ref(a, w, bias, act, res)
+    got = out.cpu().float()
+    if f32_out:  # fp32 accumulate of K products of O(1): summation-order noise only
+        assert torch.allclose(got, ref, atol=2e-4, rtol=1e-4), (got - ref).abs().max()
+    else:        # plus one bf16 rounding (2^-9 relative)
+        assert torch.allclose(got, ref, atol=1e-3, rtol=2 ** -8), (got - ref).abs().max()
+
+
+@pytest.mark.parametrize("block_rows", [1, 2])
+def test_gemm_patch_embed_remap(dev, block_rows):
+    """patch-embed epilogue: row b*196+p -> row b*197+1+p, + pos_embed[1+p]; CLS rows untouched."""
+    from sais_b200 import ops
+    B = 2 * block_rows
+    a = rnd(B * 196, 768, seed=1)
+    w = rnd(384, 768, seed=2, std=1 / math.sqrt(768))
+    bias, pos = rnd(384, seed=3), rnd(196, 384, seed=4)
+    out = torch.full((B * 197, 384), -7.0, device=dev)
+    ops.gemm_bias_act(a.to(dev).bfloat16(), w.to(dev).bfloat16(), bias.to(dev), out=out, row_add=pos.to(dev),
+                      remap_group=196)
+    got = out.cpu().view(B, 197, 384)
+    ref = _gemm_ref(a, w, bias, 0, None).view(B, 196, 384) + pos
+    assert torch.all(got[:, 0] == -7.0)
+    assert torch.allclose(got[:, 1:], ref, atol=2e-4, rtol=1e-4)
+
+
+def test_gemm_in_place_residual(dev):
+    """x = x + A W^T + b with residual == out (how proj / fc2 update the fp32 residual stream)."""
+    from sais_b200 import ops
+    a, w, bias, x = rnd(500, 384, seed=1), rnd(384, 384, seed=2, std=0.05), rnd(384, seed=3), rnd(500, 384, seed=4)
+    xd = x.to(dev).clone()
+    ops.gemm_bias_act(a.to(dev).bfloat16(), w.to(dev).bfloat16(), bias.to(dev), residual=xd, out=xd)
+    assert torch.allclose(xd.cpu(), _gemm_ref(a, w, bias, 0, x), atol=2e-4, rtol=1e-4)
+
+
+def test_gemm_rejects_bad_shapes(dev):
+    from sais_b200 import SaisError, ops
+    a, w = torch.zeros(8, 100, device=dev).bfloat16(), torch.zeros(384, 100, device=dev).bfloat16()
+    with pytest.raises(SaisError):
+        ops.gemm_bias_act(a, w)  # K not a multiple of 64 (and pitch not 16-byte aligned)
+
+
+# ------------------------------------------------------------------------------------------------ ViT attention
+def _vit_attn_ref(qkv, B):
+    q, k, v = bf(qkv).view(B, 197, 3, 6, 64).permute(2, 0, 3, 1, 4)
+    p = torch.softmax((q @ k.transpose(-2, -1)) * 0.125, dim=-1)
+    return (p @ v).transpose(1, 2).reshape(B * 197, 384), p
+
+
+@pytest.mark.parametrize("B,scale", [(1, 1.0), (3, 3.0)])
+def test_vit_attention(dev, B, scale):
+    from sais_b200 import ops
+    qkv = rnd(B * 197, 1152, seed=B)
+    qkv[:, :768] *= scale  # sharper logits
+    out, probs = ops.vit_attention(qkv.to(dev).bfloat16(), B, emit_probs=True)
+    ref_o, ref_p = _vit_attn_ref(qkv, B)
+    # probabilities: fp32 softmax of fp32-accumulated logits
+    assert torch.allclose(probs.cpu(), ref_p, atol=2e-5, rtol=2e-4), (probs.cpu() - ref_p).abs().max()
+    assert torch.allclose(probs.sum(-1).cpu(), torch.ones(B, 6, 197), atol=1e-5)
+    # outputs: P is rounded to bf16 before PV (2^-9 relative per term) and the result to bf16
+    assert torch.allclose(out.cpu().float(), ref_o, atol=1.5e-2, rtol=2e-2), (out.cpu().float() - ref_o).abs().max()
+    out2, none = ops.vit_attention(qkv.to(dev).bfloat16(), B, emit_probs=False)
+    assert none is None and torch.equal(out2, out)
+
+
+# ------------------------------------------------------------------------------------------------ temporal attention
+def _tmp_attn_ref(qkv, lens_S, pads):
+    outs, attns, t0 = [], [], 0
+    for i, S in enumerate(lens_S):
+        blk = bf(qkv[t0:t0 + S])
+        q, k, v = blk.view(S, 3, 4, 96).permute(1, 2, 0, 3)
+        logit = (q @ k.transpose(-2, -1)) * 96 ** -0.5
+        if pads is not None:
+            logit = logit.masked_fill(pads[t0:t0 + S].bool().view(1, 1, S), float("-inf"))
+        p = torch.softmax(logit, -1)
+        outs.append((p @ v).permute(1, 0, 2).reshape(S, 384))
+        attns.append(p.mean(0))
+        t0 += S
+    return torch.cat(outs), attns
+
+
+@pytest.mark.parametrize("lens_S", [[11], [31] * 5, [16, 13, 10, 3, 3, 2], [65, 40], [200, 31]])
+def test_temporal_attention(dev, lens_S):
+    from sais_b200 import ops
+    total = sum(lens_S)
+    qkv = rnd(total, 1152, seed=total) * 1.5
+    g = torch.Generator().manual_seed(5)
+    pads = torch.zeros(total, dtype=torch.uint8)
+    t0 = 0
+    for S in lens_S:  # pad a suffix of the keys, never the CLS key
+        npad = int(torch.randint(0, max(1, S // 2), (1,), generator=g))
+        if npad:
+            pads[t0 + S - npad:t0 + S] = 1
+        t0 += S
+    offs = torch.tensor(np.concatenate([[0], np.cumsum(lens_S)]), dtype=torch.int32)
+    # emit maps for every other sequence only
+    emit = [i % 2 == 0 for i in range(len(lens_S))]
+    a_offs, cur = [], 0
+    for S, e in zip(lens_S, emit):
+        a_offs.append(cur if e else -1)
+        cur += S * S if e else 0
+    out, attn = ops.temporal_attention(qkv.to(dev).bfloat16(), offs.to(dev), pads.to(dev),
+                                       torch.tensor(a_offs, dtype=torch.int64).to(dev), max(lens_S), attn_numel=cur)
+    ref_o, ref_a = _tmp_attn_ref(qkv, lens_S, pads)
+    assert torch.allclose(out.cpu().float(), ref_o, atol=1e-2, rtol=2 ** -7), (out.cpu().float() - ref_o).abs().max()
+    attn = attn.cpu()
+    t0 = 0
+    for S, e, ao, ra in zip(lens_S, emit, a_offs, ref_a):
+        if e:
+            got = attn[ao:ao + S * S].view(S, S)
+            assert torch.allclose(got, ra, atol=2e-6, rtol=1e-4), (got - ra).abs().max()
+            assert float(got[:, pads[t0:t0 + S].bool()].abs().max() if pads[t0:t0 + S].any() else 0) == 0.0
+        t0 += S
+
+
+def test_temporal_attention_no_mask_no_maps(dev):
+    from sais_b200 import ops
+    lens_S = [31] * 3
+    qkv = rnd(93, 1152, seed=1)
+    offs = torch.tensor([0, 31, 62, 93], dtype=torch.int32)
+    out, attn = ops.temporal_attention(qkv.to(dev).bfloat16(), offs.to(dev), None, None, 31)
+    assert attn is None
+    assert torch.allclose(out.cpu().float(), _tmp_attn_ref(qkv, lens_S, None)[0], atol=1e-2, rtol=2 ** -7)
+
+
+# ------------------------------------------------------------------------------------------------ head + scoring
+@pytest.mark.parametrize("B,nsnip,flow", [(1, 1, True), (5, 1, True), (6, 3, True), (4, 2, False)])
+def test_clip_head(dev, B, nsnip, flow):
+    from sais_b200 import ops
+    a = torch.relu(rnd(B * nsnip, 384, seed=1))
+    b = torch.relu(rnd(B * nsnip, 384, seed=2)) if flow else None
+    W, bias = rnd(256, 384, seed=3, std=0.05), rnd(256, seed=4)
+    got = ops.clip_head(a.to(dev), None if b is None else b.to(dev), B, nsnip, W.to(dev), bias.to(dev)).cpu()
+    v = a.view(B, nsnip, 384).mean(1) + (b.view(B, nsnip, 384).mean(1) if flow else 0)
+    ref = torch.relu(v) @ W.t() + bias
+    assert torch.allclose(got, ref, atol=2e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("P", [1, 2, 3, 6, 33, 64])
+def test_prototype_score(dev, P, golden_dir):
+    from sais_b200 import ops
+    reps = rnd(37, 256, seed=P)
+    protos = O.make_prototypes(P)
+    probs, sims, pred = ops.prototype_score(reps.to(dev), protos.to(dev), want_sims=True)
+    rp, rs = O.prototype_probs(reps, protos)
+    assert torch.allclose(sims.cpu(), rs, atol=1e-6)
+    assert torch.allclose(probs.cpu(), rp, atol=1e-6)
+    safe = O.top2_margin(rs) > 1e-5 if P > 1 else torch.ones(37, dtype=torch.bool)
+    assert torch.equal(pred.cpu().long()[safe], rp.argmax(1)[safe])
+
+
+def test_prototype_score_golden(dev, golden_dir):
+    """against the reference's own calcProbs outputs (tests/golden/scoring.npz)."""
+    from sais_b200 import scoring
+    g = np.load(golden_dir / "scoring.npz")
+    reps = torch.from_numpy(g["reps"]).to(dev)
+    for P in (2, 6):
+        protos = O.make_prototypes(P)
+        pdict = {str(i): protos[i:i + 1] for i in range(P)}
+        _, sim, probs = scoring.calcProbs(reps, pdict)
+        np.testing.assert_allclose(sim.cpu().numpy(), g[f"sim_P{P}"], atol=1e-6)
+        np.testing.assert_allclose(probs.cpu().numpy(), g[f"probs_P{P}"], atol=1e-6)
+        pred, _ = scoring.predict(reps, pdict)
+        assert np.array_equal(pred.cpu().numpy(), g[f"probs_P{P}"].argmax(1))

@@ -1,0 +1,171 @@
+"""GPU parity tests of the drop-in modules (through the C ABI) against (a) the CPU oracle on the same seeded inputs
+and (b) the committed golden vectors produced by the unmodified reference.  Tolerances are BASELINE.json's:
+embeddings cosine >= 0.999 and max|d|/max|ref| <= 1e-2 (bf16 path), attention maps within 1e-3 absolute, predicted
+prototype class identical wherever the top-2 cosine margin exceeds 1e-3."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import make_golden as MG  # noqa: E402
+from oracle import sais_oracle as O  # noqa: E402
+
+COS_MIN, REL_MAX, ATTN_ABS, MARGIN = 0.999, 1e-2, 1e-3, 1e-3
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def _vit(sd, dev, **kw):
+    import sais_b200.vision_transformer as vits
+    m = vits.vit_small(patch_size=16, **kw)
+    m.load_state_dict(sd, strict=True)  # reference key names
+    return m.to(dev).eval()
+
+
+@pytest.mark.parametrize("name,style,wseed,n,iseed", MG.VIT_CASES)
+def test_vit_matches_oracle_and_golden(dev, golden_dir, name, style, wseed, n, iseed):
+    g = np.load(golden_dir / f"{name}.npz")
+    sd = O.make_vit_weights(wseed, style)
+    model = _vit(sd, dev)
+    fr = O.make_frames_u8(n, iseed)
+    x = O.normalize_frames(fr)
+    reps = model(x.to(dev)).cpu()
+    assert reps.shape == (n, 384) and reps.dtype == torch.float32
+    for ref in (O.vit_forward(sd, x), torch.from_numpy(g["reps"])):
+        cos, rel = O.embedding_errors(reps, ref)
+        assert cos >= COS_MIN and rel <= REL_MAX, (name, cos, rel)
+    # fused u8 path (ToTensor+Normalize inside the patch kernel) gives the same embeddings
+    reps_u8 = model.forward_u8(fr.to(dev)).cpu()
+    cos, rel = O.embedding_errors(reps_u8, torch.from_numpy(g["reps"]))
+    assert cos >= COS_MIN and rel <= REL_MAX, (name, "u8", cos, rel)
+    # last-block attention probabilities
+    attn = model.get_last_selfattention(x.to(dev)).cpu()
+    assert attn.shape == (n, 6, 197, 197)
+    assert np.abs(attn[:, :, 0, :].numpy() - g["attn_cls"]).max() <= ATTN_ABS
+    assert np.abs(attn[:, :, 100, :].numpy() - g["attn_row100"]).max() <= ATTN_ABS
+    assert np.abs(attn[0, 3].numpy() - g["attn_frame0_head3"]).max() <= ATTN_ABS
+    assert torch.allclose(attn.sum(-1), torch.ones(n, 6, 197), atol=1e-4)
+    toks = model.get_intermediate_layers(x.to(dev), 1)[0].cpu()
+    cos, rel = O.embedding_errors(toks[:, :8], torch.from_numpy(g["tokens_first8"]))
+    assert cos >= COS_MIN and rel <= 2 * REL_MAX, (name, "tokens", cos, rel)
+
+
+@pytest.mark.parametrize("B,chunk", [(1, 96), (5, 2), (9, 4), (33, 96)])
+def test_vit_chunking_is_invisible(dev, B, chunk):
+    """results must not depend on how the batch is chunked through the workspace (ragged last chunk included)."""
+    sd = O.make_vit_weights(3, "stress")
+    x = O.normalize_frames(O.make_frames_u8(B, 11)).to(dev)
+    a = _vit(sd, dev, chunk_frames=chunk)(x)
+    b = _vit(sd, dev, chunk_frames=96)(x)
+    assert torch.equal(a, b)
+    if B <= 9:
+        cos, rel = O.embedding_errors(a.cpu(), O.vit_forward(sd, x.cpu()))
+        assert cos >= COS_MIN and rel <= REL_MAX
+
+
+def test_vit_empty_batch_and_bad_inputs(dev):
+    from sais_b200 import SaisError
+    model = _vit(O.make_vit_weights(0, "init"), dev)
+    assert model(torch.zeros(0, 3, 224, 224, device=dev)).shape == (0, 384)
+    with pytest.raises(NotImplementedError):
+        model(torch.zeros(1, 3, 256, 256, device=dev))
+    with pytest.raises(SaisError):
+        model(torch.zeros(1, 3, 224, 224))  # CPU tensor: there is no CPU path
+    with pytest.raises(SaisError):
+        model.train()
+
+
+def _head(sd, dev, mods):
+    from sais_b200.prepare_model import fullModel
+    m = fullModel(data_type='reps', nclasses=2, domain='NH_02', rep_dim=384, encoder_type='ViT', modalities=mods)
+    own = m.state_dict()
+    for k, v in sd.items():
+        if k == "frame_pos_table":
+            for i in range(v.shape[0]):
+                own[f"frame_pos_embeddings.{i}"] = v[i:i + 1]
+        else:
+            own[k] = v
+    m.load_state_dict(own, strict=True)  # reference key names incl. frame_pos_embeddings.{i}
+    return m.to(dev).eval()
+
+
+@pytest.mark.parametrize("name,style,seed,mods,B,t_rgb,t_flow,ragged", MG.HEAD_CASES)
+def test_head_matches_oracle_and_golden(dev, golden_dir, name, style, seed, mods, B, t_rgb, t_flow, ragged):
+    g = np.load(golden_dir / f"{name}.npz")
+    sd = O.make_head_weights(seed, style)
+    model = _head(sd, dev, mods)
+    xs, fs, xps, fps = MG.head_inputs(B, t_rgb, t_flow, seed, ragged)
+    to = lambda ts: [t.to(dev) for t in ts]
+    is_list = len(t_rgb) > 1
+    x_in = to(xs)
+    keep = [t.clone() for t in x_in]
+    if is_list:
+        out, attn = model(x_in, to(fs), [None] * 3, [None] * 3, 'Prototypes', to(xps), to(fps), None)
+        ref_out, ref_attn = O.full_model_forward(sd, xs, fs, xps, fps, mods)
+    else:
+        out, attn = model(x_in[0], to(fs)[0], None, None, 'Prototypes', to(xps)[0], to(fps)[0], None)
+        ref_out, ref_attn = O.full_model_forward(sd, xs[0], fs[0], xps[0], fps[0], mods)
+        out, ref_out = [out], [ref_out]
+    assert all(torch.equal(a, b) for a, b in zip(x_in, keep)), "inputs must not be mutated"
+    for v, (o, r) in enumerate(zip(out, ref_out)):
+        assert o.shape == (B, 256)
+        for ref in (r, torch.from_numpy(g[f"out{v}"])):
+            cos, rel = O.embedding_errors(o.cpu(), ref)
+            assert cos >= COS_MIN and rel <= REL_MAX, (name, v, cos, rel)
+    assert attn.shape == ref_attn.shape
+    assert (attn.cpu() - ref_attn).abs().max() <= ATTN_ABS
+    assert np.abs(attn.cpu().numpy() - g["attn"]).max() <= ATTN_ABS
+    pad = xps[0].reshape(-1, xps[0].shape[-1])
+    if pad.any():  # padded keys carry exactly zero probability
+        assert float(attn.cpu()[pad.unsqueeze(1).expand_as(ref_attn)].abs().max()) == 0.0
+
+
+def test_patched_encoder_contract(dev):
+    """TransformerEncoder.forward(src[S,N,E], src_key_padding_mask=bool[N,S]) -> (out[S,N,E], attn[N,S,S])."""
+    from sais_b200.transformer import TransformerEncoder
+    sd = O.make_head_weights(4, "stress")
+    enc = TransformerEncoder()
+    enc.load_state_dict({k[len("transEncoderFrame."):]: v for k, v in sd.items() if k.startswith("transEncoderFrame.")})
+    enc = enc.to(dev).eval()
+    x, pad, _ = O.make_clip_batch(6, 12, seed=9)
+    tokens = O.temporal_prepare(sd, x).reshape(6, 13, 384)
+    out, attn = enc(tokens.permute(1, 0, 2).to(dev), src_key_padding_mask=pad.reshape(6, 13).to(dev))
+    ref_out, ref_attn = O.temporal_encoder(sd, tokens, pad.reshape(6, 13))
+    assert out.shape == (13, 6, 384) and attn.shape == (6, 13, 13)
+    cos, rel = O.embedding_errors(out.permute(1, 0, 2).cpu(), ref_out)
+    assert cos >= COS_MIN and rel <= 2 * REL_MAX, (cos, rel)
+    assert (attn.cpu() - ref_attn).abs().max() <= ATTN_ABS
+
+
+def test_class_identity_end_to_end(dev):
+    """C1-style pipeline on several clips: u8 frames -> ViT -> temporal head -> prototypes; the predicted class
+    equals the oracle's on every clip whose top-2 cosine margin exceeds the stated tolerance."""
+    from sais_b200 import scoring
+    vsd, hsd = O.make_vit_weights(0, "stress"), O.make_head_weights(0, "stress")
+    vit, head = _vit(vsd, dev), _head(hsd, dev, "RGB-Flow")
+    nclips, T = 6, 10
+    rgb, flow = O.make_frames_u8(nclips * T, 21), O.make_frames_u8(nclips * T, 22)
+    er = vit.forward_u8(rgb.to(dev)).view(nclips, 1, T, 384)
+    ef = vit.forward_u8(flow.to(dev)).view(nclips, 1, T, 384)
+    pad = O.padding_mask([T] * nclips, T).to(dev)
+    out, attn = head(er, ef, None, None, 'Prototypes', pad, pad, None)
+    r_er = O.vit_forward(vsd, O.normalize_frames(rgb)).view(nclips, 1, T, 384)
+    r_ef = O.vit_forward(vsd, O.normalize_frames(flow)).view(nclips, 1, T, 384)
+    r_out, r_attn = O.full_model_forward(hsd, r_er, r_ef, pad.cpu(), pad.cpu())
+    cos, rel = O.embedding_errors(out.cpu(), r_out)
+    assert cos >= COS_MIN and rel <= REL_MAX, (cos, rel)
+    assert (attn.cpu() - r_attn).abs().max() <= ATTN_ABS
+    for P in (2, 6):
+        # prototypes = a few reference clip vectors + noise, so classes are balanced
+        protos = r_out[:P] + 0.5 * O.make_prototypes(P, seed=P)
+        pred, probs = scoring.predict(out, protos.to(dev))
+        r_probs, r_sim = O.prototype_probs(r_out, protos)
+        safe = O.top2_margin(r_sim) > MARGIN
+        assert safe.any()
+        assert torch.equal(pred.cpu()[safe], r_probs.argmax(1)[safe])
+        assert (probs.cpu() - r_probs).abs().max() < 5e-3
