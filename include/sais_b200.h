@@ -79,22 +79,30 @@ typedef struct {
   int64_t lda, ldw, ldr, ldo32, ldo16;
   int32_t act;
   int32_t remap_group;
+  /* Split-precision ("3 x bf16", fp32-equivalent) mode.  split3: A and W each hold [hi | lo] bf16 halves
+   * side by side (2K columns; x = hi + lo to ~2^-17) and the kernel accumulates hi*hi + lo*hi + hi*lo in
+   * fp32.  split_out: out_bf16 has 2N columns and receives the result as [hi | lo] for the next split GEMM. */
+  int32_t split3;
+  int32_t split_out;
 } SaisGemmArgs;
 int sais_gemm_bias_act(const SaisGemmArgs* args, sais_stream_t stream);
 
 /* LayerNorm over the last dim (cols == 384) — nn.LayerNorm at vision_transformer.py:99,103,156
  * (eps 1e-6) and TransformerEncoderLayer.norm1/norm2 (eps 1e-5).  x: fp32, row pitch in_pitch
- * elements; writes fp32 and/or bf16 (dense [rows,384]). */
+ * elements; writes fp32 [rows,384] and/or bf16 ([rows,384], or [rows,768] = [hi | lo] if split_out). */
 int sais_layernorm(const float* x, int64_t in_pitch, const float* gamma, const float* beta, float eps,
-                   int64_t rows, int32_t cols, float* out_f32, sais_bf16* out_bf16, sais_stream_t stream);
+                   int64_t rows, int32_t cols, float* out_f32, sais_bf16* out_bf16, int32_t split_out,
+                   sais_stream_t stream);
 
 /* Frame normalisation + patch layout.  u8 variant replaces ToTensor+Normalize
  * (extract_representations.py:158-162): frames u8 [B,224,224,3] -> patches bf16 [B*196,768],
  * k = c*256 + ky*16 + kx, value = (u8/255 - mean[c]) / std[c].  f32 variant takes the already
- * normalised fp32 [B,3,224,224] tensor the reference model is called with (:370). */
+ * normalised fp32 [B,3,224,224] tensor the reference model is called with (:370).  With split_out the
+ * patch matrix is bf16 [B*196,1536] = [hi | lo] halves for the split-precision patch-embed GEMM. */
 int sais_normalize_patchify_u8(const uint8_t* frames, int32_t B, const float* mean3_host, const float* std3_host,
-                               sais_bf16* patches, sais_stream_t stream);
-int sais_patchify_f32(const float* frames_chw, int32_t B, sais_bf16* patches, sais_stream_t stream);
+                               sais_bf16* patches, int32_t split_out, sais_stream_t stream);
+int sais_patchify_f32(const float* frames_chw, int32_t B, sais_bf16* patches, int32_t split_out,
+                      sais_stream_t stream);
 
 /* ViT self-attention for one block: qkv bf16 [B*197,1152] (q|k|v, head-major inside each third,
  * vision_transformer.py:82-89) -> out bf16 [B*197,384].  probs (optional) receives the softmax
@@ -121,14 +129,17 @@ typedef struct {
 
 #define SAIS_INPUT_F32_CHW 0 /* normalised fp32 [B,3,224,224] */
 #define SAIS_INPUT_U8_HWC 1  /* raw u8 [B,224,224,3], normalised with ImageNet mean/std */
-size_t sais_vit_workspace_bytes(int32_t chunk_frames);
+size_t sais_vit_workspace_bytes(int32_t chunk_frames, int32_t precise);
 /* VisionTransformer.forward (vision_transformer.py:209-214): out_cls fp32 [B,384].
  * If out_probs != NULL also writes block 12's attention probabilities fp32 [B,6,197,197]
  * (get_last_selfattention).  Frames are processed in chunks of `chunk_frames` (workspace sized for it).
- * out_tokens (optional) receives the final-LayerNorm'd tokens fp32 [B,197,384] (get_intermediate_layers n=1). */
+ * out_tokens (optional) receives the final-LayerNorm'd tokens fp32 [B,197,384] (get_intermediate_layers n=1).
+ * precise = 0: bf16 operands, fp32 accumulate/residual (the fast path; embeddings within 1e-2 of fp32).
+ * precise = 1: fp32-equivalent mode — every bf16 weight matrix in w_host must then be packed as [hi | lo]
+ * (twice the columns), GEMMs run split-precision (3 passes) and attention runs in exact fp32. */
 int sais_vit_forward(const SaisVitWeights* w_host, const void* input, int32_t input_kind, int32_t B,
-                     int32_t chunk_frames, void* workspace, size_t workspace_bytes, float* out_cls,
-                     float* out_probs, float* out_tokens, sais_stream_t stream);
+                     int32_t chunk_frames, int32_t precise, void* workspace, size_t workspace_bytes,
+                     float* out_cls, float* out_probs, float* out_tokens, sais_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * SAIS temporal head (prepare_model.py:179-221 + README-patched nn.TransformerEncoder).
@@ -136,12 +147,13 @@ int sais_vit_forward(const SaisVitWeights* w_host, const void* input, int32_t in
  * (token 0 = frame_cls, token t+1 = frame t + frame_pos_embeddings[t]); x_frames holds the T_i frame
  * embeddings of all sequences back to back (fp32 [total_tokens - nseq, 384]).
  * ------------------------------------------------------------------------------------------- */
+/* The temporal head always runs split-precision: every bf16 matrix below is [N, 2K] = [hi | lo]. */
 typedef struct {
-  const sais_bf16* in_w; const float* in_b;   /* [1152,384], [1152] */
-  const sais_bf16* out_w; const float* out_b; /* [384,384], [384] */
+  const sais_bf16* in_w; const float* in_b;   /* [1152,2*384], [1152] */
+  const sais_bf16* out_w; const float* out_b; /* [384,2*384], [384] */
   const float* n1_w; const float* n1_b;
-  const sais_bf16* ff1_w; const float* ff1_b; /* [2048,384], [2048] */
-  const sais_bf16* ff2_w; const float* ff2_b; /* [384,2048], [384] */
+  const sais_bf16* ff1_w; const float* ff1_b; /* [2048,2*384], [2048] */
+  const sais_bf16* ff2_w; const float* ff2_b; /* [384,2*2048], [384] */
   const float* n2_w; const float* n2_b;
 } SaisTemporalLayerWeights;
 typedef struct {
@@ -151,17 +163,18 @@ typedef struct {
   SaisTemporalLayerWeights layers[SAIS_TMP_LAYERS];
 } SaisTemporalWeights;
 
-/* +pos-emb, prepend CLS (prepare_model.py:189-194): writes fp32 and bf16 token matrices [total_tokens,384]. */
+/* +pos-emb, prepend CLS (prepare_model.py:189-194): writes the token matrix as fp32 [total_tokens,384] and as
+ * bf16 [total_tokens,768] = [hi | lo] halves (operand of the split-precision in-proj GEMM). */
 int sais_temporal_prep(const float* x_frames, const int32_t* seq_offsets, int32_t nseq, int32_t total_tokens,
                        const float* frame_cls, const float* frame_pos, int32_t n_pos, float* tok_f32,
-                       sais_bf16* tok_bf16, sais_stream_t stream);
+                       sais_bf16* tok_split, sais_stream_t stream);
 
-/* Multi-head attention core of one temporal layer: qkv bf16 [total_tokens,1152] -> out bf16
- * [total_tokens,384]; 4 heads x 96, scale 96^-0.5, key_pad (u8 [total_tokens], 1 = padded key) adds -inf.
+/* Multi-head attention core of one temporal layer: qkv fp32 [total_tokens,1152] -> out bf16
+ * [total_tokens,768] = [hi | lo]; 4 heads x 96, scale 96^-0.5, key_pad (u8 [total_tokens], 1 = padded key) adds -inf.
  * If attn_out != NULL, sequence i with attn_offsets[i] >= 0 gets its head-averaged probabilities
  * fp32 [S_i,S_i] written at attn_out + attn_offsets[i] (need_weights=True semantics). */
-int sais_temporal_attention(const sais_bf16* qkv, const int32_t* seq_offsets, const uint8_t* key_pad,
-                            const int64_t* attn_offsets, int32_t nseq, int32_t max_S, sais_bf16* out,
+int sais_temporal_attention(const float* qkv, const int32_t* seq_offsets, const uint8_t* key_pad,
+                            const int64_t* attn_offsets, int32_t nseq, int32_t max_S, sais_bf16* out_split,
                             float* attn_out, sais_stream_t stream);
 
 size_t sais_temporal_workspace_bytes(int32_t total_tokens);

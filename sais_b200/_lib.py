@@ -29,7 +29,7 @@ class SaisGemmArgs(C.Structure):
         ("a", _p), ("w", _p), ("bias", _p), ("residual", _p), ("out_f32", _p), ("out_bf16", _p), ("row_add", _p),
         ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64),
         ("lda", C.c_int64), ("ldw", C.c_int64), ("ldr", C.c_int64), ("ldo32", C.c_int64), ("ldo16", C.c_int64),
-        ("act", C.c_int32), ("remap_group", C.c_int32),
+        ("act", C.c_int32), ("remap_group", C.c_int32), ("split3", C.c_int32), ("split_out", C.c_int32),
     ]
 
 
@@ -66,13 +66,13 @@ SIGNATURES = {
     "sais_profile_begin": (None, []),
     "sais_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
     "sais_gemm_bias_act": (C.c_int, [C.POINTER(SaisGemmArgs), _p]),
-    "sais_layernorm": (C.c_int, [_p, C.c_int64, _p, _p, C.c_float, C.c_int64, C.c_int32, _p, _p, _p]),
-    "sais_normalize_patchify_u8": (C.c_int, [_p, C.c_int32, _p, _p, _p, _p]),
-    "sais_patchify_f32": (C.c_int, [_p, C.c_int32, _p, _p]),
+    "sais_layernorm": (C.c_int, [_p, C.c_int64, _p, _p, C.c_float, C.c_int64, C.c_int32, _p, _p, C.c_int32, _p]),
+    "sais_normalize_patchify_u8": (C.c_int, [_p, C.c_int32, _p, _p, _p, C.c_int32, _p]),
+    "sais_patchify_f32": (C.c_int, [_p, C.c_int32, _p, C.c_int32, _p]),
     "sais_vit_attention": (C.c_int, [_p, C.c_int32, _p, _p, _p]),
-    "sais_vit_workspace_bytes": (C.c_size_t, [C.c_int32]),
-    "sais_vit_forward": (C.c_int, [C.POINTER(SaisVitWeights), _p, C.c_int32, C.c_int32, C.c_int32, _p, C.c_size_t,
-                                   _p, _p, _p, _p]),
+    "sais_vit_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "sais_vit_forward": (C.c_int, [C.POINTER(SaisVitWeights), _p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _p,
+                                   C.c_size_t, _p, _p, _p, _p]),
     "sais_temporal_prep": (C.c_int, [_p, _p, C.c_int32, C.c_int32, _p, _p, C.c_int32, _p, _p, _p]),
     "sais_temporal_attention": (C.c_int, [_p, _p, _p, _p, C.c_int32, C.c_int32, _p, _p, _p]),
     "sais_temporal_workspace_bytes": (C.c_size_t, [C.c_int32]),

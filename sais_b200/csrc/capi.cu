@@ -176,63 +176,72 @@ int sais_gemm_bias_act(const SaisGemmArgs* args, sais_stream_t stream) {
 }
 
 int sais_layernorm(const float* x, int64_t in_pitch, const float* gamma, const float* beta, float eps,
-                   int64_t rows, int32_t cols, float* out_f32, sais_bf16* out_bf16, sais_stream_t stream) {
+                   int64_t rows, int32_t cols, float* out_f32, sais_bf16* out_bf16, int32_t split_out,
+                   sais_stream_t stream) {
   if (cols != SAIS_VIT_DIM) {
     set_last_error("layernorm: cols must be 384 (got %d)", cols);
     return kErrShape;
   }
-  return layernorm(x, in_pitch, gamma, beta, eps, rows, out_f32, out_bf16, static_cast<cudaStream_t>(stream));
+  return layernorm(x, in_pitch, gamma, beta, eps, rows, out_f32, out_bf16, static_cast<cudaStream_t>(stream),
+                   split_out);
 }
 
 int sais_normalize_patchify_u8(const uint8_t* frames, int32_t B, const float* mean3_host, const float* std3_host,
-                               sais_bf16* patches, sais_stream_t stream) {
+                               sais_bf16* patches, int32_t split_out, sais_stream_t stream) {
   return normalize_patchify_u8(frames, B, mean3_host ? mean3_host : kMean, std3_host ? std3_host : kStd, patches,
-                               static_cast<cudaStream_t>(stream));
+                               static_cast<cudaStream_t>(stream), split_out);
 }
 
-int sais_patchify_f32(const float* frames_chw, int32_t B, sais_bf16* patches, sais_stream_t stream) {
-  return patchify_f32(frames_chw, B, patches, static_cast<cudaStream_t>(stream));
+int sais_patchify_f32(const float* frames_chw, int32_t B, sais_bf16* patches, int32_t split_out,
+                      sais_stream_t stream) {
+  return patchify_f32(frames_chw, B, patches, static_cast<cudaStream_t>(stream), split_out);
 }
 
 int sais_vit_attention(const sais_bf16* qkv, int32_t B, sais_bf16* out, float* probs, sais_stream_t stream) {
   return vit_attention(qkv, B, out, probs, static_cast<cudaStream_t>(stream));
 }
 
-size_t sais_vit_workspace_bytes(int32_t chunk_frames) {
+size_t sais_vit_workspace_bytes(int32_t chunk_frames, int32_t precise) {
   if (chunk_frames <= 0) return 0;
   const size_t tok = size_t(chunk_frames) * SAIS_VIT_TOKENS;
-  return a256(tok * SAIS_VIT_DIM * 4)         // x   fp32 residual stream
-         + a256(tok * SAIS_VIT_DIM * 2)       // xn  bf16 LayerNorm output / attention output
-         + a256(tok * 3 * SAIS_VIT_DIM * 2)   // qkv bf16
-         + a256(tok * SAIS_VIT_DIM * 2)       // attention output bf16
-         + a256(tok * SAIS_VIT_HIDDEN * 2);   // MLP hidden bf16 (aliased by the patch matrix)
+  const size_t s = precise ? 2 : 1;  // split-precision buffers hold [hi | lo]
+  return a256(tok * SAIS_VIT_DIM * 4)                      // x   fp32 residual stream
+         + a256(tok * SAIS_VIT_DIM * 2 * s)                // xn  bf16 LayerNorm output
+         + a256(tok * 3 * SAIS_VIT_DIM * (precise ? 4 : 2))  // qkv (fp32 in precise mode)
+         + a256(tok * SAIS_VIT_DIM * 2 * s)                // attention output bf16
+         + a256(tok * SAIS_VIT_HIDDEN * 2 * s)             // MLP hidden bf16 (aliased by the patch matrix)
+         + a256((size_t(chunk_frames) + 1) * 4);           // packed-sequence offsets (precise attention)
 }
 
 int sais_vit_forward(const SaisVitWeights* w, const void* input, int32_t input_kind, int32_t B,
-                     int32_t chunk_frames, void* workspace, size_t workspace_bytes, float* out_cls,
-                     float* out_probs, float* out_tokens, sais_stream_t stream_) {
+                     int32_t chunk_frames, int32_t precise, void* workspace, size_t workspace_bytes,
+                     float* out_cls, float* out_probs, float* out_tokens, sais_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!w || !input || !workspace || !out_cls || B < 0 || chunk_frames <= 0 ||
       (input_kind != SAIS_INPUT_F32_CHW && input_kind != SAIS_INPUT_U8_HWC)) {
     set_last_error("vit_forward: bad arguments");
     return kErrInvalidArg;
   }
-  if (workspace_bytes < sais_vit_workspace_bytes(chunk_frames)) {
+  precise = precise ? 1 : 0;
+  if (workspace_bytes < sais_vit_workspace_bytes(chunk_frames, precise)) {
     set_last_error("vit_forward: workspace too small (%zu < %zu)", workspace_bytes,
-                   sais_vit_workspace_bytes(chunk_frames));
+                   sais_vit_workspace_bytes(chunk_frames, precise));
     return kErrWorkspace;
   }
   constexpr int Dm = SAIS_VIT_DIM, Tk = SAIS_VIT_TOKENS, Hid = SAIS_VIT_HIDDEN;
+  const int s = precise ? 2 : 1;  // column multiplier of [hi | lo] buffers
   for (int b0 = 0; b0 < B; b0 += chunk_frames) {
     const int Bc = (B - b0 < chunk_frames) ? (B - b0) : chunk_frames;
     const int64_t tok = int64_t(Bc) * Tk;
+    const size_t ctok = size_t(chunk_frames) * Tk;
     Arena ar{static_cast<uint8_t*>(workspace), workspace_bytes};
-    float* x = static_cast<float*>(ar.take(size_t(chunk_frames) * Tk * Dm * 4));
-    sais_bf16* xn = static_cast<sais_bf16*>(ar.take(size_t(chunk_frames) * Tk * Dm * 2));
-    sais_bf16* qkv = static_cast<sais_bf16*>(ar.take(size_t(chunk_frames) * Tk * 3 * Dm * 2));
-    sais_bf16* ao = static_cast<sais_bf16*>(ar.take(size_t(chunk_frames) * Tk * Dm * 2));
-    sais_bf16* hid = static_cast<sais_bf16*>(ar.take(size_t(chunk_frames) * Tk * Hid * 2));
-    sais_bf16* patches = hid;  // [Bc*196, 768] <= [Bc*197, 1536]
+    float* x = static_cast<float*>(ar.take(ctok * Dm * 4));
+    sais_bf16* xn = static_cast<sais_bf16*>(ar.take(ctok * Dm * 2 * s));
+    void* qkv = ar.take(ctok * 3 * Dm * (precise ? 4 : 2));
+    sais_bf16* ao = static_cast<sais_bf16*>(ar.take(ctok * Dm * 2 * s));
+    sais_bf16* hid = static_cast<sais_bf16*>(ar.take(ctok * Hid * 2 * s));
+    int32_t* offs = static_cast<int32_t*>(ar.take((size_t(chunk_frames) + 1) * 4));
+    sais_bf16* patches = hid;  // [Bc*196, 768*s] <= [Bc*197, 1536*s]
     if (!ar.ok) {
       set_last_error("vit_forward: workspace carve failed");
       return kErrWorkspace;
@@ -241,16 +250,18 @@ int sais_vit_forward(const SaisVitWeights* w, const void* input, int32_t input_k
     // K0: frame normalisation + patch layout
     if (input_kind == SAIS_INPUT_U8_HWC)
       rc = normalize_patchify_u8(static_cast<const uint8_t*>(input) + size_t(b0) * 224 * 224 * 3, Bc, kMean, kStd,
-                                 patches, stream);
+                                 patches, stream, precise);
     else
-      rc = patchify_f32(static_cast<const float*>(input) + size_t(b0) * 3 * 224 * 224, Bc, patches, stream);
+      rc = patchify_f32(static_cast<const float*>(input) + size_t(b0) * 3 * 224 * 224, Bc, patches, stream, precise);
     if (rc) return rc;
+    if (precise && (rc = fill_offsets(offs, Bc + 1, Tk, stream))) return rc;
     // K1: patch-embed GEMM, epilogue adds bias + pos_embed[1+p] and scatters to token row b*197+1+p
     SaisGemmArgs g;
     memset(&g, 0, sizeof(g));
     g.a = patches; g.w = w->patch_w; g.bias = w->patch_b; g.out_f32 = x; g.row_add = w->pos_patch;
     g.M = int64_t(Bc) * SAIS_VIT_PATCHES; g.N = Dm; g.K = SAIS_VIT_PATCH_K;
-    g.lda = SAIS_VIT_PATCH_K; g.ldw = SAIS_VIT_PATCH_K; g.ldo32 = Dm; g.remap_group = SAIS_VIT_PATCHES;
+    g.lda = SAIS_VIT_PATCH_K * s; g.ldw = SAIS_VIT_PATCH_K * s; g.ldo32 = Dm; g.remap_group = SAIS_VIT_PATCHES;
+    g.split3 = precise;
     if ((rc = gemm_bias_act(g, stream))) return rc;
     if ((rc = write_cls_rows(w->cls_pos0, Bc, x, stream))) return rc;
 
@@ -258,31 +269,39 @@ int sais_vit_forward(const SaisVitWeights* w, const void* input, int32_t input_k
       const SaisVitBlockWeights& bw = w->blocks[l];
       const bool last = (l == SAIS_VIT_DEPTH - 1);
       // norm1
-      if ((rc = layernorm(x, Dm, bw.ln1_w, bw.ln1_b, 1e-6f, tok, nullptr, xn, stream))) return rc;
+      if ((rc = layernorm(x, Dm, bw.ln1_w, bw.ln1_b, 1e-6f, tok, nullptr, xn, stream, precise))) return rc;
       // qkv
       memset(&g, 0, sizeof(g));
-      g.a = xn; g.w = bw.qkv_w; g.bias = bw.qkv_b; g.out_bf16 = qkv;
-      g.M = tok; g.N = 3 * Dm; g.K = Dm; g.lda = Dm; g.ldw = Dm; g.ldo16 = 3 * Dm;
+      g.a = xn; g.w = bw.qkv_w; g.bias = bw.qkv_b;
+      if (precise) { g.out_f32 = static_cast<float*>(qkv); g.ldo32 = 3 * Dm; }
+      else { g.out_bf16 = static_cast<sais_bf16*>(qkv); g.ldo16 = 3 * Dm; }
+      g.M = tok; g.N = 3 * Dm; g.K = Dm; g.lda = Dm * s; g.ldw = Dm * s; g.split3 = precise;
       if ((rc = gemm_bias_act(g, stream))) return rc;
       // attention (+ probabilities of the last block on request)
       float* probs = (last && out_probs) ? out_probs + size_t(b0) * SAIS_VIT_HEADS * Tk * Tk : nullptr;
-      if ((rc = vit_attention(qkv, Bc, ao, probs, stream))) return rc;
+      if (precise)
+        rc = vit_attention_precise(static_cast<const float*>(qkv), offs, Bc, ao, probs, stream);
+      else
+        rc = vit_attention(static_cast<const sais_bf16*>(qkv), Bc, ao, probs, stream);
+      if (rc) return rc;
       // proj + residual
       memset(&g, 0, sizeof(g));
       g.a = ao; g.w = bw.proj_w; g.bias = bw.proj_b; g.residual = x; g.out_f32 = x;
-      g.M = tok; g.N = Dm; g.K = Dm; g.lda = Dm; g.ldw = Dm; g.ldr = Dm; g.ldo32 = Dm;
+      g.M = tok; g.N = Dm; g.K = Dm; g.lda = Dm * s; g.ldw = Dm * s; g.ldr = Dm; g.ldo32 = Dm; g.split3 = precise;
       if ((rc = gemm_bias_act(g, stream))) return rc;
       // norm2
-      if ((rc = layernorm(x, Dm, bw.ln2_w, bw.ln2_b, 1e-6f, tok, nullptr, xn, stream))) return rc;
+      if ((rc = layernorm(x, Dm, bw.ln2_w, bw.ln2_b, 1e-6f, tok, nullptr, xn, stream, precise))) return rc;
       // fc1 + GELU
       memset(&g, 0, sizeof(g));
       g.a = xn; g.w = bw.fc1_w; g.bias = bw.fc1_b; g.out_bf16 = hid; g.act = SAIS_ACT_GELU_ERF;
-      g.M = tok; g.N = Hid; g.K = Dm; g.lda = Dm; g.ldw = Dm; g.ldo16 = Hid;
+      g.M = tok; g.N = Hid; g.K = Dm; g.lda = Dm * s; g.ldw = Dm * s; g.ldo16 = Hid * s;
+      g.split3 = precise; g.split_out = precise;
       if ((rc = gemm_bias_act(g, stream))) return rc;
       // fc2 + residual
       memset(&g, 0, sizeof(g));
       g.a = hid; g.w = bw.fc2_w; g.bias = bw.fc2_b; g.residual = x; g.out_f32 = x;
-      g.M = tok; g.N = Dm; g.K = Hid; g.lda = Hid; g.ldw = Hid; g.ldr = Dm; g.ldo32 = Dm;
+      g.M = tok; g.N = Dm; g.K = Hid; g.lda = Hid * s; g.ldw = Hid * s; g.ldr = Dm; g.ldo32 = Dm;
+      g.split3 = precise;
       if ((rc = gemm_bias_act(g, stream))) return rc;
     }
     // final norm: only the CLS rows are consumed (vision_transformer.py:213-214)
@@ -300,25 +319,25 @@ int sais_vit_forward(const SaisVitWeights* w, const void* input, int32_t input_k
 
 int sais_temporal_prep(const float* x_frames, const int32_t* seq_offsets, int32_t nseq, int32_t total_tokens,
                        const float* frame_cls, const float* frame_pos, int32_t n_pos, float* tok_f32,
-                       sais_bf16* tok_bf16, sais_stream_t stream) {
-  return temporal_prep(x_frames, seq_offsets, nseq, total_tokens, frame_cls, frame_pos, n_pos, tok_f32, tok_bf16,
+                       sais_bf16* tok_split, sais_stream_t stream) {
+  return temporal_prep(x_frames, seq_offsets, nseq, total_tokens, frame_cls, frame_pos, n_pos, tok_f32, tok_split,
                        static_cast<cudaStream_t>(stream));
 }
 
-int sais_temporal_attention(const sais_bf16* qkv, const int32_t* seq_offsets, const uint8_t* key_pad,
-                            const int64_t* attn_offsets, int32_t nseq, int32_t max_S, sais_bf16* out,
+int sais_temporal_attention(const float* qkv, const int32_t* seq_offsets, const uint8_t* key_pad,
+                            const int64_t* attn_offsets, int32_t nseq, int32_t max_S, sais_bf16* out_split,
                             float* attn_out, sais_stream_t stream) {
-  return temporal_attention(qkv, seq_offsets, key_pad, attn_offsets, nseq, max_S, out, attn_out,
+  return temporal_attention(qkv, seq_offsets, key_pad, attn_offsets, nseq, max_S, out_split, attn_out,
                             static_cast<cudaStream_t>(stream));
 }
 
 size_t sais_temporal_workspace_bytes(int32_t total_tokens) {
   if (total_tokens <= 0) return 0;
   const size_t t = size_t(total_tokens);
-  return a256(t * SAIS_VIT_DIM * 4) * 2     // x fp32, y fp32 (pre-norm sum)
-         + a256(t * SAIS_VIT_DIM * 2) * 2   // x bf16, attention output bf16
-         + a256(t * 3 * SAIS_VIT_DIM * 2)   // qkv bf16
-         + a256(t * SAIS_TMP_FF * 2);       // FF hidden bf16
+  return a256(t * SAIS_VIT_DIM * 4) * 2       // x fp32, y fp32 (pre-norm sum)
+         + a256(t * SAIS_VIT_DIM * 2 * 2) * 2 // x [hi|lo] bf16, attention output [hi|lo] bf16
+         + a256(t * 3 * SAIS_VIT_DIM * 4)     // qkv fp32
+         + a256(t * SAIS_TMP_FF * 2 * 2);     // FF hidden [hi|lo] bf16
 }
 
 int sais_temporal_forward(const SaisTemporalWeights* w, const float* x_frames, const int32_t* seq_offsets,
@@ -341,15 +360,17 @@ int sais_temporal_forward(const SaisTemporalWeights* w, const float* x_frames, c
                    sais_temporal_workspace_bytes(total_tokens));
     return kErrWorkspace;
   }
+  // The temporal head is tiny (~1 GFLOP per clip) but decides the class, so it always runs in the
+  // split-precision (fp32-equivalent) mode: every GEMM is hi*hi + lo*hi + hi*lo over [hi | lo] bf16 operands.
   constexpr int Dm = SAIS_VIT_DIM, FF = SAIS_TMP_FF;
   const size_t t = size_t(total_tokens);
   Arena ar{static_cast<uint8_t*>(workspace), workspace_bytes};
   float* x = static_cast<float*>(ar.take(t * Dm * 4));
   float* y = static_cast<float*>(ar.take(t * Dm * 4));
-  sais_bf16* xb = static_cast<sais_bf16*>(ar.take(t * Dm * 2));
-  sais_bf16* ao = static_cast<sais_bf16*>(ar.take(t * Dm * 2));
-  sais_bf16* qkv = static_cast<sais_bf16*>(ar.take(t * 3 * Dm * 2));
-  sais_bf16* hid = static_cast<sais_bf16*>(ar.take(t * FF * 2));
+  sais_bf16* xb = static_cast<sais_bf16*>(ar.take(t * Dm * 4));
+  sais_bf16* ao = static_cast<sais_bf16*>(ar.take(t * Dm * 4));
+  float* qkv = static_cast<float*>(ar.take(t * 3 * Dm * 4));
+  sais_bf16* hid = static_cast<sais_bf16*>(ar.take(t * FF * 4));
   if (!ar.ok) {
     set_last_error("temporal_forward: workspace carve failed");
     return kErrWorkspace;
@@ -362,10 +383,10 @@ int sais_temporal_forward(const SaisTemporalWeights* w, const float* x_frames, c
   for (int l = 0; l < SAIS_TMP_LAYERS; ++l) {
     const SaisTemporalLayerWeights& lw = w->layers[l];
     const bool last = (l == SAIS_TMP_LAYERS - 1);
-    // in-proj
+    // in-proj -> fp32 q|k|v
     memset(&g, 0, sizeof(g));
-    g.a = xb; g.w = lw.in_w; g.bias = lw.in_b; g.out_bf16 = qkv;
-    g.M = total_tokens; g.N = 3 * Dm; g.K = Dm; g.lda = Dm; g.ldw = Dm; g.ldo16 = 3 * Dm;
+    g.a = xb; g.w = lw.in_w; g.bias = lw.in_b; g.out_f32 = qkv; g.split3 = 1;
+    g.M = total_tokens; g.N = 3 * Dm; g.K = Dm; g.lda = 2 * Dm; g.ldw = 2 * Dm; g.ldo32 = 3 * Dm;
     if ((rc = gemm_bias_act(g, stream))) return rc;
     // attention; only the last layer's head-mean map is returned (README-patched encoder keeps the last)
     if ((rc = temporal_attention(qkv, seq_offsets, key_pad, last ? attn_offsets : nullptr, nseq, max_S, ao,
@@ -373,21 +394,22 @@ int sais_temporal_forward(const SaisTemporalWeights* w, const float* x_frames, c
       return rc;
     // out-proj + residual -> y ; x = LN1(y)
     memset(&g, 0, sizeof(g));
-    g.a = ao; g.w = lw.out_w; g.bias = lw.out_b; g.residual = x; g.out_f32 = y;
-    g.M = total_tokens; g.N = Dm; g.K = Dm; g.lda = Dm; g.ldw = Dm; g.ldr = Dm; g.ldo32 = Dm;
+    g.a = ao; g.w = lw.out_w; g.bias = lw.out_b; g.residual = x; g.out_f32 = y; g.split3 = 1;
+    g.M = total_tokens; g.N = Dm; g.K = Dm; g.lda = 2 * Dm; g.ldw = 2 * Dm; g.ldr = Dm; g.ldo32 = Dm;
     if ((rc = gemm_bias_act(g, stream))) return rc;
-    if ((rc = layernorm(y, Dm, lw.n1_w, lw.n1_b, 1e-5f, total_tokens, x, xb, stream))) return rc;
+    if ((rc = layernorm(y, Dm, lw.n1_w, lw.n1_b, 1e-5f, total_tokens, x, xb, stream, 1))) return rc;
     // FF: linear1 + ReLU, linear2 + residual -> y ; x = LN2(y)
     memset(&g, 0, sizeof(g));
     g.a = xb; g.w = lw.ff1_w; g.bias = lw.ff1_b; g.out_bf16 = hid; g.act = SAIS_ACT_RELU;
-    g.M = total_tokens; g.N = FF; g.K = Dm; g.lda = Dm; g.ldw = Dm; g.ldo16 = FF;
+    g.split3 = 1; g.split_out = 1;
+    g.M = total_tokens; g.N = FF; g.K = Dm; g.lda = 2 * Dm; g.ldw = 2 * Dm; g.ldo16 = 2 * FF;
     if ((rc = gemm_bias_act(g, stream))) return rc;
     memset(&g, 0, sizeof(g));
-    g.a = hid; g.w = lw.ff2_w; g.bias = lw.ff2_b; g.residual = x; g.out_f32 = y;
-    g.M = total_tokens; g.N = Dm; g.K = FF; g.lda = FF; g.ldw = FF; g.ldr = Dm; g.ldo32 = Dm;
+    g.a = hid; g.w = lw.ff2_w; g.bias = lw.ff2_b; g.residual = x; g.out_f32 = y; g.split3 = 1;
+    g.M = total_tokens; g.N = Dm; g.K = FF; g.lda = 2 * FF; g.ldw = 2 * FF; g.ldr = Dm; g.ldo32 = Dm;
     if ((rc = gemm_bias_act(g, stream))) return rc;
     float* xo = (last && out_tokens) ? out_tokens : x;
-    if ((rc = layernorm(y, Dm, lw.n2_w, lw.n2_b, 1e-5f, total_tokens, xo, last ? nullptr : xb, stream))) return rc;
+    if ((rc = layernorm(y, Dm, lw.n2_w, lw.n2_b, 1e-5f, total_tokens, xo, last ? nullptr : xb, stream, 1))) return rc;
     if (last && out_cls) {
       if ((rc = gather_cls_relu(xo, seq_offsets, nseq, out_cls, stream))) return rc;
     }

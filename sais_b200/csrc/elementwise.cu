@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(256) layernorm384_kernel(const float* __restri
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, float eps, int64_t rows,
                                                            float* __restrict__ out_f32,
-                                                           __nv_bfloat16* __restrict__ out_bf16) {
+                                                           __nv_bfloat16* __restrict__ out_bf16, int split) {
   const int lane = threadIdx.x & 31;
   const int64_t row = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -54,7 +54,15 @@ __global__ void __launch_bounds__(256) layernorm384_kernel(const float* __restri
       uint2 o;
       o.x = pack_bf16x2(y.x, y.y);
       o.y = pack_bf16x2(y.z, y.w);
-      *reinterpret_cast<uint2*>(out_bf16 + row * D + c) = o;
+      if (!split) {
+        *reinterpret_cast<uint2*>(out_bf16 + row * D + c) = o;
+      } else {  // [hi | lo] halves for the split-precision GEMM
+        uint2 l;
+        l.x = pack_bf16x2(y.x - bf16_lo(o.x), y.y - bf16_hi(o.x));
+        l.y = pack_bf16x2(y.z - bf16_lo(o.y), y.w - bf16_hi(o.y));
+        *reinterpret_cast<uint2*>(out_bf16 + row * 2 * D + c) = o;
+        *reinterpret_cast<uint2*>(out_bf16 + row * 2 * D + D + c) = l;
+      }
     }
   }
 }
@@ -73,7 +81,7 @@ struct NormConsts {
 
 __global__ void __launch_bounds__(256) normalize_patchify_u8_kernel(const uint8_t* __restrict__ frames, int B,
                                                                     NormConsts nc,
-                                                                    __nv_bfloat16* __restrict__ patches) {
+                                                                    __nv_bfloat16* __restrict__ patches, int split) {
   const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t total = int64_t(B) * 224 * 14;
   if (t >= total) return;
@@ -88,26 +96,34 @@ __global__ void __launch_bounds__(256) normalize_patchify_u8_kernel(const uint8_
     w[4 * i] = u.x; w[4 * i + 1] = u.y; w[4 * i + 2] = u.z; w[4 * i + 3] = u.w;
   }
   const int py = y >> 4, ky = y & 15;
-  __nv_bfloat16* dst = patches + (b * 196 + py * 14 + px) * 768 + ky * 16;
+  const int pitch = split ? 1536 : 768;
+  __nv_bfloat16* dst = patches + (b * 196 + py * 14 + px) * pitch + ky * 16;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    uint32_t o[8];
+    uint32_t o[8], l[8];
 #pragma unroll
     for (int j = 0; j < 16; j += 2) {
       const int i0 = j * 3 + c, i1 = (j + 1) * 3 + c;
       const float f0 = float((w[i0 >> 2] >> ((i0 & 3) * 8)) & 0xff);
       const float f1 = float((w[i1 >> 2] >> ((i1 & 3) * 8)) & 0xff);
-      o[j >> 1] = pack_bf16x2(fmaf(f0, nc.scale[c], nc.shift[c]), fmaf(f1, nc.scale[c], nc.shift[c]));
+      const float v0 = fmaf(f0, nc.scale[c], nc.shift[c]), v1 = fmaf(f1, nc.scale[c], nc.shift[c]);
+      o[j >> 1] = pack_bf16x2(v0, v1);
+      l[j >> 1] = pack_bf16x2(v0 - bf16_lo(o[j >> 1]), v1 - bf16_hi(o[j >> 1]));
     }
     uint4* d4 = reinterpret_cast<uint4*>(dst + c * 256);
     d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
     d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    if (split) {
+      uint4* l4 = reinterpret_cast<uint4*>(dst + 768 + c * 256);
+      l4[0] = make_uint4(l[0], l[1], l[2], l[3]);
+      l4[1] = make_uint4(l[4], l[5], l[6], l[7]);
+    }
   }
 }
 
 // fp32 NCHW (already normalised, what the reference model is called with) -> bf16 patch matrix.
 __global__ void __launch_bounds__(256) patchify_f32_kernel(const float* __restrict__ frames, int B,
-                                                           __nv_bfloat16* __restrict__ patches) {
+                                                           __nv_bfloat16* __restrict__ patches, int split) {
   const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t total = int64_t(B) * 3 * 224 * 14;
   if (t >= total) return;
@@ -117,16 +133,31 @@ __global__ void __launch_bounds__(256) patchify_f32_kernel(const float* __restri
   const int64_t b = t / (14 * 224 * 3);
   const float4* src = reinterpret_cast<const float4*>(frames + ((b * 3 + c) * 224 + y) * 224 + px * 16);
   const int py = y >> 4, ky = y & 15;
-  uint32_t o[8];
+  uint32_t o[8], l[8];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const float4 f = __ldg(src + i);
     o[2 * i] = pack_bf16x2(f.x, f.y);
     o[2 * i + 1] = pack_bf16x2(f.z, f.w);
+    l[2 * i] = pack_bf16x2(f.x - bf16_lo(o[2 * i]), f.y - bf16_hi(o[2 * i]));
+    l[2 * i + 1] = pack_bf16x2(f.z - bf16_lo(o[2 * i + 1]), f.w - bf16_hi(o[2 * i + 1]));
   }
-  uint4* d4 = reinterpret_cast<uint4*>(patches + (b * 196 + py * 14 + px) * 768 + c * 256 + ky * 16);
+  const int pitch = split ? 1536 : 768;
+  __nv_bfloat16* dst = patches + (b * 196 + py * 14 + px) * pitch + c * 256 + ky * 16;
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
   d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
   d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  if (split) {
+    uint4* l4 = reinterpret_cast<uint4*>(dst + 768);
+    l4[0] = make_uint4(l[0], l[1], l[2], l[3]);
+    l4[1] = make_uint4(l[4], l[5], l[6], l[7]);
+  }
+}
+
+// seq_offsets[i] = i * stride (packed-sequence offsets of equally long sequences, built on device)
+__global__ void fill_offsets_kernel(int32_t* __restrict__ offs, int n, int stride) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) offs[t] = t * stride;
 }
 
 // x[b, 0, :] = cls_token + pos_embed[0]   (vision_transformer.py:201-205)
@@ -163,10 +194,14 @@ __global__ void __launch_bounds__(128) temporal_prep_kernel(const float* __restr
     }
     const int64_t o = int64_t(t0 + s) * D + c;
     *reinterpret_cast<float4*>(tok_f32 + o) = v;
-    uint2 b;
+    uint2 b, l;
     b.x = pack_bf16x2(v.x, v.y);
     b.y = pack_bf16x2(v.z, v.w);
-    *reinterpret_cast<uint2*>(tok_bf16 + o) = b;
+    l.x = pack_bf16x2(v.x - bf16_lo(b.x), v.y - bf16_hi(b.x));
+    l.y = pack_bf16x2(v.z - bf16_lo(b.y), v.w - bf16_hi(b.y));
+    const int64_t o2 = int64_t(t0 + s) * 2 * D + c;  // [hi | lo] halves, row pitch 768
+    *reinterpret_cast<uint2*>(tok_bf16 + o2) = b;
+    *reinterpret_cast<uint2*>(tok_bf16 + o2 + D) = l;
   }
 }
 
@@ -290,7 +325,7 @@ __global__ void __launch_bounds__(128) prototype_score_kernel(const float* __res
 }  // namespace
 
 int layernorm(const float* x, int64_t in_pitch, const float* gamma, const float* beta, float eps, int64_t rows,
-              float* out_f32, sais_bf16* out_bf16, cudaStream_t stream) {
+              float* out_f32, sais_bf16* out_bf16, cudaStream_t stream, int split) {
   if (rows == 0) return kOk;
   if (!x || !gamma || !beta || (!out_f32 && !out_bf16) || rows < 0 || in_pitch % 4) {
     set_last_error("layernorm: bad arguments");
@@ -299,12 +334,12 @@ int layernorm(const float* x, int64_t in_pitch, const float* gamma, const float*
   const int64_t blocks = (rows + 7) / 8;
   LaunchScope ls(kClsLayerNorm, stream, double(rows) * D * (4 + (out_f32 ? 4 : 0) + (out_bf16 ? 2 : 0)));
   layernorm384_kernel<<<unsigned(blocks), 256, 0, stream>>>(x, in_pitch, gamma, beta, eps, rows, out_f32,
-                                                            reinterpret_cast<__nv_bfloat16*>(out_bf16));
+                                                            reinterpret_cast<__nv_bfloat16*>(out_bf16), split);
   return check_cuda(cudaGetLastError(), "layernorm launch");
 }
 
 int normalize_patchify_u8(const uint8_t* frames, int B, const float* mean3, const float* std3, sais_bf16* patches,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, int split) {
   if (B == 0) return kOk;
   if (!frames || !patches || !mean3 || !std3 || B < 0) {
     set_last_error("normalize_patchify_u8: bad arguments");
@@ -318,11 +353,11 @@ int normalize_patchify_u8(const uint8_t* frames, int B, const float* mean3, cons
   const int64_t total = int64_t(B) * 224 * 14;
   LaunchScope ls(kClsPatchify, stream, double(B) * 224 * 224 * 3 * 3);
   normalize_patchify_u8_kernel<<<unsigned((total + 255) / 256), 256, 0, stream>>>(
-      frames, B, nc, reinterpret_cast<__nv_bfloat16*>(patches));
+      frames, B, nc, reinterpret_cast<__nv_bfloat16*>(patches), split);
   return check_cuda(cudaGetLastError(), "normalize_patchify_u8 launch");
 }
 
-int patchify_f32(const float* frames, int B, sais_bf16* patches, cudaStream_t stream) {
+int patchify_f32(const float* frames, int B, sais_bf16* patches, cudaStream_t stream, int split) {
   if (B == 0) return kOk;
   if (!frames || !patches || B < 0) {
     set_last_error("patchify_f32: bad arguments");
@@ -330,9 +365,16 @@ int patchify_f32(const float* frames, int B, sais_bf16* patches, cudaStream_t st
   }
   const int64_t total = int64_t(B) * 3 * 224 * 14;
   LaunchScope ls(kClsPatchify, stream, double(B) * 224 * 224 * 3 * 6);
-  patchify_f32_kernel<<<unsigned((total + 255) / 256), 256, 0, stream>>>(frames, B,
-                                                                         reinterpret_cast<__nv_bfloat16*>(patches));
+  patchify_f32_kernel<<<unsigned((total + 255) / 256), 256, 0, stream>>>(
+      frames, B, reinterpret_cast<__nv_bfloat16*>(patches), split);
   return check_cuda(cudaGetLastError(), "patchify_f32 launch");
+}
+
+int fill_offsets(int32_t* offs, int n, int stride, cudaStream_t stream) {
+  if (n <= 0) return kOk;
+  LaunchScope ls(kClsMisc, stream, double(n) * 4);
+  fill_offsets_kernel<<<(n + 255) / 256, 256, 0, stream>>>(offs, n, stride);
+  return check_cuda(cudaGetLastError(), "fill_offsets launch");
 }
 
 int write_cls_rows(const float* cls_pos0, int B, float* x, cudaStream_t stream) {

@@ -44,6 +44,8 @@ struct GemmParams {
   int M, N, K;
   int act;
   int remap_group;
+  int split3;     // 1: A and W hold [hi | lo] bf16 halves (2K columns); accumulate hi*hi + lo*hi + hi*lo
+  int split_out;  // 1: out_bf16 has 2N columns, value v is stored as hi = bf16(v) at n and lo = bf16(v - hi) at N + n
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
@@ -69,7 +71,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
   const int n_tiles = p.N / BLOCK_N;
   const int num_tiles = m_tiles * n_tiles;
-  const int k_blocks = p.K / BLOCK_K;
+  const int kb_per_pass = p.K / BLOCK_K;
+  const int k_blocks = p.split3 ? 3 * kb_per_pass : kb_per_pass;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -106,8 +109,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m0);
-          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n0);
+          // split3 passes: (A_hi, W_hi), (A_lo, W_hi), (A_hi, W_lo); halves sit side by side along K
+          int ka = kb, kw = kb;
+          if (kb >= 2 * kb_per_pass) {
+            ka = kb - 2 * kb_per_pass;
+            kw = kb - kb_per_pass;
+          } else if (kb >= kb_per_pass) {
+            kw = kb - kb_per_pass;
+          }
+          tma_load_2d(sa, &tmap_a, &full_bar[stage], ka * BLOCK_K, m0);
+          tma_load_2d(sb, &tmap_b, &full_bar[stage], kw * BLOCK_K, n0);
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
@@ -228,6 +239,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               o.z = pack_bf16x2(f[j + 4], f[j + 5]);
               o.w = pack_bf16x2(f[j + 6], f[j + 7]);
               *reinterpret_cast<uint4*>(op + j) = o;
+              if (p.split_out) {  // residual halves for the split-precision consumer
+                uint4 l;
+                l.x = pack_bf16x2(f[j] - bf16_lo(o.x), f[j + 1] - bf16_hi(o.x));
+                l.y = pack_bf16x2(f[j + 2] - bf16_lo(o.y), f[j + 3] - bf16_hi(o.y));
+                l.z = pack_bf16x2(f[j + 4] - bf16_lo(o.z), f[j + 5] - bf16_hi(o.z));
+                l.w = pack_bf16x2(f[j + 6] - bf16_lo(o.w), f[j + 7] - bf16_hi(o.w));
+                *reinterpret_cast<uint4*>(op + p.N + j) = l;
+              }
             }
           }
         }
@@ -253,9 +272,10 @@ template <int BLOCK_N>
 int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
   CUtensorMap ta, tb;
-  int rc = make_tmap_bf16_2d(&ta, a.a, uint64_t(a.M), uint64_t(a.K), uint64_t(a.lda), BLOCK_M, BLOCK_K);
+  const uint64_t kcols = uint64_t(a.K) * (a.split3 ? 2 : 1);
+  int rc = make_tmap_bf16_2d(&ta, a.a, uint64_t(a.M), kcols, uint64_t(a.lda), BLOCK_M, BLOCK_K);
   if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tb, a.w, uint64_t(a.N), uint64_t(a.K), uint64_t(a.ldw), BLOCK_N, BLOCK_K);
+  rc = make_tmap_bf16_2d(&tb, a.w, uint64_t(a.N), kcols, uint64_t(a.ldw), BLOCK_N, BLOCK_K);
   if (rc) return rc;
 
   static bool attr_set = false;
@@ -280,10 +300,12 @@ int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
   p.K = int(a.K);
   p.act = a.act;
   p.remap_group = a.remap_group;
+  p.split3 = a.split3;
+  p.split_out = a.split_out;
   const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
   const int tiles = m_tiles * (p.N / BLOCK_N);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  LaunchScope ls(kClsGemm, stream, 2.0 * double(a.M) * double(a.N) * double(a.K));
+  LaunchScope ls(kClsGemm, stream, 2.0 * double(a.M) * double(a.N) * double(a.K) * (a.split3 ? 3 : 1));
   gemm_tcgen05_kernel<BLOCK_N><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
   return check_cuda(cudaGetLastError(), "gemm_tcgen05_kernel launch");
 }

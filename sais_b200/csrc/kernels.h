@@ -27,10 +27,11 @@ int pick_block_n(int64_t M, int64_t N);
 
 // elementwise.cu
 int layernorm(const float* x, int64_t in_pitch, const float* gamma, const float* beta, float eps, int64_t rows,
-              float* out_f32, sais_bf16* out_bf16, cudaStream_t stream);
+              float* out_f32, sais_bf16* out_bf16, cudaStream_t stream, int split = 0);
 int normalize_patchify_u8(const uint8_t* frames, int B, const float* mean3, const float* std3, sais_bf16* patches,
-                          cudaStream_t stream);
-int patchify_f32(const float* frames, int B, sais_bf16* patches, cudaStream_t stream);
+                          cudaStream_t stream, int split = 0);
+int patchify_f32(const float* frames, int B, sais_bf16* patches, cudaStream_t stream, int split = 0);
+int fill_offsets(int32_t* offs, int n, int stride, cudaStream_t stream);
 int write_cls_rows(const float* cls_pos0, int B, float* x, cudaStream_t stream);
 int temporal_prep(const float* x_frames, const int32_t* seq_offsets, int nseq, int total_tokens,
                   const float* frame_cls, const float* frame_pos, int n_pos, float* tok_f32, sais_bf16* tok_bf16,
@@ -45,8 +46,11 @@ int prototype_score(const float* reps, const float* protos, int B, int P, int D,
 int vit_attention(const sais_bf16* qkv, int B, sais_bf16* out, float* probs, cudaStream_t stream);
 
 // temporal_attention.cu
-int temporal_attention(const sais_bf16* qkv, const int32_t* seq_offsets, const uint8_t* key_pad,
-                       const int64_t* attn_offsets, int nseq, int max_S, sais_bf16* out, float* attn_out,
+// fp32 qkv in, bf16 [hi | lo] (row pitch 2*384) out
+int temporal_attention(const float* qkv, const int32_t* seq_offsets, const uint8_t* key_pad,
+                       const int64_t* attn_offsets, int nseq, int max_S, sais_bf16* out_split, float* attn_out,
                        cudaStream_t stream);
+int vit_attention_precise(const float* qkv, const int32_t* seq_offsets, int B, sais_bf16* out_split, float* probs,
+                          cudaStream_t stream);
 
 }  // namespace sais

@@ -14,18 +14,30 @@ _IMAGENET_MEAN = (0.485, 0.456, 0.406)  # extract_representations.py:161
 _IMAGENET_STD = (0.229, 0.224, 0.225)
 
 
+def split_bf16(t):
+    """fp32 [R,C] -> bf16 [R,2C] = [hi | lo] with hi = bf16(t), lo = bf16(t - hi): t == hi + lo to ~2^-17."""
+    t = t.float()
+    hi = t.to(torch.bfloat16)
+    lo = (t - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, lo], dim=-1).contiguous()
+
+
 def gemm_bias_act(a, w, bias=None, act=_lib.ACT_NONE, residual=None, out_dtype=torch.bfloat16, out=None,
-                  row_add=None, remap_group=0):
-    """out = act(a @ w.T + bias) [+ residual].  a: bf16 [M,K]; w: bf16 [N,K]; bias/residual fp32."""
+                  row_add=None, remap_group=0, split3=False, split_out=False):
+    """out = act(a @ w.T + bias) [+ residual].  a: bf16 [M,K]; w: bf16 [N,K]; bias/residual fp32.
+    split3: a and w are [hi | lo] halves ([M,2K], [N,2K], see split_bf16) and the product is fp32-equivalent;
+    split_out: the bf16 output is written as [hi | lo] ([M,2N])."""
     require_cuda(a, "a")
     require_cuda(w, "w")
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
     assert a.stride(-1) == 1 and w.stride(-1) == 1
     M, K = a.shape
+    if split3:
+        K //= 2
     N = w.shape[0]
     rows_out = M if remap_group == 0 else (M // remap_group) * (remap_group + 1)
     if out is None:
-        out = torch.empty((rows_out, N), device=a.device, dtype=out_dtype)
+        out = torch.empty((rows_out, N * (2 if split_out else 1)), device=a.device, dtype=out_dtype)
     g = SaisGemmArgs()
     g.a, g.w, g.bias = ptr(a), ptr(w), ptr(bias)
     g.residual = ptr(residual)
@@ -38,11 +50,12 @@ def gemm_bias_act(a, w, bias=None, act=_lib.ACT_NONE, residual=None, out_dtype=t
     g.lda, g.ldw = a.stride(0), w.stride(0)
     g.ldr = residual.stride(0) if residual is not None else 0
     g.act, g.remap_group = act, remap_group
+    g.split3, g.split_out = int(split3), int(split_out)
     check(lib().sais_gemm_bias_act(C.byref(g), current_stream()), "sais_gemm_bias_act")
     return out
 
 
-def layernorm(x, gamma, beta, eps, out_f32=False, out_bf16=True, in_pitch=None, rows=None):
+def layernorm(x, gamma, beta, eps, out_f32=False, out_bf16=True, in_pitch=None, rows=None, split_out=False):
     require_cuda(x, "x")
     assert x.dtype == torch.float32
     if in_pitch is None:
@@ -50,32 +63,33 @@ def layernorm(x, gamma, beta, eps, out_f32=False, out_bf16=True, in_pitch=None, 
         in_pitch, rows = x2.stride(0), x2.shape[0]
     cols = gamma.numel()
     of = torch.empty((rows, cols), device=x.device, dtype=torch.float32) if out_f32 else None
-    ob = torch.empty((rows, cols), device=x.device, dtype=torch.bfloat16) if out_bf16 else None
+    ob = torch.empty((rows, cols * (2 if split_out else 1)), device=x.device,
+                     dtype=torch.bfloat16) if out_bf16 else None
     check(lib().sais_layernorm(ptr(x), in_pitch, ptr(gamma), ptr(beta), float(eps), rows, cols, ptr(of), ptr(ob),
-                               current_stream()), "sais_layernorm")
+                               int(split_out), current_stream()), "sais_layernorm")
     return of, ob
 
 
-def normalize_patchify_u8(frames):
-    """u8 [B,224,224,3] -> bf16 patches [B*196,768] with ImageNet normalisation."""
+def normalize_patchify_u8(frames, split_out=False):
+    """u8 [B,224,224,3] -> bf16 patches [B*196,768] with ImageNet normalisation ([B*196,1536] = [hi|lo] if split)."""
     require_cuda(frames, "frames")
     assert frames.dtype == torch.uint8 and frames.is_contiguous() and tuple(frames.shape[1:]) == (224, 224, 3)
     B = frames.shape[0]
-    out = torch.empty((B * 196, 768), device=frames.device, dtype=torch.bfloat16)
+    out = torch.empty((B * 196, 768 * (2 if split_out else 1)), device=frames.device, dtype=torch.bfloat16)
     mean = (C.c_float * 3)(*_IMAGENET_MEAN)
     std = (C.c_float * 3)(*_IMAGENET_STD)
     check(lib().sais_normalize_patchify_u8(ptr(frames), B, C.cast(mean, C.c_void_p), C.cast(std, C.c_void_p),
-                                           ptr(out), current_stream()), "sais_normalize_patchify_u8")
+                                           ptr(out), int(split_out), current_stream()), "sais_normalize_patchify_u8")
     return out
 
 
-def patchify_f32(frames):
-    """fp32 [B,3,224,224] (already normalised) -> bf16 patches [B*196,768]."""
+def patchify_f32(frames, split_out=False):
+    """fp32 [B,3,224,224] (already normalised) -> bf16 patches [B*196,768] ([B*196,1536] = [hi|lo] if split)."""
     require_cuda(frames, "frames")
     assert frames.dtype == torch.float32 and frames.is_contiguous() and tuple(frames.shape[1:]) == (3, 224, 224)
     B = frames.shape[0]
-    out = torch.empty((B * 196, 768), device=frames.device, dtype=torch.bfloat16)
-    check(lib().sais_patchify_f32(ptr(frames), B, ptr(out), current_stream()), "sais_patchify_f32")
+    out = torch.empty((B * 196, 768 * (2 if split_out else 1)), device=frames.device, dtype=torch.bfloat16)
+    check(lib().sais_patchify_f32(ptr(frames), B, ptr(out), int(split_out), current_stream()), "sais_patchify_f32")
     return out
 
 
@@ -90,10 +104,12 @@ def vit_attention(qkv, B, emit_probs=False):
 
 
 def temporal_attention(qkv, seq_offsets, key_pad=None, attn_offsets=None, max_S=None, attn_numel=0):
-    """qkv bf16 [tokens,1152]; seq_offsets int32 [nseq+1] (device); returns (out bf16 [tokens,384], attn flat)."""
+    """qkv fp32 [tokens,1152]; seq_offsets int32 [nseq+1] (device); returns (out bf16 [tokens,768] = [hi|lo] halves
+    of the fp32 attention output, head-averaged attention maps flat fp32 or None)."""
     require_cuda(qkv, "qkv")
+    assert qkv.dtype == torch.float32 and qkv.is_contiguous()
     nseq = seq_offsets.numel() - 1
-    out = torch.empty((qkv.shape[0], 384), device=qkv.device, dtype=torch.bfloat16)
+    out = torch.empty((qkv.shape[0], 768), device=qkv.device, dtype=torch.bfloat16)
     attn = torch.zeros(attn_numel, device=qkv.device, dtype=torch.float32) if attn_numel else None
     check(lib().sais_temporal_attention(ptr(qkv), ptr(seq_offsets), ptr(key_pad), ptr(attn_offsets), nseq,
                                         int(max_S), ptr(out), ptr(attn), current_stream()),

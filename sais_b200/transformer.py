@@ -80,8 +80,10 @@ class TransformerEncoder(nn.Module):
             keep.append(t)
             return t
 
-        def bf(t):
-            t = t.detach().to(dev, torch.float32).contiguous().to(torch.bfloat16)
+        def bf(t):  # [N,K] fp32 -> [N,2K] bf16 = [hi | lo]: the temporal head always runs split-precision
+            t = t.detach().to(dev, torch.float32).contiguous()
+            hi = t.to(torch.bfloat16)
+            t = torch.cat([hi, (t - hi.float()).to(torch.bfloat16)], dim=1).contiguous()
             keep.append(t)
             return t
 
@@ -180,8 +182,8 @@ class TransformerEncoder(nn.Module):
         zero_cls = torch.zeros(E, device=dev)
         zero_pos = torch.zeros((1, E), device=dev)
         w, _ = self.pack_weights(zero_cls, zero_pos)
-        x = tokens_nse.reshape(N * S, E)
-        xb = x.to(torch.bfloat16)
+        x = tokens_nse.reshape(N * S, E).contiguous()
+        xb = ops.split_bf16(x)
         offs = torch.arange(0, (N + 1) * S, S, device=dev, dtype=torch.int32)
         a_offs = torch.arange(0, N, device=dev, dtype=torch.int64) * (S * S)
         pad = None
@@ -191,14 +193,15 @@ class TransformerEncoder(nn.Module):
         for li, layer in enumerate(self.layers):
             lw = w.layers[li]
             last = li == len(self.layers) - 1
-            qkv = _gemm_raw(xb, lw.in_w, lw.in_b, 3 * E, E, out_dtype=torch.bfloat16)
+            qkv = _gemm_raw(xb, lw.in_w, lw.in_b, 3 * E, E, out_dtype=torch.float32)
             ao, a = ops.temporal_attention(qkv, offs, pad, a_offs if last else None, S,
                                            attn_numel=N * S * S if last else 0)
             if last:
                 attn = a.view(N, S, S)
             y = _gemm_raw(ao, lw.out_w, lw.out_b, E, E, out_dtype=torch.float32, residual=x)
             x, xb = _ln_raw(y, lw.n1_w, lw.n1_b, 1e-5)
-            h = _gemm_raw(xb, lw.ff1_w, lw.ff1_b, D_FF, E, out_dtype=torch.bfloat16, act=_lib.ACT_RELU)
+            h = _gemm_raw(xb, lw.ff1_w, lw.ff1_b, D_FF, E, out_dtype=torch.bfloat16, act=_lib.ACT_RELU,
+                          split_out=True)
             y = _gemm_raw(h, lw.ff2_w, lw.ff2_b, E, D_FF, out_dtype=torch.float32, residual=x)
             x, xb = _ln_raw(y, lw.n2_w, lw.n2_b, 1e-5)
         return x.view(N, S, E).permute(1, 0, 2).contiguous(), attn
@@ -209,19 +212,20 @@ class TransformerEncoder(nn.Module):
         return super().train(False)
 
 
-def _gemm_raw(a, w_ptr, b_ptr, N, K, out_dtype, residual=None, act=_lib.ACT_NONE):
-    """GEMM against a packed weight given by raw pointer (used by the per-layer torch-compatible path)."""
+def _gemm_raw(a, w_ptr, b_ptr, N, K, out_dtype, residual=None, act=_lib.ACT_NONE, split_out=False):
+    """Split-precision GEMM against a packed [N,2K] weight given by raw pointer (per-layer torch-compatible path)."""
     g = _lib.SaisGemmArgs()
     M = a.shape[0]
-    out = torch.empty((M, N), device=a.device, dtype=out_dtype)
+    out = torch.empty((M, N * (2 if split_out else 1)), device=a.device, dtype=out_dtype)
     g.a, g.w, g.bias = ptr(a), w_ptr, b_ptr
     g.residual = ptr(residual)
     if out_dtype == torch.float32:
-        g.out_f32, g.ldo32 = ptr(out), N
+        g.out_f32, g.ldo32 = ptr(out), out.stride(0)
     else:
-        g.out_bf16, g.ldo16 = ptr(out), N
+        g.out_bf16, g.ldo16 = ptr(out), out.stride(0)
     g.M, g.N, g.K = M, N, K
-    g.lda, g.ldw = a.stride(0), K
+    g.lda, g.ldw = a.stride(0), 2 * K
+    g.split3, g.split_out = 1, int(split_out)
     g.ldr = residual.stride(0) if residual is not None else 0
     g.act = act
     check(lib().sais_gemm_bias_act(C.byref(g), current_stream()), "sais_gemm_bias_act")
@@ -231,7 +235,7 @@ def _gemm_raw(a, w_ptr, b_ptr, N, K, out_dtype, residual=None, act=_lib.ACT_NONE
 def _ln_raw(y, w_ptr, b_ptr, eps):
     rows, cols = y.shape
     of = torch.empty_like(y)
-    ob = torch.empty((rows, cols), device=y.device, dtype=torch.bfloat16)
-    check(lib().sais_layernorm(ptr(y), y.stride(0), w_ptr, b_ptr, float(eps), rows, cols, ptr(of), ptr(ob),
+    ob = torch.empty((rows, 2 * cols), device=y.device, dtype=torch.bfloat16)
+    check(lib().sais_layernorm(ptr(y), y.stride(0), w_ptr, b_ptr, float(eps), rows, cols, ptr(of), ptr(ob), 1,
                                current_stream()), "sais_layernorm")
     return of, ob

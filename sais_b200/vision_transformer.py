@@ -73,7 +73,7 @@ class VisionTransformer(nn.Module):
 
     def __init__(self, img_size=(224,), patch_size=16, in_chans=3, num_classes=0, embed_dim=384, depth=12,
                  num_heads=6, mlp_ratio=4.0, qkv_bias=True, qk_scale=None, drop_rate=0.0, attn_drop_rate=0.0,
-                 drop_path_rate=0.0, norm_layer=None, chunk_frames=96, **kwargs):
+                 drop_path_rate=0.0, norm_layer=None, chunk_frames=96, precision="bf16", **kwargs):
         super().__init__()
         img = img_size[0] if isinstance(img_size, (list, tuple)) else img_size
         if (img, patch_size, in_chans, embed_dim, depth, num_heads, mlp_ratio, qkv_bias) != (
@@ -90,6 +90,9 @@ class VisionTransformer(nn.Module):
         self.norm = norm_layer(embed_dim)
         self.head = nn.Identity()
         self.chunk_frames = int(chunk_frames)
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' (fast path) or 'fp32' (split-precision, fp32-equivalent)")
+        self.precision = precision
         # same initial distribution as the reference (:161-172): trunc-normal(0.02), zero bias, unit LN
         nn.init.trunc_normal_(self.pos_embed, std=0.02)
         nn.init.trunc_normal_(self.cls_token, std=0.02)
@@ -101,8 +104,7 @@ class VisionTransformer(nn.Module):
             elif isinstance(m, nn.LayerNorm):
                 nn.init.ones_(m.weight)
                 nn.init.zeros_(m.bias)
-        self._packed = None
-        self._packed_key = None
+        self._packed = {}
         self._ws = None
         self.eval()
 
@@ -110,11 +112,13 @@ class VisionTransformer(nn.Module):
     def _pack_key(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
-    def pack_weights(self, force=False):
-        """fp32 parameters -> device buffers in the kernel layouts (bf16 GEMM operands, fp32 vectors)."""
+    def pack_weights(self, precise=False, force=False):
+        """fp32 parameters -> device buffers in the kernel layouts: bf16 GEMM operands ([N,K], or [N,2K] = [hi|lo]
+        halves for the fp32-equivalent mode) and fp32 vectors.  Re-packed automatically when a parameter changes."""
         key = self._pack_key()
-        if not force and self._packed is not None and self._packed_key == key:
-            return self._packed
+        hit = self._packed.get(bool(precise))
+        if not force and hit is not None and hit[0] == key:
+            return hit[1]
         dev = self.cls_token.device
         if dev.type != "cuda":
             raise _lib.SaisError("VisionTransformer parameters must live on a CUDA device (no CPU path)")
@@ -126,7 +130,12 @@ class VisionTransformer(nn.Module):
             return t
 
         def bf(t):
-            t = t.detach().to(dev, torch.float32).contiguous().to(torch.bfloat16)
+            t = t.detach().to(dev, torch.float32).contiguous()
+            if precise:
+                hi = t.to(torch.bfloat16)
+                t = torch.cat([hi, (t - hi.float()).to(torch.bfloat16)], dim=1).contiguous()
+            else:
+                t = t.to(torch.bfloat16)
             keep.append(t)
             return t
 
@@ -144,18 +153,17 @@ class VisionTransformer(nn.Module):
             b.fc1_w, b.fc1_b = ptr(bf(blk.mlp.fc1.weight)), ptr(f32(blk.mlp.fc1.bias))
             b.fc2_w, b.fc2_b = ptr(bf(blk.mlp.fc2.weight)), ptr(f32(blk.mlp.fc2.bias))
         w.norm_w, w.norm_b = ptr(f32(self.norm.weight)), ptr(f32(self.norm.bias))
-        self._packed = (w, keep)
-        self._packed_key = key
-        return self._packed
+        self._packed[bool(precise)] = (key, (w, keep))
+        return w, keep
 
-    def _workspace(self, chunk, device):
-        need = lib().sais_vit_workspace_bytes(chunk)
+    def _workspace(self, chunk, device, precise):
+        need = lib().sais_vit_workspace_bytes(chunk, int(precise))
         if self._ws is None or self._ws.numel() < need or self._ws.device != device:
             self._ws = torch.empty(need, dtype=torch.uint8, device=device)
         return self._ws, need
 
     # ------------------------------------------------------------------ forward paths
-    def _run(self, x, kind, want_probs=False, want_tokens=False):
+    def _run(self, x, kind, want_probs=False, want_tokens=False, precision=None):
         if self.training:
             raise _lib.SaisError("sais_b200.VisionTransformer is inference-only; call .eval()")
         require_cuda(x, "input")
@@ -165,15 +173,16 @@ class VisionTransformer(nn.Module):
             return (torch.empty((0, DIM), device=x.device),
                     torch.empty((0, HEADS, TOKENS, TOKENS), device=x.device) if want_probs else None,
                     torch.empty((0, TOKENS, DIM), device=x.device) if want_tokens else None)
-        w, _ = self.pack_weights()
+        precise = (precision or self.precision) == "fp32"
+        w, _ = self.pack_weights(precise)
         chunk = max(1, min(self.chunk_frames, B))
-        ws, need = self._workspace(chunk, x.device)
+        ws, need = self._workspace(chunk, x.device, precise)
         out = torch.empty((B, DIM), device=x.device, dtype=torch.float32)
         probs = torch.empty((B, HEADS, TOKENS, TOKENS), device=x.device, dtype=torch.float32) if want_probs else None
         toks = torch.empty((B, TOKENS, DIM), device=x.device, dtype=torch.float32) if want_tokens else None
         with torch.cuda.device(x.device):
-            check(lib().sais_vit_forward(C.byref(w), ptr(x), kind, B, chunk, ptr(ws), need, ptr(out), ptr(probs),
-                                         ptr(toks), current_stream()), "sais_vit_forward")
+            check(lib().sais_vit_forward(C.byref(w), ptr(x), kind, B, chunk, int(precise), ptr(ws), need, ptr(out),
+                                         ptr(probs), ptr(toks), current_stream()), "sais_vit_forward")
         return out, probs, toks
 
     @staticmethod
@@ -183,28 +192,29 @@ class VisionTransformer(nn.Module):
         return x.float()
 
     @torch.no_grad()
-    def forward(self, x):
-        """``model(inputs[B,3,224,224] fp32, normalised) -> reps[B,384]`` (extract_representations.py:370)."""
-        return self._run(self._check_f32(x), _lib.INPUT_F32_CHW)[0]
+    def forward(self, x, precision=None):
+        """``model(inputs[B,3,224,224] fp32, normalised) -> reps[B,384]`` (extract_representations.py:370).
+        ``precision`` overrides the module default: 'bf16' (fast) or 'fp32' (split-precision, ~3.5x the work)."""
+        return self._run(self._check_f32(x), _lib.INPUT_F32_CHW, precision=precision)[0]
 
     @torch.no_grad()
-    def forward_u8(self, frames):
+    def forward_u8(self, frames, precision=None):
         """Raw ``uint8 [B,224,224,3]`` frames; ToTensor+Normalize(ImageNet) is fused into the patch kernel."""
         if frames.dtype != torch.uint8 or tuple(frames.shape[1:]) != (IMG, IMG, 3):
             raise NotImplementedError(f"forward_u8 expects uint8 [B,224,224,3] (got {frames.dtype} {tuple(frames.shape)})")
-        return self._run(frames, _lib.INPUT_U8_HWC)[0]
+        return self._run(frames, _lib.INPUT_U8_HWC, precision=precision)[0]
 
     @torch.no_grad()
-    def get_last_selfattention(self, x):
+    def get_last_selfattention(self, x, precision=None):
         """Softmax probabilities of the last block, ``[B,6,197,197]`` (reference :216-223)."""
-        return self._run(self._check_f32(x), _lib.INPUT_F32_CHW, want_probs=True)[1]
+        return self._run(self._check_f32(x), _lib.INPUT_F32_CHW, want_probs=True, precision=precision)[1]
 
     @torch.no_grad()
-    def get_intermediate_layers(self, x, n=1):
+    def get_intermediate_layers(self, x, n=1, precision=None):
         """Final-norm'd tokens of the last block (reference :225-233); only ``n == 1`` is on the hot path."""
         if n != 1:
             raise NotImplementedError("get_intermediate_layers is implemented for n=1 only")
-        return [self._run(self._check_f32(x), _lib.INPUT_F32_CHW, want_tokens=True)[2]]
+        return [self._run(self._check_f32(x), _lib.INPUT_F32_CHW, want_tokens=True, precision=precision)[2]]
 
     def train(self, mode=True):
         if mode:

@@ -44,7 +44,7 @@ def test_struct_layouts_match_header_sizes():
     assert C.sizeof(_lib.SaisVitWeights) == (4 + 12 * 12 + 2) * 8
     assert C.sizeof(_lib.SaisTemporalLayerWeights) == 12 * 8
     assert C.sizeof(_lib.SaisTemporalWeights) == 2 * 8 + 8 + 4 * 12 * 8  # n_pos int32 padded to 8
-    assert C.sizeof(_lib.SaisGemmArgs) == 7 * 8 + 8 * 8 + 2 * 4
+    assert C.sizeof(_lib.SaisGemmArgs) == 7 * 8 + 8 * 8 + 4 * 4
 
 
 def test_no_cpu_fallback():

@@ -181,10 +181,16 @@ def test_vit_attention(dev, B, scale):
 
 
 # ------------------------------------------------------------------------------------------------ temporal attention
+def _unsplit(t):
+    """bf16 [R,2C] = [hi | lo] -> fp32 [R,C]"""
+    c = t.shape[1] // 2
+    return t[:, :c].float() + t[:, c:].float()
+
+
 def _tmp_attn_ref(qkv, lens_S, pads):
     outs, attns, t0 = [], [], 0
     for i, S in enumerate(lens_S):
-        blk = bf(qkv[t0:t0 + S])
+        blk = qkv[t0:t0 + S].double()
         q, k, v = blk.view(S, 3, 4, 96).permute(1, 2, 0, 3)
         logit = (q @ k.transpose(-2, -1)) * 96 ** -0.5
         if pads is not None:
@@ -216,16 +222,17 @@ def test_temporal_attention(dev, lens_S):
     for S, e in zip(lens_S, emit):
         a_offs.append(cur if e else -1)
         cur += S * S if e else 0
-    out, attn = ops.temporal_attention(qkv.to(dev).bfloat16(), offs.to(dev), pads.to(dev),
+    out, attn = ops.temporal_attention(qkv.to(dev), offs.to(dev), pads.to(dev),
                                        torch.tensor(a_offs, dtype=torch.int64).to(dev), max(lens_S), attn_numel=cur)
     ref_o, ref_a = _tmp_attn_ref(qkv, lens_S, pads)
-    assert torch.allclose(out.cpu().float(), ref_o, atol=1e-2, rtol=2 ** -7), (out.cpu().float() - ref_o).abs().max()
+    got_o = _unsplit(out.cpu())  # exact fp32 attention, output carried as [hi | lo] bf16 halves (~2^-17 relative)
+    assert torch.allclose(got_o, ref_o.float(), atol=2e-5, rtol=2e-5), (got_o - ref_o.float()).abs().max()
     attn = attn.cpu()
     t0 = 0
     for S, e, ao, ra in zip(lens_S, emit, a_offs, ref_a):
         if e:
             got = attn[ao:ao + S * S].view(S, S)
-            assert torch.allclose(got, ra, atol=2e-6, rtol=1e-4), (got - ra).abs().max()
+            assert torch.allclose(got, ra.float(), atol=2e-6, rtol=1e-4), (got - ra.float()).abs().max()
             assert float(got[:, pads[t0:t0 + S].bool()].abs().max() if pads[t0:t0 + S].any() else 0) == 0.0
         t0 += S
 
@@ -235,9 +242,9 @@ def test_temporal_attention_no_mask_no_maps(dev):
     lens_S = [31] * 3
     qkv = rnd(93, 1152, seed=1)
     offs = torch.tensor([0, 31, 62, 93], dtype=torch.int32)
-    out, attn = ops.temporal_attention(qkv.to(dev).bfloat16(), offs.to(dev), None, None, 31)
+    out, attn = ops.temporal_attention(qkv.to(dev), offs.to(dev), None, None, 31)
     assert attn is None
-    assert torch.allclose(out.cpu().float(), _tmp_attn_ref(qkv, lens_S, None)[0], atol=1e-2, rtol=2 ** -7)
+    assert torch.allclose(_unsplit(out.cpu()), _tmp_attn_ref(qkv, lens_S, None)[0].float(), atol=2e-5, rtol=2e-5)
 
 
 # ------------------------------------------------------------------------------------------------ head + scoring
@@ -279,3 +286,51 @@ def test_prototype_score_golden(dev, golden_dir):
         np.testing.assert_allclose(probs.cpu().numpy(), g[f"probs_P{P}"], atol=1e-6)
         pred, _ = scoring.predict(reps, pdict)
         assert np.array_equal(pred.cpu().numpy(), g[f"probs_P{P}"].argmax(1))
+
+
+# ------------------------------------------------------------------------------------------------ split precision
+def test_split_outputs_of_layernorm_and_patchify(dev):
+    """[hi | lo] outputs: hi is the plain bf16 result, hi + lo reproduces the fp32 value to ~2^-17."""
+    from sais_b200 import ops
+    x = rnd(301, 384, seed=5) * 2
+    w, b = 1 + 0.1 * rnd(384, seed=1), 0.1 * rnd(384, seed=2)
+    of, ob = ops.layernorm(x.to(dev), w.to(dev), b.to(dev), 1e-5, out_f32=True, out_bf16=True, split_out=True)
+    assert ob.shape == (301, 768)
+    assert torch.equal(ob[:, :384].float(), bf(of))
+    assert torch.allclose(_unsplit(ob), of, atol=1e-6, rtol=2 ** -16)
+    fr = rnd(2, 3, 224, 224, seed=3)
+    p1, p2 = ops.patchify_f32(fr.to(dev)), ops.patchify_f32(fr.to(dev), split_out=True)
+    assert torch.equal(p2[:, :768], p1)
+    assert torch.allclose(_unsplit(p2).cpu(), _patches_ref(fr), atol=1e-6, rtol=2 ** -16)
+    u8 = O.make_frames_u8(2, seed=4)
+    q1, q2 = ops.normalize_patchify_u8(u8.to(dev)), ops.normalize_patchify_u8(u8.to(dev), split_out=True)
+    assert torch.equal(q2[:, :768], q1)
+    assert torch.allclose(_unsplit(q2).cpu(), _patches_ref(O.normalize_frames(u8)), atol=2e-6, rtol=1e-5)
+
+
+@pytest.mark.parametrize("M,N,K,act,use_res", [(300, 384, 384, 0, True), (1000, 1152, 384, 0, False),
+                                               (257, 1536, 384, 1, False), (64, 384, 2048, 0, True),
+                                               (197 * 40, 2048, 384, 2, False), (11, 1152, 384, 0, False)])
+def test_gemm_split_precision(dev, M, N, K, act, use_res):
+    """3-pass split-bf16 GEMM is fp32-equivalent: compare with an fp64 product of the UNROUNDED fp32 operands."""
+    from sais_b200 import ops
+    a = rnd(M, K, seed=M + 1)
+    w = rnd(N, K, seed=K + 1, std=1 / math.sqrt(K))
+    bias = rnd(N, seed=7, std=0.5)
+    res = rnd(M, N, seed=9) if use_res else None
+    out = ops.gemm_bias_act(ops.split_bf16(a.to(dev)), ops.split_bf16(w.to(dev)), bias.to(dev), act=act,
+                            residual=None if res is None else res.to(dev), out_dtype=torch.float32, split3=True)
+    y = a.double() @ w.double().t() + bias.double()
+    if act == 1:
+        y = 0.5 * y * (1 + torch.erf(y / math.sqrt(2)))
+    elif act == 2:
+        y = torch.relu(y)
+    if res is not None:
+        y = y + res.double()
+    err = (out.cpu().double() - y).abs().max().item()
+    assert err < 3e-5, err  # plain bf16 operands would be ~1e-2 here
+    if not use_res:  # [hi | lo] output feeds the next split GEMM
+        o2 = ops.gemm_bias_act(ops.split_bf16(a.to(dev)), ops.split_bf16(w.to(dev)), bias.to(dev), act=act,
+                               out_dtype=torch.bfloat16, split3=True, split_out=True)
+        assert o2.shape == (M, 2 * N)
+        assert torch.allclose(_unsplit(o2).cpu(), out.cpu(), atol=1e-5, rtol=2 ** -15)
