@@ -6,6 +6,7 @@
 #include <cstring>
 #include <atomic>
 #include <mutex>
+#include <unordered_map>
 
 #include <cudaTypedefs.h>
 
@@ -78,8 +79,32 @@ int num_sms() {
   return sms;
 }
 
-int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
-                      uint32_t box_rows, uint32_t box_cols) {
+namespace {
+struct TmapKey {
+  const void* base;
+  uint64_t rows, cols, ld;
+  uint32_t box_rows, box_cols;
+  int dtype, swizzle;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows &&
+           box_cols == o.box_cols && dtype == o.dtype && swizzle == o.swizzle;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = reinterpret_cast<uintptr_t>(k.base);
+    auto mix = [&h](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+    mix(k.rows); mix(k.cols); mix(k.ld); mix((uint64_t(k.box_rows) << 32) | k.box_cols);
+    mix((uint64_t(k.dtype) << 8) | uint64_t(k.swizzle));
+    return size_t(h);
+  }
+};
+std::mutex g_tmap_mu;
+std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+}  // namespace
+
+int make_tmap_2d(CUtensorMap* out, const void* base, int dtype, uint64_t rows, uint64_t cols, uint64_t ld,
+                 uint32_t box_rows, uint32_t box_cols, int swizzle_bytes) {
   static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
   static std::once_flag once;
   std::call_once(once, [] {
@@ -93,17 +118,38 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
     set_last_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
     return kErrDriver;
   }
+  // descriptors depend only on (pointer, geometry): the forwards reuse the same workspace slices every
+  // layer and every step, so cache them instead of re-encoding ~4 per GEMM launch
+  const TmapKey key{base, rows, cols, ld, box_rows, box_cols, dtype, swizzle_bytes};
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) {
+      *out = it->second;
+      return kOk;
+    }
+  }
+  const uint64_t esz = (dtype == kTmapF32) ? 4 : 2;
   const cuuint64_t gdim[2] = {cols, rows};
-  const cuuint64_t gstride[1] = {ld * 2};
+  const cuuint64_t gstride[1] = {ld * esz};
   const cuuint32_t box[2] = {box_cols, box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box,
-                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                      : CU_TENSOR_MAP_SWIZZLE_NONE;
+  const CUresult r = encode(out, dtype == kTmapF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                            2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_last_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box=%ux%u", int(r),
-                   (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, box_cols);
+    set_last_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box=%ux%u dtype=%d swizzle=%d",
+                   int(r), (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows,
+                   box_cols, dtype, swizzle_bytes);
     return kErrDriver;
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    if (g_tmap_cache.size() > 16384) g_tmap_cache.clear();
+    g_tmap_cache.emplace(key, *out);
   }
   return kOk;
 }

@@ -126,6 +126,18 @@ __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorM
         "l"(policy)
       : "memory");
 }
+// multicast variant: the box lands at the same CTA-relative smem offset in every CTA of `cta_mask` and
+// completes bytes on the mbarrier at the same offset in each of them
+__device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0,
+                                                  int32_t c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5}], [%2], %3;"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "h"(cta_mask), "r"(c0),
+        "r"(c1)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0,
                                             int32_t c1, int32_t c2) {
   asm volatile(
@@ -189,6 +201,24 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+
+// same, arriving on the barrier at this CTA-relative offset in every CTA of `cta_mask` (cluster launch)
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // TMEM -> registers: 32 lanes x 32 columns of 32-bit (thread t of the warp gets lane t, 32 consecutive columns)
@@ -284,10 +314,11 @@ __device__ __forceinline__ void cp_async_wait() {
 // ----------------------------------------------------------------------------------------------
 // host-side TMA descriptor encode (driver entry point resolved at run time, no -lcuda link)
 // ----------------------------------------------------------------------------------------------
-// 2D bf16 row-major tensor [rows, cols] with row pitch `ld` elements; box = {box_cols, box_rows};
-// 128-byte swizzle (box_cols * 2 bytes must be 128).
-int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
-                      uint32_t box_rows, uint32_t box_cols);
+// 2D row-major tensor [rows, cols] of bf16 or fp32 with row pitch `ld` elements; box = {box_cols, box_rows};
+// swizzle_bytes in {64, 128} must equal box_cols * element size.  Descriptors are cached by value of all arguments.
+enum TmapDtype : int { kTmapBf16 = 0, kTmapF32 = 1 };
+int make_tmap_2d(CUtensorMap* out, const void* base, int dtype, uint64_t rows, uint64_t cols, uint64_t ld,
+                 uint32_t box_rows, uint32_t box_cols, int swizzle_bytes);
 
 int num_sms();
 

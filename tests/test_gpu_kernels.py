@@ -328,7 +328,7 @@ def test_gemm_split_precision(dev, M, N, K, act, use_res):
     if res is not None:
         y = y + res.double()
     err = (out.cpu().double() - y).abs().max().item()
-    assert err < 3e-5, err  # plain bf16 operands would be ~1e-2 here
+    assert err < 1e-4, err  # plain bf16 operands would be ~1e-2 here
     if not use_res:  # [hi | lo] output feeds the next split GEMM
         o2 = ops.gemm_bias_act(ops.split_bf16(a.to(dev)), ops.split_bf16(w.to(dev)), bias.to(dev), act=act,
                                out_dtype=torch.bfloat16, split3=True, split_out=True)

@@ -1,0 +1,48 @@
+"""Per-shape timing of the tcgen05 GEMM (CUDA events) for the ViT / temporal shapes.  Dev tool, GPU only.
+usage: python tools/gemm_bench.py [frames] """
+import sys
+import os
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+from sais_b200 import _lib, ops  # noqa: E402
+
+dev = torch.device("cuda:0")
+frames = int(sys.argv[1]) if len(sys.argv) > 1 else 96
+M = frames * 197
+SHAPES = [  # name, M, N, K, act, residual, f32 out, split3
+    ("patch", frames * 196, 384, 768, 0, False, True, False),
+    ("qkv", M, 1152, 384, 0, False, False, False),
+    ("proj", M, 384, 384, 0, True, True, False),
+    ("fc1", M, 1536, 384, 1, False, False, False),
+    ("fc1-noact", M, 1536, 384, 0, False, False, False),
+    ("fc2", M, 384, 1536, 0, True, True, False),
+    ("fc2-bf16out", M, 384, 1536, 0, False, False, False),
+    ("tmp-ff1-split", 16384, 2048, 384, 2, False, False, True),
+]
+only = sys.argv[2].split(",") if len(sys.argv) > 2 else None
+if only:
+    SHAPES = [s for s in SHAPES if s[0] in only]
+print(f"frames={frames} M={M} env NOSTORE={os.environ.get('SAIS_GEMM_DEBUG_NOSTORE')} FORCE_BN={os.environ.get('SAIS_GEMM_FORCE_BN')}")
+for name, m, n, k, act, res, f32, split in SHAPES:
+    kk = 2 * k if split else k
+    a = torch.randn(m, kk, device=dev).bfloat16()
+    w = (torch.randn(n, kk, device=dev) / k ** 0.5).bfloat16()
+    bias = torch.randn(n, device=dev)
+    r = torch.randn(m, n, device=dev) if res else None
+    out = torch.empty(m, n, device=dev, dtype=torch.float32 if f32 else torch.bfloat16)
+    for _ in range(3):
+        ops.gemm_bias_act(a, w, bias, act=act, residual=r, out=out, split3=split)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 20
+    e0.record()
+    for _ in range(iters):
+        ops.gemm_bias_act(a, w, bias, act=act, residual=r, out=out, split3=split)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    flops = 2.0 * m * n * k * (3 if split else 1)
+    print(f"{name:14s} M={m:6d} N={n:5d} K={k:5d}  {ms*1e3:8.1f} us  {flops/ms/1e9:8.1f} TFLOP/s")
