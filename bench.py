@@ -186,7 +186,7 @@ def workload_config(n_gpus):
                     "+ SAIS temporal head on 8 clips x 16 frames (RGB+flow) + 2 prototypes",
         "frames_per_gpu_per_step": FRAMES_PER_STEP, "clips_per_gpu_per_step": CLIPS_PER_STEP, "clip_frames": CLIP_T,
         "sharding": "frame range per rank; all-gather of embeddings when n_gpus > 1",
-        "l2": "inputs rotate over 4 distinct 38.5 MB frame batches and the 160 MB per-chunk working set exceeds "
+        "l2": "inputs rotate over 4 distinct 38.5 MB frame batches and the 426 MB per-step working set exceeds "
               "the 126 MB L2",
         "parallelism": f"dp{n_gpus}",
     }
@@ -200,7 +200,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="sais_b200", choices=["sais_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--chunk", type=int, default=96, help="ViT frames per workspace chunk")
+    ap.add_argument("--chunk", type=int, default=256, help="ViT frames per workspace chunk")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -97,6 +97,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking poll (mbarrier.try_wait may suspend the thread for a while; test_wait never does)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
@@ -243,7 +257,52 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t* r) {
       : "r"(taddr)
       : "memory");
 }
+// registers -> TMEM (thread t of the warp writes lane t, N consecutive 32-bit columns)
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      :
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               :
+               : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem desc]: A operand read from tensor memory (lane = row, packed 16-bit pairs)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait + make every later use of r[] data-dependent on the wait (the compiler must not hoist register uses of an
+// asynchronous tcgen05.ld result above the wait; zero instructions are emitted for the second statement)
+template <int N>
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&r)[N]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < N; i += 8)
+    asm volatile("" : "+r"(r[i]), "+r"(r[i + 1]), "+r"(r[i + 2]), "+r"(r[i + 3]), "+r"(r[i + 4]), "+r"(r[i + 5]),
+                      "+r"(r[i + 6]), "+r"(r[i + 7])::"memory");
+}
 
 // Shared-memory matrix descriptor for a K-major bf16 tile stored as rows of 128 bytes with the
 // 128-byte swizzle (what TMA SWIZZLE_128B writes for a {64 x rows} bf16 box).  8-row groups are
@@ -319,6 +378,11 @@ __device__ __forceinline__ void cp_async_wait() {
 enum TmapDtype : int { kTmapBf16 = 0, kTmapF32 = 1 };
 int make_tmap_2d(CUtensorMap* out, const void* base, int dtype, uint64_t rows, uint64_t cols, uint64_t ld,
                  uint32_t box_rows, uint32_t box_cols, int swizzle_bytes);
+
+// 3D bf16 tensor [d2][d1][d0] (d0 contiguous; ld1 / ld2 = pitches of d1 / d2 in elements), box {box0, box1, 1},
+// 128-byte swizzle (box0 * 2 bytes must be 128).  Out-of-range coordinates are zero-filled on load.
+int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld1,
+                      uint64_t ld2, uint32_t box0, uint32_t box1);
 
 int num_sms();
 

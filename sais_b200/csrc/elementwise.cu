@@ -16,52 +16,89 @@ constexpr int D = 384;
 // Reference: nn.LayerNorm in vision_transformer.py:99,103,156 (eps 1e-6) and
 // nn.TransformerEncoderLayer.norm1/norm2 (eps 1e-5).
 // ----------------------------------------------------------------------------------------------
+constexpr int kLnRows = 4;  // rows per warp per iteration: 12 independent 16-byte loads in flight per lane
+
 __global__ void __launch_bounds__(256) layernorm384_kernel(const float* __restrict__ x, int64_t in_pitch,
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, float eps, int64_t rows,
                                                            float* __restrict__ out_f32,
                                                            __nv_bfloat16* __restrict__ out_bf16, int split) {
   const int lane = threadIdx.x & 31;
-  const int64_t row = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const float* xr = x + row * in_pitch;
-  float4 v[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) v[i] = *reinterpret_cast<const float4*>(xr + i * 128 + lane * 4);
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < 3; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-  const float mean = warp_sum(s) * (1.0f / D);
-  float ss = 0.f;
+  const int64_t warp_global = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t warps_total = int64_t(gridDim.x) * (blockDim.x >> 5);
+  float4 g[3], b[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-    ss += (a * a + b * b) + (c * c + d * d);
+    g[i] = __ldg(reinterpret_cast<const float4*>(gamma + i * 128 + lane * 4));
+    b[i] = __ldg(reinterpret_cast<const float4*>(beta + i * 128 + lane * 4));
   }
-  const float rstd = rsqrtf(warp_sum(ss) * (1.0f / D) + eps);
+  for (int64_t row0 = warp_global * kLnRows; row0 < rows; row0 += warps_total * kLnRows) {
+    float4 v[kLnRows][3];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const int c = i * 128 + lane * 4;
-    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
-    float4 y;
-    y.x = (v[i].x - mean) * rstd * g.x + b.x;
-    y.y = (v[i].y - mean) * rstd * g.y + b.y;
-    y.z = (v[i].z - mean) * rstd * g.z + b.z;
-    y.w = (v[i].w - mean) * rstd * g.w + b.w;
-    if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * D + c) = y;
-    if (out_bf16) {
-      uint2 o;
-      o.x = pack_bf16x2(y.x, y.y);
-      o.y = pack_bf16x2(y.z, y.w);
-      if (!split) {
-        *reinterpret_cast<uint2*>(out_bf16 + row * D + c) = o;
-      } else {  // [hi | lo] halves for the split-precision GEMM
-        uint2 l;
-        l.x = pack_bf16x2(y.x - bf16_lo(o.x), y.y - bf16_hi(o.x));
-        l.y = pack_bf16x2(y.z - bf16_lo(o.y), y.w - bf16_hi(o.y));
-        *reinterpret_cast<uint2*>(out_bf16 + row * 2 * D + c) = o;
-        *reinterpret_cast<uint2*>(out_bf16 + row * 2 * D + D + c) = l;
+    for (int r = 0; r < kLnRows; ++r) {
+      const int64_t row = (row0 + r < rows) ? row0 + r : rows - 1;  // clamp: tail rows are recomputed, not stored
+      const float* xr = x + row * in_pitch;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) v[r][i] = *reinterpret_cast<const float4*>(xr + i * 128 + lane * 4);
+    }
+    float mean[kLnRows], rstd[kLnRows];
+#pragma unroll
+    for (int r = 0; r < kLnRows; ++r) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) s += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
+      mean[r] = s;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int r = 0; r < kLnRows; ++r) mean[r] += __shfl_xor_sync(0xffffffffu, mean[r], o);
+    }
+#pragma unroll
+    for (int r = 0; r < kLnRows; ++r) {
+      mean[r] *= (1.0f / D);
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const float a = v[r][i].x - mean[r], bb = v[r][i].y - mean[r], c = v[r][i].z - mean[r],
+                    d = v[r][i].w - mean[r];
+        ss += (a * a + bb * bb) + (c * c + d * d);
+      }
+      rstd[r] = ss;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int r = 0; r < kLnRows; ++r) rstd[r] += __shfl_xor_sync(0xffffffffu, rstd[r], o);
+    }
+#pragma unroll
+    for (int r = 0; r < kLnRows; ++r) {
+      const int64_t row = row0 + r;
+      if (row >= rows) break;
+      const float rs = rsqrtf(rstd[r] * (1.0f / D) + eps);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int c = i * 128 + lane * 4;
+        float4 y;
+        y.x = (v[r][i].x - mean[r]) * rs * g[i].x + b[i].x;
+        y.y = (v[r][i].y - mean[r]) * rs * g[i].y + b[i].y;
+        y.z = (v[r][i].z - mean[r]) * rs * g[i].z + b[i].z;
+        y.w = (v[r][i].w - mean[r]) * rs * g[i].w + b[i].w;
+        if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * D + c) = y;
+        if (out_bf16) {
+          uint2 o;
+          o.x = pack_bf16x2(y.x, y.y);
+          o.y = pack_bf16x2(y.z, y.w);
+          if (!split) {
+            *reinterpret_cast<uint2*>(out_bf16 + row * D + c) = o;
+          } else {  // [hi | lo] halves for the split-precision GEMM
+            uint2 l;
+            l.x = pack_bf16x2(y.x - bf16_lo(o.x), y.y - bf16_hi(o.x));
+            l.y = pack_bf16x2(y.z - bf16_lo(o.y), y.w - bf16_hi(o.y));
+            *reinterpret_cast<uint2*>(out_bf16 + row * 2 * D + c) = o;
+            *reinterpret_cast<uint2*>(out_bf16 + row * 2 * D + D + c) = l;
+          }
+        }
       }
     }
   }
@@ -331,7 +368,9 @@ int layernorm(const float* x, int64_t in_pitch, const float* gamma, const float*
     set_last_error("layernorm: bad arguments");
     return kErrInvalidArg;
   }
-  const int64_t blocks = (rows + 7) / 8;
+  int64_t blocks = (rows + 8 * kLnRows - 1) / (8 * kLnRows);
+  const int64_t cap = int64_t(num_sms()) * 8;  // persistent beyond one full wave (8 blocks x 8 warps per SM)
+  if (blocks > cap) blocks = cap;
   LaunchScope ls(kClsLayerNorm, stream, double(rows) * D * (4 + (out_f32 ? 4 : 0) + (out_bf16 ? 2 : 0)));
   layernorm384_kernel<<<unsigned(blocks), 256, 0, stream>>>(x, in_pitch, gamma, beta, eps, rows, out_f32,
                                                             reinterpret_cast<__nv_bfloat16*>(out_bf16), split);

@@ -315,9 +315,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int c = half + 2 * ci;
         const int n = n0 + c * CW;
         float f[32];
-        tmem_ld_wait();
+        tmem_ld_wait_dep(v);
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+#pragma unroll
+        for (int j = 0; j < 32; j += 8)  // pin the copies before v is handed to the next asynchronous load
+          asm volatile("" : "+f"(f[j]), "+f"(f[j + 1]), "+f"(f[j + 2]), "+f"(f[j + 3]), "+f"(f[j + 4]), "+f"(f[j + 5]),
+                            "+f"(f[j + 6]), "+f"(f[j + 7]));
         if (ci + 1 < NCW) {
           tmem_ld_32x32(t_row + (c + 2) * CW, v);  // next chunk's accumulator streams in under this chunk's math
         } else {  // last TMEM read of this tile by this warp: hand the accumulator back early

@@ -45,6 +45,9 @@ int prototype_score(const float* reps, const float* protos, int B, int P, int D,
 // vit_attention.cu
 int vit_attention(const sais_bf16* qkv, int B, sais_bf16* out, float* probs, cudaStream_t stream);
 
+// vit_attention_tc.cu (tcgen05 path, no probabilities)
+int vit_attention_tc(const sais_bf16* qkv, int B, sais_bf16* out, cudaStream_t stream);
+
 // temporal_attention.cu
 // fp32 qkv in, bf16 [hi | lo] (row pitch 2*384) out
 int temporal_attention(const float* qkv, const int32_t* seq_offsets, const uint8_t* key_pad,

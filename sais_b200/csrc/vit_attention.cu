@@ -4,6 +4,8 @@
 // 112-key chunks entirely in registers (warp-level bf16 MMA, fp32 accumulate); the probabilities never
 // touch HBM unless the caller asks for them (get_last_selfattention, :216-223), in which case a second
 // pass recomputes the logits and writes exp(s - max)/sum as fp32 [B,6,197,197].
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -213,6 +215,10 @@ int vit_attention(const sais_bf16* qkv, int B, sais_bf16* out, float* probs, cud
     set_last_error("vit_attention: bad arguments");
     return kErrInvalidArg;
   }
+  // default path: tcgen05 kernel (vit_attention_tc.cu); this register-level kernel serves the probabilities-
+  // emitting variant (and SAIS_ATTN_LEGACY=1 for A/B comparisons)
+  static const bool legacy = getenv("SAIS_ATTN_LEGACY") != nullptr && atoi(getenv("SAIS_ATTN_LEGACY")) != 0;
+  if (probs == nullptr && !legacy) return vit_attention_tc(qkv, B, out, stream);
   static bool attr_set = false;
   if (!attr_set) {
     int rc = check_cuda(cudaFuncSetAttribute(vit_attention_kernel<false>,

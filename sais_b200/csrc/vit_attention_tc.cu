@@ -1,0 +1,414 @@
+// tcgen05 flash-style self-attention for the ViT blocks: T = 197 tokens, 6 heads x 64
+// (SAIS/scripts/dino-main/vision_transformer.py:80-92), one (frame, head) item at a time per persistent CTA.
+//
+//   warp 8 (one thread): TMA loads of Q, K, V (3-D tensor map [frame, token, 1152]; tokens beyond 196 are
+//                        zero-filled by TMA) into a double-buffered smem slot, then
+//                        S = Q K^T   : tcgen05.mma  M=128 (x2 row tiles), N=208, K=64,  fp32 in TMEM
+//                        O = P V     : tcgen05.mma  M=128 (x2),           N=64,  K=208, V consumed MN-major
+//   warps 0..7         : one thread per query row: exact softmax straight out of TMEM (two passes: max, then
+//                        exp2 / sum); P is rounded to bf16 and written back INTO TMEM over the dead logits
+//                        (tcgen05.st) where the second MMA reads it as its A operand, so probabilities touch
+//                        neither shared memory nor HBM; finally O / sum -> bf16 -> global.
+// TMEM map per row tile mt (256-column window): S fp32 [0,208) -> P bf16x2 [0,104) + O fp32 [128,192).
+// kPInTmem = false keeps P in a 128B-swizzled K-major smem tile instead (one buffer shared by the two row tiles;
+// slower, kept as the conservative fallback: SAIS_ATTN_PSMEM=1).
+// The probabilities-emitting variant (get_last_selfattention) stays on the register-level kernel in vit_attention.cu.
+#include <cstdio>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sais {
+
+namespace {
+
+constexpr int T = 197;
+constexpr int HEADS = 6;
+constexpr int HD = 64;
+constexpr int KEYS = 208;                  // keys padded to a multiple of 16 (UMMA N / K granularity)
+constexpr int MAT_BYTES = KEYS * 128;      // one of Q / K / V in smem: 208 rows x 128 B (SWIZZLE_128B)
+constexpr int SLOT_BYTES = 3 * MAT_BYTES;  // Q, K, V of one item
+constexpr int P_BYTES = 4 * 128 * 128;     // smem P tile (fallback): 128 rows x 256 keys bf16 = 4 k-blocks of 16 KB
+constexpr int kThreads = 11 * 32;  // 8 softmax warps + loader + one MMA-issuing warp per row-tile window
+constexpr int kTmemCols = 512;             // row tile 0 at column 0, row tile 1 at column 256
+constexpr int kOCol = 128;                 // O accumulator inside the row tile's window
+
+constexpr int kOutStage = 8 * 4096;        // per softmax warp: 32 rows x 128 B staging tile for the TMA store of O
+template <bool kPInTmem>
+constexpr int smem_bytes() {
+  return 2 * SLOT_BYTES + (kPInTmem ? 16384 /*overrun pad for the 2nd Q row tile*/ + kOutStage : P_BYTES) + 1024 + 256;
+}
+
+__device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+template <bool kPInTmem>
+__global__ void __launch_bounds__(kThreads, 1)
+vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out,
+                        __nv_bfloat16* __restrict__ out, int n_items,
+                        long long* __restrict__ dbg) {
+  // dev knob (SAIS_ATTN_TIMELINE=<file>): CTA 0 records clock64() at every phase boundary, [role][item][event]
+  auto stamp = [&](int role, int idx, int ev) {
+    if (dbg != nullptr && blockIdx.x == 0 && idx < 16) dbg[(role * 16 + idx) * 8 + ev] = clock64();
+  };
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* p_smem = smem + 2 * SLOT_BYTES;
+  uint8_t* o_stage = p_smem + 16384;  // (P-in-TMEM build only)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + (kPInTmem ? 16384 + kOutStage : P_BYTES));
+  uint64_t* ld_full = bars;       // [2] item slot loaded
+  uint64_t* ld_empty = bars + 2;  // [2] item slot free again
+  uint64_t* s_full = bars + 4;    // [2] S[mt] in TMEM
+  uint64_t* p_full = bars + 6;    // [2] P[mt] ready
+  uint64_t* o_full = bars + 8;    // [2] O[mt] in TMEM (also: P no longer read by the tensor core)
+  uint64_t* t_free = bars + 10;   // [2] TMEM window of row tile mt drained
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmap_qkv);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ld_full[i], 1);
+      mbar_init(&ld_empty[i], 2);  // both windows' MMA streams must have retired
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&t_free[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 8) {
+    tmem_alloc(tmem_base_smem, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp >= 8) {
+    // ===================== single-thread roles: loader (warp 8), MMA issuer of window 0 / 1 (warps 9 / 10) ======
+    // Each role blocks on its own mbarriers, so the two row-tile windows advance independently: window w may
+    // already run S = QK^T of the next item while the other window is still in its softmax.
+    if (lane == 0) {
+      const int n_my = (n_items - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+      if (warp == 8) {
+        for (int idx = 0; idx < n_my; ++idx) {
+          const int slot = idx & 1;
+          if (idx >= 2) mbar_wait(&ld_empty[slot], ((idx - 2) >> 1) & 1);  // previous occupant fully consumed
+          const int item = int(blockIdx.x) + idx * int(gridDim.x);
+          const int b = item / HEADS, h = item % HEADS;
+          uint8_t* dst = smem + slot * SLOT_BYTES;
+          mbar_arrive_expect_tx(&ld_full[slot], SLOT_BYTES);
+          tma_load_3d(dst, &tmap_qkv, &ld_full[slot], h * HD, 0, b);
+          tma_load_3d(dst + MAT_BYTES, &tmap_qkv, &ld_full[slot], 384 + h * HD, 0, b);
+          tma_load_3d(dst + 2 * MAT_BYTES, &tmap_qkv, &ld_full[slot], 768 + h * HD, 0, b);
+        }
+      } else {
+        constexpr uint32_t idesc_s = umma_idesc_bf16(128, KEYS, 0, 0);  // Q (K-major) x K (K-major)
+        constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);    // P (K-major) x V (MN-major)
+        const int w = warp - 9;
+        const uint32_t win = tmem_base + w * 256;
+        // the second window starts half an item late so that the two windows' exp-heavy softmax passes (MUFU-bound)
+        // interleave with each other's MMA round trips instead of colliding
+
+        for (int idx = 0; idx < n_my; ++idx) {
+          const int slot = idx & 1;
+          const uint32_t q_s = smem_u32(smem + slot * SLOT_BYTES);
+          const uint32_t k_s = q_s + MAT_BYTES, v_s = q_s + 2 * MAT_BYTES;
+          mbar_wait(&ld_full[slot], (idx >> 1) & 1);
+          if (w == 1 && idx == 0) __nanosleep(1800);  // (see above) stagger the windows once the first item has landed
+          stamp(2 + w, idx, 0);
+          mbar_wait(&t_free[w], (idx & 1) ^ 1);  // window drained by the softmax warps
+          tc_fence_after();
+          stamp(2 + w, idx, 1);
+          {
+            const uint64_t da = umma_desc_sw128_kmajor(q_s + w * 128 * 128);
+            const uint64_t db = umma_desc_sw128_kmajor(k_s);
+#pragma unroll
+            for (int k = 0; k < HD / 16; ++k) umma_f16(win, da + 2 * k, db + 2 * k, idesc_s, k != 0);
+            umma_commit(&s_full[w]);
+          }
+          stamp(2 + w, idx, 2);
+          mbar_wait(&p_full[w], idx & 1);
+          tc_fence_after();
+          stamp(2 + w, idx, 3);
+          const uint32_t p_s = smem_u32(p_smem);
+#pragma unroll
+          for (int ks = 0; ks < KEYS / 16; ++ks) {
+            const uint64_t db = umma_desc_sw128_mnmajor(v_s + ks * 2048, 0);
+            if (kPInTmem) {
+              umma_f16_ts(win + kOCol, win + ks * 8, db, idesc_o, ks != 0);
+            } else {
+              const uint64_t da = umma_desc_sw128_kmajor(p_s + (ks >> 2) * 16384 + (ks & 3) * 32);
+              umma_f16(win + kOCol, da, db, idesc_o, ks != 0);
+            }
+          }
+          umma_commit(&o_full[w]);
+          umma_commit(&ld_empty[slot]);  // this window's reads of the slot have retired (barrier counts both windows)
+          stamp(2 + w, idx, 4);
+        }
+      }
+    }
+  } else {
+    // ===================== softmax / output warps =====================
+    const int mt = warp >> 2, q = warp & 3;
+    const int row = mt * 128 + q * 32 + lane;  // query row inside the frame
+    const bool warp_has_rows = (mt * 128 + q * 32) < T;
+    const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + mt * 256;
+    const uint32_t p_row = smem_u32(p_smem) + (q * 32 + lane) * 128;
+    const int sw = lane & 7;
+    const float sl2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
+
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const uint32_t ph = it & 1;
+      const int b = item / HEADS, h = item % HEADS;
+      const bool st_on = (q == 0 && lane == 0);
+      if (st_on) stamp(mt, it, 0);
+      mbar_wait(&s_full[mt], ph);
+      tc_fence_after();
+      if (st_on) stamp(mt, it, 1);
+      float row_sum = 1.0f;
+      if (warp_has_rows) {
+        // pass 1: row maximum over the 197 real keys (next chunk streams in while the current one is reduced)
+        float m = -INFINITY;
+        {
+          uint32_t v[32], w[32];
+          tmem_ld_32x32(t_row, v);
+#pragma unroll
+          for (int c = 0; c < 6; c += 2) {
+            tmem_ld_wait_dep(v);
+            tmem_ld_32x32(t_row + (c + 1) * 32, w);  // streams in while v is reduced
+            float mv = m;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mv = fmaxf(mv, __uint_as_float(v[j]));
+            asm volatile("" : "+f"(mv));  // v fully consumed before it is handed to the next asynchronous load
+            tmem_ld_wait_dep(w);
+            if (c + 2 < 6) tmem_ld_32x32(t_row + (c + 2) * 32, v); else tmem_ld_32x16(t_row + 192, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mv = fmaxf(mv, __uint_as_float(w[j]));
+            asm volatile("" : "+f"(mv));
+            m = mv;
+          }
+          tmem_ld_wait_dep(v);
+#pragma unroll
+          for (int j = 0; j < T - 192; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+        }
+        const float mb = m * sl2;
+        if (st_on) stamp(mt, it, 2);
+        if (!kPInTmem) {
+          // the single smem P buffer is shared by the two row tiles: wait until the tensor core has finished reading
+          // the previous tile's probabilities (tile 0 follows tile 1 of the previous item, tile 1 follows tile 0)
+          if (mt == 0) {
+            if (it > 0) mbar_wait(&o_full[1], (it - 1) & 1);
+          } else {
+            mbar_wait(&o_full[0], ph);
+          }
+        }
+        // pass 2: p = exp2((s - max) * scale), row sum, bf16 P
+        float sum = 0.f;
+        auto softmax_chunk = [&](const uint32_t(&v)[32], int c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), sl2, -mb));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), sl2, -mb));
+            sum += p0 + p1;
+            pk[j] = pack_bf16x2(p0, p1);
+          }
+          if (kPInTmem) {
+            tmem_st_32x16(t_row + c * 16, pk);  // over logits this thread has already consumed
+          } else {
+            const uint32_t kb_base = p_row + (c >> 1) * 16384;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              sts128u(kb_base + ((((c & 1) * 4 + j) ^ sw) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          }
+        };
+        {
+          uint32_t v[32], w[32];
+          tmem_ld_32x32(t_row, v);
+#pragma unroll 1
+          for (int c = 0; c < 6; c += 2) {
+            tmem_ld_wait_dep(v);
+            tmem_ld_32x32(t_row + (c + 1) * 32, w);  // next chunk streams in under this chunk's exponentials
+            softmax_chunk(v, c);
+            asm volatile("" : "+f"(sum));
+            tmem_ld_wait_dep(w);
+            if (c + 2 < 6) tmem_ld_32x32(t_row + (c + 2) * 32, v); else tmem_ld_32x16(t_row + 192, v);
+            softmax_chunk(w, c + 1);
+            asm volatile("" : "+f"(sum));
+          }
+          tmem_ld_wait_dep(v);
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float p0 = (2 * j < T - 192) ? ex2_approx(fmaf(__uint_as_float(v[2 * j]), sl2, -mb)) : 0.0f;
+            const float p1 = (2 * j + 1 < T - 192) ? ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), sl2, -mb)) : 0.0f;
+            sum += p0 + p1;
+            pk[j] = pack_bf16x2(p0, p1);
+          }
+          if (kPInTmem) {
+            tmem_st_32x8(t_row + 96, pk);
+          } else {
+            const uint32_t kb_base = p_row + 3 * 16384;
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              sts128u(kb_base + ((j ^ sw) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          }
+        }
+        row_sum = sum;
+        if (kPInTmem) tmem_st_wait();
+      } else if (!kPInTmem) {
+        // rows 224..255 do not exist: keep the barrier protocol, skip the math (their P rows stay stale/unused)
+        mbar_wait(&o_full[0], ph);
+      }
+      tc_fence_before();
+      if (!kPInTmem) fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[mt]);
+      if (st_on) stamp(mt, it, 3);
+
+      // ---- O[mt] / sum -> bf16 -> global ----
+      mbar_wait(&o_full[mt], ph);
+      tc_fence_after();
+      if (st_on) stamp(mt, it, 4);
+      if (warp_has_rows) {
+        const float inv = 1.0f / row_sum;
+        __nv_bfloat16* op = out + (int64_t(b) * T + row) * 384 + h * HD;
+        uint32_t v[32], w[32];
+        tmem_ld_32x32(t_row + kOCol, v);
+        tmem_ld_32x32(t_row + kOCol + 32, w);
+        tmem_ld_wait_dep(v);
+        tmem_ld_wait_dep(w);
+        if (kPInTmem) {
+          // O tile of this warp (32 rows x 64) -> swizzled staging -> one TMA store; rows beyond token 196 are
+          // clipped by the [frame, token, 384] tensor map
+          const uint32_t st = smem_u32(o_stage) + warp * 4096 + lane * 128;
+          if (lane == 0) tma_store_wait_read<0>();  // previous item's store has finished reading the tile
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            sts128u(st + ((j ^ sw) << 4),
+                    pack_bf16x2(__uint_as_float(v[8 * j]) * inv, __uint_as_float(v[8 * j + 1]) * inv),
+                    pack_bf16x2(__uint_as_float(v[8 * j + 2]) * inv, __uint_as_float(v[8 * j + 3]) * inv),
+                    pack_bf16x2(__uint_as_float(v[8 * j + 4]) * inv, __uint_as_float(v[8 * j + 5]) * inv),
+                    pack_bf16x2(__uint_as_float(v[8 * j + 6]) * inv, __uint_as_float(v[8 * j + 7]) * inv));
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            sts128u(st + (((j + 4) ^ sw) << 4),
+                    pack_bf16x2(__uint_as_float(w[8 * j]) * inv, __uint_as_float(w[8 * j + 1]) * inv),
+                    pack_bf16x2(__uint_as_float(w[8 * j + 2]) * inv, __uint_as_float(w[8 * j + 3]) * inv),
+                    pack_bf16x2(__uint_as_float(w[8 * j + 4]) * inv, __uint_as_float(w[8 * j + 5]) * inv),
+                    pack_bf16x2(__uint_as_float(w[8 * j + 6]) * inv, __uint_as_float(w[8 * j + 7]) * inv));
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                         :
+                         : "l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(smem_u32(o_stage) + warp * 4096),
+                           "r"(h * HD), "r"(mt * 128 + q * 32), "r"(b)
+                         : "memory");
+            tma_store_commit();
+          }
+        } else if (row < T) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(v[8 * j]) * inv, __uint_as_float(v[8 * j + 1]) * inv);
+            o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]) * inv, __uint_as_float(v[8 * j + 3]) * inv);
+            o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]) * inv, __uint_as_float(v[8 * j + 5]) * inv);
+            o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) * inv, __uint_as_float(v[8 * j + 7]) * inv);
+            *reinterpret_cast<uint4*>(op + j * 8) = o;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(w[8 * j]) * inv, __uint_as_float(w[8 * j + 1]) * inv);
+            o.y = pack_bf16x2(__uint_as_float(w[8 * j + 2]) * inv, __uint_as_float(w[8 * j + 3]) * inv);
+            o.z = pack_bf16x2(__uint_as_float(w[8 * j + 4]) * inv, __uint_as_float(w[8 * j + 5]) * inv);
+            o.w = pack_bf16x2(__uint_as_float(w[8 * j + 6]) * inv, __uint_as_float(w[8 * j + 7]) * inv);
+            *reinterpret_cast<uint4*>(op + 32 + j * 8) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_free[mt]);
+      if (st_on) stamp(mt, it, 5);
+    }
+    if (kPInTmem && lane == 0) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+template <bool kPInTmem>
+int launch_attn(const CUtensorMap& tm, const CUtensorMap& tm_out, sais_bf16* out, int items, cudaStream_t stream,
+                long long* dbg) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    int rc = check_cuda(cudaFuncSetAttribute(vit_attention_tc_kernel<kPInTmem>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<kPInTmem>()),
+                        "cudaFuncSetAttribute(vit_attention_tc)");
+    if (rc) return rc;
+    attr_set = true;
+  }
+  const int grid = items < num_sms() ? items : num_sms();
+  vit_attention_tc_kernel<kPInTmem><<<grid, kThreads, smem_bytes<kPInTmem>(), stream>>>(
+      tm, tm_out, reinterpret_cast<__nv_bfloat16*>(out), items, dbg);
+  return check_cuda(cudaGetLastError(), "vit_attention_tc launch");
+}
+
+}  // namespace
+
+int vit_attention_tc(const sais_bf16* qkv, int B, sais_bf16* out, cudaStream_t stream) {
+  if (B == 0) return kOk;
+  CUtensorMap tm;
+  int rc = make_tmap_bf16_3d(&tm, qkv, /*d0=*/1152, /*d1=*/T, /*d2=*/uint64_t(B), /*ld1=*/1152,
+                             /*ld2=*/uint64_t(T) * 1152, /*box0=*/HD, /*box1=*/KEYS);
+  if (rc) return rc;
+  CUtensorMap tm_out;
+  rc = make_tmap_bf16_3d(&tm_out, out, /*d0=*/384, /*d1=*/T, /*d2=*/uint64_t(B), /*ld1=*/384, /*ld2=*/uint64_t(T) * 384,
+                         /*box0=*/HD, /*box1=*/32);
+  if (rc) return rc;
+  static const bool p_smem = getenv("SAIS_ATTN_PSMEM") != nullptr && atoi(getenv("SAIS_ATTN_PSMEM")) != 0;
+  static const char* timeline = getenv("SAIS_ATTN_TIMELINE");
+  long long* dbg = nullptr;
+  if (timeline) {
+    if (cudaMalloc(&dbg, 4 * 16 * 8 * sizeof(long long)) != cudaSuccess) dbg = nullptr;
+    if (dbg) cudaMemsetAsync(dbg, 0, 4 * 16 * 8 * sizeof(long long), stream);
+  }
+  {
+    LaunchScope ls(kClsVitAttn, stream, 4.0 * double(B) * 6 * 197 * 197 * 64);
+    rc = p_smem ? launch_attn<false>(tm, tm_out, out, B * HEADS, stream, dbg)
+                : launch_attn<true>(tm, tm_out, out, B * HEADS, stream, dbg);
+  }
+  if (dbg) {
+    long long h[4 * 16 * 8];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(dbg);
+    if (FILE* f = fopen(timeline, "w")) {
+      for (int r = 0; r < 4; ++r)
+        for (int i = 0; i < 16; ++i) {
+          fprintf(f, "%d %d", r, i);
+          for (int e = 0; e < 8; ++e) fprintf(f, " %lld", h[(r * 16 + i) * 8 + e]);
+          fprintf(f, "\n");
+        }
+      fclose(f);
+    }
+  }
+  return rc;
+}
+
+}  // namespace sais

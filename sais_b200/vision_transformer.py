@@ -73,7 +73,7 @@ class VisionTransformer(nn.Module):
 
     def __init__(self, img_size=(224,), patch_size=16, in_chans=3, num_classes=0, embed_dim=384, depth=12,
                  num_heads=6, mlp_ratio=4.0, qkv_bias=True, qk_scale=None, drop_rate=0.0, attn_drop_rate=0.0,
-                 drop_path_rate=0.0, norm_layer=None, chunk_frames=96, precision="bf16", **kwargs):
+                 drop_path_rate=0.0, norm_layer=None, chunk_frames=256, precision="bf16", **kwargs):
         super().__init__()
         img = img_size[0] if isinstance(img_size, (list, tuple)) else img_size
         if (img, patch_size, in_chans, embed_dim, depth, num_heads, mlp_ratio, qkv_bias) != (

@@ -176,8 +176,20 @@ def test_vit_attention(dev, B, scale):
     assert torch.allclose(probs.sum(-1).cpu(), torch.ones(B, 6, 197), atol=1e-5)
     # outputs: P is rounded to bf16 before PV (2^-9 relative per term) and the result to bf16
     assert torch.allclose(out.cpu().float(), ref_o, atol=1.5e-2, rtol=2e-2), (out.cpu().float() - ref_o).abs().max()
+    # without probabilities the tcgen05 kernel runs (S and O in TMEM, P through swizzled smem)
     out2, none = ops.vit_attention(qkv.to(dev).bfloat16(), B, emit_probs=False)
-    assert none is None and torch.equal(out2, out)
+    assert none is None
+    assert torch.allclose(out2.cpu().float(), ref_o, atol=1.5e-2, rtol=2e-2), (out2.cpu().float() - ref_o).abs().max()
+
+
+@pytest.mark.parametrize("B", [7, 150])
+def test_vit_attention_tc_many_items(dev, B):
+    """persistent loop: more (frame, head) items than SMs, odd counts, double-buffered slots."""
+    from sais_b200 import ops
+    qkv = rnd(B * 197, 1152, seed=B) * 1.5
+    out, _ = ops.vit_attention(qkv.to(dev).bfloat16(), B)
+    ref_o, _ = _vit_attn_ref(qkv, B)
+    assert torch.allclose(out.cpu().float(), ref_o, atol=2e-2, rtol=2e-2), (out.cpu().float() - ref_o).abs().max()
 
 
 # ------------------------------------------------------------------------------------------------ temporal attention
