@@ -1,0 +1,121 @@
+"""CPU: the sharding / window / TTA arithmetic around the hot path and the N>1 exchange step (world_size-2 ``gloo``).
+No kernels are launched: the all-gather is exercised on CPU tensors, the ViT is replaced by a stand-in."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from sais_b200 import pipeline
+
+
+@pytest.mark.parametrize("n,world", [(0, 1), (1, 4), (7, 2), (3600, 8), (3601, 8), (125, 3)])
+def test_frame_range_partitions_every_frame_once(n, world):
+    ranges = [pipeline.frame_range(n, r, world) for r in range(world)]
+    assert ranges[0][0] == 0 and ranges[-1][1] == n
+    for (lo, hi), (lo2, _) in zip(ranges, ranges[1:]):
+        assert hi == lo2 and lo <= hi
+    sizes = [hi - lo for lo, hi in ranges]
+    assert max(sizes) - min(sizes) <= 1  # balanced
+    with pytest.raises(ValueError):
+        pipeline.frame_range(n, world, world)
+
+
+def test_shard_items_round_robin():
+    parts = [pipeline.shard_items(1000, r, 8) for r in range(8)]
+    assert sorted(np.concatenate(parts).tolist()) == list(range(1000))
+    assert parts[3][:3].tolist() == [3, 11, 19]
+    assert pipeline.shard_items(2, 5, 8).size == 0  # more ranks than items: empty shard, not an error
+
+
+def test_sliding_windows_tta_views_share_the_window_end():
+    """Custom_Gestures inference windows: 15 frames, hop 15, TTA offsets 0/3/6 -> lengths 15/12/9, same end
+    (reference prepare_dataset.py:1711-1726, 2646-2651)."""
+    views = pipeline.sliding_windows(100, 15, 15, (0, 3, 6))
+    assert [v.shape for v in views] == [(6, 15), (6, 12), (6, 9)]
+    for v in views:
+        assert np.array_equal(v[:, -1], views[0][:, -1])
+    assert views[1][2, 0] == 2 * 15 + 3 and views[2][0, 0] == 6
+    # step-recognition form: 20 frames, hop 10 (prepare_dataset.py:469-473,2324)
+    v = pipeline.sliding_windows(3600, 20, 10)[0]
+    assert v.shape == (359, 20) and v[-1, -1] == 3599
+    assert pipeline.sliding_windows(10, 15, 15)[0].shape == (0, 15)  # video shorter than one window
+    with pytest.raises(ValueError):
+        pipeline.sliding_windows(10, 15, 15, (15,))
+
+
+def test_gather_windows_and_mask_layout():
+    emb = torch.arange(50 * 384, dtype=torch.float32).view(50, 384)
+    idx = pipeline.sliding_windows(50, 15, 15, (0, 3))[1]
+    w = pipeline.gather_windows(emb, idx)
+    assert w.shape == (3, 1, 12, 384)
+    assert torch.equal(w[1, 0, 0], emb[15 + 3]) and torch.equal(w[2, 0, -1], emb[44])
+    m = pipeline.full_mask(3, 12, "cpu")
+    assert m.shape == (3, 1, 13) and m.dtype == torch.bool and not m.any()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _gather_worker(rank, world, port, n_frames, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        full = torch.arange(n_frames * 384, dtype=torch.float32).view(n_frames, 384)
+        lo, hi = pipeline.frame_range(n_frames, rank, world)
+        got = pipeline.gather_embeddings(full[lo:hi].clone(), n_frames)
+        ok = torch.equal(got, full)
+        # window ownership after the gather: round-robin, disjoint, complete
+        nw = pipeline.sliding_windows(n_frames, 20, 10)[0].shape[0]
+        mine = pipeline.shard_items(nw, rank, world)
+        counts = torch.zeros(nw, dtype=torch.int64)
+        counts[torch.from_numpy(mine)] += 1
+        dist.all_reduce(counts)
+        ok = ok and bool((counts == 1).all())
+        # a rank holding the wrong number of rows must be rejected, not silently padded
+        try:
+            pipeline.gather_embeddings(full[lo:hi + 1 if hi < n_frames else hi - 1].clone(), n_frames)
+            bad = False
+        except ValueError:
+            bad = True
+        q.put((rank, ok, bad))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_frames", [64, 61])  # even split (single collective) and ragged split (pad + trim)
+def test_gather_embeddings_world2_gloo(n_frames):
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, n_frames, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    res = sorted(q.get() for _ in range(2))
+    assert res == [(0, True, True), (1, True, True)]
+
+
+class _FakeVit(torch.nn.Module):
+    """Stand-in with the product ViT's ``forward_u8`` contract (embedding = per-frame mean colour, repeated)."""
+
+    def __init__(self):
+        super().__init__()
+        self.p = torch.nn.Parameter(torch.zeros(1))
+
+    def forward_u8(self, frames, precision=None):
+        return frames.float().mean(dim=(1, 2)).repeat(1, 128)
+
+
+def test_extract_features_empty_video():
+    """batch loop of extractFeatures (extract_representations.py:365-371) on a video with no frames."""
+    frames = torch.zeros((0, 224, 224, 3), dtype=torch.uint8)
+    assert pipeline.extract_features(_FakeVit(), frames, 8, device="cpu").shape == (0, 384)
