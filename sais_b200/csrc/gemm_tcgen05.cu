@@ -20,6 +20,7 @@
 // Reference call sites this kernel replaces: nn.Linear / conv-as-GEMM in
 // SAIS/scripts/dino-main/vision_transformer.py:60-63,82,90,126-130 and the in/out/FF projections of
 // nn.TransformerEncoderLayer reached via SAIS/scripts/prepare_model.py:213.
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -39,10 +40,10 @@ constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int CW = 32;               // epilogue chunk width (columns)
 constexpr int kStageBufBytes = 4096;  // one staging buffer: 32 rows x 128 B (fp32) or 2 x (32 rows x 64 B) (bf16 hi, lo)
 
-template <int BLOCK_N>
+template <int BLOCK_N, int CG>
 struct GemmCfg {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
-  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kBBytes = (BLOCK_N / CG) * BLOCK_K * 2;  // a CTA pair splits the W tile's rows
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = (2 * BLOCK_N <= 256) ? 256 : 512;
   static constexpr int kMaxStages = 6;
@@ -73,10 +74,10 @@ struct GemmParams {
   int split_out;      // 1: out_bf16 has 2N columns: hi = bf16(v) at n, lo = bf16(v - hi) at N + n
   int exact_gelu;     // 1: erff-based GELU (precise mode); 0: tanh.approx form fitted to the erf definition
   int debug_nostore;  // dev knob (SAIS_GEMM_DEBUG_NOSTORE=1): skip all epilogue global traffic
+  long long* dbg;     // dev knob (SAIS_GEMM_TIMELINE=<file>): CTA 0 records clock64() per role / tile / event
   int stages;         // depth of the operand ring
   int stage_buf;      // bytes per epilogue staging buffer (4096 or 2048)
   int nbuf;           // staging buffers per epilogue warp (2..4)
-  int cluster;        // 1, or 2: CTA pairs work on vertically adjacent m-tiles and share every W tile via TMA multicast
 };
 
 __device__ __forceinline__ float gelu_erf_exact(float x) {
@@ -130,12 +131,15 @@ __device__ __forceinline__ void tma_store_2d_s(const CUtensorMap* m, uint32_t sm
                : "memory");
 }
 
-template <int BLOCK_N, int MODE>
+// CG = 1: one CTA per 128 x BLOCK_N tile.  CG = 2: a CTA pair (2-CTA cluster, tcgen05 cta_group::2) per
+// 256 x BLOCK_N tile — each CTA loads its own 128 rows of A but only HALF of the W tile, so the bytes every SM
+// pulls from L2 per flop drop by 1/3 (the measured limiter of the CG = 1 kernel at K = 384).
+template <int BLOCK_N, int MODE, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                     const GemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, CG>;
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled UMMA/TMA tiles need 1024-byte aligned bases
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -152,11 +156,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // timeline rows: 0 producer, 1 MMA issuer, 2 epilogue warp 0, 3 epilogue warp 4; 16 tiles x 16 events each
+  auto stamp = [&](int role, int idx, int ev) {
+    if (p.dbg != nullptr && blockIdx.x == 0 && idx < 16 && ev < 16) p.dbg[(role * 16 + idx) * 16 + ev] = clock64();
+  };
 
   // Work units: (m-tile group, n-tile); a group is `cluster` vertically adjacent m-tiles, one per CTA of the
   // cluster.  Units are walked n-fastest; a CTA whose m-tile lies beyond M just computes on zero-filled rows.
-  const int csize = p.cluster;
-  const uint32_t crank = csize > 1 ? cluster_ctarank() : 0;
+  constexpr int csize = CG;
+  const uint32_t crank = CG > 1 ? cluster_ctarank() : 0;
   const int unit0 = blockIdx.x / csize;
   const int unit_stride = gridDim.x / csize;
   const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
@@ -171,18 +179,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     tma_prefetch_desc(&tmap_b);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], csize);  // every CTA of the cluster must have consumed the slot
+      mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], kEpiWarps);
+      mbar_init(&tempty_bar[s], kEpiWarps * CG);  // (leader's copy) the epilogue warps of BOTH CTAs drain the tile
     }
     for (int s = 0; s < 2 * kEpiWarps; ++s) mbar_init(&res_bar[s], 1);
     fence_mbar_init();
   }
   if (warp == kMmaWarp) {
-    tmem_alloc(tmem_base_smem, Cfg::kTmemCols);
-    tmem_relinquish();
+    if (CG == 1) {
+      tmem_alloc(tmem_base_smem, Cfg::kTmemCols);
+      tmem_relinquish();
+    } else {
+      tmem_alloc_cg2(tmem_base_smem, Cfg::kTmemCols);
+      tmem_relinquish_cg2();
+    }
   }
   tc_fence_before();
   if (csize > 1) cluster_sync_all(); else __syncthreads();
@@ -195,14 +208,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
+      int tidx = 0;
+      for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++tidx) {
         const int m0 = tile_m0(tile);
         const int n0 = (tile % n_tiles) * BLOCK_N;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          stamp(0, tidx, kb);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          if (CG == 1 || crank == 0) mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes * CG);
           // split3 passes: (A_hi, W_hi), (A_lo, W_hi), (A_hi, W_lo); halves sit side by side along K
           int ka = kb, kw = kb;
           if (kb >= 2 * kb_per_pass) {
@@ -211,14 +226,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           } else if (kb >= kb_per_pass) {
             kw = kb - kb_per_pass;
           }
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], ka * BLOCK_K, m0);
-          if (csize == 1) {
+          if (CG == 1) {
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], ka * BLOCK_K, m0);
             tma_load_2d(sb, &tmap_b, &full_bar[stage], kw * BLOCK_K, n0);
           } else {
-            // each CTA fetches half of the W tile and multicasts it into both CTAs' stage buffers
-            constexpr int kHalfRows = BLOCK_N / 2;
-            tma_load_2d_mcast(sb + crank * (kHalfRows * 128), &tmap_b, &full_bar[stage], kw * BLOCK_K,
-                              n0 + int(crank) * kHalfRows, uint16_t(0b11));
+            // both CTAs' loads complete on the LEADER's full barrier (its MMA thread is the only consumer)
+            const uint32_t lbar = leader_smem_u32(&full_bar[stage]);
+            tma_load_2d_cg2(sa, &tmap_a, lbar, ka * BLOCK_K, m0);
+            tma_load_2d_cg2(sb, &tmap_b, lbar, kw * BLOCK_K, n0 + int(crank) * (BLOCK_N / 2));
           }
           if (++stage == kStages) {
             stage = 0;
@@ -229,19 +244,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+    if (lane == 0 && crank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M * CG, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int astage = 0;
       uint32_t aphase = 0;
-      for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
+      int tidx = 0;
+      for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++tidx) {
+        stamp(1, tidx, 0);
         mbar_wait(&tempty_bar[astage], aphase ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
+        stamp(1, tidx, 1);
         const uint32_t d_tmem = tmem_base + astage * BLOCK_N;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          stamp(1, tidx, 2 + kb);
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + Cfg::kABytes;
           const uint64_t da = umma_desc_sw128_kmajor(sa);
@@ -249,16 +268,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advancing K inside the 128-byte swizzle row: +32 bytes = +2 in 16-byte address units
-            umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            if (CG == 1) umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            else umma_f16_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           }
-          // frees the smem slot (in every CTA that multicasts into it) once these MMAs retire
-          if (csize == 1) umma_commit(&empty_bar[stage]); else umma_commit_mcast(&empty_bar[stage], uint16_t(0b11));
+          // frees the smem slot (in both CTAs of a pair) once these MMAs retire
+          if (CG == 1) umma_commit(&empty_bar[stage]); else umma_commit_cg2_mcast(&empty_bar[stage], uint16_t(0b11));
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull_bar[astage]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if (CG == 1) umma_commit(&tfull_bar[astage]); else umma_commit_cg2_mcast(&tfull_bar[astage], uint16_t(0b11));
         if (++astage == 2) {
           astage = 0;
           aphase ^= 1;
@@ -292,9 +313,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       tma_load_2d_s(my_stage, &tmap_res, &my_res_bar[0], n0 + half * CW, m0 + q * 32);
     }
 
-    for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
+    int tidx = 0;
+    const int erole = (ew == 0) ? 2 : (ew == 4 ? 3 : -1);
+    for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++tidx) {
       const int m0 = tile_m0(tile);
       const int n0 = (tile % n_tiles) * BLOCK_N;
+      if (erole >= 0 && lane == 0) stamp(erole, tidx, 0);
       // this tile's bias slice -> per-warp smem while the MMAs are still running (keeps the global-load
       // latency off the post-MMA critical path; later reads are broadcast LDS)
       __syncwarp();
@@ -305,6 +329,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
       mbar_wait(&tfull_bar[astage], aphase);
       tc_fence_after();
+      if (erole >= 0 && lane == 0) stamp(erole, tidx, 1);
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + astage * BLOCK_N;
       const int row = m0 + q * 32 + lane;
 
@@ -326,7 +351,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           tmem_ld_32x32(t_row + (c + 2) * CW, v);  // next chunk's accumulator streams in under this chunk's math
         } else {  // last TMEM read of this tile by this warp: hand the accumulator back early
           tc_fence_before();
-          if (lane == 0) mbar_arrive(&tempty_bar[astage]);
+          if (lane == 0) {
+            if (CG == 1) mbar_arrive(&tempty_bar[astage]);
+            else mbar_arrive_cluster(leader_smem_u32(&tempty_bar[astage]));
+          }
         }
         {
           const float4* b4p = reinterpret_cast<const float4*>(my_bias + ci * CW);
@@ -424,6 +452,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
           ++it;
           if (++bufi == nbuf) bufi = 0;
+          if (erole >= 0 && lane == 0) stamp(erole, tidx, 2 + ci);
         } else if (MODE == kModeGeneric) {
           if (row < p.M && !p.debug_nostore) {
             // ---- direct path (patch-embed row remap: GEMM row g*G + i -> token row g*(G+1) + 1 + i, + row_add[i]) ----
@@ -477,23 +506,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (csize > 1) cluster_sync_all(); else __syncthreads();
   if (warp == kMmaWarp) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (CG == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols); else tmem_dealloc_cg2(tmem_base, Cfg::kTmemCols);
   }
 }
 
-template <int BLOCK_N, int MODE>
+template <int BLOCK_N, int MODE, int CG>
 int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, CG>;
   CUtensorMap ta, tb, tout, tres;
   const uint64_t kcols = uint64_t(a.K) * (a.split3 ? 2 : 1);
   int rc = make_tmap_2d(&ta, a.a, kTmapBf16, uint64_t(a.M), kcols, uint64_t(a.lda), BLOCK_M, BLOCK_K, 128);
   if (rc) return rc;
   const int m_tiles = int((a.M + BLOCK_M - 1) / BLOCK_M);
-  // CTA pairs with W-tile TMA multicast (SAIS_GEMM_CLUSTER=2) are implemented and parity-tested, but measured
-  // no faster on B200: multicast halves the L2 *output* traffic, while the limiter is each SM's own fill port,
-  // which still receives the full W tile.  Default is therefore single-CTA scheduling.
-  static const int env_cluster = getenv("SAIS_GEMM_CLUSTER") ? atoi(getenv("SAIS_GEMM_CLUSTER")) : 1;
-  const int cluster = (env_cluster == 2 && m_tiles >= 2) ? 2 : 1;
+  constexpr int cluster = CG;
   rc = make_tmap_2d(&tb, a.w, kTmapBf16, uint64_t(a.N), kcols, uint64_t(a.ldw), BLOCK_N / cluster, BLOCK_K, 128);
   if (rc) return rc;
   tout = ta;
@@ -513,7 +538,7 @@ int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
 
   static bool attr_set = false;
   if (!attr_set) {
-    rc = check_cuda(cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    rc = check_cuda(cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, MODE, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024),
                     "cudaFuncSetAttribute(gemm)");
     if (rc) return rc;
@@ -539,13 +564,19 @@ int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
   p.exact_gelu = a.split3;  // the fp32-equivalent mode keeps the erff form
   static const int nostore = getenv("SAIS_GEMM_DEBUG_NOSTORE") ? atoi(getenv("SAIS_GEMM_DEBUG_NOSTORE")) : 0;
   p.debug_nostore = nostore;
+  static const char* timeline = getenv("SAIS_GEMM_TIMELINE");
+  p.dbg = nullptr;
+  constexpr int kDbgN = 4 * 16 * 16;
+  if (timeline) {
+    if (cudaMalloc(&p.dbg, kDbgN * sizeof(long long)) != cudaSuccess) p.dbg = nullptr;
+    if (p.dbg) cudaMemsetAsync(p.dbg, 0, kDbgN * sizeof(long long), stream);
+  }
   static const int env_nbuf = getenv("SAIS_GEMM_NBUF") ? atoi(getenv("SAIS_GEMM_NBUF")) : 0;
   int nbuf = 2;
   if (!a.residual && env_nbuf >= 2 && env_nbuf <= 4) nbuf = env_nbuf;
   p.nbuf = nbuf;
   p.stages = Cfg::stages(wide, nbuf);
   p.stage_buf = wide ? kStageBufBytes : kStageBufBytes / 2;
-  p.cluster = cluster;
   const int units = ((m_tiles + cluster - 1) / cluster) * (p.N / BLOCK_N);
   int grid = units * cluster < num_sms() ? units * cluster : num_sms();
   grid -= grid % cluster;
@@ -562,8 +593,28 @@ int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return check_cuda(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BLOCK_N, MODE>, ta, tb, tout, tres, p),
-                    "gemm_tcgen05_kernel launch");
+  rc = check_cuda(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BLOCK_N, MODE, CG>, ta, tb, tout, tres, p),
+                  "gemm_tcgen05_kernel launch");
+  if (p.dbg) {  // dev knob: dump CTA 0's timeline (cycles relative to the first stamp), last call wins
+    static long long h[kDbgN];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(p.dbg);
+    long long t0 = 0;
+    for (long long v : h) if (v && (!t0 || v < t0)) t0 = v;
+    if (FILE* f = fopen(timeline, "w")) {
+      fprintf(f, "# M=%d N=%d K=%d BN=%d mode=%d CG=%d grid=%d stages=%d\n", p.M, p.N, p.K, BLOCK_N, MODE, CG, grid, p.stages);
+      const char* names[4] = {"producer", "mma", "epi_w0", "epi_w4"};
+      for (int r = 0; r < 4; ++r)
+        for (int i = 0; i < 16; ++i) {
+          fprintf(f, "%-8s tile %2d:", names[r], i);
+          for (int e = 0; e < 16; ++e) fprintf(f, " %7lld", h[(r * 16 + i) * 16 + e] ? h[(r * 16 + i) * 16 + e] - t0 : -1);
+          fprintf(f, "\n");
+        }
+      fclose(f);
+    }
+  }
+  return rc;
 }
 
 }  // namespace
@@ -631,19 +682,27 @@ int gemm_bias_act(const SaisGemmArgs& a, cudaStream_t stream, int force_block_n)
     else if (a.out_bf16 && !a.residual && a.act == 1) mode = kModeBf16Gelu;
     else if (a.out_bf16 && !a.residual) mode = kModeBf16;
   }
-#define SAIS_GEMM_DISPATCH(BN)                                              \
-  switch (mode) {                                                           \
-    case kModeBf16: return launch_gemm<BN, kModeBf16>(a, stream);           \
-    case kModeBf16Gelu: return launch_gemm<BN, kModeBf16Gelu>(a, stream);   \
-    case kModeF32: return launch_gemm<BN, kModeF32>(a, stream);             \
-    default: return launch_gemm<BN, kModeGeneric>(a, stream);               \
+  // CTA pairs (cta_group::2) whenever there are at least two m-tiles per SM-pair's worth of work; tiny problems
+  // (the C1-sized temporal head) stay on single CTAs.  SAIS_GEMM_CG=1|2 forces either (A/B comparisons).
+  static const int env_cg = getenv("SAIS_GEMM_CG") ? atoi(getenv("SAIS_GEMM_CG")) : 0;
+  const int64_t m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M;
+  const int cg = env_cg ? env_cg : (m_tiles * (a.N / bn) >= 2 * num_sms() ? 2 : 1);
+#define SAIS_GEMM_DISPATCH_CG(BN, CG)                                           \
+  switch (mode) {                                                               \
+    case kModeBf16: return launch_gemm<BN, kModeBf16, CG>(a, stream);           \
+    case kModeBf16Gelu: return launch_gemm<BN, kModeBf16Gelu, CG>(a, stream);   \
+    case kModeF32: return launch_gemm<BN, kModeF32, CG>(a, stream);             \
+    default: return launch_gemm<BN, kModeGeneric, CG>(a, stream);               \
   }
+#define SAIS_GEMM_DISPATCH(BN) \
+  if (cg == 2) { SAIS_GEMM_DISPATCH_CG(BN, 2) } else { SAIS_GEMM_DISPATCH_CG(BN, 1) }
   switch (bn) {
     case 256: SAIS_GEMM_DISPATCH(256)
     case 192: SAIS_GEMM_DISPATCH(192)
     case 128: SAIS_GEMM_DISPATCH(128)
   }
 #undef SAIS_GEMM_DISPATCH
+#undef SAIS_GEMM_DISPATCH_CG
   set_last_error("gemm: bad tile %d", bn);
   return kErrShape;
 }
