@@ -87,6 +87,13 @@ typedef struct {
 } SaisGemmArgs;
 int sais_gemm_bias_act(const SaisGemmArgs* args, sais_stream_t stream);
 
+/* Fused ViT MLP with residual:  x += fc2(GELU_erf(fc1(xn) + fc1_b)) + fc2_b   — Mlp.forward and the residual add of
+ * Block.forward (vision_transformer.py:56-65,107) in ONE kernel: the [rows,1536] hidden activations stay in
+ * shared / tensor memory.  xn bf16 [rows,384] (LayerNorm output), fc1_w bf16 [1536,384], fc2_w bf16 [384,1536],
+ * biases fp32, x fp32 [rows,384] updated in place (the add happens in L2 through a TMA reduce store). */
+int sais_vit_mlp(const sais_bf16* xn, const sais_bf16* fc1_w, const float* fc1_b, const sais_bf16* fc2_w,
+                 const float* fc2_b, float* x, int64_t rows, sais_stream_t stream);
+
 /* LayerNorm over the last dim (cols == 384) — nn.LayerNorm at vision_transformer.py:99,103,156
  * (eps 1e-6) and TransformerEncoderLayer.norm1/norm2 (eps 1e-5).  x: fp32, row pitch in_pitch
  * elements; writes fp32 [rows,384] and/or bf16 ([rows,384], or [rows,768] = [hi | lo] if split_out). */

@@ -66,6 +66,7 @@ SIGNATURES = {
     "sais_profile_begin": (None, []),
     "sais_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
     "sais_gemm_bias_act": (C.c_int, [C.POINTER(SaisGemmArgs), _p]),
+    "sais_vit_mlp": (C.c_int, [_p, _p, _p, _p, _p, _p, C.c_int64, _p]),
     "sais_layernorm": (C.c_int, [_p, C.c_int64, _p, _p, C.c_float, C.c_int64, C.c_int32, _p, _p, C.c_int32, _p]),
     "sais_normalize_patchify_u8": (C.c_int, [_p, C.c_int32, _p, _p, _p, C.c_int32, _p]),
     "sais_patchify_f32": (C.c_int, [_p, C.c_int32, _p, C.c_int32, _p]),

@@ -3,6 +3,7 @@
 // composed forwards (ViT-S/16 backbone, SAIS temporal encoder) that sequence the kernels on one stream.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <atomic>
 #include <mutex>
@@ -251,6 +252,11 @@ int sais_gemm_bias_act(const SaisGemmArgs* args, sais_stream_t stream) {
   return gemm_bias_act(*args, static_cast<cudaStream_t>(stream));
 }
 
+int sais_vit_mlp(const sais_bf16* xn, const sais_bf16* fc1_w, const float* fc1_b, const sais_bf16* fc2_w,
+                 const float* fc2_b, float* x, int64_t rows, sais_stream_t stream) {
+  return vit_mlp_fused(xn, fc1_w, fc1_b, fc2_w, fc2_b, x, rows, static_cast<cudaStream_t>(stream));
+}
+
 int sais_layernorm(const float* x, int64_t in_pitch, const float* gamma, const float* beta, float eps,
                    int64_t rows, int32_t cols, float* out_f32, sais_bf16* out_bf16, int32_t split_out,
                    sais_stream_t stream) {
@@ -367,6 +373,11 @@ int sais_vit_forward(const SaisVitWeights* w, const void* input, int32_t input_k
       if ((rc = gemm_bias_act(g, stream))) return rc;
       // norm2
       if ((rc = layernorm(x, Dm, bw.ln2_w, bw.ln2_b, 1e-6f, tok, nullptr, xn, stream, precise))) return rc;
+      static const bool mlp_unfused = getenv("SAIS_MLP_UNFUSED") != nullptr && atoi(getenv("SAIS_MLP_UNFUSED")) != 0;
+      if (!precise && !mlp_unfused) {  // fused fc1 + GELU + fc2 + residual: the hidden activations stay on chip
+        if ((rc = vit_mlp_fused(xn, bw.fc1_w, bw.fc1_b, bw.fc2_w, bw.fc2_b, x, tok, stream))) return rc;
+        continue;
+      }
       // fc1 + GELU
       memset(&g, 0, sizeof(g));
       g.a = xn; g.w = bw.fc1_w; g.bias = bw.fc1_b; g.out_bf16 = hid; g.act = SAIS_ACT_GELU_ERF;

@@ -80,22 +80,6 @@ struct GemmParams {
   int nbuf;           // staging buffers per epilogue warp (2..4)
 };
 
-__device__ __forceinline__ float gelu_erf_exact(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
-}
-// GELU(x) = x * Phi(x) with Phi(x) = 0.5 (1 + tanh(g(x))), g(x) = atanh(erf(x / sqrt 2)) fitted by the odd
-// polynomial x (a0 + a1 x^2 + a2 x^4): |error| <= 2.6e-5 against the erf definition over all x (the usual
-// "tanh GELU" constants give 4.7e-4), plus tanh.approx's 2^-11 — far below the bf16 rounding of the result.
-__device__ __forceinline__ float gelu_erf_fast(float x) {
-  const float x2 = fminf(x * x, 81.0f);  // beyond |x| = 9 the polynomial is clamped; tanh is saturated there anyway
-  float p = fmaf(-0.00035151765347133106f, x2, 0.03700565178240022f);
-  p = fmaf(p, x2, 0.7975078774032182f);
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * p));
-  const float hx = 0.5f * x;
-  return fmaf(hx, t, hx);
-}
-
 // byte offset of 16-byte chunk `j` of row `r` inside a staging tile written/read by TMA
 __device__ __forceinline__ uint32_t stage_off_f32(int r, int j) { return uint32_t(r * 128 + ((j ^ (r & 7)) << 4)); }        // SWIZZLE_128B
 __device__ __forceinline__ uint32_t stage_off_bf16(int r, int j) { return uint32_t(r * 64 + ((j ^ ((r >> 1) & 3)) << 4)); }  // SWIZZLE_64B

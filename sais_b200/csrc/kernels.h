@@ -25,6 +25,10 @@ struct LaunchScope {
 int gemm_bias_act(const SaisGemmArgs& a, cudaStream_t stream, int force_block_n = 0);
 int pick_block_n(int64_t M, int64_t N);
 
+// mlp_fused.cu: x += fc2(GELU(fc1(xn) + b1)) + b2 over bf16 xn [rows,384], fp32 x [rows,384] (in place)
+int vit_mlp_fused(const sais_bf16* xn, const sais_bf16* w1, const float* b1, const sais_bf16* w2, const float* b2,
+                  float* x, int64_t rows, cudaStream_t stream);
+
 // elementwise.cu
 int layernorm(const float* x, int64_t in_pitch, const float* gamma, const float* beta, float eps, int64_t rows,
               float* out_f32, sais_bf16* out_bf16, cudaStream_t stream, int split = 0);

@@ -1,0 +1,487 @@
+// Fused ViT MLP for sm_100a:   x += fc2( GELU( fc1(xn) + b1 ) ) + b2      (hidden activations never leave the SM)
+//
+// Reference: Mlp.forward + the residual add of Block.forward, SAIS/scripts/dino-main/vision_transformer.py:56-65,107.
+//
+// Why fused: at dim 384 the two GEMMs are bound by the memory hierarchy, not by the tensor pipe — the unfused pair
+// writes and re-reads the [rows,1536] hidden matrix through HBM (6,144 B/row) and pulls 128x256-tile operands
+// through L2 at ~2x the ~45 B/clk/SM the L2 can deliver.  Here a CTA PAIR (2-CTA cluster, tcgen05 cta_group::2) owns
+// 256 rows: the LayerNorm'd rows A[256,384] stay resident in shared memory, the hidden dimension is walked in
+// chunks of 64, and per chunk j
+//     G1(j):  S_j[256,64]   = A · W1[j]ᵀ                 (24 MMAs 256x64x16,  accumulator S in TMEM, double buffered)
+//     E1(j):  H_j           = bf16(GELU(S_j + b1[j]))     (epilogue warps, TMEM -> registers -> swizzled smem tile)
+//     G2(j):  acc[256,384] += H_j · W2[:, j]ᵀ             (8 MMAs 256x192x16, accumulator acc in TMEM)
+// with the tensor pipe running G1(j+1) while the epilogue warps do E1(j).  Only the weights stream (each CTA loads
+// half of every W1/W2 chunk; the pair exchanges operand halves in hardware), 48 KB per chunk per CTA.  The finished
+// accumulator (+ b2) is added to the fp32 residual stream IN L2 by a TMA reduce-add store, so the residual is never
+// loaded into the SM at all.
+//
+//   warps 0..7 : E1 and the output epilogue (two warps per TMEM lane quarter)
+//   warp 8     : TMA producer (A tile, then the W1/W2 chunk ring in exactly the order the MMAs consume it)
+//   warp 9     : TMEM allocator + single-thread MMA issuer (leader CTA of the pair only)
+// TMEM columns: acc [0,384) | S0 [384,448) | S1 [448,512).
+// Work units: (row tile, chunk range).  Whole tiles are dealt round-robin to the 74 pairs; the tiles of the last,
+// partial round are split `tail_split` ways along the hidden dimension (legal because the output is a reduce-add),
+// which removes most of the wave-quantisation loss (197 tiles on 74 pairs: 2.66 -> 3 rounds otherwise).
+#include <cstdio>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sais {
+
+namespace {
+
+constexpr int MT = 128;             // rows per CTA (256 per pair)
+constexpr int DM = 384;             // model dim (K of fc1, N of fc2)
+constexpr int HID = 1536;           // hidden dim
+constexpr int HC = 64;              // hidden chunk (N of G1, K of G2)
+constexpr int NCHUNK = HID / HC;    // 24
+constexpr int KB = DM / 64;         // 6 k-blocks of A
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 32 * (kEpiWarps + 2);
+constexpr int A_BYTES = KB * MT * 128;    // 98,304: six 128-row x 128-byte swizzled k-blocks
+constexpr int STAGE_BYTES = 24576;        // one W1 chunk half (6 x 32 rows x 128 B) or one W2 chunk half (2 x 96 rows x 128 B)
+constexpr int NSTAGE = 4;
+constexpr int H_BYTES = MT * 128;         // 16,384: H_j tile, 128 rows x 64 bf16
+constexpr int kTmemCols = 512;
+constexpr int kAccCols = DM;              // acc at column 0
+constexpr int kSCol = DM;                 // S0 at 384, S1 at 448
+constexpr int kTailBytes = 256 /*barriers*/ + DM * 4 /*b2*/;
+constexpr int kSmemBytes = 1024 + A_BYTES + NSTAGE * STAGE_BYTES + 2 * H_BYTES + kTailBytes;
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+
+struct MlpParams {
+  const float* b1;
+  const float* b2;
+  int num_tiles;    // 256-row tiles
+  int full_units;   // leading units that are whole tiles
+  int tail_split;   // remaining tiles are split this many ways along the hidden dimension (1, 2, 3, 4, 6, ...)
+  int num_units;
+  long long* dbg;
+};
+
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void sts128m(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
+
+struct Unit {
+  int tile, j0, nj;
+};
+__device__ __forceinline__ Unit decode_unit(const MlpParams& p, int u) {
+  Unit r;
+  if (u < p.full_units) {
+    r.tile = u;
+    r.j0 = 0;
+    r.nj = NCHUNK;
+  } else {
+    const int v = u - p.full_units;
+    r.tile = p.full_units + v / p.tail_split;
+    r.nj = NCHUNK / p.tail_split;
+    r.j0 = (v % p.tail_split) * r.nj;
+  }
+  return r;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w1,
+                 const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_out,
+                 const MlpParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_smem = smem;
+  uint8_t* w_smem = smem + A_BYTES;
+  uint8_t* h_smem = w_smem + NSTAGE * STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(h_smem + 2 * H_BYTES);
+  uint64_t* w_full = bars;            // [NSTAGE] (leader's copy is the one that counts)
+  uint64_t* w_empty = bars + NSTAGE;  // [NSTAGE]
+  uint64_t* a_full = bars + 8;
+  uint64_t* a_empty = bars + 9;
+  uint64_t* s_full = bars + 10;   // [2]
+  uint64_t* s_empty = bars + 12;  // [2] leader's, 16 arrivals
+  uint64_t* h_full = bars + 14;   // [2] leader's, 16 arrivals
+  uint64_t* h_empty = bars + 16;  // [2]
+  uint64_t* acc_full = bars + 18;
+  uint64_t* acc_empty = bars + 19;  // leader's, 16 arrivals
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 20);
+  float* b2_smem = reinterpret_cast<float*>(bars + 32);  // [384]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int npairs = gridDim.x >> 1;
+  auto stamp = [&](int role, int idx, int ev) {
+    if (p.dbg != nullptr && blockIdx.x == 0 && idx < 32 && ev < 4) p.dbg[(role * 32 + idx) * 4 + ev] = clock64();
+  };
+
+  constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
+  if (warp == kProducerWarp && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_w1);
+    tma_prefetch_desc(&tmap_w2);
+    tma_prefetch_desc(&tmap_out);
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&w_full[s], 1);
+      mbar_init(&w_empty[s], 1);
+    }
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], 2 * kEpiWarps);
+      mbar_init(&h_full[s], 2 * kEpiWarps);
+      mbar_init(&h_empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 2 * kEpiWarps);
+    fence_mbar_init();
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc_cg2(tmem_base_smem, kTmemCols);
+    tmem_relinquish_cg2();
+  }
+  for (int i = threadIdx.x; i < DM; i += kThreads) b2_smem[i] = __ldg(p.b2 + i);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp == kProducerWarp) {
+    // ===================== TMA producer (one thread per CTA) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t wphase = 0;
+      uint32_t ui = 0;
+      int pg = 0, pg2 = 0;  // chunk counters (timeline only)
+      auto load_w1 = [&](int j) {
+        mbar_wait(&w_empty[stage], wphase ^ 1);
+        stamp(3, pg, 0);
+        if (crank == 0) mbar_arrive_expect_tx(&w_full[stage], 2 * STAGE_BYTES);
+        const uint32_t lbar = leader_smem_u32(&w_full[stage]);
+        uint8_t* dst = w_smem + stage * STAGE_BYTES;
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb)
+          tma_load_2d_cg2(dst + kb * 4096, &tmap_w1, lbar, kb * 64, j * HC + int(crank) * (HC / 2));
+        ++pg;
+        if (++stage == NSTAGE) { stage = 0; wphase ^= 1; }
+      };
+      auto load_w2 = [&](int j) {
+        mbar_wait(&w_empty[stage], wphase ^ 1);
+        stamp(3, pg2, 1);
+        if (crank == 0) mbar_arrive_expect_tx(&w_full[stage], 2 * STAGE_BYTES);
+        const uint32_t lbar = leader_smem_u32(&w_full[stage]);
+        uint8_t* dst = w_smem + stage * STAGE_BYTES;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          tma_load_2d_cg2(dst + h * 12288, &tmap_w2, lbar, j * HC, h * 192 + int(crank) * 96);
+        ++pg2;
+        if (++stage == NSTAGE) { stage = 0; wphase ^= 1; }
+      };
+      for (int u = pair; u < p.num_units; u += npairs, ++ui) {
+        const Unit un = decode_unit(p, u);
+        const int m0 = un.tile * (2 * MT) + int(crank) * MT;
+        mbar_wait(a_empty, (ui & 1) ^ 1);  // the previous unit's G1s have retired
+        if (crank == 0) mbar_arrive_expect_tx(a_full, 2 * A_BYTES);
+        {
+          const uint32_t lbar = leader_smem_u32(a_full);
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb) tma_load_2d_cg2(a_smem + kb * (MT * 128), &tmap_a, lbar, kb * 64, m0);
+        }
+        for (int jj = 0; jj <= un.nj; ++jj) {
+          if (jj < un.nj) load_w1(un.j0 + jj);
+          if (jj >= 1) load_w2(un.j0 + jj - 1);
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ===================== MMA issuer (leader CTA, one thread) =====================
+    if (lane == 0 && crank == 0) {
+      constexpr uint32_t idesc1 = umma_idesc_bf16(2 * MT, HC);
+      constexpr uint32_t idesc2 = umma_idesc_bf16(2 * MT, 192);
+      int stage = 0;
+      uint32_t wphase = 0;
+      uint32_t g = 0;  // chunks issued so far by this pair (selects S / H buffers and their barrier phases)
+      uint32_t ui = 0;
+      const uint32_t a_s = smem_u32(a_smem);
+      const uint32_t h_s = smem_u32(h_smem);
+      for (int u = pair; u < p.num_units; u += npairs, ++ui) {
+        const Unit un = decode_unit(p, u);
+        mbar_wait(a_full, ui & 1);
+        tc_fence_after();
+        stamp(2, ui, 0);
+        for (int jj = 0; jj <= un.nj; ++jj) {
+          if (jj < un.nj) {  // ---- G1: S[b] = A · W1[j]ᵀ
+            const uint32_t gg = g + jj, b = gg & 1;
+            mbar_wait(&s_empty[b], ((gg >> 1) & 1) ^ 1);
+            stamp(0, gg, 0);
+            mbar_wait(&w_full[stage], wphase);
+            tc_fence_after();
+            stamp(0, gg, 1);
+            const uint32_t w_s = smem_u32(w_smem + stage * STAGE_BYTES);
+            const uint32_t d = tmem_base + kSCol + b * HC;
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb) {
+              const uint64_t da = umma_desc_sw128_kmajor(a_s + kb * (MT * 128));
+              const uint64_t db = umma_desc_sw128_kmajor(w_s + kb * 4096);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_f16_cg2(d, da + 2 * k, db + 2 * k, idesc1, (kb | k) != 0);
+            }
+            umma_commit_cg2_mcast(&w_empty[stage], uint16_t(0b11));
+            if (jj == un.nj - 1) umma_commit_cg2_mcast(a_empty, uint16_t(0b11));
+            umma_commit_cg2_mcast(&s_full[b], uint16_t(0b11));
+            if (++stage == NSTAGE) { stage = 0; wphase ^= 1; }
+          }
+          if (jj >= 1) {  // ---- G2: acc += H[b] · W2[:, j]ᵀ
+            const uint32_t gg = g + jj - 1, b = gg & 1;
+            if (jj == 1) {
+              mbar_wait(acc_empty, (ui & 1) ^ 1);  // the previous unit's output epilogue has drained acc
+              stamp(2, ui, 1);
+            }
+            mbar_wait(&h_full[b], (gg >> 1) & 1);
+            stamp(0, gg, 2);
+            mbar_wait(&w_full[stage], wphase);
+            tc_fence_after();
+            stamp(0, gg, 3);
+            const uint32_t w_s = smem_u32(w_smem + stage * STAGE_BYTES);
+            const uint64_t da = umma_desc_sw128_kmajor(h_s + b * H_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const uint64_t db = umma_desc_sw128_kmajor(w_s + h * 12288);
+                umma_f16_cg2(tmem_base + h * 192, da + 2 * k, db + 2 * k, idesc2, (jj > 1) || (k > 0));
+              }
+            }
+            umma_commit_cg2_mcast(&w_empty[stage], uint16_t(0b11));
+            umma_commit_cg2_mcast(&h_empty[b], uint16_t(0b11));
+            if (jj == un.nj) {
+              umma_commit_cg2_mcast(acc_full, uint16_t(0b11));
+            }
+            if (++stage == NSTAGE) { stage = 0; wphase ^= 1; }
+          }
+        }
+        g += un.nj;
+      }
+    }
+  } else {
+    // ===================== epilogue warps 0..7 =====================
+    const int ew = warp;
+    const int q = ew & 3;      // TMEM lane quarter
+    const int half = ew >> 2;  // column half (E1: 32 of 64; output: 192 of 384)
+    const int row = q * 32 + lane;
+    const uint32_t t_lane = tmem_base + (uint32_t(q * 32) << 16);
+    const uint32_t h_row = smem_u32(h_smem) + row * 128;
+    const int sw = row & 7;
+    const uint32_t my_stage = smem_u32(h_smem) + ew * 4096;  // output staging: 2 x (32 rows x 64 B), aliasing H
+    uint32_t g = 0, ui = 0;
+    for (int u = pair; u < p.num_units; u += npairs, ++ui) {
+      const Unit un = decode_unit(p, u);
+      const int m0 = un.tile * (2 * MT) + int(crank) * MT;
+      for (int jj = 0; jj < un.nj; ++jj) {
+        const uint32_t gg = g + jj, b = gg & 1;
+        const int j = un.j0 + jj;
+        float4 bias[8];
+        {
+          const float4* bp = reinterpret_cast<const float4*>(p.b1 + j * HC + half * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bias[i] = __ldg(bp + i);
+        }
+        mbar_wait(&s_full[b], (gg >> 1) & 1);
+        tc_fence_after();
+        if (ew == 0 && lane == 0) stamp(1, gg, 0);
+        uint32_t v[32];
+        tmem_ld_32x32(t_lane + kSCol + b * HC + half * 32, v);
+        tmem_ld_wait_dep(v);
+        tc_fence_before();
+        if (lane == 0) mbar_arrive_cluster(leader_smem_u32(&s_empty[b]));  // S[b] may be overwritten by G1(gg + 2)
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float f0 = gelu_erf_fast(__uint_as_float(v[4 * i]) + bias[i].x);
+          const float f1 = gelu_erf_fast(__uint_as_float(v[4 * i + 1]) + bias[i].y);
+          const float f2 = gelu_erf_fast(__uint_as_float(v[4 * i + 2]) + bias[i].z);
+          const float f3 = gelu_erf_fast(__uint_as_float(v[4 * i + 3]) + bias[i].w);
+          pk[2 * i] = pack_bf16x2(f0, f1);
+          pk[2 * i + 1] = pack_bf16x2(f2, f3);
+        }
+        mbar_wait(&h_empty[b], ((gg >> 1) & 1) ^ 1);  // G2(gg - 2) has finished reading H[b]
+        if (ew == 0 && lane == 0) stamp(1, gg, 1);
+        const uint32_t hb = h_row + b * H_BYTES;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          sts128m(hb + (((half * 4 + i) ^ sw) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(leader_smem_u32(&h_full[b]));
+        if (ew == 0 && lane == 0) stamp(1, gg, 2);
+      }
+      g += un.nj;
+
+      // ---- output epilogue: acc (+ b2) -> swizzled staging -> TMA reduce-add into the residual stream
+      mbar_wait(acc_full, ui & 1);
+      tc_fence_after();
+      if (ew == 0 && lane == 0) stamp(2, ui, 2);
+      const bool add_bias = (un.j0 == 0);
+      constexpr int NOC = (DM / 2) / 16;  // 12 chunks of 16 columns per warp
+      uint32_t v[16], w[16];
+      tmem_ld_32x16(t_lane + half * 192, v);
+#pragma unroll 1
+      for (int c = 0; c < NOC; c += 2) {
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) {
+          uint32_t(&cur)[16] = s2 == 0 ? v : w;
+          uint32_t(&nxt)[16] = s2 == 0 ? w : v;
+          const int cc = c + s2;
+          const int col = half * 192 + cc * 16;
+          tmem_ld_wait_dep(cur);
+          if (cc + 1 < NOC) {
+            tmem_ld_32x16(t_lane + col + 16, nxt);
+          } else {
+            tc_fence_before();
+            if (lane == 0) mbar_arrive_cluster(leader_smem_u32(acc_empty));  // acc fully read by this warp
+          }
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(cur[i]);
+          if (add_bias) {
+            const float4* bp = reinterpret_cast<const float4*>(b2_smem + col);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 b4 = bp[i];
+              f[4 * i] += b4.x; f[4 * i + 1] += b4.y; f[4 * i + 2] += b4.z; f[4 * i + 3] += b4.w;
+            }
+          }
+          const uint32_t buf = my_stage + s2 * 2048;
+          if (lane == 0) tma_store_wait_read<1>();  // the store issued from this buffer two chunks ago has read it
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            sts128m(buf + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4), __float_as_uint(f[4 * i]),
+                    __float_as_uint(f[4 * i + 1]), __float_as_uint(f[4 * i + 2]), __float_as_uint(f[4 * i + 3]));
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_reduce_add_2d(&tmap_out, buf, col, m0 + q * 32);
+            tma_store_commit();
+          }
+        }
+      }
+      if (lane == 0) tma_store_wait_read<0>();
+      if (ew == 0 && lane == 0) stamp(2, ui, 3);
+      epi_bar_sync();  // every warp's staging (which aliases H) has been read before any warp writes H again
+    }
+    if (lane == 0) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc_cg2(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace
+
+int vit_mlp_fused(const sais_bf16* xn, const sais_bf16* w1, const float* b1, const sais_bf16* w2, const float* b2,
+                  float* x, int64_t rows, cudaStream_t stream) {
+  if (rows == 0) return kOk;
+  if (!xn || !w1 || !b1 || !w2 || !b2 || !x || rows < 0) {
+    set_last_error("vit_mlp: bad arguments");
+    return kErrInvalidArg;
+  }
+  if ((reinterpret_cast<uintptr_t>(xn) | reinterpret_cast<uintptr_t>(w1) | reinterpret_cast<uintptr_t>(w2) |
+       reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(b1)) & 15) {
+    set_last_error("vit_mlp: operands must be 16-byte aligned");
+    return kErrInvalidArg;
+  }
+  CUtensorMap ta, tw1, tw2, tout;
+  int rc = make_tmap_2d(&ta, xn, kTmapBf16, uint64_t(rows), DM, DM, MT, 64, 128);
+  if (rc) return rc;
+  if ((rc = make_tmap_2d(&tw1, w1, kTmapBf16, HID, DM, DM, HC / 2, 64, 128))) return rc;
+  if ((rc = make_tmap_2d(&tw2, w2, kTmapBf16, DM, HID, HID, 96, 64, 128))) return rc;
+  if ((rc = make_tmap_2d(&tout, x, kTmapF32, uint64_t(rows), DM, DM, 32, 16, 64))) return rc;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    rc = check_cuda(cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes),
+                    "cudaFuncSetAttribute(mlp_fused)");
+    if (rc) return rc;
+    attr_set = true;
+  }
+  MlpParams p;
+  p.b1 = b1;
+  p.b2 = b2;
+  p.num_tiles = int((rows + 2 * MT - 1) / (2 * MT));
+  const int pairs_max = num_sms() / 2;
+  // whole tiles for the full rounds; the last partial round is split along the hidden dimension when that shortens
+  // the makespan (cost model: a unit costs its chunks + ~3 chunk-times of A load / output epilogue)
+  static const int env_split = getenv("SAIS_MLP_TAIL_SPLIT") ? atoi(getenv("SAIS_MLP_TAIL_SPLIT")) : 0;
+  const int rem = p.num_tiles % pairs_max;
+  int split = 1;
+  if (rem > 0) {
+    double best = NCHUNK + 3.0;
+    const int cands[6] = {2, 3, 4, 6, 8, 12};
+    for (int s : cands) {
+      const int rounds = (rem * s + pairs_max - 1) / pairs_max;
+      const double cost = rounds * (double(NCHUNK) / s + 3.0);
+      if (cost < best - 0.5) {
+        best = cost;
+        split = s;
+      }
+    }
+  }
+  if (env_split > 0 && NCHUNK % env_split == 0) split = env_split;
+  p.tail_split = split;
+  p.full_units = (split > 1) ? p.num_tiles - rem : p.num_tiles;
+  p.num_units = p.full_units + (p.num_tiles - p.full_units) * split;
+  const int pairs = p.num_units < pairs_max ? p.num_units : pairs_max;
+
+  static const char* timeline = getenv("SAIS_MLP_TIMELINE");
+  p.dbg = nullptr;
+  constexpr int kDbgN = 4 * 32 * 4;
+  if (timeline) {
+    if (cudaMalloc(&p.dbg, kDbgN * sizeof(long long)) != cudaSuccess) p.dbg = nullptr;
+    if (p.dbg) cudaMemsetAsync(p.dbg, 0, kDbgN * sizeof(long long), stream);
+  }
+  {
+    LaunchScope ls(kClsGemm, stream, 4.0 * double(rows) * DM * HID);
+    mlp_fused_kernel<<<2 * pairs, kThreads, kSmemBytes, stream>>>(ta, tw1, tw2, tout, p);
+    rc = check_cuda(cudaGetLastError(), "mlp_fused_kernel launch");
+  }
+  if (p.dbg) {
+    static long long h[kDbgN];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(p.dbg);
+    long long t0 = 0;
+    for (long long v : h) if (v && (!t0 || v < t0)) t0 = v;
+    if (FILE* f = fopen(timeline, "w")) {
+      fprintf(f, "# rows=%lld tiles=%d units=%d split=%d pairs=%d\n", (long long)rows, p.num_tiles, p.num_units, split, pairs);
+      const char* names[4] = {"mma(chunk: s_empty ok, w_full(W1) ok, h_full ok, w_full(W2) ok)",
+                              "e1(chunk: s_full, h_empty, h_full arrive)",
+                              "unit(mma a_full, mma acc_empty, out acc_full, out done)",
+                              "producer(chunk: w_empty for W1 ok, w_empty for W2 ok)"};
+      for (int r = 0; r < 4; ++r) {
+        fprintf(f, "%s\n", names[r]);
+        for (int i = 0; i < 32; ++i) {
+          fprintf(f, "  %2d:", i);
+          for (int e = 0; e < 4; ++e) fprintf(f, " %8lld", h[(r * 32 + i) * 4 + e] ? h[(r * 32 + i) * 4 + e] - t0 : -1);
+          fprintf(f, "\n");
+        }
+      }
+      fclose(f);
+    }
+  }
+  return rc;
+}
+
+}  // namespace sais

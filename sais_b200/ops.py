@@ -55,6 +55,20 @@ def gemm_bias_act(a, w, bias=None, act=_lib.ACT_NONE, residual=None, out_dtype=t
     return out
 
 
+def vit_mlp(xn, fc1_w, fc1_b, fc2_w, fc2_b, x):
+    """x += fc2(GELU(fc1(xn) + fc1_b)) + fc2_b in one kernel.  xn bf16 [rows,384]; weights bf16; x fp32 [rows,384],
+    updated IN PLACE and returned."""
+    require_cuda(xn, "xn")
+    require_cuda(x, "x")
+    assert xn.dtype == torch.bfloat16 and x.dtype == torch.float32 and xn.is_contiguous() and x.is_contiguous()
+    assert fc1_w.dtype == torch.bfloat16 and fc2_w.dtype == torch.bfloat16
+    assert tuple(fc1_w.shape) == (1536, 384) and tuple(fc2_w.shape) == (384, 1536) and xn.shape[1] == 384
+    assert fc1_w.is_contiguous() and fc2_w.is_contiguous() and x.shape == xn.shape
+    check(lib().sais_vit_mlp(ptr(xn), ptr(fc1_w), ptr(fc1_b), ptr(fc2_w), ptr(fc2_b), ptr(x), xn.shape[0],
+                             current_stream()), "sais_vit_mlp")
+    return x
+
+
 def layernorm(x, gamma, beta, eps, out_f32=False, out_bf16=True, in_pitch=None, rows=None, split_out=False):
     require_cuda(x, "x")
     assert x.dtype == torch.float32

@@ -157,6 +157,48 @@ def test_gemm_rejects_bad_shapes(dev):
         ops.gemm_bias_act(a, w)  # K not a multiple of 64 (and pitch not 16-byte aligned)
 
 
+# ------------------------------------------------------------------------------------------------ fused MLP
+def _mlp_ref(xn, w1, b1, w2, b2, x):
+    """fc1 -> erf-GELU -> (hidden rounded to bf16, as the kernel hands it to the second MMA) -> fc2 -> + residual."""
+    h = bf(xn).double() @ bf(w1).double().t() + b1.double()
+    h = 0.5 * h * (1 + torch.erf(h / math.sqrt(2)))
+    h = h.float().to(torch.bfloat16).double()
+    return (x.double() + h @ bf(w2).double().t() + b2.double()).float()
+
+
+# rows: single partial tile; ragged; one pair tile; several tiles (tail split along the hidden dim on 74 pairs);
+# exactly 74 tiles (no split); 80 tiles (one full round + a split tail)
+@pytest.mark.parametrize("rows", [1, 130, 256, 1000, 197 * 96, 256 * 80 - 57])
+def test_vit_mlp_fused(dev, rows):
+    from sais_b200 import ops
+    xn = rnd(rows, 384, seed=rows)
+    w1, b1 = rnd(1536, 384, seed=1, std=1 / math.sqrt(384)), rnd(1536, seed=2, std=0.5)
+    w2, b2 = rnd(384, 1536, seed=3, std=1 / math.sqrt(1536)), rnd(384, seed=4, std=0.5)
+    x = rnd(rows, 384, seed=5)
+    xd = x.to(dev).clone()
+    ops.vit_mlp(xn.to(dev).bfloat16(), w1.to(dev).bfloat16(), b1.to(dev), w2.to(dev).bfloat16(), b2.to(dev), xd)
+    ref = _mlp_ref(xn, w1, b1, w2, b2, x)
+    got = xd.cpu()
+    # fp32 accumulation over 1536 bf16-rounded hidden values of O(1): the fast erf-GELU (|err| <= 3e-5 before the
+    # bf16 rounding) can flip a hidden value by one bf16 ulp (2^-8 relative) now and then -> ~1e-3 absolute
+    assert torch.allclose(got, ref, atol=3e-3, rtol=1e-3), (got - ref).abs().max()
+    assert (got - ref).abs().mean() < 2e-4
+
+
+def test_vit_mlp_fused_matches_unfused_gemms(dev):
+    """same arithmetic as the two-GEMM path (fc1+GELU -> bf16 hidden -> fc2 + residual) up to summation order."""
+    from sais_b200 import _lib, ops
+    rows = 3000
+    xn = rnd(rows, 384, seed=11).to(dev).bfloat16()
+    w1, b1 = rnd(1536, 384, seed=1, std=0.05).to(dev).bfloat16(), rnd(1536, seed=2, std=0.5).to(dev)
+    w2, b2 = rnd(384, 1536, seed=3, std=0.03).to(dev).bfloat16(), rnd(384, seed=4, std=0.5).to(dev)
+    x = rnd(rows, 384, seed=5).to(dev)
+    hid = ops.gemm_bias_act(xn, w1, b1, act=_lib.ACT_GELU_ERF)
+    ref = ops.gemm_bias_act(hid, w2, b2, residual=x, out_dtype=torch.float32)
+    got = ops.vit_mlp(xn, w1, b1, w2, b2, x.clone())
+    assert torch.allclose(got, ref, atol=1e-4, rtol=1e-4), (got - ref).abs().max()
+
+
 # ------------------------------------------------------------------------------------------------ ViT attention
 def _vit_attn_ref(qkv, B):
     q, k, v = bf(qkv).view(B, 197, 3, 6, 64).permute(2, 0, 3, 1, 4)
