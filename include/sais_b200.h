@@ -84,6 +84,20 @@ typedef struct {
    * fp32.  split_out: out_bf16 has 2N columns and receives the result as [hi | lo] for the next split GEMM. */
   int32_t split3;
   int32_t split_out;
+  /* LayerNorm folding (bf16 fast path).  LayerNorm is affine per row, so  LN(x) Wᵀ + b = rstd (x W'ᵀ - mean c) + d
+   * with W' = gamma ∘ W, c_n = sum_k W'_nk, d_n = sum_k beta_k W_nk + b_n.
+   * Consumer (qkv, fc1): a = bf16 copy of the UN-normalised rows, w = W', bias = d, ln_colsum = c and
+   *   ln_stats_in = fp32 [M][4][2] partial (sum, sum of squares) of each input row; mean / rstd are applied in the
+   *   epilogue (before the activation).  bf16 output only.
+   * Producer (proj, fc2; N = 384, fp32 out + residual): additionally writes out2_bf16 = bf16(out) (pitch ldo2) and
+   *   ln_stats_out = fp32 [M][4][2] partials of its output rows for the consumer that follows. */
+  const float* ln_stats_in;
+  const float* ln_colsum;
+  float* ln_stats_out;
+  sais_bf16* out2_bf16;
+  int64_t ldo2;
+  float ln_eps;
+  int32_t reserved_;
 } SaisGemmArgs;
 int sais_gemm_bias_act(const SaisGemmArgs* args, sais_stream_t stream);
 
@@ -94,12 +108,25 @@ int sais_gemm_bias_act(const SaisGemmArgs* args, sais_stream_t stream);
 int sais_vit_mlp(const sais_bf16* xn, const sais_bf16* fc1_w, const float* fc1_b, const sais_bf16* fc2_w,
                  const float* fc2_b, float* x, int64_t rows, sais_stream_t stream);
 
+/* Linear + residual add + the FOLLOWING LayerNorm in one kernel (N = 384 = one full row per tile):
+ *   x <- x + A · Wᵀ + bias   (fp32 [M,384], in place);   xn <- LayerNorm(x; gamma, beta, eps) as bf16 [M,384].
+ * Replaces `x = x + attn(...)` / `x = x + mlp(...)` plus the next `norm2(x)` / `norm1(x)` of Block.forward
+ * (vision_transformer.py:103-108).  A bf16 [M,K] (pitch lda), W bf16 [384,K] (pitch ldw), K % 64 == 0.
+ * xn == NULL skips the LayerNorm (gamma / beta may then be NULL). */
+int sais_gemm_residual_layernorm(const sais_bf16* a, int64_t lda, const sais_bf16* w, int64_t ldw, const float* bias,
+                                 float* x, const float* gamma, const float* beta, float eps, sais_bf16* xn,
+                                 int64_t M, int64_t K, sais_stream_t stream);
+
 /* LayerNorm over the last dim (cols == 384) — nn.LayerNorm at vision_transformer.py:99,103,156
  * (eps 1e-6) and TransformerEncoderLayer.norm1/norm2 (eps 1e-5).  x: fp32, row pitch in_pitch
  * elements; writes fp32 [rows,384] and/or bf16 ([rows,384], or [rows,768] = [hi | lo] if split_out). */
 int sais_layernorm(const float* x, int64_t in_pitch, const float* gamma, const float* beta, float eps,
                    int64_t rows, int32_t cols, float* out_f32, sais_bf16* out_bf16, int32_t split_out,
                    sais_stream_t stream);
+
+/* Entry of the LayerNorm-folded path: xb = bf16(x) and stats[row] = {sum, sum of squares, 0,0,0,0,0,0} for fp32 rows
+ * of 384 (x: [rows,384]; xb: bf16 [rows,384]; stats: fp32 [rows,8]). */
+int sais_rowstats_cast(const float* x, int64_t rows, sais_bf16* xb, float* stats, sais_stream_t stream);
 
 /* Frame normalisation + patch layout.  u8 variant replaces ToTensor+Normalize
  * (extract_representations.py:158-162): frames u8 [B,224,224,3] -> patches bf16 [B*196,768],
@@ -124,6 +151,10 @@ typedef struct {
   const float* ln2_w; const float* ln2_b;
   const sais_bf16* fc1_w; const float* fc1_b;   /* [1536,384], [1536] */
   const sais_bf16* fc2_w; const float* fc2_b;   /* [384,1536], [384] */
+  /* LayerNorm-folded operands of the bf16 fast path (see SaisGemmArgs): W' = gamma ∘ W as bf16, c_n = sum_k W'_nk,
+   * d_n = sum_k beta_k W_nk + b_n.  All NULL -> the forward keeps separate LayerNorm kernels. */
+  const sais_bf16* qkv_wg; const float* qkv_c; const float* qkv_d; /* norm1 folded into qkv */
+  const sais_bf16* fc1_wg; const float* fc1_c; const float* fc1_d; /* norm2 folded into fc1 */
 } SaisVitBlockWeights;
 typedef struct {
   const sais_bf16* patch_w; /* [384,768] = patch_embed.proj.weight.view(384,-1) */

@@ -30,12 +30,15 @@ class SaisGemmArgs(C.Structure):
         ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64),
         ("lda", C.c_int64), ("ldw", C.c_int64), ("ldr", C.c_int64), ("ldo32", C.c_int64), ("ldo16", C.c_int64),
         ("act", C.c_int32), ("remap_group", C.c_int32), ("split3", C.c_int32), ("split_out", C.c_int32),
+        ("ln_stats_in", _p), ("ln_colsum", _p), ("ln_stats_out", _p), ("out2_bf16", _p), ("ldo2", C.c_int64),
+        ("ln_eps", C.c_float), ("reserved_", C.c_int32),
     ]
 
 
 class SaisVitBlockWeights(C.Structure):
     _fields_ = [(n, _p) for n in (
-        "ln1_w", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ln2_w", "ln2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
+        "ln1_w", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ln2_w", "ln2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b",
+        "qkv_wg", "qkv_c", "qkv_d", "fc1_wg", "fc1_c", "fc1_d")]
 
 
 class SaisVitWeights(C.Structure):
@@ -67,6 +70,9 @@ SIGNATURES = {
     "sais_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
     "sais_gemm_bias_act": (C.c_int, [C.POINTER(SaisGemmArgs), _p]),
     "sais_vit_mlp": (C.c_int, [_p, _p, _p, _p, _p, _p, C.c_int64, _p]),
+    "sais_gemm_residual_layernorm": (C.c_int, [_p, C.c_int64, _p, C.c_int64, _p, _p, _p, _p, C.c_float, _p,
+                                               C.c_int64, C.c_int64, _p]),
+    "sais_rowstats_cast": (C.c_int, [_p, C.c_int64, _p, _p, _p]),
     "sais_layernorm": (C.c_int, [_p, C.c_int64, _p, _p, C.c_float, C.c_int64, C.c_int32, _p, _p, C.c_int32, _p]),
     "sais_normalize_patchify_u8": (C.c_int, [_p, C.c_int32, _p, _p, _p, C.c_int32, _p]),
     "sais_patchify_f32": (C.c_int, [_p, C.c_int32, _p, C.c_int32, _p]),

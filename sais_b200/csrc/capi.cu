@@ -257,6 +257,16 @@ int sais_vit_mlp(const sais_bf16* xn, const sais_bf16* fc1_w, const float* fc1_b
   return vit_mlp_fused(xn, fc1_w, fc1_b, fc2_w, fc2_b, x, rows, static_cast<cudaStream_t>(stream));
 }
 
+int sais_gemm_residual_layernorm(const sais_bf16* a, int64_t lda, const sais_bf16* w, int64_t ldw, const float* bias,
+                                 float* x, const float* gamma, const float* beta, float eps, sais_bf16* xn,
+                                 int64_t M, int64_t K, sais_stream_t stream) {
+  return gemm_residual_layernorm(a, lda, w, ldw, bias, x, gamma, beta, eps, xn, M, K, static_cast<cudaStream_t>(stream));
+}
+
+int sais_rowstats_cast(const float* x, int64_t rows, sais_bf16* xb, float* stats, sais_stream_t stream) {
+  return rowstats_cast(x, rows, xb, stats, static_cast<cudaStream_t>(stream));
+}
+
 int sais_layernorm(const float* x, int64_t in_pitch, const float* gamma, const float* beta, float eps,
                    int64_t rows, int32_t cols, float* out_f32, sais_bf16* out_bf16, int32_t split_out,
                    sais_stream_t stream) {
@@ -292,7 +302,8 @@ size_t sais_vit_workspace_bytes(int32_t chunk_frames, int32_t precise) {
          + a256(tok * 3 * SAIS_VIT_DIM * (precise ? 4 : 2))  // qkv (fp32 in precise mode)
          + a256(tok * SAIS_VIT_DIM * 2 * s)                // attention output bf16
          + a256(tok * SAIS_VIT_HIDDEN * 2 * s)             // MLP hidden bf16 (aliased by the patch matrix)
-         + a256((size_t(chunk_frames) + 1) * 4);           // packed-sequence offsets (precise attention)
+         + a256((size_t(chunk_frames) + 1) * 4)            // packed-sequence offsets (precise attention)
+         + a256(tok * 8 * 4);                              // LayerNorm row-statistics partials (folded path)
 }
 
 int sais_vit_forward(const SaisVitWeights* w, const void* input, int32_t input_kind, int32_t B,
@@ -323,6 +334,7 @@ int sais_vit_forward(const SaisVitWeights* w, const void* input, int32_t input_k
     sais_bf16* ao = static_cast<sais_bf16*>(ar.take(ctok * Dm * 2 * s));
     sais_bf16* hid = static_cast<sais_bf16*>(ar.take(ctok * Hid * 2 * s));
     int32_t* offs = static_cast<int32_t*>(ar.take((size_t(chunk_frames) + 1) * 4));
+    float* stats = static_cast<float*>(ar.take(ctok * 8 * 4));
     sais_bf16* patches = hid;  // [Bc*196, 768*s] <= [Bc*197, 1536*s]
     if (!ar.ok) {
       set_last_error("vit_forward: workspace carve failed");
@@ -347,14 +359,32 @@ int sais_vit_forward(const SaisVitWeights* w, const void* input, int32_t input_k
     if ((rc = gemm_bias_act(g, stream))) return rc;
     if ((rc = write_cls_rows(w->cls_pos0, Bc, x, stream))) return rc;
 
+    // Fast-path variants (A/B knobs):
+    //   default          : LayerNorm folded into the GEMMs (no LayerNorm kernels inside the blocks)
+    //   SAIS_LN_FOLD=0   : separate LayerNorm kernels
+    //   SAIS_ROWLN=1     : proj / fc2 + residual + LayerNorm in the full-row kernel (gemm_rowln.cu), unfolded consumers
+    //   SAIS_MLP_FUSED=1 : fc1 + GELU + fc2 + residual as one kernel (mlp_fused.cu); LayerNorms stay separate
+    static const bool env_nofold = getenv("SAIS_LN_FOLD") != nullptr && atoi(getenv("SAIS_LN_FOLD")) == 0;
+    static const bool env_rowln = getenv("SAIS_ROWLN") != nullptr && atoi(getenv("SAIS_ROWLN")) != 0;
+    static const bool env_mlp = getenv("SAIS_MLP_FUSED") != nullptr && atoi(getenv("SAIS_MLP_FUSED")) != 0;
+    const bool have_folded = w->blocks[0].qkv_wg != nullptr;
+    const bool fold = !precise && have_folded && !env_nofold && !env_rowln && !env_mlp;
+    const bool rowln = !precise && env_rowln && !env_mlp;
+    bool xn_ready = false;  // xn already holds what the coming block's qkv GEMM consumes
+    if (fold) {  // bf16 copy + row statistics of the embedded tokens: operand of block 0's folded qkv GEMM
+      if ((rc = rowstats_cast(x, tok, xn, stats, stream))) return rc;
+      xn_ready = true;
+    }
     for (int l = 0; l < SAIS_VIT_DEPTH; ++l) {
       const SaisVitBlockWeights& bw = w->blocks[l];
       const bool last = (l == SAIS_VIT_DEPTH - 1);
       // norm1
-      if ((rc = layernorm(x, Dm, bw.ln1_w, bw.ln1_b, 1e-6f, tok, nullptr, xn, stream, precise))) return rc;
+      if (!xn_ready && (rc = layernorm(x, Dm, bw.ln1_w, bw.ln1_b, 1e-6f, tok, nullptr, xn, stream, precise))) return rc;
+      xn_ready = false;
       // qkv
       memset(&g, 0, sizeof(g));
       g.a = xn; g.w = bw.qkv_w; g.bias = bw.qkv_b;
+      if (fold) { g.w = bw.qkv_wg; g.bias = bw.qkv_d; g.ln_colsum = bw.qkv_c; g.ln_stats_in = stats; g.ln_eps = 1e-6f; }
       if (precise) { g.out_f32 = static_cast<float*>(qkv); g.ldo32 = 3 * Dm; }
       else { g.out_bf16 = static_cast<sais_bf16*>(qkv); g.ldo16 = 3 * Dm; }
       g.M = tok; g.N = 3 * Dm; g.K = Dm; g.lda = Dm * s; g.ldw = Dm * s; g.split3 = precise;
@@ -366,30 +396,48 @@ int sais_vit_forward(const SaisVitWeights* w, const void* input, int32_t input_k
       else
         rc = vit_attention(static_cast<const sais_bf16*>(qkv), Bc, ao, probs, stream);
       if (rc) return rc;
-      // proj + residual
-      memset(&g, 0, sizeof(g));
-      g.a = ao; g.w = bw.proj_w; g.bias = bw.proj_b; g.residual = x; g.out_f32 = x;
-      g.M = tok; g.N = Dm; g.K = Dm; g.lda = Dm * s; g.ldw = Dm * s; g.ldr = Dm; g.ldo32 = Dm; g.split3 = precise;
-      if ((rc = gemm_bias_act(g, stream))) return rc;
-      // norm2
-      if ((rc = layernorm(x, Dm, bw.ln2_w, bw.ln2_b, 1e-6f, tok, nullptr, xn, stream, precise))) return rc;
-      static const bool mlp_unfused = getenv("SAIS_MLP_UNFUSED") != nullptr && atoi(getenv("SAIS_MLP_UNFUSED")) != 0;
-      if (!precise && !mlp_unfused) {  // fused fc1 + GELU + fc2 + residual: the hidden activations stay on chip
+      if (rowln) {
+        // proj + residual + norm2 in one kernel
+        if ((rc = gemm_residual_layernorm(ao, Dm, bw.proj_w, Dm, bw.proj_b, x, bw.ln2_w, bw.ln2_b, 1e-6f, xn, tok, Dm,
+                                          stream)))
+          return rc;
+      } else {
+        // proj + residual (folded path: + bf16 copy and row statistics for fc1)
+        memset(&g, 0, sizeof(g));
+        g.a = ao; g.w = bw.proj_w; g.bias = bw.proj_b; g.residual = x; g.out_f32 = x;
+        g.M = tok; g.N = Dm; g.K = Dm; g.lda = Dm * s; g.ldw = Dm * s; g.ldr = Dm; g.ldo32 = Dm; g.split3 = precise;
+        if (fold) { g.ln_stats_out = stats; g.out2_bf16 = xn; g.ldo2 = Dm; }
+        if ((rc = gemm_bias_act(g, stream))) return rc;
+        // norm2
+        if (!fold && (rc = layernorm(x, Dm, bw.ln2_w, bw.ln2_b, 1e-6f, tok, nullptr, xn, stream, precise))) return rc;
+      }
+      if (!precise && env_mlp) {  // fc1 + GELU + fc2 + residual: the hidden activations stay on chip
         if ((rc = vit_mlp_fused(xn, bw.fc1_w, bw.fc1_b, bw.fc2_w, bw.fc2_b, x, tok, stream))) return rc;
         continue;
       }
       // fc1 + GELU
       memset(&g, 0, sizeof(g));
       g.a = xn; g.w = bw.fc1_w; g.bias = bw.fc1_b; g.out_bf16 = hid; g.act = SAIS_ACT_GELU_ERF;
+      if (fold) { g.w = bw.fc1_wg; g.bias = bw.fc1_d; g.ln_colsum = bw.fc1_c; g.ln_stats_in = stats; g.ln_eps = 1e-6f; }
       g.M = tok; g.N = Hid; g.K = Dm; g.lda = Dm * s; g.ldw = Dm * s; g.ldo16 = Hid * s;
       g.split3 = precise; g.split_out = precise;
       if ((rc = gemm_bias_act(g, stream))) return rc;
-      // fc2 + residual
-      memset(&g, 0, sizeof(g));
-      g.a = hid; g.w = bw.fc2_w; g.bias = bw.fc2_b; g.residual = x; g.out_f32 = x;
-      g.M = tok; g.N = Dm; g.K = Hid; g.lda = Hid * s; g.ldw = Hid * s; g.ldr = Dm; g.ldo32 = Dm;
-      g.split3 = precise;
-      if ((rc = gemm_bias_act(g, stream))) return rc;
+      if (rowln) {
+        // fc2 + residual + the next block's norm1 (the final norm reads the fp32 stream itself)
+        const SaisVitBlockWeights* nb = last ? nullptr : &w->blocks[l + 1];
+        if ((rc = gemm_residual_layernorm(hid, Hid, bw.fc2_w, Hid, bw.fc2_b, x, nb ? nb->ln1_w : nullptr,
+                                          nb ? nb->ln1_b : nullptr, 1e-6f, nb ? xn : nullptr, tok, Hid, stream)))
+          return rc;
+        xn_ready = !last;
+      } else {
+        // fc2 + residual (folded path: + bf16 copy and row statistics for the next block's qkv)
+        memset(&g, 0, sizeof(g));
+        g.a = hid; g.w = bw.fc2_w; g.bias = bw.fc2_b; g.residual = x; g.out_f32 = x;
+        g.M = tok; g.N = Dm; g.K = Hid; g.lda = Hid * s; g.ldw = Hid * s; g.ldr = Dm; g.ldo32 = Dm;
+        g.split3 = precise;
+        if (fold && !last) { g.ln_stats_out = stats; g.out2_bf16 = xn; g.ldo2 = Dm; xn_ready = true; }
+        if ((rc = gemm_bias_act(g, stream))) return rc;
+      }
     }
     // final norm: only the CLS rows are consumed (vision_transformer.py:213-214)
     if ((rc = layernorm(x, int64_t(Tk) * Dm, w->norm_w, w->norm_b, 1e-6f, Bc, out_cls + size_t(b0) * Dm, nullptr,

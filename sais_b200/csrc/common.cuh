@@ -64,6 +64,37 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Packed fp32x2 arithmetic (sm_100 FADD2 / FMUL2 / FFMA2): one instruction on a 64-bit register pair does two fp32
+// operations — the GEMM epilogues are bound by the FMA pipe, not by the tensor pipe, without it.
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t pack2u(uint32_t a, uint32_t b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 // GELU (nn.GELU() default, erf form; vision_transformer.py:50)
 __device__ __forceinline__ float gelu_erf_exact(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
@@ -79,6 +110,22 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * p));
   const float hx = 0.5f * x;
   return fmaf(hx, t, hx);
+}
+// two elements at a time (same polynomial and tanh.approx, so bit-identical to gelu_erf_fast per element)
+__device__ __forceinline__ void gelu_erf_fast2(float& a, float& b) {
+  const uint64_t x = pack2(a, b);
+  float s0, s1;
+  unpack2(mul2(x, x), s0, s1);
+  const uint64_t x2 = pack2(fminf(s0, 81.0f), fminf(s1, 81.0f));
+  uint64_t p = fma2(pack2(-0.00035151765347133106f, -0.00035151765347133106f), x2,
+                    pack2(0.03700565178240022f, 0.03700565178240022f));
+  p = fma2(p, x2, pack2(0.7975078774032182f, 0.7975078774032182f));
+  float u0, u1, t0, t1;
+  unpack2(mul2(x, p), u0, u1);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(u0));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(u1));
+  const uint64_t hx = mul2(x, pack2(0.5f, 0.5f));
+  unpack2(fma2(hx, pack2(t0, t1), hx), a, b);
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -104,6 +104,38 @@ __global__ void __launch_bounds__(256) layernorm384_kernel(const float* __restri
   }
 }
 
+// Row statistics + bf16 cast of the fp32 residual stream: the entry point of the LayerNorm-folded fast path (the
+// GEMM that consumes the rows applies mean / rstd in its epilogue, see gemm_tcgen05.cu).  One warp per row.
+// stats[row] = {sum, sum of squares, 0, 0, 0, 0, 0, 0}  (slot 0 of the four partial slots the GEMM epilogues fill).
+__global__ void __launch_bounds__(256) rowstats_cast384_kernel(const float* __restrict__ x, int64_t rows,
+                                                               __nv_bfloat16* __restrict__ xb,
+                                                               float* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t warps_total = int64_t(gridDim.x) * (blockDim.x >> 5);
+  for (int64_t row = warp_global; row < rows; row += warps_total) {
+    const float* xr = x + row * D;
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const float4 v = *reinterpret_cast<const float4*>(xr + i * 128 + lane * 4);
+      s += (v.x + v.y) + (v.z + v.w);
+      q = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, q))));
+      uint2 o;
+      o.x = pack_bf16x2(v.x, v.y);
+      o.y = pack_bf16x2(v.z, v.w);
+      *reinterpret_cast<uint2*>(xb + row * D + i * 128 + lane * 4) = o;
+    }
+    s = warp_sum(s);
+    q = warp_sum(q);
+    if (lane < 2) {
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lane == 0) { o.x = s; o.y = q; }
+      *reinterpret_cast<float4*>(stats + row * 8 + lane * 4) = o;
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // Frame normalisation fused with the patch layout the patch-embed GEMM consumes.
 // One thread = one (frame, image row y, patch column px): reads 16 pixels x 3 channels (48 bytes,
@@ -375,6 +407,20 @@ int layernorm(const float* x, int64_t in_pitch, const float* gamma, const float*
   layernorm384_kernel<<<unsigned(blocks), 256, 0, stream>>>(x, in_pitch, gamma, beta, eps, rows, out_f32,
                                                             reinterpret_cast<__nv_bfloat16*>(out_bf16), split);
   return check_cuda(cudaGetLastError(), "layernorm launch");
+}
+
+int rowstats_cast(const float* x, int64_t rows, sais_bf16* xb, float* stats, cudaStream_t stream) {
+  if (rows == 0) return kOk;
+  if (!x || !xb || !stats || rows < 0) {
+    set_last_error("rowstats_cast: bad arguments");
+    return kErrInvalidArg;
+  }
+  int64_t blocks = (rows + 7) / 8;
+  const int64_t cap = int64_t(num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  LaunchScope ls(kClsLayerNorm, stream, double(rows) * D * 6);
+  rowstats_cast384_kernel<<<unsigned(blocks), 256, 0, stream>>>(x, rows, reinterpret_cast<__nv_bfloat16*>(xb), stats);
+  return check_cuda(cudaGetLastError(), "rowstats_cast launch");
 }
 
 int normalize_patchify_u8(const uint8_t* frames, int B, const float* mean3, const float* std3, sais_bf16* patches,

@@ -17,6 +17,12 @@
 // Split-precision mode (split3): A and W carry [hi | lo] bf16 halves and three passes hi·hi + lo·hi + hi·lo
 // accumulate into the same TMEM tile — an fp32-equivalent product on the bf16 tensor pipe.
 //
+// LayerNorm folding (fast path): LayerNorm is affine per row, so  LN(x) · Wᵀ + b  =  rstd · (x · W'ᵀ − mean · c) + d  with
+// W' = gamma ∘ W, c_n = Σ_k W'_nk, d_n = Σ_k beta_k W_nk + b_n.  A CONSUMER GEMM (qkv, fc1) therefore reads the raw
+// bf16 residual stream and applies mean / rstd per row in its epilogue (ln_stats_in); the PRODUCER GEMM before it
+// (proj, fc2) writes that bf16 copy next to the fp32 stream and per-row (sum, sum of squares) partials, one slot
+// per (n-tile, epilogue-warp half), so no LayerNorm kernel and no atomics are needed (ln_stats_out / out2_bf16).
+//
 // Reference call sites this kernel replaces: nn.Linear / conv-as-GEMM in
 // SAIS/scripts/dino-main/vision_transformer.py:60-63,82,90,126-130 and the in/out/FF projections of
 // nn.TransformerEncoderLayer reached via SAIS/scripts/prepare_model.py:213.
@@ -34,29 +40,35 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kEpiWarps = 8;
-constexpr int kGemmThreads = 32 * (2 + kEpiWarps);
-constexpr int kEpiThreads = 32 * kEpiWarps;
+// Epilogue warps per CTA (template parameter EW): 8 (two per TMEM lane quarter) or 16 (four per quarter).  The epilogue is
+// latency-bound with two warps per scheduler (ncu: 22% issue-active), so the bf16-output GEMMs of the big ViT shapes
+// run with 16; the fp32-output modes stay at 8 (their staging tiles are twice as large).
 constexpr int CW = 32;               // epilogue chunk width (columns)
 constexpr int kStageBufBytes = 4096;  // one staging buffer: 32 rows x 128 B (fp32) or 2 x (32 rows x 64 B) (bf16 hi, lo)
 
-template <int BLOCK_N, int CG>
+template <int BLOCK_N, int CG, int EW>
 struct GemmCfg {
+  static constexpr int kEpiWarps = EW;
+  static constexpr int kSub = EW / 4;                                    // epilogue warps per TMEM lane quarter
+  static constexpr int kChunksPerWarp = (BLOCK_N / CW + kSub - 1) / kSub;  // at most this many 32-column chunks per warp
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
   static constexpr int kBBytes = (BLOCK_N / CG) * BLOCK_K * 2;  // a CTA pair splits the W tile's rows
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = (2 * BLOCK_N <= 256) ? 256 : 512;
   static constexpr int kMaxStages = 6;
-  static constexpr int kTailBytes = 512 /*barriers*/ + kEpiWarps * (BLOCK_N / 2) * 4 /*bias slices*/;
+  static constexpr int kTailBytes = 512 /*barriers*/ + 2 * kEpiWarps * kChunksPerWarp * CW * 4 /*bias + column-sum slices*/;
   static constexpr int kSmemBudget = 227 * 1024 - 1024 /*align slack*/ - kTailBytes;
   // staging per epilogue warp: two buffers of 32 rows x 128 B (fp32 / bf16 hi+lo) or 32 rows x 64 B (plain bf16)
-  static int epi_bytes(bool wide, int nbuf) { return kEpiWarps * nbuf * (wide ? kStageBufBytes : kStageBufBytes / 2); }
-  static int stages(bool wide, int nbuf) {
-    const int s = (kSmemBudget - epi_bytes(wide, nbuf)) / kStageBytes;
+  // + xb: one extra 2 KB tile per warp for the bf16 copy a LayerNorm-producer GEMM writes next to its fp32 output
+  static int epi_bytes(bool wide, int nbuf, int xb = 0) {
+    return kEpiWarps * (nbuf * (wide ? kStageBufBytes : kStageBufBytes / 2) + xb);
+  }
+  static int stages(bool wide, int nbuf, int xb = 0) {
+    const int s = (kSmemBudget - epi_bytes(wide, nbuf, xb)) / kStageBytes;
     return s > kMaxStages ? kMaxStages : s;
   }
-  static int smem_bytes(bool wide, int nbuf) {
-    return stages(wide, nbuf) * kStageBytes + epi_bytes(wide, nbuf) + 1024 + kTailBytes;
+  static int smem_bytes(bool wide, int nbuf, int xb = 0) {
+    return stages(wide, nbuf, xb) * kStageBytes + epi_bytes(wide, nbuf, xb) + 1024 + kTailBytes;
   }
 };
 
@@ -70,6 +82,8 @@ struct GemmParams {
   int M, N, K;
   int act;
   int remap_group;
+  __nv_bfloat16* out2_bf16;  // LayerNorm-producer mode: bf16 copy of the fp32 output (pitch ldo2)
+  int64_t ldo2;
   int split3;         // 1: A and W hold [hi | lo] bf16 halves (2K columns); accumulate hi*hi + lo*hi + hi*lo
   int split_out;      // 1: out_bf16 has 2N columns: hi = bf16(v) at n, lo = bf16(v - hi) at N + n
   int exact_gelu;     // 1: erff-based GELU (precise mode); 0: tanh.approx form fitted to the erf definition
@@ -78,6 +92,13 @@ struct GemmParams {
   int stages;         // depth of the operand ring
   int stage_buf;      // bytes per epilogue staging buffer (4096 or 2048)
   int nbuf;           // staging buffers per epilogue warp (2..4)
+  // LayerNorm folding (see the file comment)
+  const float* ln_stats_in;  // consumer: [M][4][2] (sum, sumsq) partials of the K-wide input rows
+  const float* ln_colsum;    // consumer: c_n = sum_k W'_nk
+  float ln_eps;
+  float ln_inv_k;            // 1 / row length of the normalised input (= 1 / K)
+  float* ln_stats_out;       // producer: [M][4][2], slot = n_tile * 2 + warp half (needs N / BLOCK_N == 2)
+  int xb_buf;                // producer: bytes of the extra bf16 staging tile per warp (2048) or 0
 };
 
 // byte offset of 16-byte chunk `j` of row `r` inside a staging tile written/read by TMA
@@ -118,25 +139,28 @@ __device__ __forceinline__ void tma_store_2d_s(const CUtensorMap* m, uint32_t sm
 // CG = 1: one CTA per 128 x BLOCK_N tile.  CG = 2: a CTA pair (2-CTA cluster, tcgen05 cta_group::2) per
 // 256 x BLOCK_N tile — each CTA loads its own 128 rows of A but only HALF of the W tile, so the bytes every SM
 // pulls from L2 per flop drop by 1/3 (the measured limiter of the CG = 1 kernel at K = 384).
-template <int BLOCK_N, int MODE, int CG>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int BLOCK_N, int MODE, int CG, int EW>
+__global__ void __launch_bounds__(32 * (2 + EW), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
-                    const GemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N, CG>;
+                    const __grid_constant__ CUtensorMap tmap_out2, const GemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N, CG, EW>;
+  constexpr int kEpiWarps = EW;
+  constexpr int kSub = Cfg::kSub;
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled UMMA/TMA tiles need 1024-byte aligned bases
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int kStages = p.stages;
   uint8_t* epi_smem = smem + kStages * Cfg::kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + kEpiWarps * p.nbuf * p.stage_buf);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + kEpiWarps * (p.nbuf * p.stage_buf + p.xb_buf));
   uint64_t* full_bar = bars;                        // [kMaxStages]
   uint64_t* empty_bar = bars + Cfg::kMaxStages;     // [kMaxStages]
   uint64_t* tfull_bar = bars + 2 * Cfg::kMaxStages; // [2]
   uint64_t* tempty_bar = tfull_bar + 2;           // [2]
   uint64_t* res_bar = tempty_bar + 2;             // [kEpiWarps][2]
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(res_bar + 2 * kEpiWarps);
-  float* bias_smem = reinterpret_cast<float*>(bars + 64);  // [kEpiWarps][BLOCK_N / 2]
+  float* bias_smem = reinterpret_cast<float*>(bars + 64);                  // [kEpiWarps][kChunksPerWarp * CW]
+  float* csum_smem = bias_smem + kEpiWarps * (Cfg::kChunksPerWarp * CW);  // [kEpiWarps][kChunksPerWarp * CW]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -274,15 +298,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // ===================== epilogue (warps 0..7) =====================
     const int ew = warp;       // 0..7
     const int q = warp & 3;    // TMEM lane quarter this warp may access
-    const int half = ew >> 2;  // which of the two warps of the quarter: takes chunks half, half+2, ...
+    const int half = ew >> 2;  // which of the kSub warps of the quarter: takes chunks half, half + kSub, ...
     constexpr int NC = BLOCK_N / CW;
-    constexpr int NCW = NC / 2;  // chunks per warp per tile
+    constexpr int NCWmax = Cfg::kChunksPerWarp;
+    const int NCW = (NC - half + kSub - 1) / kSub;  // chunks of this warp per tile
     const int kBuf = p.stage_buf;
     const int nbuf = p.nbuf;
-    const uint32_t my_stage = smem_u32(epi_smem + ew * nbuf * kBuf);
+    const uint32_t my_stage = smem_u32(epi_smem + ew * (nbuf * kBuf + p.xb_buf));
     int bufi = 0;  // staging buffer ring index (it % nbuf)
     uint64_t* my_res_bar = res_bar + 2 * ew;
-    float* my_bias = bias_smem + ew * (NCW * CW);
+    float* my_bias = bias_smem + ew * (NCWmax * CW);
+    float* my_csum = csum_smem + ew * (NCWmax * CW);
+    const bool ln_in = (MODE == kModeBf16 || MODE == kModeBf16Gelu) && p.ln_stats_in != nullptr;
+    const bool ln_out = (MODE == kModeF32) && p.ln_stats_out != nullptr;
     const bool tma_epi = (MODE != kModeGeneric) || (p.remap_group == 0);
     const bool has_res = (MODE == kModeF32 || MODE == kModeGeneric) && tma_epi && (p.residual != nullptr);
     const bool f32_out = (MODE == kModeF32) || (MODE == kModeGeneric && p.out_f32 != nullptr);
@@ -297,18 +325,51 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       tma_load_2d_s(my_stage, &tmap_res, &my_res_bar[0], n0 + half * CW, m0 + q * 32);
     }
 
+    // Per-tile vectors (bias slice, folded-LayerNorm column sums, row statistics) are fetched one tile AHEAD into
+    // registers: the epilogue is the critical path of these GEMMs, so a global-load latency at the top of every tile
+    // would be paid in full (16 tiles x ~800 cycles = 7 us at batch 256).
+    float pf_bias[NCWmax], pf_csum[NCWmax];
+    float4 pf_s0 = make_float4(0.f, 0.f, 0.f, 0.f), pf_s1 = pf_s0;
+    auto prefetch_tile = [&](int t) {
+      if (t >= num_tiles) return;
+      const int pm0 = tile_m0(t), pn0 = (t % n_tiles) * BLOCK_N;
+#pragma unroll
+      for (int ci = 0; ci < NCWmax; ++ci) {
+        pf_bias[ci] = (ci < NCW && p.bias) ? __ldg(p.bias + pn0 + (half + kSub * ci) * CW + lane) : 0.0f;
+        if (ln_in) pf_csum[ci] = (ci < NCW) ? __ldg(p.ln_colsum + pn0 + (half + kSub * ci) * CW + lane) : 0.0f;
+      }
+      if (ln_in) {
+        const int r = pm0 + q * 32 + lane;
+        const float4* sp = reinterpret_cast<const float4*>(p.ln_stats_in + int64_t(r < p.M ? r : p.M - 1) * 8);
+        pf_s0 = __ldg(sp);
+        pf_s1 = __ldg(sp + 1);
+      }
+    };
+    prefetch_tile(unit0);
+
     int tidx = 0;
     const int erole = (ew == 0) ? 2 : (ew == 4 ? 3 : -1);
     for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++tidx) {
       const int m0 = tile_m0(tile);
       const int n0 = (tile % n_tiles) * BLOCK_N;
       if (erole >= 0 && lane == 0) stamp(erole, tidx, 0);
-      // this tile's bias slice -> per-warp smem while the MMAs are still running (keeps the global-load
-      // latency off the post-MMA critical path; later reads are broadcast LDS)
+      // this tile's vectors: registers -> per-warp smem (later reads are broadcast loads), then fetch the next tile's
       __syncwarp();
 #pragma unroll
-      for (int ci = 0; ci < NCW; ++ci)
-        my_bias[ci * CW + lane] = p.bias ? __ldg(p.bias + n0 + (half + 2 * ci) * CW + lane) : 0.0f;
+      for (int ci = 0; ci < NCWmax; ++ci)
+        if (ci < NCW) my_bias[ci * CW + lane] = pf_bias[ci];
+      float ln_rstd = 1.0f, ln_nmr = 0.0f;  // consumer: out = acc * rstd + (-mean * rstd) * c_n + d_n
+      if (ln_in) {
+#pragma unroll
+        for (int ci = 0; ci < NCWmax; ++ci)
+          if (ci < NCW) my_csum[ci * CW + lane] = pf_csum[ci];
+        const float mean = ((pf_s0.x + pf_s0.z) + (pf_s1.x + pf_s1.z)) * p.ln_inv_k;
+        const float var = fmaxf(((pf_s0.y + pf_s0.w) + (pf_s1.y + pf_s1.w)) * p.ln_inv_k - mean * mean, 0.0f);
+        ln_rstd = rsqrtf(var + p.ln_eps);
+        ln_nmr = -mean * ln_rstd;
+      }
+      prefetch_tile(tile + unit_stride);
+      uint64_t ln_sum2 = 0, ln_sq2 = 0;  // producer: this warp's share of the row statistics of the tile (packed pairs)
       __syncwarp();
 
       mbar_wait(&tfull_bar[astage], aphase);
@@ -321,18 +382,34 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       tmem_ld_32x32(t_row + half * CW, v);
 #pragma unroll 1
       for (int ci = 0; ci < NCW; ++ci) {
-        const int c = half + 2 * ci;
+        const int c = half + kSub * ci;
         const int n = n0 + c * CW;
         float f[32];
         tmem_ld_wait_dep(v);
+        {
+          // bias add (or the folded LayerNorm's  acc * rstd + (-mean * rstd) * c_n + d_n) in packed fp32x2; this is
+          // also what moves the accumulator out of v, so the next chunk's TMEM load can be issued right after it
+          const ulonglong2* b2p = reinterpret_cast<const ulonglong2*>(my_bias + ci * CW);
+          if (ln_in) {
+            const ulonglong2* c2p = reinterpret_cast<const ulonglong2*>(my_csum + ci * CW);
+            const uint64_t rs2 = pack2(ln_rstd, ln_rstd), nm2 = pack2(ln_nmr, ln_nmr);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            for (int j = 0; j < 8; ++j) {
+              const ulonglong2 b2 = b2p[j], c2 = c2p[j];
+              unpack2(fma2(pack2u(v[4 * j], v[4 * j + 1]), rs2, fma2(nm2, c2.x, b2.x)), f[4 * j], f[4 * j + 1]);
+              unpack2(fma2(pack2u(v[4 * j + 2], v[4 * j + 3]), rs2, fma2(nm2, c2.y, b2.y)), f[4 * j + 2], f[4 * j + 3]);
+            }
+          } else {
 #pragma unroll
-        for (int j = 0; j < 32; j += 8)  // pin the copies before v is handed to the next asynchronous load
-          asm volatile("" : "+f"(f[j]), "+f"(f[j + 1]), "+f"(f[j + 2]), "+f"(f[j + 3]), "+f"(f[j + 4]), "+f"(f[j + 5]),
-                            "+f"(f[j + 6]), "+f"(f[j + 7]));
+            for (int j = 0; j < 8; ++j) {
+              const ulonglong2 b2 = b2p[j];
+              unpack2(add2(pack2u(v[4 * j], v[4 * j + 1]), b2.x), f[4 * j], f[4 * j + 1]);
+              unpack2(add2(pack2u(v[4 * j + 2], v[4 * j + 3]), b2.y), f[4 * j + 2], f[4 * j + 3]);
+            }
+          }
+        }
         if (ci + 1 < NCW) {
-          tmem_ld_32x32(t_row + (c + 2) * CW, v);  // next chunk's accumulator streams in under this chunk's math
+          tmem_ld_32x32(t_row + (c + kSub) * CW, v);  // next chunk's accumulator streams in under this chunk's math
         } else {  // last TMEM read of this tile by this warp: hand the accumulator back early
           tc_fence_before();
           if (lane == 0) {
@@ -340,17 +417,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             else mbar_arrive_cluster(leader_smem_u32(&tempty_bar[astage]));
           }
         }
-        {
-          const float4* b4p = reinterpret_cast<const float4*>(my_bias + ci * CW);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b4 = b4p[j];
-            f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
-          }
-        }
         if (MODE == kModeBf16Gelu) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = gelu_erf_fast(f[j]);
+          for (int j = 0; j < 32; j += 2) gelu_erf_fast2(f[j], f[j + 1]);
         } else if (MODE == kModeBf16) {
           if (p.act == 2) {
 #pragma unroll
@@ -363,7 +432,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               for (int j = 0; j < 32; ++j) f[j] = gelu_erf_exact(f[j]);
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = gelu_erf_fast(f[j]);
+              for (int j = 0; j < 32; j += 2) gelu_erf_fast2(f[j], f[j + 1]);
             }
           } else if (p.act == 2) {
 #pragma unroll
@@ -378,7 +447,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 r4 = lds128(buf + stage_off_f32(lane, j));
-              f[4 * j] += r4.x; f[4 * j + 1] += r4.y; f[4 * j + 2] += r4.z; f[4 * j + 3] += r4.w;
+              unpack2(add2(pack2(f[4 * j], f[4 * j + 1]), pack2(r4.x, r4.y)), f[4 * j], f[4 * j + 1]);
+              unpack2(add2(pack2(f[4 * j + 2], f[4 * j + 3]), pack2(r4.z, r4.w)), f[4 * j + 2], f[4 * j + 3]);
+            }
+            if (ln_out) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                const uint64_t x2 = pack2(f[j], f[j + 1]);
+                ln_sum2 = add2(ln_sum2, x2);
+                ln_sq2 = fma2(x2, x2, ln_sq2);
+              }
+              // bf16 copy of the row segment straight from registers (64 contiguous bytes per thread): no staging
+              // tile, so the operand ring keeps its depth
+              if (row < p.M) {
+                uint4* xp = reinterpret_cast<uint4*>(p.out2_bf16 + int64_t(row) * p.ldo2 + n);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  xp[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                     pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+              }
             }
           } else {
             // the store issued from this buffer nbuf chunks ago must have finished reading it
@@ -416,7 +503,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               // every earlier store has finished reading smem -> the other buffer is free: prefetch the
               // residual tile of this warp's next chunk into it
               tma_store_wait_read<0>();
-              int nt = tile, nc = c + 2;
+              int nt = tile, nc = c + kSub;
               if (nc >= NC) {
                 nt = tile + unit_stride;
                 nc = half;
@@ -477,6 +564,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
         }
       }
+      if (ln_out && row < p.M) {
+        const int slot = (tile % n_tiles) * 2 + half;
+        float s0, s1, q0, q1;
+        unpack2(ln_sum2, s0, s1);
+        unpack2(ln_sq2, q0, q1);
+        *reinterpret_cast<float2*>(p.ln_stats_out + int64_t(row) * 8 + slot * 2) = make_float2(s0 + s1, q0 + q1);
+      }
       if (++astage == 2) {
         astage = 0;
         aphase ^= 1;
@@ -494,10 +588,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 }
 
-template <int BLOCK_N, int MODE, int CG>
+template <int BLOCK_N, int MODE, int CG, int EW>
 int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N, CG>;
-  CUtensorMap ta, tb, tout, tres;
+  using Cfg = GemmCfg<BLOCK_N, CG, EW>;
+  CUtensorMap ta, tb, tout, tres, tout2;
   const uint64_t kcols = uint64_t(a.K) * (a.split3 ? 2 : 1);
   int rc = make_tmap_2d(&ta, a.a, kTmapBf16, uint64_t(a.M), kcols, uint64_t(a.lda), BLOCK_M, BLOCK_K, 128);
   if (rc) return rc;
@@ -507,6 +601,7 @@ int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
   if (rc) return rc;
   tout = ta;
   tres = ta;
+  tout2 = ta;
   if (a.remap_group == 0) {
     if (a.out_f32)
       rc = make_tmap_2d(&tout, a.out_f32, kTmapF32, uint64_t(a.M), uint64_t(a.N), uint64_t(a.ldo32), 32, CW, 128);
@@ -518,11 +613,15 @@ int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
       rc = make_tmap_2d(&tres, a.residual, kTmapF32, uint64_t(a.M), uint64_t(a.N), uint64_t(a.ldr), 32, CW, 128);
       if (rc) return rc;
     }
+    if (a.out2_bf16) {
+      rc = make_tmap_2d(&tout2, a.out2_bf16, kTmapBf16, uint64_t(a.M), uint64_t(a.N), uint64_t(a.ldo2), 32, CW, 64);
+      if (rc) return rc;
+    }
   }
 
   static bool attr_set = false;
   if (!attr_set) {
-    rc = check_cuda(cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, MODE, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    rc = check_cuda(cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, MODE, CG, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024),
                     "cudaFuncSetAttribute(gemm)");
     if (rc) return rc;
@@ -559,7 +658,15 @@ int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
   int nbuf = 2;
   if (!a.residual && env_nbuf >= 2 && env_nbuf <= 4) nbuf = env_nbuf;
   p.nbuf = nbuf;
-  p.stages = Cfg::stages(wide, nbuf);
+  p.ln_stats_in = a.ln_stats_in;
+  p.ln_colsum = a.ln_colsum;
+  p.ln_eps = a.ln_eps;
+  p.ln_inv_k = 1.0f / float(a.K);
+  p.ln_stats_out = a.ln_stats_out;
+  p.out2_bf16 = reinterpret_cast<__nv_bfloat16*>(a.out2_bf16);
+  p.ldo2 = a.ldo2;
+  p.xb_buf = 0;
+  p.stages = Cfg::stages(wide, nbuf, p.xb_buf);
   p.stage_buf = wide ? kStageBufBytes : kStageBufBytes / 2;
   const int units = ((m_tiles + cluster - 1) / cluster) * (p.N / BLOCK_N);
   int grid = units * cluster < num_sms() ? units * cluster : num_sms();
@@ -567,8 +674,8 @@ int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
   LaunchScope ls(kClsGemm, stream, 2.0 * double(a.M) * double(a.N) * double(a.K) * (a.split3 ? 3 : 1));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kGemmThreads);
-  cfg.dynamicSmemBytes = Cfg::smem_bytes(wide, nbuf);
+  cfg.blockDim = dim3(32 * (2 + EW));
+  cfg.dynamicSmemBytes = Cfg::smem_bytes(wide, nbuf, p.xb_buf);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -577,7 +684,7 @@ int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  rc = check_cuda(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BLOCK_N, MODE, CG>, ta, tb, tout, tres, p),
+  rc = check_cuda(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BLOCK_N, MODE, CG, EW>, ta, tb, tout, tres, tout2, p),
                   "gemm_tcgen05_kernel launch");
   if (p.dbg) {  // dev knob: dump CTA 0's timeline (cycles relative to the first stamp), last call wins
     static long long h[kDbgN];
@@ -653,6 +760,19 @@ int gemm_bias_act(const SaisGemmArgs& a, cudaStream_t stream, int force_block_n)
     set_last_error("gemm: bad activation %d", a.act);
     return kErrInvalidArg;
   }
+  if (a.ln_stats_in && (!a.ln_colsum || !a.bias || !a.out_bf16 || a.residual || a.split3 || a.split_out || a.remap_group ||
+                        a.act == 2)) {
+    set_last_error("gemm: ln_stats_in needs ln_colsum, bias, a bf16 output and act none/GELU (no residual / split / remap)");
+    return kErrInvalidArg;
+  }
+  if (a.ln_stats_out || a.out2_bf16) {
+    if (!a.ln_stats_out || !a.out2_bf16 || !a.out_f32 || !a.residual || a.N != 384 || a.act != 0 || a.split_out ||
+        a.remap_group || a.ldo2 % 8 || (reinterpret_cast<uintptr_t>(a.out2_bf16) & 15)) {
+      set_last_error("gemm: ln_stats_out / out2_bf16 go together and need N = 384, fp32 output + residual, no activation");
+      return kErrInvalidArg;
+    }
+    force_block_n = 192;  // the statistics slots are (n-tile, warp half): exactly two n-tiles per row
+  }
   static const int env_bn = getenv("SAIS_GEMM_FORCE_BN") ? atoi(getenv("SAIS_GEMM_FORCE_BN")) : 0;
   if (!force_block_n && env_bn && a.N % env_bn == 0) force_block_n = env_bn;
   const int bn = force_block_n ? force_block_n : pick_block_n(a.M, a.N);
@@ -671,12 +791,21 @@ int gemm_bias_act(const SaisGemmArgs& a, cudaStream_t stream, int force_block_n)
   static const int env_cg = getenv("SAIS_GEMM_CG") ? atoi(getenv("SAIS_GEMM_CG")) : 0;
   const int64_t m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M;
   const int cg = env_cg ? env_cg : (m_tiles * (a.N / bn) >= 2 * num_sms() ? 2 : 1);
-#define SAIS_GEMM_DISPATCH_CG(BN, CG)                                           \
-  switch (mode) {                                                               \
-    case kModeBf16: return launch_gemm<BN, kModeBf16, CG>(a, stream);           \
-    case kModeBf16Gelu: return launch_gemm<BN, kModeBf16Gelu, CG>(a, stream);   \
-    case kModeF32: return launch_gemm<BN, kModeF32, CG>(a, stream);             \
-    default: return launch_gemm<BN, kModeGeneric, CG>(a, stream);               \
+  // 16 epilogue warps for the bf16-output modes once every SM has several tiles to chew through (SAIS_GEMM_EW=8|16 forces)
+  static const int env_ew = getenv("SAIS_GEMM_EW") ? atoi(getenv("SAIS_GEMM_EW")) : 0;
+  const int ewn = (env_ew == 16 || env_ew == 12) ? env_ew : 8;
+#define SAIS_GEMM_DISPATCH_CG(BN, CG)                                                              \
+  switch (mode) {                                                                                  \
+    case kModeBf16:                                                                                \
+      return ewn == 16   ? launch_gemm<BN, kModeBf16, CG, 16>(a, stream)                           \
+             : ewn == 12 ? launch_gemm<BN, kModeBf16, CG, 12>(a, stream)                           \
+                         : launch_gemm<BN, kModeBf16, CG, 8>(a, stream);                           \
+    case kModeBf16Gelu:                                                                            \
+      return ewn == 16   ? launch_gemm<BN, kModeBf16Gelu, CG, 16>(a, stream)                       \
+             : ewn == 12 ? launch_gemm<BN, kModeBf16Gelu, CG, 12>(a, stream)                       \
+                         : launch_gemm<BN, kModeBf16Gelu, CG, 8>(a, stream);                       \
+    case kModeF32: return launch_gemm<BN, kModeF32, CG, 8>(a, stream);                             \
+    default: return launch_gemm<BN, kModeGeneric, CG, 8>(a, stream);                               \
   }
 #define SAIS_GEMM_DISPATCH(BN) \
   if (cg == 2) { SAIS_GEMM_DISPATCH_CG(BN, 2) } else { SAIS_GEMM_DISPATCH_CG(BN, 1) }

@@ -29,9 +29,15 @@ int pick_block_n(int64_t M, int64_t N);
 int vit_mlp_fused(const sais_bf16* xn, const sais_bf16* w1, const float* b1, const sais_bf16* w2, const float* b2,
                   float* x, int64_t rows, cudaStream_t stream);
 
+// gemm_rowln.cu: x += A · Wᵀ + bias (fp32 [M,384], in place); xn = LayerNorm(x) as bf16 [M,384] (xn may be null)
+int gemm_residual_layernorm(const sais_bf16* a, int64_t lda, const sais_bf16* w, int64_t ldw, const float* bias,
+                            float* x, const float* gamma, const float* beta, float eps, sais_bf16* xn, int64_t M,
+                            int64_t K, cudaStream_t stream);
+
 // elementwise.cu
 int layernorm(const float* x, int64_t in_pitch, const float* gamma, const float* beta, float eps, int64_t rows,
               float* out_f32, sais_bf16* out_bf16, cudaStream_t stream, int split = 0);
+int rowstats_cast(const float* x, int64_t rows, sais_bf16* xb, float* stats, cudaStream_t stream);
 int normalize_patchify_u8(const uint8_t* frames, int B, const float* mean3, const float* std3, sais_bf16* patches,
                           cudaStream_t stream, int split = 0);
 int patchify_f32(const float* frames, int B, sais_bf16* patches, cudaStream_t stream, int split = 0);

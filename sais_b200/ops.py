@@ -23,7 +23,8 @@ def split_bf16(t):
 
 
 def gemm_bias_act(a, w, bias=None, act=_lib.ACT_NONE, residual=None, out_dtype=torch.bfloat16, out=None,
-                  row_add=None, remap_group=0, split3=False, split_out=False):
+                  row_add=None, remap_group=0, split3=False, split_out=False, ln_stats_in=None, ln_colsum=None,
+                  ln_eps=1e-6, ln_stats_out=None, out2=None):
     """out = act(a @ w.T + bias) [+ residual].  a: bf16 [M,K]; w: bf16 [N,K]; bias/residual fp32.
     split3: a and w are [hi | lo] halves ([M,2K], [N,2K], see split_bf16) and the product is fp32-equivalent;
     split_out: the bf16 output is written as [hi | lo] ([M,2N])."""
@@ -51,8 +52,28 @@ def gemm_bias_act(a, w, bias=None, act=_lib.ACT_NONE, residual=None, out_dtype=t
     g.ldr = residual.stride(0) if residual is not None else 0
     g.act, g.remap_group = act, remap_group
     g.split3, g.split_out = int(split3), int(split_out)
+    # LayerNorm folding (see include/sais_b200.h): consumer side / producer side
+    g.ln_stats_in, g.ln_colsum, g.ln_eps = ptr(ln_stats_in), ptr(ln_colsum), float(ln_eps)
+    g.ln_stats_out, g.out2_bf16 = ptr(ln_stats_out), ptr(out2)
+    g.ldo2 = out2.stride(0) if out2 is not None else 0
     check(lib().sais_gemm_bias_act(C.byref(g), current_stream()), "sais_gemm_bias_act")
     return out
+
+
+def rowstats_cast(x):
+    """fp32 [rows,384] -> (bf16 copy [rows,384], stats fp32 [rows,8] = {sum, sum of squares, 0...})."""
+    require_cuda(x, "x")
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == 384
+    xb = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    stats = torch.empty((x.shape[0], 8), device=x.device, dtype=torch.float32)
+    check(lib().sais_rowstats_cast(ptr(x), x.shape[0], ptr(xb), ptr(stats), current_stream()), "sais_rowstats_cast")
+    return xb, stats
+
+
+def fold_layernorm(gamma, beta, weight, bias):
+    """LN(x) W^T + b = rstd (x W'^T - mean c) + d:  returns (W' bf16 [N,K], c fp32 [N], d fp32 [N])."""
+    wg = (weight.float() * gamma.float()[None, :]).to(torch.bfloat16).contiguous()
+    return wg, wg.float().sum(dim=1).contiguous(), (weight.float() @ beta.float() + bias.float()).contiguous()
 
 
 def vit_mlp(xn, fc1_w, fc1_b, fc2_w, fc2_b, x):
@@ -67,6 +88,20 @@ def vit_mlp(xn, fc1_w, fc1_b, fc2_w, fc2_b, x):
     check(lib().sais_vit_mlp(ptr(xn), ptr(fc1_w), ptr(fc1_b), ptr(fc2_w), ptr(fc2_b), ptr(x), xn.shape[0],
                              current_stream()), "sais_vit_mlp")
     return x
+
+
+def gemm_residual_layernorm(a, w, bias, x, gamma=None, beta=None, eps=1e-6, want_ln=True):
+    """x += a @ w.T + bias (fp32 [M,384], IN PLACE); returns (x, LayerNorm(x) as bf16 [M,384] or None)."""
+    require_cuda(a, "a")
+    require_cuda(x, "x")
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.dtype == torch.float32
+    assert a.stride(-1) == 1 and w.stride(-1) == 1 and x.is_contiguous() and x.shape[1] == 384 and w.shape[0] == 384
+    M, K = a.shape
+    xn = torch.empty((M, 384), device=x.device, dtype=torch.bfloat16) if want_ln else None
+    check(lib().sais_gemm_residual_layernorm(ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(bias), ptr(x), ptr(gamma),
+                                             ptr(beta), float(eps), ptr(xn), M, K, current_stream()),
+          "sais_gemm_residual_layernorm")
+    return x, xn
 
 
 def layernorm(x, gamma, beta, eps, out_f32=False, out_bf16=True, in_pitch=None, rows=None, split_out=False):

@@ -139,6 +139,16 @@ class VisionTransformer(nn.Module):
             keep.append(t)
             return t
 
+        def fold(norm, linear):
+            gamma = norm.weight.detach().to(dev, torch.float32)
+            beta = norm.bias.detach().to(dev, torch.float32)
+            wt = linear.weight.detach().to(dev, torch.float32)
+            wg = (wt * gamma[None, :]).to(torch.bfloat16).contiguous()
+            c = wg.float().sum(dim=1).contiguous()  # column sums of the operand the tensor cores actually see
+            d = (wt @ beta + linear.bias.detach().to(dev, torch.float32)).contiguous()
+            keep.extend((wg, c, d))
+            return wg, c, d
+
         w = SaisVitWeights()
         w.patch_w = ptr(bf(self.patch_embed.proj.weight.reshape(DIM, -1)))
         w.patch_b = ptr(f32(self.patch_embed.proj.bias))
@@ -152,6 +162,10 @@ class VisionTransformer(nn.Module):
             b.ln2_w, b.ln2_b = ptr(f32(blk.norm2.weight)), ptr(f32(blk.norm2.bias))
             b.fc1_w, b.fc1_b = ptr(bf(blk.mlp.fc1.weight)), ptr(f32(blk.mlp.fc1.bias))
             b.fc2_w, b.fc2_b = ptr(bf(blk.mlp.fc2.weight)), ptr(f32(blk.mlp.fc2.bias))
+            if not precise:
+                # LayerNorm folded into the consumer GEMM: LN(x) W^T + b = rstd (x W'^T - mean c) + d  (sais_b200.h)
+                b.qkv_wg, b.qkv_c, b.qkv_d = (ptr(t) for t in fold(blk.norm1, blk.attn.qkv))
+                b.fc1_wg, b.fc1_c, b.fc1_d = (ptr(t) for t in fold(blk.norm2, blk.mlp.fc1))
         w.norm_w, w.norm_b = ptr(f32(self.norm.weight)), ptr(f32(self.norm.bias))
         self._packed[bool(precise)] = (key, (w, keep))
         return w, keep

@@ -40,11 +40,11 @@ def test_struct_layouts_match_header_sizes():
     """ctypes mirrors of the header structs: pointer-count bookkeeping catches a forgotten field."""
     import ctypes as C
     from sais_b200 import _lib
-    assert C.sizeof(_lib.SaisVitBlockWeights) == 12 * 8
-    assert C.sizeof(_lib.SaisVitWeights) == (4 + 12 * 12 + 2) * 8
+    assert C.sizeof(_lib.SaisVitBlockWeights) == 18 * 8
+    assert C.sizeof(_lib.SaisVitWeights) == (4 + 12 * 18 + 2) * 8
     assert C.sizeof(_lib.SaisTemporalLayerWeights) == 12 * 8
     assert C.sizeof(_lib.SaisTemporalWeights) == 2 * 8 + 8 + 4 * 12 * 8  # n_pos int32 padded to 8
-    assert C.sizeof(_lib.SaisGemmArgs) == 7 * 8 + 8 * 8 + 4 * 4
+    assert C.sizeof(_lib.SaisGemmArgs) == 7 * 8 + 8 * 8 + 4 * 4 + 5 * 8 + 2 * 4
 
 
 def test_no_cpu_fallback():

@@ -157,6 +157,93 @@ def test_gemm_rejects_bad_shapes(dev):
         ops.gemm_bias_act(a, w)  # K not a multiple of 64 (and pitch not 16-byte aligned)
 
 
+# ------------------------------------------------------------------------------------------------ LayerNorm folding
+@pytest.mark.parametrize("rows", [1, 33, 4099])
+def test_rowstats_cast(dev, rows):
+    from sais_b200 import ops
+    x = rnd(rows, 384, seed=rows) * 2 + 0.7
+    xb, stats = ops.rowstats_cast(x.to(dev))
+    assert torch.equal(xb.cpu().float(), bf(x))
+    st = stats.cpu()
+    assert torch.allclose(st[:, 0], x.sum(1), atol=1e-3, rtol=1e-5)
+    assert torch.allclose(st[:, 1], (x * x).sum(1), atol=1e-3, rtol=1e-5)
+    assert torch.all(st[:, 2:] == 0)
+
+
+@pytest.mark.parametrize("M,N,act", [(300, 1152, 0), (5000, 1536, 1), (11, 1152, 0), (197 * 160, 1536, 1)])
+def test_gemm_layernorm_folded_consumer(dev, M, N, act):
+    """qkv / fc1 with norm1 / norm2 folded in: raw bf16 rows in, mean / rstd applied in the epilogue."""
+    from sais_b200 import ops
+    x = rnd(M, 384, seed=M) * 1.7 + 0.4
+    x[:, 5] *= 8.0  # an outlier channel, as trained ViTs have
+    gamma, beta = 1 + 0.2 * rnd(384, seed=1), 0.2 * rnd(384, seed=2)
+    w, b = rnd(N, 384, seed=3, std=1 / math.sqrt(384)), rnd(N, seed=4, std=0.3)
+    wg, c, d = ops.fold_layernorm(gamma, beta, w, b)
+    xb, stats = ops.rowstats_cast(x.to(dev))
+    out = ops.gemm_bias_act(xb, wg.to(dev), d.to(dev), act=act, ln_stats_in=stats, ln_colsum=c.to(dev), ln_eps=1e-6)
+    got = out.cpu().float()
+    # (a) the algebra, on exactly the operands the kernel sees: rstd (bf16(x) W'^T - mean c) + d
+    mean, var = x.double().mean(1, keepdim=True), x.double().var(1, unbiased=False, keepdim=True)
+    rstd = (var + 1e-6).rsqrt()
+    y = rstd * (bf(x).double() @ wg.double().t() - mean * c.double()) + d.double()
+    if act == 1:
+        y = 0.5 * y * (1 + torch.erf(y / math.sqrt(2)))
+    assert torch.allclose(got, y.float(), atol=2e-3, rtol=2 ** -8), (got - y.float()).abs().max()
+    # (b) against the reference formulation LayerNorm -> Linear in fp32: differs by the bf16 rounding of x and W'
+    ref = O.layer_norm(x, gamma, beta, 1e-6) @ w.t() + b
+    if act == 1:
+        ref = torch.nn.functional.gelu(ref)
+    assert torch.allclose(got, ref, atol=3e-2, rtol=2e-2), (got - ref).abs().max()
+    # same relative error as the unfolded bf16 path (bf16(LN(x)) @ bf16(W)): ~0.25 % in L2 (+ bf16 output rounding)
+    assert float((got.double() - ref.double()).norm() / ref.double().norm()) < 5e-3
+
+
+@pytest.mark.parametrize("M,K", [(300, 384), (777, 1536), (197 * 96, 384), (256 * 80 - 57, 1536)])
+def test_gemm_layernorm_producer(dev, M, K):
+    """proj / fc2: fp32 residual update + bf16 copy + per-row (sum, sumsq) partials in four slots."""
+    from sais_b200 import ops
+    a, w, bias = rnd(M, K, seed=M), rnd(384, K, seed=K, std=1 / math.sqrt(K)), rnd(384, seed=7, std=0.5)
+    x = rnd(M, 384, seed=9) * 2 + 0.3
+    xd = x.to(dev).clone()
+    stats = torch.full((M, 8), float("nan"), device=dev)
+    xb = torch.empty((M, 384), device=dev, dtype=torch.bfloat16)
+    ops.gemm_bias_act(a.to(dev).bfloat16(), w.to(dev).bfloat16(), bias.to(dev), residual=xd, out=xd,
+                      ln_stats_out=stats, out2=xb)
+    got = xd.cpu()
+    assert torch.allclose(got, _gemm_ref(a, w, bias, 0, x), atol=2e-4, rtol=1e-4)
+    assert torch.equal(xb.cpu().float(), bf(got))
+    st = stats.cpu().view(M, 4, 2).sum(1)
+    assert torch.allclose(st[:, 0], got.sum(1), atol=2e-3, rtol=1e-5)
+    assert torch.allclose(st[:, 1], (got * got).sum(1), atol=2e-3, rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ GEMM + residual + LN
+@pytest.mark.parametrize("M,K,want_ln", [(1, 384, True), (300, 384, True), (777, 1536, True), (256, 384, False),
+                                         (197 * 96, 384, True), (256 * 80 - 57, 1536, True), (5000, 1536, False)])
+def test_gemm_residual_layernorm(dev, M, K, want_ln):
+    """x += A W^T + b in place (proj / fc2) and xn = LayerNorm(x) from the same epilogue."""
+    from sais_b200 import ops
+    a = rnd(M, K, seed=M + K)
+    w = rnd(384, K, seed=K, std=1 / math.sqrt(K))
+    bias = rnd(384, seed=7, std=0.5)
+    x = rnd(M, 384, seed=9) * 2 + 0.3
+    gamma, beta = 1 + 0.1 * rnd(384, seed=1), 0.1 * rnd(384, seed=2)
+    xd = x.to(dev).clone()
+    _, xn = ops.gemm_residual_layernorm(a.to(dev).bfloat16(), w.to(dev).bfloat16(), bias.to(dev), xd,
+                                        gamma.to(dev) if want_ln else None, beta.to(dev) if want_ln else None,
+                                        eps=1e-6, want_ln=want_ln)
+    ref_x = _gemm_ref(a, w, bias, 0, x)
+    got_x = xd.cpu()
+    assert torch.allclose(got_x, ref_x, atol=2e-4, rtol=1e-4), (got_x - ref_x).abs().max()
+    if want_ln:
+        # LayerNorm of the kernel's own fp32 row (exact two-pass statistics), rounded once to bf16
+        ref_n = O.layer_norm(got_x, gamma, beta, 1e-6)
+        got_n = xn.cpu().float()
+        assert torch.allclose(got_n, ref_n, atol=2e-5 + 2 ** -8 * float(ref_n.abs().max()), rtol=2 ** -8)
+        assert (got_n - bf(ref_n)).abs().max() <= 2 ** -6  # at most one bf16 ulp of O(3) values
+        assert ((got_n - bf(ref_n)) != 0).float().mean() < 0.01
+
+
 # ------------------------------------------------------------------------------------------------ fused MLP
 def _mlp_ref(xn, w1, b1, w2, b2, x):
     """fc1 -> erf-GELU -> (hidden rounded to bf16, as the kernel hands it to the second MMA) -> fc2 -> + residual."""

@@ -21,6 +21,11 @@ SHAPES = [  # name, M, N, K, act, residual, f32 out, split3
     ("fc2", M, 384, 1536, 0, True, True, False),
     ("fc2-bf16out", M, 384, 1536, 0, False, False, False),
     ("tmp-ff1-split", 16384, 2048, 384, 2, False, False, True),
+    # LayerNorm-folded variants (name suffix selects the mode)
+    ("qkv+lnin", M, 1152, 384, 0, False, False, False),
+    ("fc1+lnin", M, 1536, 384, 1, False, False, False),
+    ("proj+lnout", M, 384, 384, 0, True, True, False),
+    ("fc2+lnout", M, 384, 1536, 0, True, True, False),
 ]
 only = sys.argv[2].split(",") if len(sys.argv) > 2 else None
 if only:
@@ -33,14 +38,19 @@ for name, m, n, k, act, res, f32, split in SHAPES:
     bias = torch.randn(n, device=dev)
     r = torch.randn(m, n, device=dev) if res else None
     out = torch.empty(m, n, device=dev, dtype=torch.float32 if f32 else torch.bfloat16)
+    kw = {}
+    if name.endswith("+lnin"):
+        kw = dict(ln_stats_in=torch.rand(m, 8, device=dev) * 384, ln_colsum=torch.randn(n, device=dev))
+    elif name.endswith("+lnout"):
+        kw = dict(ln_stats_out=torch.empty(m, 8, device=dev), out2=torch.empty(m, n, device=dev, dtype=torch.bfloat16))
     for _ in range(3):
-        ops.gemm_bias_act(a, w, bias, act=act, residual=r, out=out, split3=split)
+        ops.gemm_bias_act(a, w, bias, act=act, residual=r, out=out, split3=split, **kw)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     iters = 20
     e0.record()
     for _ in range(iters):
-        ops.gemm_bias_act(a, w, bias, act=act, residual=r, out=out, split3=split)
+        ops.gemm_bias_act(a, w, bias, act=act, residual=r, out=out, split3=split, **kw)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
