@@ -97,7 +97,11 @@ typedef struct {
   sais_bf16* out2_bf16;
   int64_t ldo2;
   float ln_eps;
-  int32_t reserved_;
+  /* Accumulate mode (0 = off).  k_slices >= 1: out_f32 += A · Wᵀ — the product is ADDED to what out_f32 already holds
+   * (the caller pre-loads residual + bias there), computed in k_slices slices of K by independent CTAs whose partial
+   * sums meet in L2 through TMA reduce-add stores.  For small-M GEMMs with a long K (the temporal FF2) this spreads the
+   * operand stream over many SMs instead of 9.  bias, residual and act must be NULL / 0. */
+  int32_t k_slices;
 } SaisGemmArgs;
 int sais_gemm_bias_act(const SaisGemmArgs* args, sais_stream_t stream);
 

@@ -31,7 +31,7 @@ class SaisGemmArgs(C.Structure):
         ("lda", C.c_int64), ("ldw", C.c_int64), ("ldr", C.c_int64), ("ldo32", C.c_int64), ("ldo16", C.c_int64),
         ("act", C.c_int32), ("remap_group", C.c_int32), ("split3", C.c_int32), ("split_out", C.c_int32),
         ("ln_stats_in", _p), ("ln_colsum", _p), ("ln_stats_out", _p), ("out2_bf16", _p), ("ldo2", C.c_int64),
-        ("ln_eps", C.c_float), ("reserved_", C.c_int32),
+        ("ln_eps", C.c_float), ("k_slices", C.c_int32),
     ]
 
 

@@ -469,7 +469,7 @@ int sais_temporal_attention(const float* qkv, const int32_t* seq_offsets, const 
 size_t sais_temporal_workspace_bytes(int32_t total_tokens) {
   if (total_tokens <= 0) return 0;
   const size_t t = size_t(total_tokens);
-  return a256(t * SAIS_VIT_DIM * 4) * 2       // x fp32, y fp32 (pre-norm sum)
+  return a256(t * SAIS_VIT_DIM * 4) * 3       // x fp32, y / y2 fp32 (pre-norm sums)
          + a256(t * SAIS_VIT_DIM * 2 * 2) * 2 // x [hi|lo] bf16, attention output [hi|lo] bf16
          + a256(t * 3 * SAIS_VIT_DIM * 4)     // qkv fp32
          + a256(t * SAIS_TMP_FF * 2 * 2);     // FF hidden [hi|lo] bf16
@@ -502,6 +502,7 @@ int sais_temporal_forward(const SaisTemporalWeights* w, const float* x_frames, c
   Arena ar{static_cast<uint8_t*>(workspace), workspace_bytes};
   float* x = static_cast<float*>(ar.take(t * Dm * 4));
   float* y = static_cast<float*>(ar.take(t * Dm * 4));
+  float* y2 = static_cast<float*>(ar.take(t * Dm * 4));
   sais_bf16* xb = static_cast<sais_bf16*>(ar.take(t * Dm * 4));
   sais_bf16* ao = static_cast<sais_bf16*>(ar.take(t * Dm * 4));
   float* qkv = static_cast<float*>(ar.take(t * 3 * Dm * 4));
@@ -510,9 +511,15 @@ int sais_temporal_forward(const SaisTemporalWeights* w, const float* x_frames, c
     set_last_error("temporal_forward: workspace carve failed");
     return kErrWorkspace;
   }
+  // Small batches (the C1 / bench head: a few hundred tokens) are latency-bound: each residual GEMM would run on 9 CTAs,
+  // every one streaming its whole K range through one SM's L2 port (FF2: 3 MB, ~30 us).  There the residual GEMMs run in
+  // accumulate mode: the kernel before them pre-loads y = x + bias, the GEMM adds its product in K slices spread over
+  // many SMs (TMA reduce-add in L2).  Large batches keep the fused bias + residual epilogue.
+  static const int env_sk = getenv("SAIS_TMP_SPLITK") ? atoi(getenv("SAIS_TMP_SPLITK")) : -1;
+  const bool splitk = env_sk >= 0 ? env_sk != 0 : total_tokens <= 2048;
   int rc;
   if ((rc = temporal_prep(x_frames, seq_offsets, nseq, total_tokens, w->frame_cls, w->frame_pos, w->n_pos, x, xb,
-                          stream)))
+                          stream, splitk ? y : nullptr, splitk ? w->layers[0].out_b : nullptr)))
     return rc;
   SaisGemmArgs g;
   for (int l = 0; l < SAIS_TMP_LAYERS; ++l) {
@@ -529,22 +536,29 @@ int sais_temporal_forward(const SaisTemporalWeights* w, const float* x_frames, c
       return rc;
     // out-proj + residual -> y ; x = LN1(y)
     memset(&g, 0, sizeof(g));
-    g.a = ao; g.w = lw.out_w; g.bias = lw.out_b; g.residual = x; g.out_f32 = y; g.split3 = 1;
-    g.M = total_tokens; g.N = Dm; g.K = Dm; g.lda = 2 * Dm; g.ldw = 2 * Dm; g.ldr = Dm; g.ldo32 = Dm;
+    g.a = ao; g.w = lw.out_w; g.out_f32 = y; g.split3 = 1;
+    if (splitk) g.k_slices = 3; else { g.bias = lw.out_b; g.residual = x; g.ldr = Dm; }
+    g.M = total_tokens; g.N = Dm; g.K = Dm; g.lda = 2 * Dm; g.ldw = 2 * Dm; g.ldo32 = Dm;
     if ((rc = gemm_bias_act(g, stream))) return rc;
-    if ((rc = layernorm(y, Dm, lw.n1_w, lw.n1_b, 1e-5f, total_tokens, x, xb, stream, 1))) return rc;
-    // FF: linear1 + ReLU, linear2 + residual -> y ; x = LN2(y)
+    if ((rc = layernorm(y, Dm, lw.n1_w, lw.n1_b, 1e-5f, total_tokens, x, xb, stream, 1, splitk ? y2 : nullptr,
+                        splitk ? lw.ff2_b : nullptr)))
+      return rc;
+    // FF: linear1 + ReLU, linear2 + residual -> y2 ; x = LN2(y2)
     memset(&g, 0, sizeof(g));
     g.a = xb; g.w = lw.ff1_w; g.bias = lw.ff1_b; g.out_bf16 = hid; g.act = SAIS_ACT_RELU;
     g.split3 = 1; g.split_out = 1;
     g.M = total_tokens; g.N = FF; g.K = Dm; g.lda = 2 * Dm; g.ldw = 2 * Dm; g.ldo16 = 2 * FF;
     if ((rc = gemm_bias_act(g, stream))) return rc;
     memset(&g, 0, sizeof(g));
-    g.a = hid; g.w = lw.ff2_w; g.bias = lw.ff2_b; g.residual = x; g.out_f32 = y; g.split3 = 1;
-    g.M = total_tokens; g.N = Dm; g.K = FF; g.lda = 2 * FF; g.ldw = 2 * FF; g.ldr = Dm; g.ldo32 = Dm;
+    g.a = hid; g.w = lw.ff2_w; g.out_f32 = y2; g.split3 = 1;
+    if (splitk) g.k_slices = 12; else { g.bias = lw.ff2_b; g.residual = x; g.ldr = Dm; }
+    g.M = total_tokens; g.N = Dm; g.K = FF; g.lda = 2 * FF; g.ldw = 2 * FF; g.ldo32 = Dm;
     if ((rc = gemm_bias_act(g, stream))) return rc;
     float* xo = (last && out_tokens) ? out_tokens : x;
-    if ((rc = layernorm(y, Dm, lw.n2_w, lw.n2_b, 1e-5f, total_tokens, xo, last ? nullptr : xb, stream, 1))) return rc;
+    const bool preload = splitk && !last;
+    if ((rc = layernorm(y2, Dm, lw.n2_w, lw.n2_b, 1e-5f, total_tokens, xo, last ? nullptr : xb, stream, 1,
+                        preload ? y : nullptr, preload ? w->layers[l + 1].out_b : nullptr)))
+      return rc;
     if (last && out_cls) {
       if ((rc = gather_cls_relu(xo, seq_offsets, nseq, out_cls, stream))) return rc;
     }

@@ -22,7 +22,9 @@ __global__ void __launch_bounds__(256) layernorm384_kernel(const float* __restri
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, float eps, int64_t rows,
                                                            float* __restrict__ out_f32,
-                                                           __nv_bfloat16* __restrict__ out_bf16, int split) {
+                                                           __nv_bfloat16* __restrict__ out_bf16, int split,
+                                                           float* __restrict__ out_plus,
+                                                           const float* __restrict__ plus_vec) {
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t warps_total = int64_t(gridDim.x) * (blockDim.x >> 5);
@@ -85,6 +87,10 @@ __global__ void __launch_bounds__(256) layernorm384_kernel(const float* __restri
         y.z = (v[r][i].z - mean[r]) * rs * g[i].z + b[i].z;
         y.w = (v[r][i].w - mean[r]) * rs * g[i].w + b[i].w;
         if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * D + c) = y;
+        if (out_plus) {  // y + vector: the pre-loaded accumulator of the next residual GEMM (accumulate mode)
+          const float4 pv = __ldg(reinterpret_cast<const float4*>(plus_vec + c));
+          *reinterpret_cast<float4*>(out_plus + row * D + c) = make_float4(y.x + pv.x, y.y + pv.y, y.z + pv.z, y.w + pv.w);
+        }
         if (out_bf16) {
           uint2 o;
           o.x = pack_bf16x2(y.x, y.y);
@@ -246,7 +252,9 @@ __global__ void __launch_bounds__(128) temporal_prep_kernel(const float* __restr
                                                             const float* __restrict__ frame_cls,
                                                             const float* __restrict__ frame_pos,
                                                             float* __restrict__ tok_f32,
-                                                            __nv_bfloat16* __restrict__ tok_bf16) {
+                                                            __nv_bfloat16* __restrict__ tok_bf16,
+                                                            float* __restrict__ tok_plus,
+                                                            const float* __restrict__ plus_vec) {
   const int i = blockIdx.x;
   const int t0 = seq_offsets[i];
   const int S = seq_offsets[i + 1] - t0;
@@ -263,6 +271,10 @@ __global__ void __launch_bounds__(128) temporal_prep_kernel(const float* __restr
     }
     const int64_t o = int64_t(t0 + s) * D + c;
     *reinterpret_cast<float4*>(tok_f32 + o) = v;
+    if (tok_plus) {
+      const float4 pv = __ldg(reinterpret_cast<const float4*>(plus_vec + c));
+      *reinterpret_cast<float4*>(tok_plus + o) = make_float4(v.x + pv.x, v.y + pv.y, v.z + pv.z, v.w + pv.w);
+    }
     uint2 b, l;
     b.x = pack_bf16x2(v.x, v.y);
     b.y = pack_bf16x2(v.z, v.w);
@@ -394,9 +406,10 @@ __global__ void __launch_bounds__(128) prototype_score_kernel(const float* __res
 }  // namespace
 
 int layernorm(const float* x, int64_t in_pitch, const float* gamma, const float* beta, float eps, int64_t rows,
-              float* out_f32, sais_bf16* out_bf16, cudaStream_t stream, int split) {
+              float* out_f32, sais_bf16* out_bf16, cudaStream_t stream, int split, float* out_plus,
+              const float* plus_vec) {
   if (rows == 0) return kOk;
-  if (!x || !gamma || !beta || (!out_f32 && !out_bf16) || rows < 0 || in_pitch % 4) {
+  if (!x || !gamma || !beta || (!out_f32 && !out_bf16) || rows < 0 || in_pitch % 4 || (out_plus && !plus_vec)) {
     set_last_error("layernorm: bad arguments");
     return kErrInvalidArg;
   }
@@ -405,7 +418,8 @@ int layernorm(const float* x, int64_t in_pitch, const float* gamma, const float*
   if (blocks > cap) blocks = cap;
   LaunchScope ls(kClsLayerNorm, stream, double(rows) * D * (4 + (out_f32 ? 4 : 0) + (out_bf16 ? 2 : 0)));
   layernorm384_kernel<<<unsigned(blocks), 256, 0, stream>>>(x, in_pitch, gamma, beta, eps, rows, out_f32,
-                                                            reinterpret_cast<__nv_bfloat16*>(out_bf16), split);
+                                                            reinterpret_cast<__nv_bfloat16*>(out_bf16), split, out_plus,
+                                                            plus_vec);
   return check_cuda(cudaGetLastError(), "layernorm launch");
 }
 
@@ -472,7 +486,7 @@ int write_cls_rows(const float* cls_pos0, int B, float* x, cudaStream_t stream) 
 
 int temporal_prep(const float* x_frames, const int32_t* seq_offsets, int nseq, int total_tokens,
                   const float* frame_cls, const float* frame_pos, int n_pos, float* tok_f32, sais_bf16* tok_bf16,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, float* tok_plus, const float* plus_vec) {
   (void)n_pos;
   if (nseq == 0) return kOk;
   if (!seq_offsets || !frame_cls || !frame_pos || !tok_f32 || !tok_bf16 || nseq < 0) {
@@ -481,7 +495,7 @@ int temporal_prep(const float* x_frames, const int32_t* seq_offsets, int nseq, i
   }
   LaunchScope ls(kClsMisc, stream, double(total_tokens) * D * 14);
   temporal_prep_kernel<<<nseq, 128, 0, stream>>>(x_frames, seq_offsets, frame_cls, frame_pos, tok_f32,
-                                                 reinterpret_cast<__nv_bfloat16*>(tok_bf16));
+                                                 reinterpret_cast<__nv_bfloat16*>(tok_bf16), tok_plus, plus_vec);
   return check_cuda(cudaGetLastError(), "temporal_prep launch");
 }
 

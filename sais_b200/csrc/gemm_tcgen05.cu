@@ -98,6 +98,8 @@ struct GemmParams {
   float ln_eps;
   float ln_inv_k;            // 1 / row length of the normalised input (= 1 / K)
   float* ln_stats_out;       // producer: [M][4][2], slot = n_tile * 2 + warp half (needs N / BLOCK_N == 2)
+  int k_slices;              // >= 1; > 1 only in accumulate mode
+  int accumulate;            // fp32 output is ADDED to what out_f32 holds (TMA reduce-add), no bias / residual
   int xb_buf;                // producer: bytes of the extra bf16 staging tile per warp (2048) or 0
 };
 
@@ -128,6 +130,12 @@ __device__ __forceinline__ void tma_load_2d_s(uint32_t smem_dst, const CUtensorM
       :
       : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d_s(const CUtensorMap* m, uint32_t smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
 }
 __device__ __forceinline__ void tma_store_2d_s(const CUtensorMap* m, uint32_t smem_src, int32_t c0, int32_t c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -180,6 +188,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int num_tiles = ((m_tiles + csize - 1) / csize) * n_tiles;  // number of work units
   const int kb_per_pass = p.K / BLOCK_K;
   const int k_blocks = p.split3 ? 3 * kb_per_pass : kb_per_pass;
+  // split-K (accumulate mode, small M): a work unit is (tile, K slice); partial products meet in L2 (TMA reduce-add)
+  const int S = p.k_slices;
+  const int num_units = num_tiles * S;
+  const int kbs = (k_blocks + S - 1) / S;
 
   constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
   if (warp == kProducerWarp && lane == 0) {
@@ -217,12 +229,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       int tidx = 0;
-      for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++tidx) {
+      for (int u = unit0; u < num_units; u += unit_stride, ++tidx) {
+        const int tile = u / S;
+        const int kb0 = (u % S) * kbs, kb1 = (kb0 + kbs < k_blocks) ? kb0 + kbs : k_blocks;
         const int m0 = tile_m0(tile);
         const int n0 = (tile % n_tiles) * BLOCK_N;
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          stamp(0, tidx, kb);
+          stamp(0, tidx, kb - kb0);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
           if (CG == 1 || crank == 0) mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes * CG);
@@ -259,16 +273,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int astage = 0;
       uint32_t aphase = 0;
       int tidx = 0;
-      for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++tidx) {
+      for (int u = unit0; u < num_units; u += unit_stride, ++tidx) {
+        const int kb0 = (u % S) * kbs, kb1 = (kb0 + kbs < k_blocks) ? kb0 + kbs : k_blocks;
         stamp(1, tidx, 0);
         mbar_wait(&tempty_bar[astage], aphase ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
         stamp(1, tidx, 1);
         const uint32_t d_tmem = tmem_base + astage * BLOCK_N;
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          stamp(1, tidx, 2 + kb);
+          stamp(1, tidx, 2 + kb - kb0);
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + Cfg::kABytes;
           const uint64_t da = umma_desc_sw128_kmajor(sa);
@@ -276,8 +291,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advancing K inside the 128-byte swizzle row: +32 bytes = +2 in 16-byte address units
-            if (CG == 1) umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-            else umma_f16_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            if (CG == 1) umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb != kb0) || (k != 0));
+            else umma_f16_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb != kb0) || (k != 0));
           }
           // frees the smem slot (in both CTAs of a pair) once these MMAs retire
           if (CG == 1) umma_commit(&empty_bar[stage]); else umma_commit_cg2_mcast(&empty_bar[stage], uint16_t(0b11));
@@ -319,7 +334,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint32_t aphase = 0;
     uint32_t it = 0;  // chunks processed by this warp (selects staging buffer / residual barrier phase)
 
-    if (has_res && lane == 0 && unit0 < num_tiles) {  // prime the residual pipeline
+    if (has_res && lane == 0 && unit0 < num_units) {  // prime the residual pipeline (S == 1 whenever there is a residual)
       const int m0 = tile_m0(unit0), n0 = (unit0 % n_tiles) * BLOCK_N;
       mbar_arrive_expect_tx(&my_res_bar[0], 32 * 128);
       tma_load_2d_s(my_stage, &tmap_res, &my_res_bar[0], n0 + half * CW, m0 + q * 32);
@@ -331,8 +346,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     float pf_bias[NCWmax], pf_csum[NCWmax];
     float4 pf_s0 = make_float4(0.f, 0.f, 0.f, 0.f), pf_s1 = pf_s0;
     auto prefetch_tile = [&](int t) {
-      if (t >= num_tiles) return;
-      const int pm0 = tile_m0(t), pn0 = (t % n_tiles) * BLOCK_N;
+      if (t >= num_units) return;
+      const int pm0 = tile_m0(t / S), pn0 = ((t / S) % n_tiles) * BLOCK_N;
 #pragma unroll
       for (int ci = 0; ci < NCWmax; ++ci) {
         pf_bias[ci] = (ci < NCW && p.bias) ? __ldg(p.bias + pn0 + (half + kSub * ci) * CW + lane) : 0.0f;
@@ -349,7 +364,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
     int tidx = 0;
     const int erole = (ew == 0) ? 2 : (ew == 4 ? 3 : -1);
-    for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++tidx) {
+    for (int u = unit0; u < num_units; u += unit_stride, ++tidx) {
+      const int tile = u / S;
       const int m0 = tile_m0(tile);
       const int n0 = (tile % n_tiles) * BLOCK_N;
       if (erole >= 0 && lane == 0) stamp(erole, tidx, 0);
@@ -368,7 +384,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         ln_rstd = rsqrtf(var + p.ln_eps);
         ln_nmr = -mean * ln_rstd;
       }
-      prefetch_tile(tile + unit_stride);
+      prefetch_tile(u + unit_stride);
       uint64_t ln_sum2 = 0, ln_sq2 = 0;  // producer: this warp's share of the row statistics of the tile (packed pairs)
       __syncwarp();
 
@@ -505,10 +521,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               tma_store_wait_read<0>();
               int nt = tile, nc = c + kSub;
               if (nc >= NC) {
-                nt = tile + unit_stride;
+                nt = u + unit_stride;
                 nc = half;
               }
-              if (nt < num_tiles) {
+              if (nt < num_units) {
                 const int nm0 = tile_m0(nt), nn0 = (nt % n_tiles) * BLOCK_N;
                 uint64_t* rb = &my_res_bar[(it + 1) & 1];
                 mbar_arrive_expect_tx(rb, 32 * 128);
@@ -516,7 +532,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               }
             }
             if (!p.debug_nostore) {
-              tma_store_2d_s(&tmap_out, buf, n, m0 + q * 32);
+              if (MODE == kModeF32 && p.accumulate) tma_reduce_add_2d_s(&tmap_out, buf, n, m0 + q * 32);
+              else tma_store_2d_s(&tmap_out, buf, n, m0 + q * 32);
               if (MODE == kModeGeneric && p.split_out) tma_store_2d_s(&tmap_out, buf + 2048, p.N + n, m0 + q * 32);
             }
             tma_store_commit();
@@ -666,9 +683,17 @@ int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
   p.out2_bf16 = reinterpret_cast<__nv_bfloat16*>(a.out2_bf16);
   p.ldo2 = a.ldo2;
   p.xb_buf = 0;
+  p.accumulate = a.k_slices > 0;
+  p.k_slices = 1;
+  if (a.k_slices > 1) {  // every slice must own at least one k-block
+    const int kb_total = int(a.K / BLOCK_K) * (a.split3 ? 3 : 1);
+    int want = a.k_slices < kb_total ? a.k_slices : kb_total;
+    const int per = (kb_total + want - 1) / want;
+    p.k_slices = (kb_total + per - 1) / per;
+  }
   p.stages = Cfg::stages(wide, nbuf, p.xb_buf);
   p.stage_buf = wide ? kStageBufBytes : kStageBufBytes / 2;
-  const int units = ((m_tiles + cluster - 1) / cluster) * (p.N / BLOCK_N);
+  const int units = ((m_tiles + cluster - 1) / cluster) * (p.N / BLOCK_N) * p.k_slices;
   int grid = units * cluster < num_sms() ? units * cluster : num_sms();
   grid -= grid % cluster;
   LaunchScope ls(kClsGemm, stream, 2.0 * double(a.M) * double(a.N) * double(a.K) * (a.split3 ? 3 : 1));
@@ -758,6 +783,11 @@ int gemm_bias_act(const SaisGemmArgs& a, cudaStream_t stream, int force_block_n)
   }
   if (a.act < 0 || a.act > 2) {
     set_last_error("gemm: bad activation %d", a.act);
+    return kErrInvalidArg;
+  }
+  if (a.k_slices < 0 || (a.k_slices > 0 && (!a.out_f32 || a.bias || a.residual || a.act != 0 || a.remap_group ||
+                                            a.split_out || a.ln_stats_out || a.ln_stats_in))) {
+    set_last_error("gemm: accumulate mode (k_slices >= 1) needs an fp32 output and no bias / residual / activation");
     return kErrInvalidArg;
   }
   if (a.ln_stats_in && (!a.ln_colsum || !a.bias || !a.out_bf16 || a.residual || a.split3 || a.split_out || a.remap_group ||

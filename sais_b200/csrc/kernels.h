@@ -35,8 +35,10 @@ int gemm_residual_layernorm(const sais_bf16* a, int64_t lda, const sais_bf16* w,
                             int64_t K, cudaStream_t stream);
 
 // elementwise.cu
+// out_plus (optional) = LayerNorm output + plus_vec[384]: the pre-loaded accumulator of an accumulate-mode GEMM
 int layernorm(const float* x, int64_t in_pitch, const float* gamma, const float* beta, float eps, int64_t rows,
-              float* out_f32, sais_bf16* out_bf16, cudaStream_t stream, int split = 0);
+              float* out_f32, sais_bf16* out_bf16, cudaStream_t stream, int split = 0, float* out_plus = nullptr,
+              const float* plus_vec = nullptr);
 int rowstats_cast(const float* x, int64_t rows, sais_bf16* xb, float* stats, cudaStream_t stream);
 int normalize_patchify_u8(const uint8_t* frames, int B, const float* mean3, const float* std3, sais_bf16* patches,
                           cudaStream_t stream, int split = 0);
@@ -45,7 +47,7 @@ int fill_offsets(int32_t* offs, int n, int stride, cudaStream_t stream);
 int write_cls_rows(const float* cls_pos0, int B, float* x, cudaStream_t stream);
 int temporal_prep(const float* x_frames, const int32_t* seq_offsets, int nseq, int total_tokens,
                   const float* frame_cls, const float* frame_pos, int n_pos, float* tok_f32, sais_bf16* tok_bf16,
-                  cudaStream_t stream);
+                  cudaStream_t stream, float* tok_plus = nullptr, const float* plus_vec = nullptr);
 int gather_cls_relu(const float* tok_f32, const int32_t* seq_offsets, int nseq, float* out_cls, cudaStream_t stream);
 int clip_head(const float* cls_a, const float* cls_b, int B, int nsnip, const float* lin_w, const float* lin_b,
               float* out, cudaStream_t stream);

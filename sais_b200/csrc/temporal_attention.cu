@@ -4,9 +4,10 @@
 // prepare_model.py:213 with the README-patched layer that also returns the head-averaged weights).
 // Sequences are short (S = nframes + 1, typically 10..65) and packed back to back, so this is a
 // latency/L2-bound SIMT kernel rather than a tensor-core one: one CTA per sequence keeps that sequence's K and
-// V (all heads) in shared memory, each warp owns query rows, runs the heads in turn (fp32 logits, -inf on
-// padded keys, exact softmax) and sums the per-head probabilities in shared memory so the head-mean map
-// [S,S] is written once, coalesced.  Second use: the fp32-equivalent ("precise") mode of the ViT
+// V (all heads) in shared memory; the CTA's warps form an (H heads) x (RG row groups) grid, so RG query rows are in
+// flight with all their heads at once (fp32 logits, -inf on padded keys, exact softmax).  The per-head probabilities
+// of a row batch stay in shared memory and are averaged in a fixed head order (deterministic, no atomics), so
+// the head-mean map [S,S] is written once, coalesced.  Second use: the fp32-equivalent ("precise") mode of the ViT
 // (6 heads x 64, S = 197, vision_transformer.py:80-92), which optionally emits per-head probabilities.
 //
 // q, k, v arrive as fp32 (the split-precision in-proj GEMM writes fp32); the output is written as bf16
@@ -18,8 +19,6 @@ namespace sais {
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
 
 __host__ __device__ inline int round_up32(int s) { return (s + 31) & ~31; }
 
@@ -29,21 +28,25 @@ struct AttnCfg {
   static constexpr int LD = 3 * E;        // qkv row pitch (fp32 elements)
   static constexpr int KV_PITCH = E + 4;  // smem row pitch: conflict-free float4 row reads
   static constexpr int kMaxSmemS = 64;
+  static constexpr int RG = (H == 4) ? 4 : 3;  // row groups: 16 warps for the temporal head, 18 for the ViT (6 heads)
+  static constexpr int kWarps = H * RG;
+  static constexpr int kThreads = 32 * kWarps;
   static size_t smem_bytes(int max_S, bool smem_kv) {
-    size_t b = size_t(kWarps) * (HD * 4 + 2 * size_t(round_up32(max_S)) * 4);
+    size_t b = size_t(kWarps) * (HD * 4 + size_t(round_up32(max_S)) * 4);
     if (smem_kv) b += 2 * size_t(max_S) * KV_PITCH * 4;
     return b;
   }
 };
 
 template <int H, int HD, bool kSmemKV>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(32 * H * ((H == 4) ? 4 : 3))
 seq_attention_f32_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ seq_offsets,
                          const uint8_t* __restrict__ key_pad, const int64_t* __restrict__ attn_offsets, int max_S,
                          float scale, __nv_bfloat16* __restrict__ out_split, float* __restrict__ attn_mean,
                          float* __restrict__ probs_per_head) {
   using Cfg = AttnCfg<H, HD>;
   constexpr int E = Cfg::E, LD = Cfg::LD;
+  constexpr int kWarps = Cfg::kWarps, kThreads = Cfg::kThreads, RG = Cfg::RG;
   constexpr int DPL = HD / 32;  // output dims per lane
   extern __shared__ __align__(16) uint8_t smem[];
   const int i = blockIdx.x;
@@ -54,14 +57,14 @@ seq_attention_f32_kernel(const float* __restrict__ qkv, const int32_t* __restric
   const int Sp = round_up32(max_S);
 
   float* qs = reinterpret_cast<float*>(smem) + warp * HD;                    // [kWarps][HD]
-  float* sc = reinterpret_cast<float*>(smem) + kWarps * HD + warp * 2 * Sp;  // [kWarps][Sp]
-  float* acc = sc + Sp;                                                      // [kWarps][Sp]
+  float* sc_all = reinterpret_cast<float*>(smem) + kWarps * HD;              // [kWarps][Sp]
+  float* sc = sc_all + warp * Sp;
 
   const float* Kb;
   const float* Vb;
   int pitch;
   if constexpr (kSmemKV) {
-    float* Ks = reinterpret_cast<float*>(smem + size_t(kWarps) * (HD * 4 + 2 * size_t(Sp) * 4));
+    float* Ks = reinterpret_cast<float*>(smem + size_t(kWarps) * (HD * 4 + size_t(Sp) * 4));
     float* Vs = Ks + size_t(max_S) * Cfg::KV_PITCH;
     constexpr int CH = 2 * E / 4;  // float4 chunks per token (K then V)
     for (int e = threadIdx.x; e < S * CH; e += kThreads) {
@@ -81,9 +84,11 @@ seq_attention_f32_kernel(const float* __restrict__ qkv, const int32_t* __restric
   const int64_t aoff = (attn_mean != nullptr && attn_offsets != nullptr) ? attn_offsets[i] : -1;
   const uint8_t* pad = key_pad ? key_pad + t0 : nullptr;
 
-  for (int r = warp; r < S; r += kWarps) {
-    for (int j = lane; j < S; j += 32) acc[j] = 0.f;
-    for (int h = 0; h < H; ++h) {
+  const int h = warp % H;    // this warp's head
+  const int rg = warp / H;   // and row group
+  for (int r0 = 0; r0 < S; r0 += RG) {
+    const int r = r0 + rg;
+    if (r < S) {
       const float* qp = qkv + int64_t(t0 + r) * LD + h * HD;
 #pragma unroll
       for (int c = 0; c < DPL; ++c) qs[lane + 32 * c] = qp[lane + 32 * c];
@@ -99,25 +104,24 @@ seq_attention_f32_kernel(const float* __restrict__ qkv, const int32_t* __restric
           dot = fmaf(kk.x, qq.x, dot); dot = fmaf(kk.y, qq.y, dot);
           dot = fmaf(kk.z, qq.z, dot); dot = fmaf(kk.w, qq.w, dot);
         }
-        float s = dot * scale;
-        if (pad && pad[j]) s = -INFINITY;
-        sc[j] = s;
-        lmax = fmaxf(lmax, s);
+        float sv = dot * scale;
+        if (pad && pad[j]) sv = -INFINITY;
+        sc[j] = sv;
+        lmax = fmaxf(lmax, sv);
       }
       const float m = warp_max(lmax);
       float lsum = 0.f;
       for (int j = lane; j < S; j += 32) {
-        const float p = expf(sc[j] - m);
-        sc[j] = p;
-        lsum += p;
+        const float pe = expf(sc[j] - m);
+        sc[j] = pe;
+        lsum += pe;
       }
       const float inv = 1.0f / warp_sum(lsum);
       float* ph = probs_per_head ? probs_per_head + ((int64_t(i) * H + h) * S + r) * S : nullptr;
       for (int j = lane; j < S; j += 32) {
-        const float p = sc[j] * inv;
-        sc[j] = p;
-        acc[j] += p;
-        if (ph) ph[j] = p;
+        const float pn = sc[j] * inv;
+        sc[j] = pn;
+        if (ph) ph[j] = pn;
       }
       __syncwarp();
       // O = P V for this head: lane owns dims lane, lane+32, ...
@@ -126,10 +130,10 @@ seq_attention_f32_kernel(const float* __restrict__ qkv, const int32_t* __restric
       for (int c = 0; c < DPL; ++c) o[c] = 0.f;
       const float* vp = Vb + h * HD + lane;
       for (int j = 0; j < S; ++j) {
-        const float p = sc[j];
+        const float pj = sc[j];
         const float* v = vp + int64_t(j) * pitch;
 #pragma unroll
-        for (int c = 0; c < DPL; ++c) o[c] = fmaf(p, v[32 * c], o[c]);
+        for (int c = 0; c < DPL; ++c) o[c] = fmaf(pj, v[32 * c], o[c]);
       }
       __nv_bfloat16* op = out_split + int64_t(t0 + r) * (2 * E) + h * HD + lane;
 #pragma unroll
@@ -138,13 +142,22 @@ seq_attention_f32_kernel(const float* __restrict__ qkv, const int32_t* __restric
         op[32 * c] = hi;
         op[E + 32 * c] = __float2bfloat16(o[c] - __bfloat162float(hi));
       }
+    }
+    if (aoff >= 0) {  // head mean of this row batch, heads summed in a fixed order (block-uniform branch)
+      __syncthreads();
+      for (int e = threadIdx.x; e < RG * S; e += kThreads) {
+        const int g = e / S, j = e % S;
+        if (r0 + g < S) {
+          float a = 0.f;
+#pragma unroll
+          for (int hh = 0; hh < H; ++hh) a += sc_all[(g * H + hh) * Sp + j];
+          attn_mean[aoff + int64_t(r0 + g) * S + j] = a * (1.0f / H);
+        }
+      }
+      __syncthreads();
+    } else {
       __syncwarp();
     }
-    if (aoff >= 0) {
-      float* ap = attn_mean + aoff + int64_t(r) * S;
-      for (int j = lane; j < S; j += 32) ap[j] = acc[j] * (1.0f / H);
-    }
-    __syncwarp();
   }
 }
 
@@ -177,10 +190,10 @@ int launch_seq_attention(const float* qkv, const int32_t* seq_offsets, const uin
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_split);
   LaunchScope ls(cls, stream, 0.0);
   if (smem_kv)
-    seq_attention_f32_kernel<H, HD, true><<<nseq, kThreads, sm, stream>>>(qkv, seq_offsets, key_pad, attn_offsets,
+    seq_attention_f32_kernel<H, HD, true><<<nseq, Cfg::kThreads, sm, stream>>>(qkv, seq_offsets, key_pad, attn_offsets,
                                                                           max_S, scale, o, attn_mean, probs_per_head);
   else
-    seq_attention_f32_kernel<H, HD, false><<<nseq, kThreads, sm, stream>>>(qkv, seq_offsets, key_pad, attn_offsets,
+    seq_attention_f32_kernel<H, HD, false><<<nseq, Cfg::kThreads, sm, stream>>>(qkv, seq_offsets, key_pad, attn_offsets,
                                                                            max_S, scale, o, attn_mean, probs_per_head);
   return check_cuda(cudaGetLastError(), "seq_attention launch");
 }

@@ -44,7 +44,7 @@ __device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, u
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-template <bool kPInTmem>
+template <bool kPInTmem, bool kTurns>
 __global__ void __launch_bounds__(kThreads, 1)
 vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out,
                         __nv_bfloat16* __restrict__ out, int n_items,
@@ -65,6 +65,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
   uint64_t* o_full = bars + 8;    // [2] O[mt] in TMEM (also: P no longer read by the tensor core)
   uint64_t* t_free = bars + 10;   // [2] TMEM window of row tile mt drained
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* turn = bars + 14;     // [2][4] exp-pass turn of (row tile, lane quarter): the two warps of a scheduler alternate
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -77,6 +78,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
       mbar_init(&p_full[i], 4);
       mbar_init(&o_full[i], 1);
       mbar_init(&t_free[i], 4);
+      for (int j = 0; j < 4; ++j) mbar_init(&turn[i * 4 + j], 1);
     }
     fence_mbar_init();
   }
@@ -120,7 +122,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
           const uint32_t q_s = smem_u32(smem + slot * SLOT_BYTES);
           const uint32_t k_s = q_s + MAT_BYTES, v_s = q_s + 2 * MAT_BYTES;
           mbar_wait(&ld_full[slot], (idx >> 1) & 1);
-          if (w == 1 && idx == 0) __nanosleep(1800);  // (see above) stagger the windows once the first item has landed
+          if (!kTurns && w == 1 && idx == 0) __nanosleep(1800);  // (see above) stagger the windows once the first item has landed
           stamp(2 + w, idx, 0);
           mbar_wait(&t_free[w], (idx & 1) ^ 1);  // window drained by the softmax warps
           tc_fence_after();
@@ -209,6 +211,10 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
             mbar_wait(&o_full[0], ph);
           }
         }
+        // The exp pass is MUFU-bound (208 ex2 per row at 4 /clk per scheduler) and the two warps of a scheduler (row tile
+        // 0 and 1 of the same lane quarter) would otherwise run it at the same time at half speed each and leave the
+        // MUFU idle while both wait for their MMAs: take turns, so one tile's exponentials hide the other's MMA round trips.
+        if (kTurns) mbar_wait(&turn[mt * 4 + q], (mt == 0) ? (ph ^ 1) : ph);
         // pass 2: p = exp2((s - max) * scale), row sum, bf16 P
         float sum = 0.f;
         auto softmax_chunk = [&](const uint32_t(&v)[32], int c) {
@@ -262,10 +268,15 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
           }
         }
         row_sum = sum;
+        if (kTurns && lane == 0) mbar_arrive(&turn[(mt ^ 1) * 4 + q]);
         if (kPInTmem) tmem_st_wait();
-      } else if (!kPInTmem) {
-        // rows 224..255 do not exist: keep the barrier protocol, skip the math (their P rows stay stale/unused)
-        mbar_wait(&o_full[0], ph);
+      } else {
+        if (kTurns) {  // rows 224..255 do not exist: pass the turn straight on
+          mbar_wait(&turn[mt * 4 + q], (mt == 0) ? (ph ^ 1) : ph);
+          if (lane == 0) mbar_arrive(&turn[(mt ^ 1) * 4 + q]);
+        }
+        // keep the barrier protocol, skip the math (their P rows stay stale/unused)
+        if (!kPInTmem) mbar_wait(&o_full[0], ph);
       }
       tc_fence_before();
       if (!kPInTmem) fence_proxy_async_smem();
@@ -285,6 +296,11 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
         tmem_ld_32x32(t_row + kOCol + 32, w);
         tmem_ld_wait_dep(v);
         tmem_ld_wait_dep(w);
+        // O is in registers: the whole TMEM window of this row tile is dead, so hand it back BEFORE the staging / store
+        // work — the next item's S = QK^T then runs under this epilogue instead of after it
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_free[mt]);
         if (kPInTmem) {
           // O tile of this warp (32 rows x 64) -> swizzled staging -> one TMA store; rows beyond token 196 are
           // clipped by the [frame, token, 384] tensor map
@@ -336,9 +352,11 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&t_free[mt]);
+      if (!warp_has_rows) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_free[mt]);
+      }
       if (st_on) stamp(mt, it, 5);
     }
     if (kPInTmem && lane == 0) tma_store_wait<0>();
@@ -352,19 +370,19 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
   }
 }
 
-template <bool kPInTmem>
+template <bool kPInTmem, bool kTurns>
 int launch_attn(const CUtensorMap& tm, const CUtensorMap& tm_out, sais_bf16* out, int items, cudaStream_t stream,
                 long long* dbg) {
   static bool attr_set = false;
   if (!attr_set) {
-    int rc = check_cuda(cudaFuncSetAttribute(vit_attention_tc_kernel<kPInTmem>,
+    int rc = check_cuda(cudaFuncSetAttribute(vit_attention_tc_kernel<kPInTmem, kTurns>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<kPInTmem>()),
                         "cudaFuncSetAttribute(vit_attention_tc)");
     if (rc) return rc;
     attr_set = true;
   }
   const int grid = items < num_sms() ? items : num_sms();
-  vit_attention_tc_kernel<kPInTmem><<<grid, kThreads, smem_bytes<kPInTmem>(), stream>>>(
+  vit_attention_tc_kernel<kPInTmem, kTurns><<<grid, kThreads, smem_bytes<kPInTmem>(), stream>>>(
       tm, tm_out, reinterpret_cast<__nv_bfloat16*>(out), items, dbg);
   return check_cuda(cudaGetLastError(), "vit_attention_tc launch");
 }
@@ -390,8 +408,10 @@ int vit_attention_tc(const sais_bf16* qkv, int B, sais_bf16* out, cudaStream_t s
   }
   {
     LaunchScope ls(kClsVitAttn, stream, 4.0 * double(B) * 6 * 197 * 197 * 64);
-    rc = p_smem ? launch_attn<false>(tm, tm_out, out, B * HEADS, stream, dbg)
-                : launch_attn<true>(tm, tm_out, out, B * HEADS, stream, dbg);
+    static const bool no_turns = getenv("SAIS_ATTN_NOTURNS") != nullptr && atoi(getenv("SAIS_ATTN_NOTURNS")) != 0;
+    rc = p_smem ? launch_attn<false, false>(tm, tm_out, out, B * HEADS, stream, dbg)
+         : no_turns ? launch_attn<true, false>(tm, tm_out, out, B * HEADS, stream, dbg)
+                    : launch_attn<true, true>(tm, tm_out, out, B * HEADS, stream, dbg);
   }
   if (dbg) {
     long long h[4 * 16 * 8];

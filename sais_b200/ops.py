@@ -24,7 +24,7 @@ def split_bf16(t):
 
 def gemm_bias_act(a, w, bias=None, act=_lib.ACT_NONE, residual=None, out_dtype=torch.bfloat16, out=None,
                   row_add=None, remap_group=0, split3=False, split_out=False, ln_stats_in=None, ln_colsum=None,
-                  ln_eps=1e-6, ln_stats_out=None, out2=None):
+                  ln_eps=1e-6, ln_stats_out=None, out2=None, k_slices=0):
     """out = act(a @ w.T + bias) [+ residual].  a: bf16 [M,K]; w: bf16 [N,K]; bias/residual fp32.
     split3: a and w are [hi | lo] halves ([M,2K], [N,2K], see split_bf16) and the product is fp32-equivalent;
     split_out: the bf16 output is written as [hi | lo] ([M,2N])."""
@@ -56,6 +56,7 @@ def gemm_bias_act(a, w, bias=None, act=_lib.ACT_NONE, residual=None, out_dtype=t
     g.ln_stats_in, g.ln_colsum, g.ln_eps = ptr(ln_stats_in), ptr(ln_colsum), float(ln_eps)
     g.ln_stats_out, g.out2_bf16 = ptr(ln_stats_out), ptr(out2)
     g.ldo2 = out2.stride(0) if out2 is not None else 0
+    g.k_slices = int(k_slices)  # >= 1: accumulate mode, out += a @ w.T in that many K slices (TMA reduce-add)
     check(lib().sais_gemm_bias_act(C.byref(g), current_stream()), "sais_gemm_bias_act")
     return out
 

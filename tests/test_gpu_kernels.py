@@ -157,6 +157,25 @@ def test_gemm_rejects_bad_shapes(dev):
         ops.gemm_bias_act(a, w)  # K not a multiple of 64 (and pitch not 16-byte aligned)
 
 
+@pytest.mark.parametrize("M,K,slices,split3", [(272, 2048, 12, True), (272, 384, 3, True), (50, 2048, 1, False),
+                                               (700, 1536, 5, False), (272, 2048, 200, True)])
+def test_gemm_accumulate_split_k(dev, M, K, slices, split3):
+    """accumulate mode: out += A W^T with the K range split over CTAs (partials meet in L2 by TMA reduce-add)."""
+    from sais_b200 import ops
+    a, w = rnd(M, K, seed=M + K), rnd(384, K, seed=K, std=1 / math.sqrt(K))
+    y0 = rnd(M, 384, seed=5)
+    y = y0.to(dev).clone()
+    if split3:
+        ops.gemm_bias_act(ops.split_bf16(a.to(dev)), ops.split_bf16(w.to(dev)), out=y, split3=True, k_slices=slices)
+        ref = (y0.double() + a.double() @ w.double().t()).float()
+        tol = dict(atol=3e-4, rtol=1e-4)  # fp32-equivalent product
+    else:
+        ops.gemm_bias_act(a.to(dev).bfloat16(), w.to(dev).bfloat16(), out=y, k_slices=slices)
+        ref = (y0.double() + bf(a).double() @ bf(w).double().t()).float()
+        tol = dict(atol=2e-4, rtol=1e-4)
+    assert torch.allclose(y.cpu(), ref, **tol), (y.cpu() - ref).abs().max()
+
+
 # ------------------------------------------------------------------------------------------------ LayerNorm folding
 @pytest.mark.parametrize("rows", [1, 33, 4099])
 def test_rowstats_cast(dev, rows):
