@@ -180,6 +180,16 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def gemm_traffic():
+    """DRAM bytes per bf16 GEMM launch from the committed ncu --set full capture (profiles/gemm_traffic.json, written
+    by tools/ncu_traffic.py from the same batch-256 step); null when no capture is committed."""
+    p = ROOT / "profiles" / "gemm_traffic.json"
+    if not p.exists():
+        return {"traffic": None}
+    d = json.loads(p.read_text())
+    return {"traffic": d.get("dram_bytes_per_launch"), "traffic_unit": "B/launch", "traffic_source": d.get("source")}
+
+
 def workload_config(n_gpus):
     return {
         "workload": "C2: DINO ViT-S/16 feature extraction, batch 256 u8 frames 224x224 (128 RGB + 128 flow) per GPU, "
@@ -297,7 +307,7 @@ def main():
 
     # roofline leg: same steps with every launch bracketed by CUDA events, per kernel class
     import ctypes as C
-    ncls = 6
+    ncls = 7
     ms_c, work_c, n_c = (C.c_double * ncls)(), (C.c_double * ncls)(), (C.c_int64 * ncls)()
     prof_steps = min(args.steps, 10)
     barrier()
@@ -313,7 +323,7 @@ def main():
         e2e = n_global * args.steps / (ms_e2e * 1e-3)
         gemm_ms = ms_c[0] / max(n_c[0], 1)
         gemm_tflops = (work_c[0] / 1e12) / (ms_c[0] * 1e-3) if ms_c[0] > 0 else 0.0
-        classes = ["gemm", "vit_attention", "layernorm", "patchify", "temporal_attention", "misc"]
+        classes = ["gemm", "vit_attention", "layernorm", "patchify", "temporal_attention", "misc", "gemm_split3_head"]
         total_prof = sum(ms_c) or 1.0
         shares = {c: {"ms_per_step": ms_c[i] / prof_steps, "launches_per_step": n_c[i] / prof_steps,
                       "share": ms_c[i] / total_prof} for i, c in enumerate(classes)}
@@ -328,10 +338,13 @@ def main():
                     "d2h_bytes_per_step": FRAMES_PER_STEP * 384 * 4 + CLIPS_PER_STEP * 2 * 4},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all GEMM launches of a step)",
+            "roofline": {"bound": "tensor",
+                         "kernel": "gemm_tcgen05_kernel, bf16 (the 49 ViT GEMM launches of a step: patch, qkv, proj, "
+                                   "fc1, fc2)",
                          "achieved": gemm_tflops, "peak": sustained, "unit": "TFLOP/s",
                          "frac": gemm_tflops / sustained, "frac_of_burst": gemm_tflops / burst, "peak_source": src,
-                         "avg_launch_ms": gemm_ms, "traffic": None},
+                         "avg_launch_ms": gemm_ms, "flop_per_launch": work_c[0] / max(n_c[0], 1),
+                         **gemm_traffic()},
             "kernel_classes": shares,
         }
         if not args.no_cpu_baseline:

@@ -51,9 +51,10 @@ int64_t sais_launch_count(void);
 
 /* Optional per-kernel-class CUDA-event profiler (bench.py's roofline leg).  Between begin and end every
  * launch is bracketed by events on its stream; end synchronises the device and returns, per class
- * (0 GEMM, 1 ViT attention, 2 LayerNorm, 3 patchify, 4 temporal attention, 5 misc): summed milliseconds,
- * summed algorithmic work (flops for classes 0-1, bytes otherwise) and launch counts.  All arrays are HOST. */
-#define SAIS_NUM_KERNEL_CLASSES 6
+ * (0 bf16 GEMM, 1 ViT attention, 2 LayerNorm / row statistics, 3 patchify, 4 temporal attention, 5 misc,
+ * 6 split-precision GEMM of the temporal head / fp32 mode): summed milliseconds, summed algorithmic work (flops for
+ * classes 0, 1 and 6, bytes otherwise) and launch counts.  All arrays are HOST. */
+#define SAIS_NUM_KERNEL_CLASSES 7
 void sais_profile_begin(void);
 int sais_profile_end(double* ms_per_class, double* work_per_class, int64_t* launches_per_class, int32_t n_classes);
 

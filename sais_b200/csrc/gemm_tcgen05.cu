@@ -118,6 +118,11 @@ enum : int {
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ ulonglong2 lds128_pairs(uint32_t addr) {  // two packed fp32x2 operands
+  ulonglong2 v;
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
@@ -388,6 +393,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint64_t ln_sum2 = 0, ln_sq2 = 0;  // producer: this warp's share of the row statistics of the tile (packed pairs)
       __syncwarp();
 
+      // chunk 0's bias pairs -> registers before the accumulator is ready; every chunk reloads them for the next one
+      // right after its first op, so the shared-memory latency never sits in front of the epilogue math
+      const uint32_t bias_s = smem_u32(my_bias), csum_s = smem_u32(my_csum);
+      ulonglong2 bv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bv[j] = lds128_pairs(bias_s + j * 16);
+
       mbar_wait(&tfull_bar[astage], aphase);
       tc_fence_after();
       if (erole >= 0 && lane == 0) stamp(erole, tidx, 1);
@@ -405,23 +417,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         {
           // bias add (or the folded LayerNorm's  acc * rstd + (-mean * rstd) * c_n + d_n) in packed fp32x2; this is
           // also what moves the accumulator out of v, so the next chunk's TMEM load can be issued right after it
-          const ulonglong2* b2p = reinterpret_cast<const ulonglong2*>(my_bias + ci * CW);
           if (ln_in) {
-            const ulonglong2* c2p = reinterpret_cast<const ulonglong2*>(my_csum + ci * CW);
             const uint64_t rs2 = pack2(ln_rstd, ln_rstd), nm2 = pack2(ln_nmr, ln_nmr);
+            ulonglong2 cv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cv[j] = lds128_pairs(csum_s + (ci * CW + j * 4) * 4);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const ulonglong2 b2 = b2p[j], c2 = c2p[j];
+              const ulonglong2 b2 = bv[j], c2 = cv[j];
               unpack2(fma2(pack2u(v[4 * j], v[4 * j + 1]), rs2, fma2(nm2, c2.x, b2.x)), f[4 * j], f[4 * j + 1]);
               unpack2(fma2(pack2u(v[4 * j + 2], v[4 * j + 3]), rs2, fma2(nm2, c2.y, b2.y)), f[4 * j + 2], f[4 * j + 3]);
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const ulonglong2 b2 = b2p[j];
+              const ulonglong2 b2 = bv[j];
               unpack2(add2(pack2u(v[4 * j], v[4 * j + 1]), b2.x), f[4 * j], f[4 * j + 1]);
               unpack2(add2(pack2u(v[4 * j + 2], v[4 * j + 3]), b2.y), f[4 * j + 2], f[4 * j + 3]);
             }
+          }
+          if (ci + 1 < NCW) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bv[j] = lds128_pairs(bias_s + ((ci + 1) * CW + j * 4) * 4);
           }
         }
         if (ci + 1 < NCW) {
@@ -485,7 +502,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
           } else {
             // the store issued from this buffer nbuf chunks ago must have finished reading it
-            if (lane == 0) {
+            __syncwarp();
+            if (elect_one()) {
               if (nbuf == 2) tma_store_wait_read<1>();
               else if (nbuf == 3) tma_store_wait_read<2>();
               else tma_store_wait_read<3>();
@@ -514,7 +532,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (elect_one()) {  // (the same lane every time: it owns this warp's bulk-async groups)
             if (has_res) {
               // every earlier store has finished reading smem -> the other buffer is free: prefetch the
               // residual tile of this warp's next chunk into it
@@ -593,7 +611,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         aphase ^= 1;
       }
     }
-    if (lane == 0) tma_store_wait<0>();  // smem must stay valid until the bulk stores have drained
+    __syncwarp();
+    if (elect_one()) tma_store_wait<0>();  // smem must stay valid until the bulk stores have drained
   }
 
   tc_fence_before();
@@ -696,7 +715,8 @@ int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
   const int units = ((m_tiles + cluster - 1) / cluster) * (p.N / BLOCK_N) * p.k_slices;
   int grid = units * cluster < num_sms() ? units * cluster : num_sms();
   grid -= grid % cluster;
-  LaunchScope ls(kClsGemm, stream, 2.0 * double(a.M) * double(a.N) * double(a.K) * (a.split3 ? 3 : 1));
+  LaunchScope ls(a.split3 ? kClsGemmSplit : kClsGemm, stream,
+                 2.0 * double(a.M) * double(a.N) * double(a.K) * (a.split3 ? 3 : 1));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(32 * (2 + EW));

@@ -9,7 +9,11 @@
 namespace sais {
 
 // kernel classes for the launch counter / optional CUDA-event profiler (sais_profile_*)
-enum LaunchClass : int { kClsGemm = 0, kClsVitAttn, kClsLayerNorm, kClsPatchify, kClsTemporalAttn, kClsMisc, kNumClasses };
+enum LaunchClass : int {
+  kClsGemm = 0, kClsVitAttn, kClsLayerNorm, kClsPatchify, kClsTemporalAttn, kClsMisc,
+  kClsGemmSplit,  // split-precision (3-pass) GEMM launches: the temporal head and the fp32-equivalent ViT mode
+  kNumClasses
+};
 
 // RAII around one kernel launch: counts it and, when profiling is on, brackets it with CUDA events on `stream`
 // and books `work` (flops for GEMM/attention classes, algorithmic bytes for the memory-bound ones).
