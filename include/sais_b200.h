@@ -148,6 +148,10 @@ int sais_patchify_f32(const float* frames_chw, int32_t B, sais_bf16* patches, in
  * probabilities fp32 [B,6,197,197] (get_last_selfattention, :216-223). */
 int sais_vit_attention(const sais_bf16* qkv, int32_t B, sais_bf16* out, float* probs, sais_stream_t stream);
 
+/* CLS-query attention of one block: out_cls bf16 [B,384] = attention output of token 0 of every frame only.  Used for
+ * the LAST block, whose other rows VisionTransformer.forward discards (vision_transformer.py:213-214). */
+int sais_vit_cls_attention(const sais_bf16* qkv, int32_t B, sais_bf16* out_cls, sais_stream_t stream);
+
 /* Whole ViT-S/16 backbone. */
 typedef struct {
   const float* ln1_w; const float* ln1_b;

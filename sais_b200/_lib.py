@@ -77,6 +77,7 @@ SIGNATURES = {
     "sais_normalize_patchify_u8": (C.c_int, [_p, C.c_int32, _p, _p, _p, C.c_int32, _p]),
     "sais_patchify_f32": (C.c_int, [_p, C.c_int32, _p, C.c_int32, _p]),
     "sais_vit_attention": (C.c_int, [_p, C.c_int32, _p, _p, _p]),
+    "sais_vit_cls_attention": (C.c_int, [_p, C.c_int32, _p, _p]),
     "sais_vit_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "sais_vit_forward": (C.c_int, [C.POINTER(SaisVitWeights), _p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _p,
                                    C.c_size_t, _p, _p, _p, _p]),

@@ -61,6 +61,9 @@ int prototype_score(const float* reps, const float* protos, int B, int P, int D,
 // vit_attention.cu
 int vit_attention(const sais_bf16* qkv, int B, sais_bf16* out, float* probs, cudaStream_t stream);
 
+// last block, CLS query only: qkv bf16 [B*197,1152] -> out_cls bf16 [B,384]
+int vit_cls_attention(const sais_bf16* qkv, int B, sais_bf16* out_cls, cudaStream_t stream);
+
 // vit_attention_tc.cu (tcgen05 path, no probabilities)
 int vit_attention_tc(const sais_bf16* qkv, int B, sais_bf16* out, cudaStream_t stream);
 

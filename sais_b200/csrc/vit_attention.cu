@@ -207,7 +207,104 @@ vit_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// CLS-query attention for the LAST block: VisionTransformer.forward returns only x[:, 0] (vision_transformer.py:
+// 213-214), so after the last block's K and V are known, every other query row of that block — and every other row of
+// its proj / MLP — is dead work.  One warp per (frame, head): logits of the CLS query against the 197 keys (lanes over
+// keys), exact softmax, then the probability-weighted sum of V (lanes over the 64 dims).  fp32 math on bf16 q/k/v,
+// bf16 output [B,384] — the same rounding points as the full kernel.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) vit_cls_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int B,
+                                                                __nv_bfloat16* __restrict__ out_cls) {
+  // lane = (key group kg = lane / 8, 16-byte chunk dc = lane % 8): one warp instruction covers four whole 128-byte
+  // K (or V) rows, fully coalesced; 50 iterations walk the 197 keys.
+  __shared__ float p_s[4][200];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * 4 + warp;
+  if (item >= B * HEADS) return;
+  const int b = item / HEADS, h = item % HEADS;
+  const int kg = lane >> 3, dc = lane & 7;
+  const __nv_bfloat16* base = qkv + int64_t(b) * T * QKV_LD + h * HD;
+  float q[8];
+  {
+    const uint4 qq = __ldg(reinterpret_cast<const uint4*>(base) + dc);  // CLS token = row 0 of the frame
+    q[0] = bf16_lo(qq.x); q[1] = bf16_hi(qq.x); q[2] = bf16_lo(qq.y); q[3] = bf16_hi(qq.y);
+    q[4] = bf16_lo(qq.z); q[5] = bf16_hi(qq.z); q[6] = bf16_lo(qq.w); q[7] = bf16_hi(qq.w);
+  }
+  float m = -INFINITY;
+#pragma unroll 10
+  for (int j0 = 0; j0 < T; j0 += 4) {
+    const int j = j0 + kg;
+    float dot = 0.f;
+    if (j < T) {
+      const uint4 kk = __ldg(reinterpret_cast<const uint4*>(base + int64_t(j) * QKV_LD + 384) + dc);
+      dot = fmaf(bf16_lo(kk.x), q[0], dot); dot = fmaf(bf16_hi(kk.x), q[1], dot);
+      dot = fmaf(bf16_lo(kk.y), q[2], dot); dot = fmaf(bf16_hi(kk.y), q[3], dot);
+      dot = fmaf(bf16_lo(kk.z), q[4], dot); dot = fmaf(bf16_hi(kk.z), q[5], dot);
+      dot = fmaf(bf16_lo(kk.w), q[6], dot); dot = fmaf(bf16_hi(kk.w), q[7], dot);
+    }
+    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+    dot *= 0.125f;  // head_dim^-0.5
+    if (j < T) {
+      if (dc == 0) p_s[warp][j] = dot;
+      m = fmaxf(m, dot);
+    }
+  }
+  m = warp_max(m);
+  __syncwarp();
+  float sum = 0.f;
+  for (int j = lane; j < T; j += 32) {
+    const float e = __expf(p_s[warp][j] - m);
+    p_s[warp][j] = e;
+    sum += e;
+  }
+  const float inv = 1.0f / warp_sum(sum);
+  __syncwarp();
+  float o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = 0.f;
+#pragma unroll 10
+  for (int j0 = 0; j0 < T; j0 += 4) {
+    const int j = j0 + kg;
+    if (j < T) {
+      const uint4 vv = __ldg(reinterpret_cast<const uint4*>(base + int64_t(j) * QKV_LD + 768) + dc);
+      const float pj = p_s[warp][j];
+      o[0] = fmaf(pj, bf16_lo(vv.x), o[0]); o[1] = fmaf(pj, bf16_hi(vv.x), o[1]);
+      o[2] = fmaf(pj, bf16_lo(vv.y), o[2]); o[3] = fmaf(pj, bf16_hi(vv.y), o[3]);
+      o[4] = fmaf(pj, bf16_lo(vv.z), o[4]); o[5] = fmaf(pj, bf16_hi(vv.z), o[5]);
+      o[6] = fmaf(pj, bf16_lo(vv.w), o[6]); o[7] = fmaf(pj, bf16_hi(vv.w), o[7]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {  // sum the four key groups
+    o[i] += __shfl_xor_sync(0xffffffffu, o[i], 8);
+    o[i] += __shfl_xor_sync(0xffffffffu, o[i], 16);
+  }
+  if (kg == 0) {
+    uint4 r;
+    r.x = pack_bf16x2(o[0] * inv, o[1] * inv);
+    r.y = pack_bf16x2(o[2] * inv, o[3] * inv);
+    r.z = pack_bf16x2(o[4] * inv, o[5] * inv);
+    r.w = pack_bf16x2(o[6] * inv, o[7] * inv);
+    *(reinterpret_cast<uint4*>(out_cls + int64_t(b) * OUT_LD + h * HD) + dc) = r;
+  }
+}
+
 }  // namespace
+
+int vit_cls_attention(const sais_bf16* qkv, int B, sais_bf16* out_cls, cudaStream_t stream) {
+  if (B == 0) return kOk;
+  if (!qkv || !out_cls || B < 0) {
+    set_last_error("vit_cls_attention: bad arguments");
+    return kErrInvalidArg;
+  }
+  LaunchScope ls(kClsVitAttn, stream, 4.0 * double(B) * 6 * 197 * 64);
+  vit_cls_attention_kernel<<<(B * HEADS + 3) / 4, 128, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), B,
+                                                                    reinterpret_cast<__nv_bfloat16*>(out_cls));
+  return check_cuda(cudaGetLastError(), "vit_cls_attention launch");
+}
 
 int vit_attention(const sais_bf16* qkv, int B, sais_bf16* out, float* probs, cudaStream_t stream) {
   if (B == 0) return kOk;

@@ -153,6 +153,15 @@ def vit_attention(qkv, B, emit_probs=False):
     return out, probs
 
 
+def vit_cls_attention(qkv, B):
+    """qkv bf16 [B*197,1152] -> attention output of the CLS query only, bf16 [B,384] (last-block shortcut)."""
+    require_cuda(qkv, "qkv")
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and qkv.shape == (B * 197, 1152)
+    out = torch.empty((B, 384), device=qkv.device, dtype=torch.bfloat16)
+    check(lib().sais_vit_cls_attention(ptr(qkv), B, ptr(out), current_stream()), "sais_vit_cls_attention")
+    return out
+
+
 def temporal_attention(qkv, seq_offsets, key_pad=None, attn_offsets=None, max_S=None, attn_numel=0):
     """qkv fp32 [tokens,1152]; seq_offsets int32 [nseq+1] (device); returns (out bf16 [tokens,768] = [hi|lo] halves
     of the fp32 attention output, head-averaged attention maps flat fp32 or None)."""

@@ -263,6 +263,21 @@ def test_gemm_residual_layernorm(dev, M, K, want_ln):
         assert ((got_n - bf(ref_n)) != 0).float().mean() < 0.01
 
 
+@pytest.mark.parametrize("B,scale", [(1, 1.0), (5, 3.0)])
+def test_vit_cls_attention(dev, B, scale):
+    """last-block shortcut: attention output of the CLS query row only == row 0 of the full attention."""
+    from sais_b200 import ops
+    qkv = rnd(B * 197, 1152, seed=B + 40)
+    qkv[:, :768] *= scale
+    got = ops.vit_cls_attention(qkv.to(dev).bfloat16(), B).cpu().float()
+    ref_o, _ = _vit_attn_ref(qkv, B)
+    ref = ref_o.view(B, 197, 384)[:, 0]
+    assert torch.allclose(got, ref, atol=2e-3 * scale, rtol=2 ** -7), (got - ref).abs().max()
+    full, _ = ops.vit_attention(qkv.to(dev).bfloat16(), B)
+    full0 = full.cpu().float().view(B, 197, 384)[:, 0]
+    assert (got - full0).abs().max() <= 2e-2 * scale  # the tcgen05 kernel rounds P to bf16 before PV; this one keeps fp32
+
+
 # ------------------------------------------------------------------------------------------------ fused MLP
 def _mlp_ref(xn, w1, b1, w2, b2, x):
     """fc1 -> erf-GELU -> (hidden rounded to bf16, as the kernel hands it to the second MMA) -> fc2 -> + residual."""
