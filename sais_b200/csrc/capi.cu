@@ -69,6 +69,11 @@ LaunchScope::~LaunchScope() {
   if (slot_ >= 0) cudaEventRecord(g_prof.ev[slot_][1], stream_);
 }
 
+bool pdl_enabled() {
+  static const bool on = !(getenv("SAIS_PDL") && atoi(getenv("SAIS_PDL")) == 0);
+  return on;
+}
+
 int num_sms() {
   static int sms = 0;
   if (sms == 0) {

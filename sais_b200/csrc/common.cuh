@@ -508,4 +508,45 @@ int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t 
 
 int num_sms();
 
+// ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Every kernel of the library is launched through launch_pdl():
+// with the stream-serialization attribute set, the NEXT kernel of the stream may be scheduled while this
+// one is still running (as soon as every CTA of this grid has executed pdl_trigger() or exited), so its
+// launch latency and its prologue (mbarrier init, TMEM allocation, tensor-map prefetch) hide under this
+// kernel's tail.  The contract every kernel keeps: pdl_wait() — which returns once ALL prerequisite grids
+// have completed and flushed — precedes the first global-memory access of any kind (reads of data a
+// predecessor wrote, and writes a predecessor may still read), so results are identical to plain stream
+// order.  SAIS_PDL=0 drops the attribute (both instructions are then no-ops).
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster,
+                       Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  unsigned n = 0;
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = unsigned(cluster);
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace sais

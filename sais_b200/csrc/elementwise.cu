@@ -25,6 +25,8 @@ __global__ void __launch_bounds__(256) layernorm384_kernel(const float* __restri
                                                            __nv_bfloat16* __restrict__ out_bf16, int split,
                                                            float* __restrict__ out_plus,
                                                            const float* __restrict__ plus_vec) {
+  pdl_trigger();
+  pdl_wait();  // (PDL, common.cuh) no global access above this line
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t warps_total = int64_t(gridDim.x) * (blockDim.x >> 5);
@@ -116,6 +118,8 @@ __global__ void __launch_bounds__(256) layernorm384_kernel(const float* __restri
 __global__ void __launch_bounds__(256) rowstats_cast384_kernel(const float* __restrict__ x, int64_t rows,
                                                                __nv_bfloat16* __restrict__ xb,
                                                                float* __restrict__ stats) {
+  pdl_trigger();
+  pdl_wait();  // (PDL, common.cuh) no global access above this line
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t warps_total = int64_t(gridDim.x) * (blockDim.x >> 5);
@@ -157,6 +161,8 @@ struct NormConsts {
 __global__ void __launch_bounds__(256) normalize_patchify_u8_kernel(const uint8_t* __restrict__ frames, int B,
                                                                     NormConsts nc,
                                                                     __nv_bfloat16* __restrict__ patches, int split) {
+  pdl_trigger();
+  pdl_wait();  // (PDL, common.cuh) no global access above this line
   const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t total = int64_t(B) * 224 * 14;
   if (t >= total) return;
@@ -199,6 +205,8 @@ __global__ void __launch_bounds__(256) normalize_patchify_u8_kernel(const uint8_
 // fp32 NCHW (already normalised, what the reference model is called with) -> bf16 patch matrix.
 __global__ void __launch_bounds__(256) patchify_f32_kernel(const float* __restrict__ frames, int B,
                                                            __nv_bfloat16* __restrict__ patches, int split) {
+  pdl_trigger();
+  pdl_wait();  // (PDL, common.cuh) no global access above this line
   const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t total = int64_t(B) * 3 * 224 * 14;
   if (t >= total) return;
@@ -231,12 +239,16 @@ __global__ void __launch_bounds__(256) patchify_f32_kernel(const float* __restri
 
 // seq_offsets[i] = i * stride (packed-sequence offsets of equally long sequences, built on device)
 __global__ void fill_offsets_kernel(int32_t* __restrict__ offs, int n, int stride) {
+  pdl_trigger();
+  pdl_wait();  // (PDL, common.cuh) no global access above this line
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) offs[t] = t * stride;
 }
 
 // x[b, 0, :] = cls_token + pos_embed[0]   (vision_transformer.py:201-205)
 __global__ void write_cls_rows_kernel(const float* __restrict__ cls_pos0, int B, float* __restrict__ x) {
+  pdl_trigger();
+  pdl_wait();  // (PDL, common.cuh) no global access above this line
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= B * (D / 4)) return;
   const int b = t / (D / 4), c = (t % (D / 4)) * 4;
@@ -255,6 +267,8 @@ __global__ void __launch_bounds__(128) temporal_prep_kernel(const float* __restr
                                                             __nv_bfloat16* __restrict__ tok_bf16,
                                                             float* __restrict__ tok_plus,
                                                             const float* __restrict__ plus_vec) {
+  pdl_trigger();
+  pdl_wait();  // (PDL, common.cuh) no global access above this line
   const int i = blockIdx.x;
   const int t0 = seq_offsets[i];
   const int S = seq_offsets[i + 1] - t0;
@@ -289,6 +303,8 @@ __global__ void __launch_bounds__(128) temporal_prep_kernel(const float* __restr
 // out_cls[i] = relu(tokens[seq_offsets[i]])   (prepare_model.py:215,220)
 __global__ void gather_cls_relu_kernel(const float* __restrict__ tok, const int32_t* __restrict__ seq_offsets,
                                        int nseq, float* __restrict__ out_cls) {
+  pdl_trigger();
+  pdl_wait();  // (PDL, common.cuh) no global access above this line
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nseq * (D / 4)) return;
   const int i = t / (D / 4), c = (t % (D / 4)) * 4;
@@ -308,6 +324,8 @@ __global__ void __launch_bounds__(256) clip_head_kernel(const float* __restrict_
                                                         const float* __restrict__ cls_b, int B, int nsnip,
                                                         const float* __restrict__ W, const float* __restrict__ bias,
                                                         float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();  // (PDL, common.cuh) no global access above this line
   __shared__ float v[kClipsPerBlock][D];
   const int b0 = blockIdx.x * kClipsPerBlock;
   const float inv = 1.0f / float(nsnip);
@@ -354,6 +372,8 @@ __global__ void __launch_bounds__(128) prototype_score_kernel(const float* __res
                                                               const float* __restrict__ protos, int B, int P, int Dd,
                                                               float* __restrict__ probs, float* __restrict__ sims,
                                                               int32_t* __restrict__ pred) {
+  pdl_trigger();
+  pdl_wait();  // (PDL, common.cuh) no global access above this line
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
@@ -417,10 +437,10 @@ int layernorm(const float* x, int64_t in_pitch, const float* gamma, const float*
   const int64_t cap = int64_t(num_sms()) * 8;  // persistent beyond one full wave (8 blocks x 8 warps per SM)
   if (blocks > cap) blocks = cap;
   LaunchScope ls(kClsLayerNorm, stream, double(rows) * D * (4 + (out_f32 ? 4 : 0) + (out_bf16 ? 2 : 0)));
-  layernorm384_kernel<<<unsigned(blocks), 256, 0, stream>>>(x, in_pitch, gamma, beta, eps, rows, out_f32,
+  return check_cuda(launch_pdl(layernorm384_kernel, dim3(unsigned(blocks)), dim3(256), size_t(0), stream, 1, x, in_pitch, gamma, beta, eps, rows, out_f32,
                                                             reinterpret_cast<__nv_bfloat16*>(out_bf16), split, out_plus,
-                                                            plus_vec);
-  return check_cuda(cudaGetLastError(), "layernorm launch");
+                                                            plus_vec),
+                    "layernorm launch");
 }
 
 int rowstats_cast(const float* x, int64_t rows, sais_bf16* xb, float* stats, cudaStream_t stream) {
@@ -433,8 +453,8 @@ int rowstats_cast(const float* x, int64_t rows, sais_bf16* xb, float* stats, cud
   const int64_t cap = int64_t(num_sms()) * 8;
   if (blocks > cap) blocks = cap;
   LaunchScope ls(kClsLayerNorm, stream, double(rows) * D * 6);
-  rowstats_cast384_kernel<<<unsigned(blocks), 256, 0, stream>>>(x, rows, reinterpret_cast<__nv_bfloat16*>(xb), stats);
-  return check_cuda(cudaGetLastError(), "rowstats_cast launch");
+  return check_cuda(launch_pdl(rowstats_cast384_kernel, dim3(unsigned(blocks)), dim3(256), size_t(0), stream, 1, x, rows, reinterpret_cast<__nv_bfloat16*>(xb), stats),
+                    "rowstats_cast launch");
 }
 
 int normalize_patchify_u8(const uint8_t* frames, int B, const float* mean3, const float* std3, sais_bf16* patches,
@@ -451,9 +471,9 @@ int normalize_patchify_u8(const uint8_t* frames, int B, const float* mean3, cons
   }
   const int64_t total = int64_t(B) * 224 * 14;
   LaunchScope ls(kClsPatchify, stream, double(B) * 224 * 224 * 3 * 3);
-  normalize_patchify_u8_kernel<<<unsigned((total + 255) / 256), 256, 0, stream>>>(
-      frames, B, nc, reinterpret_cast<__nv_bfloat16*>(patches), split);
-  return check_cuda(cudaGetLastError(), "normalize_patchify_u8 launch");
+  return check_cuda(launch_pdl(normalize_patchify_u8_kernel, dim3(unsigned((total + 255) / 256)), dim3(256), size_t(0), stream, 1, 
+      frames, B, nc, reinterpret_cast<__nv_bfloat16*>(patches), split),
+                    "normalize_patchify_u8 launch");
 }
 
 int patchify_f32(const float* frames, int B, sais_bf16* patches, cudaStream_t stream, int split) {
@@ -464,24 +484,24 @@ int patchify_f32(const float* frames, int B, sais_bf16* patches, cudaStream_t st
   }
   const int64_t total = int64_t(B) * 3 * 224 * 14;
   LaunchScope ls(kClsPatchify, stream, double(B) * 224 * 224 * 3 * 6);
-  patchify_f32_kernel<<<unsigned((total + 255) / 256), 256, 0, stream>>>(
-      frames, B, reinterpret_cast<__nv_bfloat16*>(patches), split);
-  return check_cuda(cudaGetLastError(), "patchify_f32 launch");
+  return check_cuda(launch_pdl(patchify_f32_kernel, dim3(unsigned((total + 255) / 256)), dim3(256), size_t(0), stream, 1, 
+      frames, B, reinterpret_cast<__nv_bfloat16*>(patches), split),
+                    "patchify_f32 launch");
 }
 
 int fill_offsets(int32_t* offs, int n, int stride, cudaStream_t stream) {
   if (n <= 0) return kOk;
   LaunchScope ls(kClsMisc, stream, double(n) * 4);
-  fill_offsets_kernel<<<(n + 255) / 256, 256, 0, stream>>>(offs, n, stride);
-  return check_cuda(cudaGetLastError(), "fill_offsets launch");
+  return check_cuda(launch_pdl(fill_offsets_kernel, dim3((n + 255) / 256), dim3(256), size_t(0), stream, 1, offs, n, stride),
+                    "fill_offsets launch");
 }
 
 int write_cls_rows(const float* cls_pos0, int B, float* x, cudaStream_t stream) {
   if (B == 0) return kOk;
   const int total = B * (D / 4);
   LaunchScope ls(kClsMisc, stream, double(B) * D * 8);
-  write_cls_rows_kernel<<<(total + 255) / 256, 256, 0, stream>>>(cls_pos0, B, x);
-  return check_cuda(cudaGetLastError(), "write_cls_rows launch");
+  return check_cuda(launch_pdl(write_cls_rows_kernel, dim3((total + 255) / 256), dim3(256), size_t(0), stream, 1, cls_pos0, B, x),
+                    "write_cls_rows launch");
 }
 
 int temporal_prep(const float* x_frames, const int32_t* seq_offsets, int nseq, int total_tokens,
@@ -494,9 +514,9 @@ int temporal_prep(const float* x_frames, const int32_t* seq_offsets, int nseq, i
     return kErrInvalidArg;
   }
   LaunchScope ls(kClsMisc, stream, double(total_tokens) * D * 14);
-  temporal_prep_kernel<<<nseq, 128, 0, stream>>>(x_frames, seq_offsets, frame_cls, frame_pos, tok_f32,
-                                                 reinterpret_cast<__nv_bfloat16*>(tok_bf16), tok_plus, plus_vec);
-  return check_cuda(cudaGetLastError(), "temporal_prep launch");
+  return check_cuda(launch_pdl(temporal_prep_kernel, dim3(nseq), dim3(128), size_t(0), stream, 1, x_frames, seq_offsets, frame_cls, frame_pos, tok_f32,
+                                                 reinterpret_cast<__nv_bfloat16*>(tok_bf16), tok_plus, plus_vec),
+                    "temporal_prep launch");
 }
 
 int gather_cls_relu(const float* tok_f32, const int32_t* seq_offsets, int nseq, float* out_cls,
@@ -504,8 +524,8 @@ int gather_cls_relu(const float* tok_f32, const int32_t* seq_offsets, int nseq, 
   if (nseq == 0) return kOk;
   const int total = nseq * (D / 4);
   LaunchScope ls(kClsMisc, stream, double(nseq) * D * 8);
-  gather_cls_relu_kernel<<<(total + 255) / 256, 256, 0, stream>>>(tok_f32, seq_offsets, nseq, out_cls);
-  return check_cuda(cudaGetLastError(), "gather_cls_relu launch");
+  return check_cuda(launch_pdl(gather_cls_relu_kernel, dim3((total + 255) / 256), dim3(256), size_t(0), stream, 1, tok_f32, seq_offsets, nseq, out_cls),
+                    "gather_cls_relu launch");
 }
 
 int clip_head(const float* cls_a, const float* cls_b, int B, int nsnip, const float* lin_w, const float* lin_b,
@@ -516,9 +536,9 @@ int clip_head(const float* cls_a, const float* cls_b, int B, int nsnip, const fl
     return kErrInvalidArg;
   }
   LaunchScope ls(kClsMisc, stream, double(B) * (nsnip * D * 8 + 1024));
-  clip_head_kernel<<<(B + kClipsPerBlock - 1) / kClipsPerBlock, 256, 0, stream>>>(cls_a, cls_b, B, nsnip, lin_w,
-                                                                                 lin_b, out);
-  return check_cuda(cudaGetLastError(), "clip_head launch");
+  return check_cuda(launch_pdl(clip_head_kernel, dim3((B + kClipsPerBlock - 1) / kClipsPerBlock), dim3(256), size_t(0), stream, 1, cls_a, cls_b, B, nsnip, lin_w,
+                                                                                 lin_b, out),
+                    "clip_head launch");
 }
 
 int prototype_score(const float* reps, const float* protos, int B, int P, int Dd, float* probs, float* sims,
@@ -529,8 +549,8 @@ int prototype_score(const float* reps, const float* protos, int B, int P, int Dd
     return kErrInvalidArg;
   }
   LaunchScope ls(kClsMisc, stream, double(B) * (Dd * 4 + P * 8));
-  prototype_score_kernel<<<(B + 3) / 4, 128, 0, stream>>>(reps, protos, B, P, Dd, probs, sims, pred);
-  return check_cuda(cudaGetLastError(), "prototype_score launch");
+  return check_cuda(launch_pdl(prototype_score_kernel, dim3((B + 3) / 4), dim3(128), size_t(0), stream, 1, reps, protos, B, P, Dd, probs, sims, pred),
+                    "prototype_score launch");
 }
 
 }  // namespace sais

@@ -226,6 +226,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (csize > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+  // PDL: the set-up above overlapped the previous kernel's tail; nothing before this line touched global memory
+  pdl_trigger();
+  pdl_wait();
   auto tile_m0 = [&](int unit) { return ((unit / n_tiles) * csize + int(crank)) * BLOCK_M; };
 
   if (warp == kProducerWarp) {
@@ -717,19 +720,8 @@ int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
   grid -= grid % cluster;
   LaunchScope ls(a.split3 ? kClsGemmSplit : kClsGemm, stream,
                  2.0 * double(a.M) * double(a.N) * double(a.K) * (a.split3 ? 3 : 1));
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(32 * (2 + EW));
-  cfg.dynamicSmemBytes = Cfg::smem_bytes(wide, nbuf, p.xb_buf);
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cluster;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  rc = check_cuda(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BLOCK_N, MODE, CG, EW>, ta, tb, tout, tres, tout2, p),
+  rc = check_cuda(launch_pdl(gemm_tcgen05_kernel<BLOCK_N, MODE, CG, EW>, dim3(grid), dim3(32 * (2 + EW)),
+                             size_t(Cfg::smem_bytes(wide, nbuf, p.xb_buf)), stream, cluster, ta, tb, tout, tres, tout2, p),
                   "gemm_tcgen05_kernel launch");
   if (p.dbg) {  // dev knob: dump CTA 0's timeline (cycles relative to the first stamp), last call wins
     static long long h[kDbgN];

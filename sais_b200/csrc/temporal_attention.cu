@@ -44,6 +44,8 @@ seq_attention_f32_kernel(const float* __restrict__ qkv, const int32_t* __restric
                          const uint8_t* __restrict__ key_pad, const int64_t* __restrict__ attn_offsets, int max_S,
                          float scale, __nv_bfloat16* __restrict__ out_split, float* __restrict__ attn_mean,
                          float* __restrict__ probs_per_head) {
+  pdl_trigger();
+  pdl_wait();  // (PDL, common.cuh) no global access above this line
   using Cfg = AttnCfg<H, HD>;
   constexpr int E = Cfg::E, LD = Cfg::LD;
   constexpr int kWarps = Cfg::kWarps, kThreads = Cfg::kThreads, RG = Cfg::RG;
@@ -189,13 +191,10 @@ int launch_seq_attention(const float* qkv, const int32_t* seq_offsets, const uin
   }
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_split);
   LaunchScope ls(cls, stream, 0.0);
-  if (smem_kv)
-    seq_attention_f32_kernel<H, HD, true><<<nseq, Cfg::kThreads, sm, stream>>>(qkv, seq_offsets, key_pad, attn_offsets,
-                                                                          max_S, scale, o, attn_mean, probs_per_head);
-  else
-    seq_attention_f32_kernel<H, HD, false><<<nseq, Cfg::kThreads, sm, stream>>>(qkv, seq_offsets, key_pad, attn_offsets,
-                                                                           max_S, scale, o, attn_mean, probs_per_head);
-  return check_cuda(cudaGetLastError(), "seq_attention launch");
+  auto kern = smem_kv ? seq_attention_f32_kernel<H, HD, true> : seq_attention_f32_kernel<H, HD, false>;
+  return check_cuda(launch_pdl(kern, dim3(nseq), dim3(Cfg::kThreads), size_t(sm), stream, 1, qkv, seq_offsets, key_pad,
+                               attn_offsets, max_S, scale, o, attn_mean, probs_per_head),
+                    "seq_attention launch");
 }
 
 }  // namespace

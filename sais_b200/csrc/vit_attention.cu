@@ -50,6 +50,8 @@ template <bool kEmitProbs>
 __global__ void __launch_bounds__(kThreads, 2)
 vit_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                      float* __restrict__ probs) {
+  pdl_trigger();
+  pdl_wait();  // (PDL, common.cuh) no global access above this line
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t qs = smem_u32(smem);
   const uint32_t ks = qs + Q_ROWS * 128;
@@ -216,6 +218,8 @@ vit_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) vit_cls_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int B,
                                                                 __nv_bfloat16* __restrict__ out_cls) {
+  pdl_trigger();
+  pdl_wait();  // (PDL, common.cuh) no global access above this line
   // lane = (key group kg = lane / 8, 16-byte chunk dc = lane % 8): one warp instruction covers four whole 128-byte
   // K (or V) rows, fully coalesced; 50 iterations walk the 197 keys.
   __shared__ float p_s[4][200];
@@ -301,9 +305,9 @@ int vit_cls_attention(const sais_bf16* qkv, int B, sais_bf16* out_cls, cudaStrea
     return kErrInvalidArg;
   }
   LaunchScope ls(kClsVitAttn, stream, 4.0 * double(B) * 6 * 197 * 64);
-  vit_cls_attention_kernel<<<(B * HEADS + 3) / 4, 128, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), B,
-                                                                    reinterpret_cast<__nv_bfloat16*>(out_cls));
-  return check_cuda(cudaGetLastError(), "vit_cls_attention launch");
+  return check_cuda(launch_pdl(vit_cls_attention_kernel, dim3((B * HEADS + 3) / 4), dim3(128), size_t(0), stream, 1, reinterpret_cast<const __nv_bfloat16*>(qkv), B,
+                                                                    reinterpret_cast<__nv_bfloat16*>(out_cls)),
+                    "vit_cls_attention launch");
 }
 
 int vit_attention(const sais_bf16* qkv, int B, sais_bf16* out, float* probs, cudaStream_t stream) {
@@ -331,11 +335,9 @@ int vit_attention(const sais_bf16* qkv, int B, sais_bf16* out, float* probs, cud
   const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(qkv);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
   LaunchScope ls(kClsVitAttn, stream, 4.0 * double(B) * 6 * 197 * 197 * 64);
-  if (probs)
-    vit_attention_kernel<true><<<B * HEADS, kThreads, kSmem, stream>>>(q, o, probs);
-  else
-    vit_attention_kernel<false><<<B * HEADS, kThreads, kSmem, stream>>>(q, o, nullptr);
-  return check_cuda(cudaGetLastError(), "vit_attention launch");
+  auto kern = probs ? vit_attention_kernel<true> : vit_attention_kernel<false>;
+  return check_cuda(launch_pdl(kern, dim3(B * HEADS), dim3(kThreads), size_t(kSmem), stream, 1, q, o, probs),
+                    "vit_attention launch");
 }
 
 }  // namespace sais

@@ -90,6 +90,8 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+  pdl_trigger();
+  pdl_wait();  // (PDL) set-up done under the previous kernel's tail; global memory only from here on
 
   if (warp >= 8) {
     // ===================== single-thread roles: loader (warp 8), MMA issuer of window 0 / 1 (warps 9 / 10) ======
@@ -382,9 +384,10 @@ int launch_attn(const CUtensorMap& tm, const CUtensorMap& tm_out, sais_bf16* out
     attr_set = true;
   }
   const int grid = items < num_sms() ? items : num_sms();
-  vit_attention_tc_kernel<kPInTmem, kTurns><<<grid, kThreads, smem_bytes<kPInTmem>(), stream>>>(
-      tm, tm_out, reinterpret_cast<__nv_bfloat16*>(out), items, dbg);
-  return check_cuda(cudaGetLastError(), "vit_attention_tc launch");
+  return check_cuda(launch_pdl(vit_attention_tc_kernel<kPInTmem, kTurns>, dim3(grid), dim3(kThreads),
+                               size_t(smem_bytes<kPInTmem>()), stream, 1, tm, tm_out,
+                               reinterpret_cast<__nv_bfloat16*>(out), items, dbg),
+                    "vit_attention_tc launch");
 }
 
 }  // namespace
