@@ -133,6 +133,23 @@ int sais_layernorm(const float* x, int64_t in_pitch, const float* gamma, const f
  * of 384 (x: [rows,384]; xb: bf16 [rows,384]; stats: fp32 [rows,8]). */
 int sais_rowstats_cast(const float* x, int64_t rows, sais_bf16* xb, float* stats, sais_stream_t stream);
 
+/* Frame front-end: centre crop + Pillow-exact antialiased bilinear resize to 224 x 224.
+ * Replaces, for decoded uint8 frames, `transforms.CenterCrop((height_frac*height, width_frac*width))`
+ * (dino-main/main_dino.py:298-301; fractions from getCropDims :317-322) and `transforms.Resize((224,224))`
+ * (extract_representations.py:158-162) = PIL Image.resize(BILINEAR): Pillow's two-pass 8-bit fixed-point triangle
+ * filter (libImaging/Resample.c), horizontal pass first.  Integer arithmetic: results are bit-identical to Pillow.
+ *   sais_center_crop_box: HOST helper, box4_host = {top, left, crop_h, crop_w} with torchvision's / PIL's rounding.
+ *   sais_resize_table_ints / sais_resize_build_table: HOST helpers; the coefficient table for one source side
+ *     (crop_w for the horizontal pass, crop_h for the vertical one): int32 [224][2] (first index, taps) followed by
+ *     [ksize][224] coefficients.  The caller copies the tables to the device (they depend on the geometry only).
+ *   sais_crop_resize_u8: frames u8 [N,H,W,3] -> out u8 [N,224,224,3]; tmp = u8 [N,crop_h,224,3] workspace. */
+int sais_center_crop_box(int32_t height, int32_t width, double height_frac, double width_frac, int32_t* box4_host);
+int64_t sais_resize_table_ints(int32_t in_size);
+int sais_resize_build_table(int32_t in_size, int32_t* table_host);
+int sais_crop_resize_u8(const uint8_t* frames, int32_t N, int32_t H, int32_t W, int32_t top, int32_t left,
+                        int32_t crop_h, int32_t crop_w, const int32_t* table_h, const int32_t* table_v, uint8_t* tmp,
+                        uint8_t* out, sais_stream_t stream);
+
 /* Frame normalisation + patch layout.  u8 variant replaces ToTensor+Normalize
  * (extract_representations.py:158-162): frames u8 [B,224,224,3] -> patches bf16 [B*196,768],
  * k = c*256 + ky*16 + kx, value = (u8/255 - mean[c]) / std[c].  f32 variant takes the already

@@ -74,6 +74,11 @@ SIGNATURES = {
                                                C.c_int64, C.c_int64, _p]),
     "sais_rowstats_cast": (C.c_int, [_p, C.c_int64, _p, _p, _p]),
     "sais_layernorm": (C.c_int, [_p, C.c_int64, _p, _p, C.c_float, C.c_int64, C.c_int32, _p, _p, C.c_int32, _p]),
+    "sais_center_crop_box": (C.c_int, [C.c_int32, C.c_int32, C.c_double, C.c_double, C.POINTER(C.c_int32)]),
+    "sais_resize_table_ints": (C.c_int64, [C.c_int32]),
+    "sais_resize_build_table": (C.c_int, [C.c_int32, C.POINTER(C.c_int32)]),
+    "sais_crop_resize_u8": (C.c_int, [_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                      _p, _p, _p, _p, _p]),
     "sais_normalize_patchify_u8": (C.c_int, [_p, C.c_int32, _p, _p, _p, C.c_int32, _p]),
     "sais_patchify_f32": (C.c_int, [_p, C.c_int32, _p, C.c_int32, _p]),
     "sais_vit_attention": (C.c_int, [_p, C.c_int32, _p, _p, _p]),
