@@ -56,19 +56,20 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = (2 * BLOCK_N <= 256) ? 256 : 512;
   static constexpr int kMaxStages = 6;
-  static constexpr int kTailBytes = 512 /*barriers*/ + 2 * kEpiWarps * kChunksPerWarp * CW * 4 /*bias + column-sum slices*/;
-  static constexpr int kSmemBudget = 227 * 1024 - 1024 /*align slack*/ - kTailBytes;
+  // tail: barriers + per-warp bias slices (+ the folded-LayerNorm column-sum slices, consumer GEMMs only)
+  static int tail_bytes(bool csum) { return 512 + (csum ? 2 : 1) * kEpiWarps * kChunksPerWarp * CW * 4; }
+  static int budget(bool csum) { return 227 * 1024 - 1024 /*align slack*/ - tail_bytes(csum); }
   // staging per epilogue warp: two buffers of 32 rows x 128 B (fp32 / bf16 hi+lo) or 32 rows x 64 B (plain bf16)
   // + xb: one extra 2 KB tile per warp for the bf16 copy a LayerNorm-producer GEMM writes next to its fp32 output
   static int epi_bytes(bool wide, int nbuf, int xb = 0) {
     return kEpiWarps * (nbuf * (wide ? kStageBufBytes : kStageBufBytes / 2) + xb);
   }
-  static int stages(bool wide, int nbuf, int xb = 0) {
-    const int s = (kSmemBudget - epi_bytes(wide, nbuf, xb)) / kStageBytes;
+  static int stages(bool wide, int nbuf, int xb = 0, bool csum = true) {
+    const int s = (budget(csum) - epi_bytes(wide, nbuf, xb)) / kStageBytes;
     return s > kMaxStages ? kMaxStages : s;
   }
-  static int smem_bytes(bool wide, int nbuf, int xb = 0) {
-    return stages(wide, nbuf, xb) * kStageBytes + epi_bytes(wide, nbuf, xb) + 1024 + kTailBytes;
+  static int smem_bytes(bool wide, int nbuf, int xb = 0, bool csum = true) {
+    return stages(wide, nbuf, xb, csum) * kStageBytes + epi_bytes(wide, nbuf, xb) + 1024 + tail_bytes(csum);
   }
 };
 
@@ -229,6 +230,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   // PDL: the set-up above overlapped the previous kernel's tail; nothing before this line touched global memory
   pdl_trigger();
   pdl_wait();
+  if (p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {  // effective SM clock of this launch: cycles vs nanoseconds
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    p.dbg[4 * 16 * 16] = (long long)ns;
+    p.dbg[4 * 16 * 16 + 1] = clock64();
+  }
   auto tile_m0 = [&](int unit) { return ((unit / n_tiles) * csize + int(crank)) * BLOCK_M; };
 
   if (warp == kProducerWarp) {
@@ -247,7 +254,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           stamp(0, tidx, kb - kb0);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          if (CG == 1 || crank == 0) mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes * CG);
+          // dev knob (SAIS_GEMM_DEBUG_NOSTORE & 8): load A only for the first n-tile of every m-tile (stale A otherwise; timing
+          // experiment that separates operand INGRESS cost from the tensor core's own shared-memory reads)
+          const bool skip_a = (p.debug_nostore & 8) && (tile % n_tiles) != 0;
+          if (CG == 1 || crank == 0)
+            mbar_arrive_expect_tx(&full_bar[stage], (skip_a ? Cfg::kBBytes : Cfg::kStageBytes) * CG);
           // split3 passes: (A_hi, W_hi), (A_lo, W_hi), (A_hi, W_lo); halves sit side by side along K
           int ka = kb, kw = kb;
           if (kb >= 2 * kb_per_pass) {
@@ -257,12 +268,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             kw = kb - kb_per_pass;
           }
           if (CG == 1) {
-            tma_load_2d(sa, &tmap_a, &full_bar[stage], ka * BLOCK_K, m0);
+            if (!skip_a) tma_load_2d(sa, &tmap_a, &full_bar[stage], ka * BLOCK_K, m0);
             tma_load_2d(sb, &tmap_b, &full_bar[stage], kw * BLOCK_K, n0);
           } else {
             // both CTAs' loads complete on the LEADER's full barrier (its MMA thread is the only consumer)
             const uint32_t lbar = leader_smem_u32(&full_bar[stage]);
-            tma_load_2d_cg2(sa, &tmap_a, lbar, ka * BLOCK_K, m0);
+            if (!skip_a) tma_load_2d_cg2(sa, &tmap_a, lbar, ka * BLOCK_K, m0);
             tma_load_2d_cg2(sb, &tmap_b, lbar, kw * BLOCK_K, n0 + int(crank) * (BLOCK_N / 2));
           }
           if (++stage == kStages) {
@@ -487,15 +498,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               unpack2(add2(pack2(f[4 * j + 2], f[4 * j + 3]), pack2(r4.z, r4.w)), f[4 * j + 2], f[4 * j + 3]);
             }
             if (ln_out) {
+              if (!(p.debug_nostore & 4))
 #pragma unroll
               for (int j = 0; j < 32; j += 2) {
                 const uint64_t x2 = pack2(f[j], f[j + 1]);
                 ln_sum2 = add2(ln_sum2, x2);
                 ln_sq2 = fma2(x2, x2, ln_sq2);
               }
-              // bf16 copy of the row segment straight from registers (64 contiguous bytes per thread): no staging
-              // tile, so the operand ring keeps its depth
-              if (row < p.M) {
+              if (p.xb_buf) {
+                // bf16 copy of the tile -> its own 64B-swizzled staging tile; leaves with the fp32 tile's TMA store below
+                // (full 64-byte row segments instead of 32 scattered 16-byte pieces per store instruction, which cost
+                // the LSU one wavefront each: 10 us per GEMM at batch 256).  The previous chunk's stores must have
+                // finished reading the tile: they were issued a whole chunk ago, so this wait is all but free.
+                __syncwarp();
+                if (elect_one()) tma_store_wait_read<0>();
+                __syncwarp();
+                const uint32_t xb = my_stage + nbuf * kBuf;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  sts128(xb + stage_off_bf16(lane, j), pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                         pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+              } else if (row < p.M && !(p.debug_nostore & 2)) {
+                // bf16 copy of the row segment straight from registers (64 contiguous bytes per thread)
                 uint4* xp = reinterpret_cast<uint4*>(p.out2_bf16 + int64_t(row) * p.ldo2 + n);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
@@ -552,10 +576,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 tma_load_2d_s(my_stage + ((it + 1) & 1) * kBuf, &tmap_res, rb, nn0 + nc * CW, nm0 + q * 32);
               }
             }
-            if (!p.debug_nostore) {
+            if (!(p.debug_nostore & 1)) {
               if (MODE == kModeF32 && p.accumulate) tma_reduce_add_2d_s(&tmap_out, buf, n, m0 + q * 32);
               else tma_store_2d_s(&tmap_out, buf, n, m0 + q * 32);
               if (MODE == kModeGeneric && p.split_out) tma_store_2d_s(&tmap_out, buf + 2048, p.N + n, m0 + q * 32);
+              if (MODE == kModeF32 && ln_out && p.xb_buf) tma_store_2d_s(&tmap_out2, my_stage + nbuf * kBuf, n, m0 + q * 32);
             }
             tma_store_commit();
           }
@@ -563,7 +588,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (++bufi == nbuf) bufi = 0;
           if (erole >= 0 && lane == 0) stamp(erole, tidx, 2 + ci);
         } else if (MODE == kModeGeneric) {
-          if (row < p.M && !p.debug_nostore) {
+          if (row < p.M && !(p.debug_nostore & 1)) {
             // ---- direct path (patch-embed row remap: GEMM row g*G + i -> token row g*(G+1) + 1 + i, + row_add[i]) ----
             const int g = row / p.remap_group;
             const int pidx = row - g * p.remap_group;
@@ -618,6 +643,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (elect_one()) tma_store_wait<0>();  // smem must stay valid until the bulk stores have drained
   }
 
+  if (p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    p.dbg[4 * 16 * 16 + 2] = (long long)ns;
+    p.dbg[4 * 16 * 16 + 3] = clock64();
+  }
   tc_fence_before();
   // (cluster) no CTA may exit while its peer can still multicast into its smem or arrive on its barriers
   if (csize > 1) cluster_sync_all(); else __syncthreads();
@@ -688,7 +719,7 @@ int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
   p.debug_nostore = nostore;
   static const char* timeline = getenv("SAIS_GEMM_TIMELINE");
   p.dbg = nullptr;
-  constexpr int kDbgN = 4 * 16 * 16;
+  constexpr int kDbgN = 4 * 16 * 16 + 4;
   if (timeline) {
     if (cudaMalloc(&p.dbg, kDbgN * sizeof(long long)) != cudaSuccess) p.dbg = nullptr;
     if (p.dbg) cudaMemsetAsync(p.dbg, 0, kDbgN * sizeof(long long), stream);
@@ -704,7 +735,9 @@ int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
   p.ln_stats_out = a.ln_stats_out;
   p.out2_bf16 = reinterpret_cast<__nv_bfloat16*>(a.out2_bf16);
   p.ldo2 = a.ldo2;
-  p.xb_buf = 0;
+  static const int env_xb = getenv("SAIS_GEMM_XB") ? atoi(getenv("SAIS_GEMM_XB")) : 1;
+  p.xb_buf = (a.out2_bf16 && env_xb) ? 2048 : 0;
+  const bool csum = a.ln_stats_in != nullptr;  // only consumer GEMMs keep column-sum slices in the tail
   p.accumulate = a.k_slices > 0;
   p.k_slices = 1;
   if (a.k_slices > 1) {  // every slice must own at least one k-block
@@ -713,7 +746,7 @@ int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
     const int per = (kb_total + want - 1) / want;
     p.k_slices = (kb_total + per - 1) / per;
   }
-  p.stages = Cfg::stages(wide, nbuf, p.xb_buf);
+  p.stages = Cfg::stages(wide, nbuf, p.xb_buf, csum);
   p.stage_buf = wide ? kStageBufBytes : kStageBufBytes / 2;
   const int units = ((m_tiles + cluster - 1) / cluster) * (p.N / BLOCK_N) * p.k_slices;
   int grid = units * cluster < num_sms() ? units * cluster : num_sms();
@@ -721,7 +754,7 @@ int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
   LaunchScope ls(a.split3 ? kClsGemmSplit : kClsGemm, stream,
                  2.0 * double(a.M) * double(a.N) * double(a.K) * (a.split3 ? 3 : 1));
   rc = check_cuda(launch_pdl(gemm_tcgen05_kernel<BLOCK_N, MODE, CG, EW>, dim3(grid), dim3(32 * (2 + EW)),
-                             size_t(Cfg::smem_bytes(wide, nbuf, p.xb_buf)), stream, cluster, ta, tb, tout, tres, tout2, p),
+                             size_t(Cfg::smem_bytes(wide, nbuf, p.xb_buf, csum)), stream, cluster, ta, tb, tout, tres, tout2, p),
                   "gemm_tcgen05_kernel launch");
   if (p.dbg) {  // dev knob: dump CTA 0's timeline (cycles relative to the first stamp), last call wins
     static long long h[kDbgN];
@@ -729,9 +762,11 @@ int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
     cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost);
     cudaFree(p.dbg);
     long long t0 = 0;
-    for (long long v : h) if (v && (!t0 || v < t0)) t0 = v;
+    for (int i = 0; i < 4 * 16 * 16; ++i) if (h[i] && (!t0 || h[i] < t0)) t0 = h[i];
     if (FILE* f = fopen(timeline, "w")) {
       fprintf(f, "# M=%d N=%d K=%d BN=%d mode=%d CG=%d grid=%d stages=%d\n", p.M, p.N, p.K, BLOCK_N, MODE, CG, grid, p.stages);
+      const long long dns = h[4 * 16 * 16 + 2] - h[4 * 16 * 16], dcy = h[4 * 16 * 16 + 3] - h[4 * 16 * 16 + 1];
+      fprintf(f, "# CTA 0 thread 0: %lld cycles in %lld ns = %.3f GHz effective SM clock\n", dcy, dns, dns > 0 ? double(dcy) / double(dns) : 0.0);
       const char* names[4] = {"producer", "mma", "epi_w0", "epi_w4"};
       for (int r = 0; r < 4; ++r)
         for (int i = 0; i < 16; ++i) {

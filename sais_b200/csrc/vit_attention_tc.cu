@@ -32,6 +32,7 @@ constexpr int SLOT_BYTES = 3 * MAT_BYTES;  // Q, K, V of one item
 constexpr int P_BYTES = 4 * 128 * 128;     // smem P tile (fallback): 128 rows x 256 keys bf16 = 4 k-blocks of 16 KB
 constexpr int kThreads = 11 * 32;  // 8 softmax warps + loader + one MMA-issuing warp per row-tile window
 constexpr int kTmemCols = 512;             // row tile 0 at column 0, row tile 1 at column 256
+constexpr int kDefaultPoly = 0;           // see ex2_poly2 (SAIS_ATTN_POLY overrides)
 constexpr int kOCol = 128;                 // O accumulator inside the row tile's window
 
 constexpr int kOutStage = 8 * 4096;        // per softmax warp: 32 rows x 128 B staging tile for the TMA store of O
@@ -44,7 +45,33 @@ __device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, u
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-template <bool kPInTmem, bool kTurns>
+// 2^x for x <= 0 on the FMA pipe (packed fp32x2): Cody-Waite split x = n + f with n = round(x), f in [-0.5, 0.5], a
+// degree-3 minimax polynomial for 2^f (max relative error 8.0e-5, far below the bf16 rounding of P) and n added into
+// the exponent field.  The exp pass of the softmax is bound by the MUFU pipe (16 ex2 / clk / SM); evaluating kPoly of
+// every 8 element pairs here instead takes that share off the MUFU at ~5.5 issue slots per element.
+__device__ __forceinline__ void ex2_poly2(float x0, float x1, float& p0, float& p1) {
+  const uint64_t x = pack2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+  const uint64_t t = add2(x, pack2(12582912.0f, 12582912.0f));  // 1.5 * 2^23: the sum's low mantissa bits hold round(x)
+  const uint64_t r = add2(t, pack2(-12582912.0f, -12582912.0f));
+  const uint64_t f = fma2(r, pack2(-1.0f, -1.0f), x);
+  uint64_t q = fma2(f, pack2(0.05519810691475868f, 0.05519810691475868f), pack2(0.24267712235450745f, 0.24267712235450745f));
+  q = fma2(q, f, pack2(0.6932618021965027f, 0.6932618021965027f));
+  q = fma2(q, f, pack2(0.9999227523803711f, 0.9999227523803711f));
+  float t0, t1, q0, q1;
+  unpack2(t, t0, t1);
+  unpack2(q, q0, q1);
+  p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
+  p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
+}
+// which of every 8 consecutive element pairs go to the polynomial (spread out so MUFU and FMA work interleave)
+__host__ __device__ constexpr bool pair_uses_poly(int j, int kPoly) {
+  return kPoly == 0 ? false
+         : kPoly == 2 ? ((j & 3) == 1)
+         : kPoly == 3 ? ((j & 7) == 1 || (j & 7) == 4 || (j & 7) == 6)
+                      : ((j & 1) == 1);
+}
+
+template <bool kPInTmem, bool kTurns, int kPoly>
 __global__ void __launch_bounds__(kThreads, 1)
 vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out,
                         __nv_bfloat16* __restrict__ out, int n_items,
@@ -223,8 +250,13 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
           uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), sl2, -mb));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), sl2, -mb));
+            float p0, p1;
+            if (pair_uses_poly(j, kPoly)) {
+              ex2_poly2(fmaf(__uint_as_float(v[2 * j]), sl2, -mb), fmaf(__uint_as_float(v[2 * j + 1]), sl2, -mb), p0, p1);
+            } else {
+              p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), sl2, -mb));
+              p1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), sl2, -mb));
+            }
             sum += p0 + p1;
             pk[j] = pack_bf16x2(p0, p1);
           }
@@ -372,19 +404,19 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
   }
 }
 
-template <bool kPInTmem, bool kTurns>
+template <bool kPInTmem, bool kTurns, int kPoly>
 int launch_attn(const CUtensorMap& tm, const CUtensorMap& tm_out, sais_bf16* out, int items, cudaStream_t stream,
                 long long* dbg) {
   static bool attr_set = false;
   if (!attr_set) {
-    int rc = check_cuda(cudaFuncSetAttribute(vit_attention_tc_kernel<kPInTmem, kTurns>,
+    int rc = check_cuda(cudaFuncSetAttribute(vit_attention_tc_kernel<kPInTmem, kTurns, kPoly>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<kPInTmem>()),
                         "cudaFuncSetAttribute(vit_attention_tc)");
     if (rc) return rc;
     attr_set = true;
   }
   const int grid = items < num_sms() ? items : num_sms();
-  return check_cuda(launch_pdl(vit_attention_tc_kernel<kPInTmem, kTurns>, dim3(grid), dim3(kThreads),
+  return check_cuda(launch_pdl(vit_attention_tc_kernel<kPInTmem, kTurns, kPoly>, dim3(grid), dim3(kThreads),
                                size_t(smem_bytes<kPInTmem>()), stream, 1, tm, tm_out,
                                reinterpret_cast<__nv_bfloat16*>(out), items, dbg),
                     "vit_attention_tc launch");
@@ -412,9 +444,14 @@ int vit_attention_tc(const sais_bf16* qkv, int B, sais_bf16* out, cudaStream_t s
   {
     LaunchScope ls(kClsVitAttn, stream, 4.0 * double(B) * 6 * 197 * 197 * 64);
     static const bool no_turns = getenv("SAIS_ATTN_NOTURNS") != nullptr && atoi(getenv("SAIS_ATTN_NOTURNS")) != 0;
-    rc = p_smem ? launch_attn<false, false>(tm, tm_out, out, B * HEADS, stream, dbg)
-         : no_turns ? launch_attn<true, false>(tm, tm_out, out, B * HEADS, stream, dbg)
-                    : launch_attn<true, true>(tm, tm_out, out, B * HEADS, stream, dbg);
+    // pairs of every 8 whose exponential runs on the FMA pipe instead of the MUFU (SAIS_ATTN_POLY=0|2|3|4)
+    static const int poly = getenv("SAIS_ATTN_POLY") ? atoi(getenv("SAIS_ATTN_POLY")) : kDefaultPoly;
+    rc = p_smem ? launch_attn<false, false, 0>(tm, tm_out, out, B * HEADS, stream, dbg)
+         : no_turns ? launch_attn<true, false, 0>(tm, tm_out, out, B * HEADS, stream, dbg)
+         : poly == 2 ? launch_attn<true, true, 2>(tm, tm_out, out, B * HEADS, stream, dbg)
+         : poly == 3 ? launch_attn<true, true, 3>(tm, tm_out, out, B * HEADS, stream, dbg)
+         : poly == 4 ? launch_attn<true, true, 4>(tm, tm_out, out, B * HEADS, stream, dbg)
+                     : launch_attn<true, true, 0>(tm, tm_out, out, B * HEADS, stream, dbg);
   }
   if (dbg) {
     long long h[4 * 16 * 8];
