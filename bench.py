@@ -320,6 +320,20 @@ def main():
     _lib.check(lib.sais_profile_end(ms_c, work_c, n_c, ncls), "sais_profile_end")
     barrier()
 
+    # effective SM clock inside the loop: a one-thread probe kernel between steps (cycle counter vs nanosecond timer);
+    # separate pass so that the timed region above stays untouched
+    probe_steps = min(args.steps, 20)
+    probe = torch.zeros((probe_steps, 4), dtype=torch.int64, device=dev)
+    for i in range(3):
+        step_resident(i)
+    for i in range(probe_steps):
+        step_resident(i)
+        _lib.check(lib.sais_clock_probe(probe[i].data_ptr(), 4000, torch.cuda.current_stream().cuda_stream), "clock_probe")
+    barrier()
+    pr = probe.cpu().double()
+    ghz = ((pr[:, 3] - pr[:, 1]) / (pr[:, 2] - pr[:, 0]).clamp(min=1.0)).tolist()
+    ghz_sorted = sorted(ghz)
+
     if rank == 0:
         burst, sustained, hbm, src = load_peaks()
         value = n_global * args.steps / (ms * 1e-3)
@@ -343,7 +357,10 @@ def main():
                     "h2d_bytes_per_step": FRAMES_PER_STEP * 224 * 224 * 3,
                     "d2h_bytes_per_step": FRAMES_PER_STEP * 384 * 4 + CLIPS_PER_STEP * 2 * 4},
             "gpu_launches": int(launches),
-            "clocks": clocks,
+            "clocks": dict(clocks or {}, sm_ghz_in_loop_median=ghz_sorted[len(ghz_sorted) // 2], sm_ghz_in_loop_min=ghz_sorted[0],
+                           sm_ghz_in_loop_max=ghz_sorted[-1],
+                           in_loop_note="clock64 / globaltimer of a probe kernel enqueued after every step of a separate "
+                                        "20-step pass"),
             "roofline": {"bound": "tensor",
                          "kernel": "gemm_tcgen05_kernel, bf16 (the 49 ViT GEMM launches of a step: patch, qkv, proj, "
                                    "fc1, fc2)",

@@ -49,6 +49,12 @@ const char* sais_last_error(void);
 /* number of kernels this library has launched since load (for bench.py's gpu_launches) */
 int64_t sais_launch_count(void);
 
+/* Measurement aid: a one-thread kernel enqueued on `stream` that records {globaltimer ns, SM cycle counter} before and
+ * after a chain of spin_iters dependent FMAs into out4 (device int64[4]): (out4[3]-out4[1]) / (out4[2]-out4[0]) is the
+ * effective SM clock in GHz at that point of the stream — what the kernels around it actually ran at (NVML sampling
+ * is too coarse to see power-cap clock dips inside a millisecond-scale step).  Not counted by sais_launch_count. */
+int sais_clock_probe(int64_t* out4, int32_t spin_iters, sais_stream_t stream);
+
 /* Optional per-kernel-class CUDA-event profiler (bench.py's roofline leg).  Between begin and end every
  * launch is bracketed by events on its stream; end synchronises the device and returns, per class
  * (0 bf16 GEMM, 1 ViT attention, 2 LayerNorm / row statistics, 3 patchify, 4 temporal attention, 5 misc,

@@ -66,6 +66,7 @@ SIGNATURES = {
     "sais_version": (C.c_int, []),
     "sais_last_error": (C.c_char_p, []),
     "sais_launch_count": (C.c_int64, []),
+    "sais_clock_probe": (C.c_int, [_p, C.c_int32, _p]),
     "sais_profile_begin": (None, []),
     "sais_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
     "sais_gemm_bias_act": (C.c_int, [C.POINTER(SaisGemmArgs), _p]),

@@ -220,7 +220,39 @@ const float kStd[3] = {0.229f, 0.224f, 0.225f};
 
 using namespace sais;
 
+namespace sais {
+namespace {
+// one thread: SM cycle counter and nanosecond timer before / after a fixed-length dependent FMA chain
+__global__ void clock_probe_kernel(long long* out4, int spin) {
+  pdl_trigger();
+  pdl_wait();
+  unsigned long long ns0, ns1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
+  const long long c0 = clock64();
+  float x = float(spin);
+  for (int i = 0; i < spin; ++i) x = fmaf(x, 0.999f, 0.5f);
+  const long long c1 = clock64();
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+  out4[0] = (long long)ns0;
+  out4[1] = c0;
+  out4[2] = (long long)ns1;
+  out4[3] = c1 + (x == 12345.678f ? 1 : 0);
+}
+}  // namespace
+}  // namespace sais
+
 extern "C" {
+
+int sais_clock_probe(int64_t* out4, int32_t spin_iters, sais_stream_t stream_) {
+  if (!out4 || spin_iters <= 0) {
+    set_last_error("clock_probe: bad arguments");
+    return kErrInvalidArg;
+  }
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  return check_cuda(launch_pdl(clock_probe_kernel, dim3(1), dim3(1), size_t(0), stream, 1,
+                               reinterpret_cast<long long*>(out4), int(spin_iters)),
+                    "clock_probe launch");
+}
 
 int sais_version(void) { return 100; }
 const char* sais_last_error(void) { return g_err; }

@@ -239,8 +239,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   auto tile_m0 = [&](int unit) { return ((unit / n_tiles) * csize + int(crank)) * BLOCK_M; };
 
   if (warp == kProducerWarp) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp, warp-uniform; only the TMA instructions are elected) =====================
+    {
       int stage = 0;
       uint32_t phase = 0;
       int tidx = 0;
@@ -251,31 +251,42 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int n0 = (tile % n_tiles) * BLOCK_N;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          stamp(0, tidx, kb - kb0);
+          if (lane == 0) stamp(0, tidx, kb - kb0);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
           // dev knob (SAIS_GEMM_DEBUG_NOSTORE & 8): load A only for the first n-tile of every m-tile (stale A otherwise; timing
           // experiment that separates operand INGRESS cost from the tensor core's own shared-memory reads)
           const bool skip_a = (p.debug_nostore & 8) && (tile % n_tiles) != 0;
-          if (CG == 1 || crank == 0)
-            mbar_arrive_expect_tx(&full_bar[stage], (skip_a ? Cfg::kBBytes : Cfg::kStageBytes) * CG);
-          // split3 passes: (A_hi, W_hi), (A_lo, W_hi), (A_hi, W_lo); halves sit side by side along K
-          int ka = kb, kw = kb;
-          if (kb >= 2 * kb_per_pass) {
-            ka = kb - 2 * kb_per_pass;
-            kw = kb - kb_per_pass;
-          } else if (kb >= kb_per_pass) {
-            kw = kb - kb_per_pass;
+          if (p.debug_nostore & 64) {  // dev knob: no operand loads at all (stale smem) — the MMA loop with resident operands
+            if ((CG == 1 || crank == 0) && lane == 0) mbar_arrive(&full_bar[stage]);
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
           }
-          if (CG == 1) {
-            if (!skip_a) tma_load_2d(sa, &tmap_a, &full_bar[stage], ka * BLOCK_K, m0);
-            tma_load_2d(sb, &tmap_b, &full_bar[stage], kw * BLOCK_K, n0);
-          } else {
-            // both CTAs' loads complete on the LEADER's full barrier (its MMA thread is the only consumer)
-            const uint32_t lbar = leader_smem_u32(&full_bar[stage]);
-            if (!skip_a) tma_load_2d_cg2(sa, &tmap_a, lbar, ka * BLOCK_K, m0);
-            tma_load_2d_cg2(sb, &tmap_b, lbar, kw * BLOCK_K, n0 + int(crank) * (BLOCK_N / 2));
+          if (elect_one()) {
+            if (CG == 1 || crank == 0)
+              mbar_arrive_expect_tx(&full_bar[stage], (skip_a ? Cfg::kBBytes : Cfg::kStageBytes) * CG);
+            // split3 passes: (A_hi, W_hi), (A_lo, W_hi), (A_hi, W_lo); halves sit side by side along K
+            int ka = kb, kw = kb;
+            if (kb >= 2 * kb_per_pass) {
+              ka = kb - 2 * kb_per_pass;
+              kw = kb - kb_per_pass;
+            } else if (kb >= kb_per_pass) {
+              kw = kb - kb_per_pass;
+            }
+            if (CG == 1) {
+              if (!skip_a) tma_load_2d(sa, &tmap_a, &full_bar[stage], ka * BLOCK_K, m0);
+              tma_load_2d(sb, &tmap_b, &full_bar[stage], kw * BLOCK_K, n0);
+            } else {
+              // both CTAs' loads complete on the LEADER's full barrier (its MMA thread is the only consumer)
+              const uint32_t lbar = leader_smem_u32(&full_bar[stage]);
+              if (!skip_a) tma_load_2d_cg2(sa, &tmap_a, lbar, ka * BLOCK_K, m0);
+              tma_load_2d_cg2(sb, &tmap_b, lbar, kw * BLOCK_K, n0 + int(crank) * (BLOCK_N / 2));
+            }
           }
+          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -285,7 +296,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && crank == 0) {
+    // The WHOLE warp walks the loop with warp-uniform control flow and values; only the tcgen05 instructions themselves
+    // sit under elect_one().  Run by a single divergent lane (if (lane == 0) ...) the descriptors live in vector
+    // registers and every tcgen05.mma costs an ELECT / 5 x R2UR.BROADCAST / branch "waterfall" on top of 64-bit vector
+    // address arithmetic — measured ~215 cycles per MMA *independent of N*, i.e. the issuing thread, not the tensor
+    // pipe, set the pace of every GEMM (profiles/r01f_mma_issue.md).
+    if (crank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M * CG, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
@@ -294,34 +310,40 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int tidx = 0;
       for (int u = unit0; u < num_units; u += unit_stride, ++tidx) {
         const int kb0 = (u % S) * kbs, kb1 = (kb0 + kbs < k_blocks) ? kb0 + kbs : k_blocks;
-        stamp(1, tidx, 0);
+        if (lane == 0) stamp(1, tidx, 0);
         mbar_wait(&tempty_bar[astage], aphase ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
-        stamp(1, tidx, 1);
+        if (lane == 0) stamp(1, tidx, 1);
         const uint32_t d_tmem = tmem_base + astage * BLOCK_N;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          stamp(1, tidx, 2 + kb - kb0);
+          if (lane == 0) stamp(1, tidx, 2 + kb - kb0);
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + Cfg::kABytes;
           const uint64_t da = umma_desc_sw128_kmajor(sa);
           const uint64_t db = umma_desc_sw128_kmajor(sb);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // advancing K inside the 128-byte swizzle row: +32 bytes = +2 in 16-byte address units
-            if (CG == 1) umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb != kb0) || (k != 0));
-            else umma_f16_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb != kb0) || (k != 0));
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              // advancing K inside the 128-byte swizzle row: +32 bytes = +2 in 16-byte address units
+              if (CG == 1) umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb != kb0) || (k != 0));
+              else umma_f16_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb != kb0) || (k != 0));
+            }
+            // frees the smem slot (in both CTAs of a pair) once these MMAs retire
+            if (CG == 1) umma_commit(&empty_bar[stage]); else umma_commit_cg2_mcast(&empty_bar[stage], uint16_t(0b11));
           }
-          // frees the smem slot (in both CTAs of a pair) once these MMAs retire
-          if (CG == 1) umma_commit(&empty_bar[stage]); else umma_commit_cg2_mcast(&empty_bar[stage], uint16_t(0b11));
+          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
         // accumulator complete -> epilogue (of both CTAs)
-        if (CG == 1) umma_commit(&tfull_bar[astage]); else umma_commit_cg2_mcast(&tfull_bar[astage], uint16_t(0b11));
+        if (elect_one()) {
+          if (CG == 1) umma_commit(&tfull_bar[astage]); else umma_commit_cg2_mcast(&tfull_bar[astage], uint16_t(0b11));
+        }
+        __syncwarp();
         if (++astage == 2) {
           astage = 0;
           aphase ^= 1;
@@ -421,13 +443,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int row = m0 + q * 32 + lane;
 
       uint32_t v[32];
-      tmem_ld_32x32(t_row + half * CW, v);
+      // dev knobs for timing experiments (results wrong): & 16 = no TMEM reads, & 32 = no staging / store (bf16 modes)
+      const bool dbg_no_ld = (p.debug_nostore & 16) != 0, dbg_no_st = (p.debug_nostore & 32) != 0 && !has_res;
+      if (dbg_no_ld) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0;
+      } else {
+        tmem_ld_32x32(t_row + half * CW, v);
+      }
 #pragma unroll 1
       for (int ci = 0; ci < NCW; ++ci) {
         const int c = half + kSub * ci;
         const int n = n0 + c * CW;
         float f[32];
-        tmem_ld_wait_dep(v);
+        if (!dbg_no_ld) tmem_ld_wait_dep(v);
         {
           // bias add (or the folded LayerNorm's  acc * rstd + (-mean * rstd) * c_n + d_n) in packed fp32x2; this is
           // also what moves the accumulator out of v, so the next chunk's TMEM load can be issued right after it
@@ -456,7 +485,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
         }
         if (ci + 1 < NCW) {
-          tmem_ld_32x32(t_row + (c + kSub) * CW, v);  // next chunk's accumulator streams in under this chunk's math
+          if (!dbg_no_ld) tmem_ld_32x32(t_row + (c + kSub) * CW, v);  // next chunk's accumulator streams in under this chunk's math
         } else {  // last TMEM read of this tile by this warp: hand the accumulator back early
           tc_fence_before();
           if (lane == 0) {
@@ -487,7 +516,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
         }
 
-        if (tma_epi) {
+        if (tma_epi && dbg_no_st) {
+          float acc = 0.f;  // keep the math alive
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc += f[j];
+          if (acc == 123.456f) p.out_bf16[0] = __float2bfloat16(acc);
+        } else if (tma_epi) {
           const uint32_t buf = my_stage + (has_res ? int(it & 1) : bufi) * kBuf;
           if (has_res) {
             mbar_wait(&my_res_bar[it & 1], (it >> 1) & 1);
@@ -747,6 +781,8 @@ int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
     p.k_slices = (kb_total + per - 1) / per;
   }
   p.stages = Cfg::stages(wide, nbuf, p.xb_buf, csum);
+  static const int env_stages = getenv("SAIS_GEMM_STAGES") ? atoi(getenv("SAIS_GEMM_STAGES")) : 0;  // dev knob: shallower ring
+  if (env_stages >= 2 && env_stages < p.stages) p.stages = env_stages;
   p.stage_buf = wide ? kStageBufBytes : kStageBufBytes / 2;
   const int units = ((m_tiles + cluster - 1) / cluster) * (p.N / BLOCK_N) * p.k_slices;
   int grid = units * cluster < num_sms() ? units * cluster : num_sms();

@@ -124,7 +124,11 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
     // ===================== single-thread roles: loader (warp 8), MMA issuer of window 0 / 1 (warps 9 / 10) ======
     // Each role blocks on its own mbarriers, so the two row-tile windows advance independently: window w may
     // already run S = QK^T of the next item while the other window is still in its softmax.
-    if (lane == 0) {
+    // All 32 lanes of a role warp walk its loop (warp-uniform control flow and values); only the TMA / tcgen05
+    // instructions sit under elect_one().  Run by one divergent lane, every tcgen05.mma cost an ELECT / R2UR.BROADCAST
+    // "waterfall" plus 64-bit vector address arithmetic (~200 cycles per instruction, more than the 13 N = 64 MMAs of
+    // O = P V take on the tensor pipe).
+    {
       const int n_my = (n_items - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
       if (warp == 8) {
         for (int idx = 0; idx < n_my; ++idx) {
@@ -133,54 +137,62 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
           const int item = int(blockIdx.x) + idx * int(gridDim.x);
           const int b = item / HEADS, h = item % HEADS;
           uint8_t* dst = smem + slot * SLOT_BYTES;
-          mbar_arrive_expect_tx(&ld_full[slot], SLOT_BYTES);
-          tma_load_3d(dst, &tmap_qkv, &ld_full[slot], h * HD, 0, b);
-          tma_load_3d(dst + MAT_BYTES, &tmap_qkv, &ld_full[slot], 384 + h * HD, 0, b);
-          tma_load_3d(dst + 2 * MAT_BYTES, &tmap_qkv, &ld_full[slot], 768 + h * HD, 0, b);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&ld_full[slot], SLOT_BYTES);
+            tma_load_3d(dst, &tmap_qkv, &ld_full[slot], h * HD, 0, b);
+            tma_load_3d(dst + MAT_BYTES, &tmap_qkv, &ld_full[slot], 384 + h * HD, 0, b);
+            tma_load_3d(dst + 2 * MAT_BYTES, &tmap_qkv, &ld_full[slot], 768 + h * HD, 0, b);
+          }
+          __syncwarp();
         }
       } else {
         constexpr uint32_t idesc_s = umma_idesc_bf16(128, KEYS, 0, 0);  // Q (K-major) x K (K-major)
         constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);    // P (K-major) x V (MN-major)
         const int w = warp - 9;
         const uint32_t win = tmem_base + w * 256;
-        // the second window starts half an item late so that the two windows' exp-heavy softmax passes (MUFU-bound)
-        // interleave with each other's MMA round trips instead of colliding
 
         for (int idx = 0; idx < n_my; ++idx) {
           const int slot = idx & 1;
           const uint32_t q_s = smem_u32(smem + slot * SLOT_BYTES);
           const uint32_t k_s = q_s + MAT_BYTES, v_s = q_s + 2 * MAT_BYTES;
           mbar_wait(&ld_full[slot], (idx >> 1) & 1);
-          if (!kTurns && w == 1 && idx == 0) __nanosleep(1800);  // (see above) stagger the windows once the first item has landed
-          stamp(2 + w, idx, 0);
+          // (no-turns build) the second window starts half an item late so that the two windows' softmax passes interleave
+          if (!kTurns && w == 1 && idx == 0) __nanosleep(1800);
+          if (lane == 0) stamp(2 + w, idx, 0);
           mbar_wait(&t_free[w], (idx & 1) ^ 1);  // window drained by the softmax warps
           tc_fence_after();
-          stamp(2 + w, idx, 1);
+          if (lane == 0) stamp(2 + w, idx, 1);
           {
             const uint64_t da = umma_desc_sw128_kmajor(q_s + w * 128 * 128);
             const uint64_t db = umma_desc_sw128_kmajor(k_s);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < HD / 16; ++k) umma_f16(win, da + 2 * k, db + 2 * k, idesc_s, k != 0);
-            umma_commit(&s_full[w]);
+              for (int k = 0; k < HD / 16; ++k) umma_f16(win, da + 2 * k, db + 2 * k, idesc_s, k != 0);
+              umma_commit(&s_full[w]);
+            }
+            __syncwarp();
           }
-          stamp(2 + w, idx, 2);
+          if (lane == 0) stamp(2 + w, idx, 2);
           mbar_wait(&p_full[w], idx & 1);
           tc_fence_after();
-          stamp(2 + w, idx, 3);
+          if (lane == 0) stamp(2 + w, idx, 3);
           const uint32_t p_s = smem_u32(p_smem);
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < KEYS / 16; ++ks) {
-            const uint64_t db = umma_desc_sw128_mnmajor(v_s + ks * 2048, 0);
-            if (kPInTmem) {
-              umma_f16_ts(win + kOCol, win + ks * 8, db, idesc_o, ks != 0);
-            } else {
-              const uint64_t da = umma_desc_sw128_kmajor(p_s + (ks >> 2) * 16384 + (ks & 3) * 32);
-              umma_f16(win + kOCol, da, db, idesc_o, ks != 0);
+            for (int ks = 0; ks < KEYS / 16; ++ks) {
+              const uint64_t db = umma_desc_sw128_mnmajor(v_s + ks * 2048, 0);
+              if (kPInTmem) {
+                umma_f16_ts(win + kOCol, win + ks * 8, db, idesc_o, ks != 0);
+              } else {
+                const uint64_t da = umma_desc_sw128_kmajor(p_s + (ks >> 2) * 16384 + (ks & 3) * 32);
+                umma_f16(win + kOCol, da, db, idesc_o, ks != 0);
+              }
             }
+            umma_commit(&o_full[w]);
+            umma_commit(&ld_empty[slot]);  // this window's reads of the slot have retired (barrier counts both windows)
           }
-          umma_commit(&o_full[w]);
-          umma_commit(&ld_empty[slot]);  // this window's reads of the slot have retired (barrier counts both windows)
-          stamp(2 + w, idx, 4);
+          __syncwarp();
+          if (lane == 0) stamp(2 + w, idx, 4);
         }
       }
     }

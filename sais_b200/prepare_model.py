@@ -92,7 +92,9 @@ class fullModel(nn.Module):  # noqa: N801 — reference class name
             if p is None:
                 pads.append(torch.zeros(n * (T + 1), dtype=torch.uint8, device=t.device))
             else:
-                pads.append(p.reshape(n * (T + 1)).to(device=t.device, dtype=torch.uint8))
+                p = p.reshape(n * (T + 1)).to(t.device)
+                # bool storage is one 0/1 byte per element: reinterpret instead of launching a conversion kernel
+                pads.append(p.view(torch.uint8) if p.dtype == torch.bool else p.to(torch.uint8))
             seq_lens += [T + 1] * n
             emit += [si == 0] * n
             spans.append((cursor, n, B, nsnip, T + 1))

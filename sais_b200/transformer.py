@@ -60,6 +60,7 @@ class TransformerEncoder(nn.Module):
         self._packed = None
         self._packed_key = None
         self._ws = None
+        self._geom = {}
 
     # ------------------------------------------------------------------ packing
     def _pack_key(self, extra):
@@ -138,8 +139,17 @@ class TransformerEncoder(nn.Module):
         a_offs[emit] = a_cum[emit]
         a_total = int(a_sizes.sum())
 
-        seq_offsets = torch.from_numpy(offs.astype(np.int32)).to(dev, non_blocking=True)
-        attn_offsets = torch.from_numpy(a_offs).to(dev, non_blocking=True) if a_total else None
+        # the offset tables depend on the batch geometry only: keep the device copies of the last few geometries
+        # (a fixed-shape inference loop then issues no host->device copy per call)
+        gkey = (str(dev), seq_lens.tobytes(), emit.tobytes())
+        cached = self._geom.get(gkey)
+        if cached is None:
+            if len(self._geom) >= 16:
+                self._geom.clear()
+            cached = (torch.from_numpy(offs.astype(np.int32)).to(dev),
+                      torch.from_numpy(a_offs).to(dev) if a_total else None)
+            self._geom[gkey] = cached
+        seq_offsets, attn_offsets = cached
         attn = torch.empty(a_total, device=dev, dtype=torch.float32) if a_total else None
         x_frames = x_frames.contiguous().float()
         if key_pad is not None:

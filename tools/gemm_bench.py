@@ -55,4 +55,12 @@ for name, m, n, k, act, res, f32, split in SHAPES:
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     flops = 2.0 * m * n * k * (3 if split else 1)
-    print(f"{name:14s} M={m:6d} N={n:5d} K={k:5d}  {ms*1e3:8.1f} us  {flops/ms/1e9:8.1f} TFLOP/s")
+    # effective SM clock while this shape runs back to back (probe kernel between launches)
+    probe = torch.zeros((iters, 4), dtype=torch.int64, device=dev)
+    for i in range(iters):
+        ops.gemm_bias_act(a, w, bias, act=act, residual=r, out=out, split3=split, **kw)
+        _lib.check(_lib.lib().sais_clock_probe(probe[i].data_ptr(), 4000, torch.cuda.current_stream().cuda_stream), "probe")
+    torch.cuda.synchronize()
+    pr = probe.cpu().double()
+    ghz = sorted(((pr[:, 3] - pr[:, 1]) / (pr[:, 2] - pr[:, 0]).clamp(min=1.0)).tolist())
+    print(f"{name:14s} M={m:6d} N={n:5d} K={k:5d}  {ms*1e3:8.1f} us  {flops/ms/1e9:8.1f} TFLOP/s   SM clock {ghz[len(ghz)//2]:.2f} GHz")

@@ -36,3 +36,4 @@ qkv = torch.randn(M, 1152, device=dev).bfloat16()
 timeit("vit_attn", lambda: ops.vit_attention(qkv, B), bytes_=M * 1536 * 2, flops=4.0 * B * 6 * 197 * 197 * 64)
 fr = torch.randint(0, 256, (B, 224, 224, 3), dtype=torch.uint8, device=dev)
 timeit("patchify_u8", lambda: ops.normalize_patchify_u8(fr), bytes_=B * 224 * 224 * 3 * 3)
+timeit("vit_cls_attn", lambda: ops.vit_cls_attention(qkv, B), bytes_=B * 197 * 768 * 2)
