@@ -1,0 +1,168 @@
+"""BASELINE.json configurations C2-C5 at their FULL sizes on the GPU, checked through size-independent properties plus
+oracle comparisons on sampled items (the oracle finishes a handful of frames / clips in seconds, not thousands):
+
+* C2  ViT-S/16 feature extraction, batch 256: sampled frames vs the oracle, batch-composition invariance;
+* C3  temporal encoder + head, 512 clips x 30 frames (RGB + flow): sampled clips vs the oracle, clip-permutation
+      equivariance, attention rows sum to one;
+* C4  60-minute 1 fps video (3,600 RGB + 3,600 flow frames) sharded by frame range over 8 ranks, windows 20 / hop 10 /
+      TTA {0,3,6}, P = 3: the union of the rank shards equals the single-rank run bit for bit, windows equal clips run alone;
+* C5  1,000 clips of 8-64 frames (flow = ceil(len/2)) sharded by clip id mod 8 with padded batches: padding invariance
+      against clips run alone, sampled clips vs the oracle, predicted class identical above the margin.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import sais_oracle as O  # noqa: E402
+from test_gpu_models import ATTN_ABS, COS_MIN, MARGIN, REL_MAX, REL_MAX_FP32, _head, _vit  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def vit(dev):
+    return _vit(O.make_vit_weights(0, "stress"), dev)
+
+
+@pytest.fixture(scope="module")
+def head_sd():
+    return O.make_head_weights(0, "stress")
+
+
+def _frames(n, seed, dev):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    return torch.randint(0, 256, (n, 224, 224, 3), dtype=torch.uint8, device=dev, generator=g)
+
+
+# ------------------------------------------------------------------------------------------------ C2
+def test_c2_vit_batch_256(dev, vit):
+    frames = _frames(256, 11, dev)
+    emb = vit.forward_u8(frames)
+    assert emb.shape == (256, 384) and bool(torch.isfinite(emb).all())
+    pick = [0, 37, 128, 255]
+    ref = O.vit_forward(O.make_vit_weights(0, "stress"), O.normalize_frames(frames[pick].cpu()))
+    cos, rel = O.embedding_errors(emb[pick].cpu(), ref)
+    assert cos >= COS_MIN and rel <= REL_MAX, (cos, rel)
+    # a frame's embedding does not depend on what else is in the batch, where it sits, or how the batch is chunked
+    perm = torch.randperm(256, generator=torch.Generator().manual_seed(5)).to(dev)
+    assert torch.equal(vit.forward_u8(frames[perm].contiguous()), emb[perm])
+    assert torch.equal(vit.forward_u8(frames[100:133].contiguous()), emb[100:133])
+
+
+# ------------------------------------------------------------------------------------------------ C3
+def test_c3_temporal_head_512x30(dev, head_sd):
+    model = _head(head_sd, dev, "RGB-Flow")
+    g = torch.Generator().manual_seed(33)
+    x = torch.randn(512, 1, 30, 384, generator=g)
+    f = torch.randn(512, 1, 30, 384, generator=g)
+    pad = O.padding_mask([30] * 512, 30)
+    out, attn = model(x.to(dev), f.to(dev), None, None, 'Prototypes', pad.to(dev), pad.to(dev), None)
+    assert out.shape == (512, 256) and attn.shape == (512, 31, 31)
+    assert float((attn.sum(-1) - 1).abs().max()) <= 1e-5
+    pick = [0, 99, 300, 511]
+    r_out, r_attn = O.full_model_forward(head_sd, x[pick], f[pick], pad[pick], pad[pick])
+    cos, rel = O.embedding_errors(out[pick].cpu(), r_out)
+    assert cos >= 1 - 1e-6 and rel <= REL_MAX_FP32, (cos, rel)
+    assert float((attn[pick].cpu() - r_attn).abs().max()) <= 1e-4
+    perm = torch.randperm(512, generator=g)
+    out_p, attn_p = model(x[perm].to(dev), f[perm].to(dev), None, None, 'Prototypes', pad.to(dev), pad.to(dev), None)
+    assert torch.equal(out_p, out[perm.to(dev)]) and torch.equal(attn_p, attn[perm.to(dev)])
+
+
+# ------------------------------------------------------------------------------------------------ C4
+def test_c4_hour_video_sharded_by_frame_range(dev, vit, head_sd):
+    from sais_b200 import pipeline, scoring
+    n, world = 3600, 8
+    head = _head(head_sd, dev, "RGB-Flow")
+    protos = O.make_prototypes(3, seed=2).to(dev)
+    pipe = pipeline.SaisPipeline(vit, head, protos, window=20, hop=10, tta_offsets=(0, 3, 6), batch_size=256)
+    emb = {}
+    for name, seed in (("rgb", 41), ("flow", 42)):
+        whole = torch.empty((n, 384), device=dev)
+        shards = []
+        for r in range(world):  # every rank's frame range through the ViT, exactly as rank r would run it
+            lo, hi = pipeline.frame_range(n, r, world)
+            g = torch.Generator(device=dev).manual_seed(seed * 100 + r)
+            fr = torch.randint(0, 256, (hi - lo, 224, 224, 3), dtype=torch.uint8, device=dev, generator=g)
+            e = pipeline.extract_features(vit, fr, batch_size=256)
+            whole[lo:hi] = e
+            shards.append((lo, hi, fr[:2].clone(), e[:2].clone()))
+        emb[name] = whole
+        lo, hi, fr2, e2 = shards[5]
+        ref = O.vit_forward(O.make_vit_weights(0, "stress"), O.normalize_frames(fr2.cpu()))
+        cos, rel = O.embedding_errors(e2.cpu(), ref)
+        assert cos >= COS_MIN and rel <= REL_MAX, (name, cos, rel)
+    pred, probs, attn, ids = pipe.score_windows(emb["rgb"], emb["flow"])
+    nw = (n - 20) // 10 + 1
+    assert ids.shape[0] == nw == 359 and probs.shape == (nw, 3) and attn.shape == (nw, 21, 21)
+    assert float((probs.sum(1) - 1).abs().max()) <= 1e-5
+    # window shards (round-robin over ranks) reassemble to the single-rank result bit for bit
+    got_pred, got_probs = torch.empty_like(pred), torch.empty_like(probs)
+    for r in range(world):
+        own = pipeline.shard_items(nw, r, world)
+        p_r, pr_r, _, ids_r = pipe.score_windows(emb["rgb"], emb["flow"], own)
+        assert np.array_equal(ids_r, own)
+        got_pred[torch.from_numpy(own).to(dev)] = p_r
+        got_probs[torch.from_numpy(own).to(dev)] = pr_r
+    assert torch.equal(got_pred, pred) and torch.equal(got_probs, probs)
+    # one window against the oracle head on the same embeddings (TTA list form: three views ending at the same frame)
+    w = 123
+    xs = [emb["rgb"][w * 10 + o: w * 10 + 20].view(1, 1, -1, 384).cpu() for o in (0, 3, 6)]
+    fs = [emb["flow"][w * 10 + o: w * 10 + 20].view(1, 1, -1, 384).cpu() for o in (0, 3, 6)]
+    pads = [O.padding_mask([t.shape[2]], t.shape[2]) for t in xs]
+    r_out, _ = O.full_model_forward(head_sd, xs, fs, pads, pads)
+    r_probs = torch.stack([O.prototype_probs(o, protos.cpu())[0] for o in r_out], 0).mean(0)
+    assert float((probs[w].cpu() - r_probs[0]).abs().max()) <= 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ C5
+def test_c5_thousand_ragged_clips_sharded_by_clip(dev, head_sd):
+    from sais_b200 import postprocess, scoring
+    head = _head(head_sd, dev, "RGB-Flow")
+    protos = O.make_prototypes(2, seed=2)
+    rng = np.random.default_rng(3)
+    lens = rng.integers(8, 65, 1000)
+    g = torch.Generator().manual_seed(55)
+    rgb = [torch.randn(1, int(n), 384, generator=g) for n in lens]
+    flow = [torch.randn(1, int((n + 1) // 2), 384, generator=g) for n in lens]
+    world, batch = 8, 32
+    outs = torch.empty((1000, 256))
+    preds = torch.empty(1000, dtype=torch.long)
+    for r in range(world):
+        own = np.arange(r, 1000, world)  # clip id mod 8
+        for b0 in range(0, len(own), batch):
+            ids = own[b0:b0 + batch]
+            x, xpad, _ = postprocess.pad_collate([rgb[i] for i in ids])
+            f, fpad, _ = postprocess.pad_collate([flow[i] for i in ids])
+            out, attn = head(x.to(dev), f.to(dev), None, None, 'Prototypes', xpad.to(dev), fpad.to(dev), None)
+            assert attn.shape == (len(ids), x.shape[2] + 1, x.shape[2] + 1)
+            # padded keys carry exactly zero probability, real rows sum to one
+            m = xpad.reshape(len(ids), -1).to(dev)
+            assert float(attn[m.unsqueeze(1).expand_as(attn)].abs().max()) == 0.0 if bool(m.any()) else True
+            pred, _ = scoring.predict(out, protos.to(dev))
+            outs[ids] = out.cpu()
+            preds[ids] = pred.cpu()
+    assert bool(torch.isfinite(outs).all())
+    # padding / batch-composition invariance: a clip run alone (no padding at all) gives the same vector
+    for i in (0, 123, 500, 777, 999):
+        x, f = rgb[i].unsqueeze(0), flow[i].unsqueeze(0)
+        xp, fp = O.padding_mask([x.shape[2]], x.shape[2]), O.padding_mask([f.shape[2]], f.shape[2])
+        alone, _ = head(x.to(dev), f.to(dev), None, None, 'Prototypes', xp.to(dev), fp.to(dev), None)
+        assert float((alone.cpu()[0] - outs[i]).abs().max()) <= 2e-5 * float(outs[i].abs().max()) + 1e-6
+        r_out, _ = O.full_model_forward(head_sd, x, f, xp, fp)
+        cos, rel = O.embedding_errors(outs[i:i + 1], r_out)
+        assert cos >= 1 - 1e-6 and rel <= REL_MAX_FP32, (i, cos, rel)
+    # predicted class identical to the oracle's wherever the top-2 margin exceeds the tolerance (sampled clips)
+    pick = list(range(0, 1000, 50))
+    xs, xps, _ = postprocess.pad_collate([rgb[i] for i in pick])
+    fs, fps, _ = postprocess.pad_collate([flow[i] for i in pick])
+    r_out, _ = O.full_model_forward(head_sd, xs, fs, xps, fps)
+    r_probs, r_sim = O.prototype_probs(r_out, protos)
+    safe = O.top2_margin(r_sim) > MARGIN
+    assert safe.any() and torch.equal(preds[pick][safe], r_probs.argmax(1)[safe])
