@@ -347,7 +347,9 @@ __global__ void __launch_bounds__(256) clip_head_kernel(const float* __restrict_
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int o = warp; o < kOut; o += 8) {
+  // blockIdx.y owns 32 of the 256 output rows (4 per warp): with a handful of clips the kernel is a chain of dependent
+  // weight-row loads, so the rows are spread over 8x more CTAs instead of walked 32 deep by each warp
+  for (int o = blockIdx.y * (kOut / 8) + warp; o < (blockIdx.y + 1) * (kOut / 8); o += 8) {
     float w[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) w[i] = __ldg(W + int64_t(o) * D + i * 32 + lane);
@@ -536,7 +538,7 @@ int clip_head(const float* cls_a, const float* cls_b, int B, int nsnip, const fl
     return kErrInvalidArg;
   }
   LaunchScope ls(kClsMisc, stream, double(B) * (nsnip * D * 8 + 1024));
-  return check_cuda(launch_pdl(clip_head_kernel, dim3((B + kClipsPerBlock - 1) / kClipsPerBlock), dim3(256), size_t(0), stream, 1, cls_a, cls_b, B, nsnip, lin_w,
+  return check_cuda(launch_pdl(clip_head_kernel, dim3((B + kClipsPerBlock - 1) / kClipsPerBlock, 8), dim3(256), size_t(0), stream, 1, cls_a, cls_b, B, nsnip, lin_w,
                                                                                  lin_b, out),
                     "clip_head launch");
 }

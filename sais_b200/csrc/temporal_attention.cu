@@ -28,7 +28,7 @@ struct AttnCfg {
   static constexpr int LD = 3 * E;        // qkv row pitch (fp32 elements)
   static constexpr int KV_PITCH = E + 4;  // smem row pitch: conflict-free float4 row reads
   static constexpr int kMaxSmemS = 64;
-  static constexpr int RG = (H == 4) ? 4 : 3;  // row groups: 16 warps for the temporal head, 18 for the ViT (6 heads)
+  static constexpr int RG = (H == 4) ? 8 : 3;  // row groups: 32 warps for the temporal head (short sequences: fewer rounds), 18 for the ViT (6 heads)
   static constexpr int kWarps = H * RG;
   static constexpr int kThreads = 32 * kWarps;
   static size_t smem_bytes(int max_S, bool smem_kv) {
@@ -39,7 +39,7 @@ struct AttnCfg {
 };
 
 template <int H, int HD, bool kSmemKV>
-__global__ void __launch_bounds__(32 * H * ((H == 4) ? 4 : 3))
+__global__ void __launch_bounds__(32 * H * ((H == 4) ? 8 : 3))
 seq_attention_f32_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ seq_offsets,
                          const uint8_t* __restrict__ key_pad, const int64_t* __restrict__ attn_offsets, int max_S,
                          float scale, __nv_bfloat16* __restrict__ out_split, float* __restrict__ attn_mean,

@@ -13,6 +13,7 @@ echo "== per-kernel timings"
 timeout 300 python tools/gemm_bench.py 256 > $OUT/gemm_bench.log 2>&1; cat $OUT/gemm_bench.log
 timeout 300 python tools/kernel_bench.py 256 > $OUT/kernel_bench.log 2>&1; cat $OUT/kernel_bench.log
 timeout 300 python tools/head_bench.py > $OUT/head_bench.log 2>&1; cat $OUT/head_bench.log
+timeout 300 python tools/frames_bench.py 32 > $OUT/frames_bench.log 2>&1; cat $OUT/frames_bench.log
 echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/bench_under_ncu.log 2>&1; echo "ncu list rc=$?"
