@@ -405,6 +405,139 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
     int tidx = 0;
     const int erole = (ew == 0) ? 2 : (ew == 4 ? 3 : -1);
+    if constexpr (EW == 16) {
+      // ---- lean bf16 epilogue: sixteen warps (four per TMEM lane quarter = four per scheduler) working on
+      // 16-column register blocks.  The 8-warp epilogue below is a ~900-cycle dependent instruction stream per 32-column
+      // chunk (sum of its SASS stall counts) on two warps per scheduler: its FMA and MUFU pipes sit idle 2/3 of the
+      // time and fc1 + GELU runs 7.5 k cycles of epilogue against 2.9 k cycles of MMA per tile.  More warps only fit the
+      // register file (65,536 / 576 threads = 112) with half-width blocks and without the register-resident bias /
+      // column-sum double buffers (four warps per scheduler hide the broadcast LDS instead).
+      static_assert(MODE == kModeBf16 || MODE == kModeBf16Gelu, "16 epilogue warps: bf16-output modes only");
+      const int d_mt = unit_stride / n_tiles, d_nt = unit_stride % n_tiles;  // unit -> (m-tile, n-tile) without divisions
+      int mt = unit0 / n_tiles, nt = unit0 % n_tiles;                        // (S == 1 in the bf16 modes)
+      const uint32_t bias_s = smem_u32(my_bias), csum_s = ln_in ? smem_u32(my_csum) : bias_s;
+      // GELU mode: the block below produces h = x / 2 straight away (bias, rstd and -mean * rstd halved: exact scalings),
+      // which is what gelu_erf_fast2_half wants
+      constexpr float kHalf = (MODE == kModeBf16Gelu) ? 0.5f : 1.0f;
+      for (int u = unit0; u < num_units; u += unit_stride, ++tidx) {
+        const int m0 = (mt * csize + int(crank)) * BLOCK_M;
+        const int n0 = nt * BLOCK_N;
+        int nmt = mt + d_mt, nnt = nt + d_nt;
+        if (nnt >= n_tiles) {
+          nnt -= n_tiles;
+          ++nmt;
+        }
+        if (erole >= 0 && lane == 0) stamp(erole, tidx, 0);
+        // accumulator ready?  (the epilogue is the slower side, so normally yes) -> start the first TMEM read right away:
+        // it streams in under the per-tile vector staging below instead of after it
+        mbar_wait(&tfull_bar[astage], aphase);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + astage * BLOCK_N;
+        uint32_t va[16], vb[16];
+        tmem_ld_32x16(t_row + half * CW, va);
+        if (erole >= 0 && lane == 0) stamp(erole, tidx, 1);
+        __syncwarp();
+#pragma unroll
+        for (int ci = 0; ci < NCWmax; ++ci)
+          if (ci < NCW) {
+            my_bias[ci * CW + lane] = pf_bias[ci] * kHalf;
+            if (ln_in) my_csum[ci * CW + lane] = pf_csum[ci];
+          }
+        float ln_rstd = kHalf, ln_nmr = 0.0f;
+        if (ln_in) {
+          const float mean = ((pf_s0.x + pf_s0.z) + (pf_s1.x + pf_s1.z)) * p.ln_inv_k;
+          const float var = fmaxf(((pf_s0.y + pf_s0.w) + (pf_s1.y + pf_s1.w)) * p.ln_inv_k - mean * mean, 0.0f);
+          const float rstd = rsqrtf(var + p.ln_eps);
+          ln_rstd = rstd * kHalf;
+          ln_nmr = -mean * rstd * kHalf;
+        }
+        if (u + unit_stride < num_units) {  // next tile's vectors (consumed at the top of the next iteration)
+          const int pm0 = (nmt * csize + int(crank)) * BLOCK_M, pn0 = nnt * BLOCK_N;
+#pragma unroll
+          for (int ci = 0; ci < NCWmax; ++ci) {
+            pf_bias[ci] = (ci < NCW && p.bias) ? __ldg(p.bias + pn0 + (half + kSub * ci) * CW + lane) : 0.0f;
+            if (ln_in) pf_csum[ci] = (ci < NCW) ? __ldg(p.ln_colsum + pn0 + (half + kSub * ci) * CW + lane) : 0.0f;
+          }
+          if (ln_in) {
+            const int r = pm0 + q * 32 + lane;
+            const float4* sp = reinterpret_cast<const float4*>(p.ln_stats_in + int64_t(r < p.M ? r : p.M - 1) * 8);
+            pf_s0 = __ldg(sp);
+            pf_s1 = __ldg(sp + 1);
+          }
+        }
+        const uint64_t rs2 = pack2(ln_rstd, ln_rstd), nm2 = pack2(ln_nmr, ln_nmr);
+        __syncwarp();
+
+        // one 16-column block: bias / folded LayerNorm, activation, bf16, two 16-byte pieces of the staging row
+        auto block16 = [&](uint32_t(&v)[16], int ci, int hh, uint32_t buf) {
+          const uint32_t voff = uint32_t((ci * CW + hh * 16) * 4);
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            // one instruction stream for both cases (a predicated if / else would issue both): without the folded LayerNorm
+            // nm2 = 0 (c2 re-reads the bias slice) and rs2 = 1 (0.5 in GELU mode), so the two FFMA2 reduce to acc + bias exactly
+            const ulonglong2 b2 = lds128_pairs(bias_s + voff + j * 16);
+            const ulonglong2 c2 = lds128_pairs(csum_s + voff + j * 16);
+            unpack2(fma2(pack2u(v[4 * j], v[4 * j + 1]), rs2, fma2(nm2, c2.x, b2.x)), f[4 * j], f[4 * j + 1]);
+            unpack2(fma2(pack2u(v[4 * j + 2], v[4 * j + 3]), rs2, fma2(nm2, c2.y, b2.y)), f[4 * j + 2], f[4 * j + 3]);
+          }
+          if (MODE == kModeBf16Gelu) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) gelu_erf_fast2_half(f[j], f[j + 1]);
+          } else if (p.act == 2) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
+          }
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            sts128(buf + stage_off_bf16(lane, hh * 2 + j), pack_bf16x2(f[8 * j], f[8 * j + 1]),
+                   pack_bf16x2(f[8 * j + 2], f[8 * j + 3]), pack_bf16x2(f[8 * j + 4], f[8 * j + 5]),
+                   pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+        };
+
+#pragma unroll 1
+        for (int ci = 0; ci < NCW; ++ci) {
+          const int c = half + kSub * ci;
+          const uint32_t buf = my_stage + bufi * kBuf;
+          tmem_ld_wait_dep(va);
+          tmem_ld_32x16(t_row + c * CW + 16, vb);  // second half streams in under the first half's math
+          // the store issued from this staging buffer nbuf chunks ago must have finished reading it
+          __syncwarp();
+          if (elect_one()) {
+            if (nbuf == 1) tma_store_wait_read<0>();
+            else if (nbuf == 2) tma_store_wait_read<1>();
+            else tma_store_wait_read<2>();
+          }
+          __syncwarp();
+          block16(va, ci, 0, buf);
+          tmem_ld_wait_dep(vb);
+          if (ci + 1 < NCW) {
+            tmem_ld_32x16(t_row + (c + kSub) * CW, va);  // next chunk's first half
+          } else {  // last TMEM read of this tile by this warp: hand the accumulator back
+            tc_fence_before();
+            if (lane == 0) {
+              if (CG == 1) mbar_arrive(&tempty_bar[astage]);
+              else mbar_arrive_cluster(leader_smem_u32(&tempty_bar[astage]));
+            }
+          }
+          block16(vb, ci, 1, buf);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (elect_one()) {  // (the same lane every time: it owns this warp's bulk-async groups)
+            if (!(p.debug_nostore & 1)) tma_store_2d_s(&tmap_out, buf, n0 + c * CW, m0 + q * 32);
+            tma_store_commit();
+          }
+          if (++bufi == nbuf) bufi = 0;
+          if (erole >= 0 && lane == 0) stamp(erole, tidx, 2 + ci);
+        }
+        if (++astage == 2) {
+          astage = 0;
+          aphase ^= 1;
+        }
+        mt = nmt;
+        nt = nnt;
+      }
+    } else
     for (int u = unit0; u < num_units; u += unit_stride, ++tidx) {
       const int tile = u / S;
       const int m0 = tile_m0(tile);
@@ -759,8 +892,8 @@ int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
     if (p.dbg) cudaMemsetAsync(p.dbg, 0, kDbgN * sizeof(long long), stream);
   }
   static const int env_nbuf = getenv("SAIS_GEMM_NBUF") ? atoi(getenv("SAIS_GEMM_NBUF")) : 0;
-  int nbuf = 2;
-  if (!a.residual && env_nbuf >= 2 && env_nbuf <= 4) nbuf = env_nbuf;
+  int nbuf = (EW == 16) ? 1 : 2;  // 16 warps x one 2 KB tile = the 8-warp epilogue's staging footprint (keeps the operand ring depth)
+  if (!a.residual && env_nbuf >= (EW == 16 ? 1 : 2) && env_nbuf <= (EW == 16 ? 3 : 4)) nbuf = env_nbuf;
   p.nbuf = nbuf;
   p.ln_stats_in = a.ln_stats_in;
   p.ln_colsum = a.ln_colsum;
@@ -904,9 +1037,10 @@ int gemm_bias_act(const SaisGemmArgs& a, cudaStream_t stream, int force_block_n)
   static const int env_cg = getenv("SAIS_GEMM_CG") ? atoi(getenv("SAIS_GEMM_CG")) : 0;
   const int64_t m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M;
   const int cg = env_cg ? env_cg : (m_tiles * (a.N / bn) >= 2 * num_sms() ? 2 : 1);
-  // 16 epilogue warps for the bf16-output modes once every SM has several tiles to chew through (SAIS_GEMM_EW=8|16 forces)
+  // Epilogue warps: the GELU epilogue (fc1) is instruction-bound, so it runs the lean 16-warp path (72.9 -> 67 us at batch
+  // 256); the plain bf16 epilogue (qkv) is faster on 8 warps (48.8 vs 51.1 us).  SAIS_GEMM_EW=8|12|16 forces one for both.
   static const int env_ew = getenv("SAIS_GEMM_EW") ? atoi(getenv("SAIS_GEMM_EW")) : 0;
-  const int ewn = (env_ew == 16 || env_ew == 12) ? env_ew : 8;
+  const int ewn = (env_ew == 16 || env_ew == 12 || env_ew == 8) ? env_ew : (mode == kModeBf16Gelu ? 16 : 8);
 #define SAIS_GEMM_DISPATCH_CG(BN, CG)                                                              \
   switch (mode) {                                                                                  \
     case kModeBf16:                                                                                \

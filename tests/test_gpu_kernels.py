@@ -124,6 +124,50 @@ def test_gemm_bias_act(dev, M, N, K, act, use_res, f32_out):
         assert torch.allclose(got, ref, atol=1e-3, rtol=2 ** -8), (got - ref).abs().max()
 
 
+_EPILOGUE_VARIANT_SCRIPT = r"""
+import math, sys, torch
+from sais_b200 import ops
+dev = torch.device("cuda:0")
+def rnd(*shape, seed=0, std=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * std
+outs = []
+for M, N, act, fold in [(5000, 1536, 1, False), (197 * 160, 1536, 1, True), (1000, 1152, 0, False), (300, 1152, 0, True),
+                        (50, 2048, 2, False), (257, 1536, 1, True)]:
+    x = rnd(M, 384, seed=M) * 1.7 + 0.4
+    w, b = rnd(N, 384, seed=3, std=1 / math.sqrt(384)), rnd(N, seed=4, std=0.3)
+    if fold:
+        gamma, beta = 1 + 0.2 * rnd(384, seed=1), 0.2 * rnd(384, seed=2)
+        wg, c, d = ops.fold_layernorm(gamma, beta, w, b)
+        xb, stats = ops.rowstats_cast(x.to(dev))
+        out = ops.gemm_bias_act(xb, wg.to(dev), d.to(dev), act=act, ln_stats_in=stats, ln_colsum=c.to(dev), ln_eps=1e-6)
+    else:
+        out = ops.gemm_bias_act(x.to(dev).bfloat16(), w.to(dev).bfloat16(), b.to(dev), act=act)
+    outs.append(out.cpu())
+torch.save(outs, sys.argv[1])
+"""
+
+
+def test_gemm_epilogue_warp_variants_bit_identical(dev, tmp_path):
+    """The 8-warp and the lean 16-warp bf16 epilogues (SAIS_GEMM_EW, read once per process) must agree bit for bit: same
+    accumulators, and the 16-warp GELU works on x / 2 with constants scaled by exact powers of two (common.cuh
+    gelu_erf_fast2_half).  Shapes: fc1 / qkv / temporal FF1, with and without the folded LayerNorm, partial tiles."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    res = {}
+    for ew in ("8", "16"):
+        env = dict(os.environ, SAIS_GEMM_EW=ew, PYTHONPATH=str(root))
+        out = tmp_path / f"ew{ew}.pt"
+        subprocess.run([sys.executable, "-c", _EPILOGUE_VARIANT_SCRIPT, str(out)], check=True, env=env, cwd=root, timeout=300)
+        res[ew] = torch.load(out)
+    for a, b in zip(res["8"], res["16"]):
+        assert a.shape == b.shape and torch.equal(a.view(torch.int16), b.view(torch.int16)), \
+            (a.float() - b.float()).abs().max()
+
+
 @pytest.mark.parametrize("block_rows", [1, 2])
 def test_gemm_patch_embed_remap(dev, block_rows):
     """patch-embed epilogue: row b*196+p -> row b*197+1+p, + pos_embed[1+p]; CLS rows untouched."""
