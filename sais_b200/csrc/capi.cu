@@ -420,6 +420,17 @@ int sais_vit_forward(const SaisVitWeights* w, const void* input, int32_t input_k
       if ((rc = rowstats_cast(x, tok, xn, stats, stream))) return rc;
       xn_ready = true;
     }
+    // "snake" row order through the chain qkv -> attention -> proj -> fc1 -> fc2 -> qkv ... (kernels.h g_tile_reverse):
+    // each kernel starts on the rows its producer finished with.  Folded path only (the stand-alone LayerNorm kernels
+    // of the other paths walk forward); SAIS_SNAKE=0 disables it for A/B runs.
+    static const bool env_nosnake = getenv("SAIS_SNAKE") != nullptr && atoi(getenv("SAIS_SNAKE")) == 0;
+    const bool snake = fold && !env_nosnake;
+    int dir = 1;  // rowstats_cast (like the patch GEMM before it) walks forward, so block 0's qkv starts from the end
+    struct DirGuard { ~DirGuard() { g_tile_reverse = 0; } } dir_guard;  // never leaks into later calls on this thread
+    auto next_dir = [&]() {
+      g_tile_reverse = snake ? dir : 0;
+      dir ^= 1;
+    };
     for (int l = 0; l < SAIS_VIT_DEPTH; ++l) {
       const SaisVitBlockWeights& bw = w->blocks[l];
       const bool last = (l == SAIS_VIT_DEPTH - 1);
@@ -433,8 +444,10 @@ int sais_vit_forward(const SaisVitWeights* w, const void* input, int32_t input_k
       if (precise) { g.out_f32 = static_cast<float*>(qkv); g.ldo32 = 3 * Dm; }
       else { g.out_bf16 = static_cast<sais_bf16*>(qkv); g.ldo16 = 3 * Dm; }
       g.M = tok; g.N = 3 * Dm; g.K = Dm; g.lda = Dm * s; g.ldw = Dm * s; g.split3 = precise;
+      next_dir();
       if ((rc = gemm_bias_act(g, stream))) return rc;
       if (last && cls_only) {
+        g_tile_reverse = 0;
         // Only x[:, 0] leaves the backbone (vision_transformer.py:213-214): with K and V of the last block known, the
         // other 196 query rows of its attention and every non-CLS row of its proj / MLP are dead work.  Run them on
         // the B CLS rows only — identical result, ~7 % fewer flops per frame.
@@ -462,6 +475,7 @@ int sais_vit_forward(const SaisVitWeights* w, const void* input, int32_t input_k
       }
       // attention (+ probabilities of the last block on request)
       float* probs = (last && out_probs) ? out_probs + size_t(b0) * SAIS_VIT_HEADS * Tk * Tk : nullptr;
+      next_dir();
       if (precise)
         rc = vit_attention_precise(static_cast<const float*>(qkv), offs, Bc, ao, probs, stream);
       else
@@ -478,6 +492,7 @@ int sais_vit_forward(const SaisVitWeights* w, const void* input, int32_t input_k
         g.a = ao; g.w = bw.proj_w; g.bias = bw.proj_b; g.residual = x; g.out_f32 = x;
         g.M = tok; g.N = Dm; g.K = Dm; g.lda = Dm * s; g.ldw = Dm * s; g.ldr = Dm; g.ldo32 = Dm; g.split3 = precise;
         if (fold) { g.ln_stats_out = stats; g.out2_bf16 = xn; g.ldo2 = Dm; }
+        next_dir();
         if ((rc = gemm_bias_act(g, stream))) return rc;
         // norm2
         if (!fold && (rc = layernorm(x, Dm, bw.ln2_w, bw.ln2_b, 1e-6f, tok, nullptr, xn, stream, precise))) return rc;
@@ -492,6 +507,7 @@ int sais_vit_forward(const SaisVitWeights* w, const void* input, int32_t input_k
       if (fold) { g.w = bw.fc1_wg; g.bias = bw.fc1_d; g.ln_colsum = bw.fc1_c; g.ln_stats_in = stats; g.ln_eps = 1e-6f; }
       g.M = tok; g.N = Hid; g.K = Dm; g.lda = Dm * s; g.ldw = Dm * s; g.ldo16 = Hid * s;
       g.split3 = precise; g.split_out = precise;
+      next_dir();
       if ((rc = gemm_bias_act(g, stream))) return rc;
       if (rowln) {
         // fc2 + residual + the next block's norm1 (the final norm reads the fp32 stream itself)
@@ -507,6 +523,7 @@ int sais_vit_forward(const SaisVitWeights* w, const void* input, int32_t input_k
         g.M = tok; g.N = Dm; g.K = Hid; g.lda = Hid * s; g.ldw = Hid * s; g.ldr = Dm; g.ldo32 = Dm;
         g.split3 = precise;
         if (fold && !last) { g.ln_stats_out = stats; g.out2_bf16 = xn; g.ldo2 = Dm; xn_ready = true; }
+        next_dir();
         if ((rc = gemm_bias_act(g, stream))) return rc;
       }
     }

@@ -35,6 +35,8 @@
 
 namespace sais {
 
+thread_local int g_tile_reverse = 0;
+
 namespace {
 
 constexpr int BLOCK_M = 128;
@@ -92,6 +94,7 @@ struct GemmParams {
   long long* dbg;     // dev knob (SAIS_GEMM_TIMELINE=<file>): CTA 0 records clock64() per role / tile / event
   int stages;         // depth of the operand ring
   int stage_buf;      // bytes per epilogue staging buffer (4096 or 2048)
+  int reverse;        // walk the m-tiles from the last to the first (kernels.h g_tile_reverse)
   int nbuf;           // staging buffers per epilogue warp (2..4)
   // LayerNorm folding (see the file comment)
   const float* ln_stats_in;  // consumer: [M][4][2] (sum, sumsq) partials of the K-wide input rows
@@ -171,8 +174,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint64_t* empty_bar = bars + Cfg::kMaxStages;     // [kMaxStages]
   uint64_t* tfull_bar = bars + 2 * Cfg::kMaxStages; // [2]
   uint64_t* tempty_bar = tfull_bar + 2;           // [2]
-  uint64_t* res_bar = tempty_bar + 2;             // [kEpiWarps][2]
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(res_bar + 2 * kEpiWarps);
+  constexpr int kResBars = (EW == 8) ? 4 : 2;     // residual-tile ring slots per epilogue warp (fp32 modes run on 8 warps)
+  uint64_t* res_bar = tempty_bar + 2;             // [kEpiWarps][kResBars]
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(res_bar + kResBars * kEpiWarps);
   float* bias_smem = reinterpret_cast<float*>(bars + 64);                  // [kEpiWarps][kChunksPerWarp * CW]
   float* csum_smem = bias_smem + kEpiWarps * (Cfg::kChunksPerWarp * CW);  // [kEpiWarps][kChunksPerWarp * CW]
 
@@ -211,7 +215,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], kEpiWarps * CG);  // (leader's copy) the epilogue warps of BOTH CTAs drain the tile
     }
-    for (int s = 0; s < 2 * kEpiWarps; ++s) mbar_init(&res_bar[s], 1);
+    for (int s = 0; s < kResBars * kEpiWarps; ++s) mbar_init(&res_bar[s], 1);
     fence_mbar_init();
   }
   if (warp == kMmaWarp) {
@@ -236,7 +240,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     p.dbg[4 * 16 * 16] = (long long)ns;
     p.dbg[4 * 16 * 16 + 1] = clock64();
   }
-  auto tile_m0 = [&](int unit) { return ((unit / n_tiles) * csize + int(crank)) * BLOCK_M; };
+  const int m_groups = (m_tiles + csize - 1) / csize;
+  auto grp_m0 = [&](int g) { return ((p.reverse ? m_groups - 1 - g : g) * csize + int(crank)) * BLOCK_M; };
+  auto tile_m0 = [&](int unit) { return grp_m0(unit / n_tiles); };
 
   if (warp == kProducerWarp) {
     // ===================== TMA producer (whole warp, warp-uniform; only the TMA instructions are elected) =====================
@@ -362,7 +368,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int nbuf = p.nbuf;
     const uint32_t my_stage = smem_u32(epi_smem + ew * (nbuf * kBuf + p.xb_buf));
     int bufi = 0;  // staging buffer ring index (it % nbuf)
-    uint64_t* my_res_bar = res_bar + 2 * ew;
+    uint64_t* my_res_bar = res_bar + kResBars * ew;
     float* my_bias = bias_smem + ew * (NCWmax * CW);
     float* my_csum = csum_smem + ew * (NCWmax * CW);
     const bool ln_in = (MODE == kModeBf16 || MODE == kModeBf16Gelu) && p.ln_stats_in != nullptr;
@@ -375,10 +381,34 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint32_t aphase = 0;
     uint32_t it = 0;  // chunks processed by this warp (selects staging buffer / residual barrier phase)
 
-    if (has_res && lane == 0 && unit0 < num_units) {  // prime the residual pipeline (S == 1 whenever there is a residual)
-      const int m0 = tile_m0(unit0), n0 = (unit0 % n_tiles) * BLOCK_N;
-      mbar_arrive_expect_tx(&my_res_bar[0], 32 * 128);
-      tma_load_2d_s(my_stage, &tmap_res, &my_res_bar[0], n0 + half * CW, m0 + q * 32);
+    // Residual pipeline (S == 1 whenever there is a residual): the fp32 residual tile of a chunk is TMA-loaded into the
+    // staging buffer the result will leave from, nbuf - 1 chunks AHEAD of its use.  One chunk ahead (nbuf = 2) leaves a
+    // single 4 KB load in flight per warp behind a store-read wait — a ~3.5 k-cycle latency chain per chunk that made
+    // proj epilogue-bound at 11.5 k cycles per tile against 2.5 k cycles of MMA (gpurun_out/s6f timelines).
+    int pf_u = unit0, pf_c = half, pf_slot = 0;  // cursor: (unit, chunk) of the next residual tile to request, its ring slot
+    const uint32_t xb_base = my_stage + nbuf * kBuf;  // bf16-copy staging tile(s) (LayerNorm-producer mode; one or two per warp)
+    uint32_t xb_tile = xb_base;
+    int rslot = 0;                               // ring slot / barrier phase of the chunk being consumed
+    uint32_t rphase = 0;
+    auto res_request = [&]() {  // one thread
+      const int rm0 = tile_m0(pf_u), rn0 = (pf_u % n_tiles) * BLOCK_N;
+      mbar_arrive_expect_tx(&my_res_bar[pf_slot], 32 * 128);
+      tma_load_2d_s(my_stage + pf_slot * kBuf, &tmap_res, &my_res_bar[pf_slot], rn0 + pf_c * CW, rm0 + q * 32);
+    };
+    auto res_advance = [&]() {  // whole warp (the cursor stays warp-uniform)
+      if (++pf_slot == nbuf) pf_slot = 0;
+      pf_c += kSub;
+      if (pf_c >= NC) {
+        pf_c = half;
+        pf_u += unit_stride;
+      }
+    };
+    if (has_res) {
+      for (int i = 0; i < nbuf - 1; ++i)
+        if (pf_u < num_units) {
+          if (lane == 0) res_request();
+          res_advance();
+        }
     }
 
     // Per-tile vectors (bias slice, folded-LayerNorm column sums, row statistics) are fetched one tile AHEAD into
@@ -420,7 +450,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       // which is what gelu_erf_fast2_half wants
       constexpr float kHalf = (MODE == kModeBf16Gelu) ? 0.5f : 1.0f;
       for (int u = unit0; u < num_units; u += unit_stride, ++tidx) {
-        const int m0 = (mt * csize + int(crank)) * BLOCK_M;
+        const int m0 = grp_m0(mt);
         const int n0 = nt * BLOCK_N;
         int nmt = mt + d_mt, nnt = nt + d_nt;
         if (nnt >= n_tiles) {
@@ -452,7 +482,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           ln_nmr = -mean * rstd * kHalf;
         }
         if (u + unit_stride < num_units) {  // next tile's vectors (consumed at the top of the next iteration)
-          const int pm0 = (nmt * csize + int(crank)) * BLOCK_M, pn0 = nnt * BLOCK_N;
+          const int pm0 = grp_m0(nmt), pn0 = nnt * BLOCK_N;
 #pragma unroll
           for (int ci = 0; ci < NCWmax; ++ci) {
             pf_bias[ci] = (ci < NCW && p.bias) ? __ldg(p.bias + pn0 + (half + kSub * ci) * CW + lane) : 0.0f;
@@ -655,9 +685,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           for (int j = 0; j < 32; ++j) acc += f[j];
           if (acc == 123.456f) p.out_bf16[0] = __float2bfloat16(acc);
         } else if (tma_epi) {
-          const uint32_t buf = my_stage + (has_res ? int(it & 1) : bufi) * kBuf;
+          const uint32_t buf = my_stage + (has_res ? rslot : bufi) * kBuf;
           if (has_res) {
-            mbar_wait(&my_res_bar[it & 1], (it >> 1) & 1);
+            mbar_wait(&my_res_bar[rslot], rphase);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 r4 = lds128(buf + stage_off_f32(lane, j));
@@ -678,9 +708,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 // the LSU one wavefront each: 10 us per GEMM at batch 256).  The previous chunk's stores must have
                 // finished reading the tile: they were issued a whole chunk ago, so this wait is all but free.
                 __syncwarp();
-                if (elect_one()) tma_store_wait_read<0>();
+                if (elect_one()) {
+                  if (p.xb_buf > 2048) tma_store_wait_read<1>();  // two tiles: only the store before the previous one
+                  else tma_store_wait_read<0>();
+                }
                 __syncwarp();
-                const uint32_t xb = my_stage + nbuf * kBuf;
+                if (p.xb_buf > 2048) xb_tile = (xb_tile == xb_base) ? xb_base + 2048u : xb_base;
+                const uint32_t xb = xb_tile;
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                   sts128(xb + stage_off_bf16(lane, j), pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
@@ -727,29 +761,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           fence_proxy_async_smem();
           __syncwarp();
           if (elect_one()) {  // (the same lane every time: it owns this warp's bulk-async groups)
-            if (has_res) {
-              // every earlier store has finished reading smem -> the other buffer is free: prefetch the
-              // residual tile of this warp's next chunk into it
+            if (has_res && pf_u < num_units) {
+              // every earlier store has finished reading smem -> the previous chunk's buffer (ring slot pf_slot) is free:
+              // request the residual tile nbuf - 1 chunks ahead into it (ahead of this chunk's store in the TMA queue)
               tma_store_wait_read<0>();
-              int nt = tile, nc = c + kSub;
-              if (nc >= NC) {
-                nt = u + unit_stride;
-                nc = half;
-              }
-              if (nt < num_units) {
-                const int nm0 = tile_m0(nt), nn0 = (nt % n_tiles) * BLOCK_N;
-                uint64_t* rb = &my_res_bar[(it + 1) & 1];
-                mbar_arrive_expect_tx(rb, 32 * 128);
-                tma_load_2d_s(my_stage + ((it + 1) & 1) * kBuf, &tmap_res, rb, nn0 + nc * CW, nm0 + q * 32);
-              }
+              res_request();
             }
             if (!(p.debug_nostore & 1)) {
               if (MODE == kModeF32 && p.accumulate) tma_reduce_add_2d_s(&tmap_out, buf, n, m0 + q * 32);
               else tma_store_2d_s(&tmap_out, buf, n, m0 + q * 32);
               if (MODE == kModeGeneric && p.split_out) tma_store_2d_s(&tmap_out, buf + 2048, p.N + n, m0 + q * 32);
-              if (MODE == kModeF32 && ln_out && p.xb_buf) tma_store_2d_s(&tmap_out2, my_stage + nbuf * kBuf, n, m0 + q * 32);
+              if (MODE == kModeF32 && ln_out && p.xb_buf) tma_store_2d_s(&tmap_out2, xb_tile, n, m0 + q * 32);
             }
             tma_store_commit();
+          }
+          if (has_res) {
+            if (pf_u < num_units) res_advance();
+            if (++rslot == nbuf) {
+              rslot = 0;
+              rphase ^= 1;
+            }
           }
           ++it;
           if (++bufi == nbuf) bufi = 0;
@@ -894,6 +925,9 @@ int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
   static const int env_nbuf = getenv("SAIS_GEMM_NBUF") ? atoi(getenv("SAIS_GEMM_NBUF")) : 0;
   int nbuf = (EW == 16) ? 1 : 2;  // 16 warps x one 2 KB tile = the 8-warp epilogue's staging footprint (keeps the operand ring depth)
   if (!a.residual && env_nbuf >= (EW == 16 ? 1 : 2) && env_nbuf <= (EW == 16 ? 3 : 4)) nbuf = env_nbuf;
+  // residual epilogue: ring of nbuf staging buffers per warp = residual tiles requested nbuf - 1 chunks ahead
+  static const int env_nbuf_res = getenv("SAIS_GEMM_NBUF_RES") ? atoi(getenv("SAIS_GEMM_NBUF_RES")) : 0;
+  if (a.residual && a.remap_group == 0 && env_nbuf_res >= 2 && env_nbuf_res <= 4) nbuf = env_nbuf_res;
   p.nbuf = nbuf;
   p.ln_stats_in = a.ln_stats_in;
   p.ln_colsum = a.ln_colsum;
@@ -904,6 +938,15 @@ int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
   p.ldo2 = a.ldo2;
   static const int env_xb = getenv("SAIS_GEMM_XB") ? atoi(getenv("SAIS_GEMM_XB")) : 1;
   p.xb_buf = (a.out2_bf16 && env_xb) ? 2048 : 0;
+  // Short-K residual GEMMs (proj: six k-blocks per tile) are bound by their epilogue's residual / store chain, not by the
+  // operand ring: trade two ring stages for a third staging buffer (residual tiles requested two chunks ahead) and a second
+  // bf16-copy tile.  Long-K ones (fc2) need the deep ring more (3 stages: 69 -> 77 us).  SAIS_GEMM_NBUF_RES / SAIS_GEMM_XB=2 force.
+  if (a.residual && a.remap_group == 0 && !a.split3 && a.K <= 512 && a.out_f32 && env_nbuf_res == 0 && !a.k_slices) {
+    nbuf = 3;
+    if (p.xb_buf) p.xb_buf = 4096;
+  }
+  if (p.xb_buf && env_xb == 2) p.xb_buf = 4096;
+  p.nbuf = nbuf;
   const bool csum = a.ln_stats_in != nullptr;  // only consumer GEMMs keep column-sum slices in the tail
   p.accumulate = a.k_slices > 0;
   p.k_slices = 1;
@@ -917,6 +960,7 @@ int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
   static const int env_stages = getenv("SAIS_GEMM_STAGES") ? atoi(getenv("SAIS_GEMM_STAGES")) : 0;  // dev knob: shallower ring
   if (env_stages >= 2 && env_stages < p.stages) p.stages = env_stages;
   p.stage_buf = wide ? kStageBufBytes : kStageBufBytes / 2;
+  p.reverse = g_tile_reverse;
   const int units = ((m_tiles + cluster - 1) / cluster) * (p.N / BLOCK_N) * p.k_slices;
   int grid = units * cluster < num_sms() ? units * cluster : num_sms();
   grid -= grid % cluster;

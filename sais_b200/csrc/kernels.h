@@ -27,6 +27,12 @@ struct LaunchScope {
 
 // gemm_tcgen05.cu
 int gemm_bias_act(const SaisGemmArgs& a, cudaStream_t stream, int force_block_n = 0);
+// Scheduling hint for the row-tiled kernels (GEMM m-tiles, attention items): 1 = walk the rows from the last tile to the
+// first.  sais_vit_forward alternates it from kernel to kernel ("snake" order): every kernel then starts on the rows its
+// producer wrote LAST, which are the ones still resident in the 126 MB L2 — walking in the producer's own order evicts
+// each line just before it is needed once a tensor is larger than the cache (qkv 116 MB, MLP hidden 155 MB at batch
+// 256).  Results do not depend on it.
+extern thread_local int g_tile_reverse;
 int pick_block_n(int64_t M, int64_t N);
 
 // mlp_fused.cu: x += fc2(GELU(fc1(xn) + b1)) + b2 over bf16 xn [rows,384], fp32 x [rows,384] (in place)

@@ -74,7 +74,7 @@ __host__ __device__ constexpr bool pair_uses_poly(int j, int kPoly) {
 template <bool kPInTmem, bool kTurns, int kPoly>
 __global__ void __launch_bounds__(kThreads, 1)
 vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out,
-                        __nv_bfloat16* __restrict__ out, int n_items,
+                        __nv_bfloat16* __restrict__ out, int n_items, int reverse,
                         long long* __restrict__ dbg) {
   // dev knob (SAIS_ATTN_TIMELINE=<file>): CTA 0 records clock64() at every phase boundary, [role][item][event]
   auto stamp = [&](int role, int idx, int ev) {
@@ -134,7 +134,8 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
         for (int idx = 0; idx < n_my; ++idx) {
           const int slot = idx & 1;
           if (idx >= 2) mbar_wait(&ld_empty[slot], ((idx - 2) >> 1) & 1);  // previous occupant fully consumed
-          const int item = int(blockIdx.x) + idx * int(gridDim.x);
+          const int item0 = int(blockIdx.x) + idx * int(gridDim.x);
+          const int item = reverse ? n_items - 1 - item0 : item0;  // (kernels.h g_tile_reverse)
           const int b = item / HEADS, h = item % HEADS;
           uint8_t* dst = smem + slot * SLOT_BYTES;
           if (elect_one()) {
@@ -207,8 +208,9 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
     const float sl2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
 
     int it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+    for (int item0 = blockIdx.x; item0 < n_items; item0 += gridDim.x, ++it) {
       const uint32_t ph = it & 1;
+      const int item = reverse ? n_items - 1 - item0 : item0;
       const int b = item / HEADS, h = item % HEADS;
       const bool st_on = (q == 0 && lane == 0);
       if (st_on) stamp(mt, it, 0);
@@ -430,7 +432,7 @@ int launch_attn(const CUtensorMap& tm, const CUtensorMap& tm_out, sais_bf16* out
   const int grid = items < num_sms() ? items : num_sms();
   return check_cuda(launch_pdl(vit_attention_tc_kernel<kPInTmem, kTurns, kPoly>, dim3(grid), dim3(kThreads),
                                size_t(smem_bytes<kPInTmem>()), stream, 1, tm, tm_out,
-                               reinterpret_cast<__nv_bfloat16*>(out), items, dbg),
+                               reinterpret_cast<__nv_bfloat16*>(out), items, g_tile_reverse, dbg),
                     "vit_attention_tc launch");
 }
 
