@@ -46,6 +46,7 @@ constexpr int UMMA_K = 16;
 // latency-bound with two warps per scheduler (ncu: 22% issue-active), so the bf16-output GEMMs of the big ViT shapes
 // run with 16; the fp32-output modes stay at 8 (their staging tiles are twice as large).
 constexpr int CW = 32;               // epilogue chunk width (columns)
+constexpr bool kAStatDefault = true;   // A-stationary K = 384 GEMMs by default (SAIS_GEMM_ASTAT overrides)
 constexpr int kStageBufBytes = 4096;  // one staging buffer: 32 rows x 128 B (fp32) or 2 x (32 rows x 64 B) (bf16 hi, lo)
 
 template <int BLOCK_N, int CG, int EW>
@@ -72,6 +73,17 @@ struct GemmCfg {
   }
   static int smem_bytes(bool wide, int nbuf, int xb = 0, bool csum = true) {
     return stages(wide, nbuf, xb, csum) * kStageBytes + epi_bytes(wide, nbuf, xb) + 1024 + tail_bytes(csum);
+  }
+  // A-stationary variant (K = kAStatKB * 64): the A rows of an m-tile group stay resident for all of its n-tiles, the ring
+  // carries W only
+  static constexpr int kAStatKB = 6;
+  static constexpr int kAResident = kAStatKB * kABytes;
+  static int stages_astat(bool wide, int nbuf, bool csum) {
+    const int s = (budget(csum) - epi_bytes(wide, nbuf, 0) - kAResident) / kBBytes;
+    return s > kMaxStages ? kMaxStages : s;
+  }
+  static int smem_bytes_astat(bool wide, int nbuf, bool csum) {
+    return kAResident + stages_astat(wide, nbuf, csum) * kBBytes + epi_bytes(wide, nbuf, 0) + 1024 + tail_bytes(csum);
   }
 };
 
@@ -156,19 +168,27 @@ __device__ __forceinline__ void tma_store_2d_s(const CUtensorMap* m, uint32_t sm
 // CG = 1: one CTA per 128 x BLOCK_N tile.  CG = 2: a CTA pair (2-CTA cluster, tcgen05 cta_group::2) per
 // 256 x BLOCK_N tile — each CTA loads its own 128 rows of A but only HALF of the W tile, so the bytes every SM
 // pulls from L2 per flop drop by 1/3 (the measured limiter of the CG = 1 kernel at K = 384).
-template <int BLOCK_N, int MODE, int CG, int EW>
+// ASTAT (A-stationary, K = 384, CTA pairs): every CTA pair owns a CONTIGUOUS range of the (m-group, n-tile) sequence and
+// keeps the six A k-blocks of the current m-group resident in shared memory for all n-tiles it covers there; the ring then
+// streams W only.  The bytes every SM pulls through L2 — what paces the K = 384 mainloops — drop by
+// ~45 % (qkv: 168 -> 94 KB per tile and CTA on average).
+template <int BLOCK_N, int MODE, int CG, int EW, bool ASTAT = false>
 __global__ void __launch_bounds__(32 * (2 + EW), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                     const __grid_constant__ CUtensorMap tmap_out2, const GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N, CG, EW>;
+  static_assert(!ASTAT || (CG == 2 && (MODE == kModeBf16 || MODE == kModeBf16Gelu)), "A-stationary: CTA pairs, bf16 outputs");
   constexpr int kEpiWarps = EW;
   constexpr int kSub = Cfg::kSub;
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled UMMA/TMA tiles need 1024-byte aligned bases
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int kStages = p.stages;
-  uint8_t* epi_smem = smem + kStages * Cfg::kStageBytes;
+  constexpr int kRingStageBytes = ASTAT ? Cfg::kBBytes : Cfg::kStageBytes;
+  uint8_t* a_res = smem;                                          // ASTAT: resident A k-blocks [kAStatKB][kABytes]
+  uint8_t* ring = smem + (ASTAT ? Cfg::kAResident : 0);
+  uint8_t* epi_smem = ring + kStages * kRingStageBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + kEpiWarps * (p.nbuf * p.stage_buf + p.xb_buf));
   uint64_t* full_bar = bars;                        // [kMaxStages]
   uint64_t* empty_bar = bars + Cfg::kMaxStages;     // [kMaxStages]
@@ -176,7 +196,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint64_t* tempty_bar = tfull_bar + 2;           // [2]
   constexpr int kResBars = (EW == 8) ? 4 : 2;     // residual-tile ring slots per epilogue warp (fp32 modes run on 8 warps)
   uint64_t* res_bar = tempty_bar + 2;             // [kEpiWarps][kResBars]
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(res_bar + kResBars * kEpiWarps);
+  uint64_t* afull_bar = res_bar + kResBars * kEpiWarps;  // ASTAT: [kAStatKB] A k-block resident / [kAStatKB] free again
+  uint64_t* aempty_bar = afull_bar + Cfg::kAStatKB;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(aempty_bar + Cfg::kAStatKB);
+  static_assert(16 + kResBars * kEpiWarps + 2 * Cfg::kAStatKB + 1 <= 64, "barrier area is 64 slots");
   float* bias_smem = reinterpret_cast<float*>(bars + 64);                  // [kEpiWarps][kChunksPerWarp * CW]
   float* csum_smem = bias_smem + kEpiWarps * (Cfg::kChunksPerWarp * CW);  // [kEpiWarps][kChunksPerWarp * CW]
 
@@ -191,16 +214,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   // cluster.  Units are walked n-fastest; a CTA whose m-tile lies beyond M just computes on zero-filled rows.
   constexpr int csize = CG;
   const uint32_t crank = CG > 1 ? cluster_ctarank() : 0;
-  const int unit0 = blockIdx.x / csize;
-  const int unit_stride = gridDim.x / csize;
   const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
   const int n_tiles = p.N / BLOCK_N;
   const int num_tiles = ((m_tiles + csize - 1) / csize) * n_tiles;  // number of work units
+  // ASTAT: CTA (pair) c walks the contiguous unit range [num_tiles * c / C, num_tiles * (c + 1) / C) one by one
+  const int n_ctas = gridDim.x / csize, cta = blockIdx.x / csize;
+  const int unit0 = ASTAT ? int(int64_t(num_tiles) * cta / n_ctas) : cta;
+  const int unit_stride = ASTAT ? 1 : n_ctas;
+  const int astat_end = int(int64_t(num_tiles) * (cta + 1) / n_ctas);
   const int kb_per_pass = p.K / BLOCK_K;
   const int k_blocks = p.split3 ? 3 * kb_per_pass : kb_per_pass;
   // split-K (accumulate mode, small M): a work unit is (tile, K slice); partial products meet in L2 (TMA reduce-add)
   const int S = p.k_slices;
-  const int num_units = num_tiles * S;
+  const int num_units = ASTAT ? astat_end : num_tiles * S;  // (loop bound of this CTA; ASTAT implies S == 1)
   const int kbs = (k_blocks + S - 1) / S;
 
   constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
@@ -216,6 +242,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_init(&tempty_bar[s], kEpiWarps * CG);  // (leader's copy) the epilogue warps of BOTH CTAs drain the tile
     }
     for (int s = 0; s < kResBars * kEpiWarps; ++s) mbar_init(&res_bar[s], 1);
+    if (ASTAT)
+      for (int s = 0; s < 2 * Cfg::kAStatKB; ++s) mbar_init(&afull_bar[s], 1);
     fence_mbar_init();
   }
   if (warp == kMmaWarp) {
@@ -250,15 +278,44 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       int tidx = 0;
+      int seg = 0;  // ASTAT: m-group segments started by this CTA (= A reloads)
       for (int u = unit0; u < num_units; u += unit_stride, ++tidx) {
         const int tile = u / S;
         const int kb0 = (u % S) * kbs, kb1 = (kb0 + kbs < k_blocks) ? kb0 + kbs : k_blocks;
         const int m0 = tile_m0(tile);
         const int n0 = (tile % n_tiles) * BLOCK_N;
+        if constexpr (ASTAT) {
+          const bool new_seg = (u == unit0) || (tile % n_tiles == 0);
+          for (int kb = 0; kb < Cfg::kAStatKB; ++kb) {
+            if (new_seg) {
+              // the MMAs of the previous segment that read A k-block kb have retired (committed with its last tile)
+              if (seg > 0) mbar_wait(&aempty_bar[kb], (seg - 1) & 1);
+              if (elect_one()) {
+                if (crank == 0) mbar_arrive_expect_tx(&afull_bar[kb], Cfg::kABytes * CG);
+                tma_load_2d_cg2(a_res + kb * Cfg::kABytes, &tmap_a, leader_smem_u32(&afull_bar[kb]), kb * BLOCK_K, m0);
+              }
+              __syncwarp();
+            }
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (lane == 0) stamp(0, tidx, kb);
+            if (elect_one()) {
+              if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], Cfg::kBBytes * CG);
+              tma_load_2d_cg2(ring + stage * kRingStageBytes, &tmap_b, leader_smem_u32(&full_bar[stage]), kb * BLOCK_K,
+                              n0 + int(crank) * (BLOCK_N / 2));
+            }
+            __syncwarp();
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          if (new_seg) ++seg;
+          continue;
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (lane == 0) stamp(0, tidx, kb - kb0);
-          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sa = ring + stage * kRingStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
           // dev knob (SAIS_GEMM_DEBUG_NOSTORE & 8): load A only for the first n-tile of every m-tile (stale A otherwise; timing
           // experiment that separates operand INGRESS cost from the tensor core's own shared-memory reads)
@@ -314,19 +371,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int astage = 0;
       uint32_t aphase = 0;
       int tidx = 0;
+      int seg = -1;  // ASTAT: index of the m-group segment being multiplied
       for (int u = unit0; u < num_units; u += unit_stride, ++tidx) {
         const int kb0 = (u % S) * kbs, kb1 = (kb0 + kbs < k_blocks) ? kb0 + kbs : k_blocks;
+        // ASTAT: first / last tile this CTA computes in the current m-group (A k-blocks arrive with the first, are released
+        // with the last)
+        const bool new_seg = ASTAT && ((u == unit0) || (u % n_tiles == 0));
+        const bool last_of_seg = ASTAT && ((u + 1 == num_units) || ((u + 1) % n_tiles == 0));
+        if (new_seg) ++seg;
         if (lane == 0) stamp(1, tidx, 0);
         mbar_wait(&tempty_bar[astage], aphase ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
         if (lane == 0) stamp(1, tidx, 1);
         const uint32_t d_tmem = tmem_base + astage * BLOCK_N;
         for (int kb = kb0; kb < kb1; ++kb) {
+          if (new_seg) mbar_wait(&afull_bar[kb], seg & 1);
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           if (lane == 0) stamp(1, tidx, 2 + kb - kb0);
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + Cfg::kABytes;
+          const uint32_t sa = ASTAT ? smem_u32(a_res + kb * Cfg::kABytes) : smem_u32(ring + stage * kRingStageBytes);
+          const uint32_t sb = ASTAT ? smem_u32(ring + stage * kRingStageBytes) : sa + Cfg::kABytes;
           const uint64_t da = umma_desc_sw128_kmajor(sa);
           const uint64_t db = umma_desc_sw128_kmajor(sb);
           if (elect_one()) {
@@ -338,6 +402,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
             // frees the smem slot (in both CTAs of a pair) once these MMAs retire
             if (CG == 1) umma_commit(&empty_bar[stage]); else umma_commit_cg2_mcast(&empty_bar[stage], uint16_t(0b11));
+            if constexpr (ASTAT) {
+              if (last_of_seg) umma_commit_cg2_mcast(&aempty_bar[kb], uint16_t(0b11));
+            }
           }
           __syncwarp();
           if (++stage == kStages) {
@@ -856,7 +923,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 }
 
-template <int BLOCK_N, int MODE, int CG, int EW>
+template <int BLOCK_N, int MODE, int CG, int EW, bool ASTAT = false>
 int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, CG, EW>;
   CUtensorMap ta, tb, tout, tres, tout2;
@@ -889,7 +956,7 @@ int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
 
   static bool attr_set = false;
   if (!attr_set) {
-    rc = check_cuda(cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, MODE, CG, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    rc = check_cuda(cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, MODE, CG, EW, ASTAT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024),
                     "cudaFuncSetAttribute(gemm)");
     if (rc) return rc;
@@ -956,7 +1023,7 @@ int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
     const int per = (kb_total + want - 1) / want;
     p.k_slices = (kb_total + per - 1) / per;
   }
-  p.stages = Cfg::stages(wide, nbuf, p.xb_buf, csum);
+  p.stages = ASTAT ? Cfg::stages_astat(wide, nbuf, csum) : Cfg::stages(wide, nbuf, p.xb_buf, csum);
   static const int env_stages = getenv("SAIS_GEMM_STAGES") ? atoi(getenv("SAIS_GEMM_STAGES")) : 0;  // dev knob: shallower ring
   if (env_stages >= 2 && env_stages < p.stages) p.stages = env_stages;
   p.stage_buf = wide ? kStageBufBytes : kStageBufBytes / 2;
@@ -966,8 +1033,9 @@ int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
   grid -= grid % cluster;
   LaunchScope ls(a.split3 ? kClsGemmSplit : kClsGemm, stream,
                  2.0 * double(a.M) * double(a.N) * double(a.K) * (a.split3 ? 3 : 1));
-  rc = check_cuda(launch_pdl(gemm_tcgen05_kernel<BLOCK_N, MODE, CG, EW>, dim3(grid), dim3(32 * (2 + EW)),
-                             size_t(Cfg::smem_bytes(wide, nbuf, p.xb_buf, csum)), stream, cluster, ta, tb, tout, tres, tout2, p),
+  const size_t smem_bytes = ASTAT ? size_t(Cfg::smem_bytes_astat(wide, nbuf, csum)) : size_t(Cfg::smem_bytes(wide, nbuf, p.xb_buf, csum));
+  rc = check_cuda(launch_pdl(gemm_tcgen05_kernel<BLOCK_N, MODE, CG, EW, ASTAT>, dim3(grid), dim3(32 * (2 + EW)), smem_bytes, stream,
+                             cluster, ta, tb, tout, tres, tout2, p),
                   "gemm_tcgen05_kernel launch");
   if (p.dbg) {  // dev knob: dump CTA 0's timeline (cycles relative to the first stamp), last call wins
     static long long h[kDbgN];
@@ -1085,6 +1153,19 @@ int gemm_bias_act(const SaisGemmArgs& a, cudaStream_t stream, int force_block_n)
   // 256); the plain bf16 epilogue (qkv) is faster on 8 warps (48.8 vs 51.1 us).  SAIS_GEMM_EW=8|12|16 forces one for both.
   static const int env_ew = getenv("SAIS_GEMM_EW") ? atoi(getenv("SAIS_GEMM_EW")) : 0;
   const int ewn = (env_ew == 16 || env_ew == 12 || env_ew == 8) ? env_ew : (mode == kModeBf16Gelu ? 16 : 8);
+  // A-stationary variant (SAIS_GEMM_ASTAT=1|0 forces / disables): K = 384 consumer GEMMs at CTA-pair sizes
+  static const int env_astat = getenv("SAIS_GEMM_ASTAT") ? atoi(getenv("SAIS_GEMM_ASTAT")) : -1;
+  const bool astat_ok = cg == 2 && a.K == 384 && !a.split3 && (mode == kModeBf16 || mode == kModeBf16Gelu) && bn >= 192 &&
+                        (ewn == 8 || ewn == 16) && !(mode == kModeBf16Gelu && ewn == 8) && !(mode == kModeBf16 && ewn == 16);
+  const bool astat = astat_ok && (env_astat < 0 ? kAStatDefault : env_astat != 0);
+  if (astat) {
+    if (bn == 256) {
+      if (mode == kModeBf16Gelu) return launch_gemm<256, kModeBf16Gelu, 2, 16, true>(a, stream);
+      return launch_gemm<256, kModeBf16, 2, 8, true>(a, stream);
+    }
+    if (mode == kModeBf16Gelu) return launch_gemm<192, kModeBf16Gelu, 2, 16, true>(a, stream);
+    return launch_gemm<192, kModeBf16, 2, 8, true>(a, stream);
+  }
 #define SAIS_GEMM_DISPATCH_CG(BN, CG)                                                              \
   switch (mode) {                                                                                  \
     case kModeBf16:                                                                                \

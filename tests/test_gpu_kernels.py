@@ -148,6 +148,27 @@ torch.save(outs, sys.argv[1])
 """
 
 
+def test_gemm_a_stationary_bit_identical(dev, tmp_path):
+    """The A-stationary K = 384 variant (contiguous tile ranges per CTA pair, A rows resident across n-tiles; SAIS_GEMM_ASTAT,
+    read once per process) accumulates the same products in the same order as the ring variant: outputs must agree bit for
+    bit.  The script's shapes include CTA-pair-sized qkv / fc1 problems (197 * 160 rows) where the variant is active."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    script = _EPILOGUE_VARIANT_SCRIPT.replace("(1000, 1152, 0, False)", "(197 * 160, 1152, 0, True), (197 * 128 + 77, 1152, 0, False)")
+    res = {}
+    for flag in ("0", "1"):
+        env = dict(os.environ, SAIS_GEMM_ASTAT=flag, PYTHONPATH=str(root))
+        out = tmp_path / f"astat{flag}.pt"
+        subprocess.run([sys.executable, "-c", script, str(out)], check=True, env=env, cwd=root, timeout=300)
+        res[flag] = torch.load(out)
+    for a, b in zip(res["0"], res["1"]):
+        assert a.shape == b.shape and torch.equal(a.view(torch.int16), b.view(torch.int16)), \
+            (a.float() - b.float()).abs().max()
+
+
 def test_gemm_epilogue_warp_variants_bit_identical(dev, tmp_path):
     """The 8-warp and the lean 16-warp bf16 epilogues (SAIS_GEMM_EW, read once per process) must agree bit for bit: same
     accumulators, and the 16-warp GELU works on x / 2 with constants scaled by exact powers of two (common.cuh
