@@ -640,6 +640,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int m0 = tile_m0(tile);
       const int n0 = (tile % n_tiles) * BLOCK_N;
       if (erole >= 0 && lane == 0) stamp(erole, tidx, 0);
+      // accumulator ready?  (the epilogue is normally the slower side, so yes) -> start the first TMEM read right away: it
+      // streams in under the per-tile vector staging below instead of after it
+      mbar_wait(&tfull_bar[astage], aphase);
+      tc_fence_after();
+      if (erole >= 0 && lane == 0) stamp(erole, tidx, 1);
+      const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + astage * BLOCK_N;
+      const int row = m0 + q * 32 + lane;
+
+      uint32_t v[32];
+      // dev knobs for timing experiments (results wrong): & 16 = no TMEM reads, & 32 = no staging / store (bf16 modes)
+      const bool dbg_no_ld = (p.debug_nostore & 16) != 0, dbg_no_st = (p.debug_nostore & 32) != 0 && !has_res;
+      if (dbg_no_ld) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0;
+      } else {
+        tmem_ld_32x32(t_row + half * CW, v);
+      }
       // this tile's vectors: registers -> per-warp smem (later reads are broadcast loads), then fetch the next tile's
       __syncwarp();
 #pragma unroll
@@ -666,21 +683,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
       for (int j = 0; j < 8; ++j) bv[j] = lds128_pairs(bias_s + j * 16);
 
-      mbar_wait(&tfull_bar[astage], aphase);
-      tc_fence_after();
-      if (erole >= 0 && lane == 0) stamp(erole, tidx, 1);
-      const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + astage * BLOCK_N;
-      const int row = m0 + q * 32 + lane;
-
-      uint32_t v[32];
-      // dev knobs for timing experiments (results wrong): & 16 = no TMEM reads, & 32 = no staging / store (bf16 modes)
-      const bool dbg_no_ld = (p.debug_nostore & 16) != 0, dbg_no_st = (p.debug_nostore & 32) != 0 && !has_res;
-      if (dbg_no_ld) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0;
-      } else {
-        tmem_ld_32x32(t_row + half * CW, v);
-      }
 #pragma unroll 1
       for (int ci = 0; ci < NCW; ++ci) {
         const int c = half + kSub * ci;
