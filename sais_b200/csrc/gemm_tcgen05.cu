@@ -271,6 +271,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int m_groups = (m_tiles + csize - 1) / csize;
   auto grp_m0 = [&](int g) { return ((p.reverse ? m_groups - 1 - g : g) * csize + int(crank)) * BLOCK_M; };
   auto tile_m0 = [&](int unit) { return grp_m0(unit / n_tiles); };
+  // unit -> (m-group, n-tile) positions are advanced incrementally where it matters (the epilogue's per-tile and per-chunk
+  // bookkeeping): the integer divisions of the direct mapping were ~900 cycles at the top of every tile
+  const int d_mt = unit_stride / n_tiles, d_nt = unit_stride % n_tiles;
+  auto pos_of = [&](int u, int& mt, int& nt) {
+    const int t = u / S;
+    mt = t / n_tiles;
+    nt = t - mt * n_tiles;
+  };
+  auto pos_next = [&](int& u, int& mt, int& nt) {  // the unit this CTA processes after u
+    u += unit_stride;
+    if (S == 1) {
+      mt += d_mt;
+      nt += d_nt;
+      if (nt >= n_tiles) {
+        nt -= n_tiles;
+        ++mt;
+      }
+    } else {
+      pos_of(u, mt, nt);
+    }
+  };
 
   if (warp == kProducerWarp) {
     // ===================== TMA producer (whole warp, warp-uniform; only the TMA instructions are elected) =====================
@@ -453,12 +474,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // single 4 KB load in flight per warp behind a store-read wait — a ~3.5 k-cycle latency chain per chunk that made
     // proj epilogue-bound at 11.5 k cycles per tile against 2.5 k cycles of MMA (gpurun_out/s6f timelines).
     int pf_u = unit0, pf_c = half, pf_slot = 0;  // cursor: (unit, chunk) of the next residual tile to request, its ring slot
+    int pf_mt, pf_nt;                            // (m-group, n-tile) of unit pf_u
+    pos_of(unit0, pf_mt, pf_nt);
     const uint32_t xb_base = my_stage + nbuf * kBuf;  // bf16-copy staging tile(s) (LayerNorm-producer mode; one or two per warp)
     uint32_t xb_tile = xb_base;
     int rslot = 0;                               // ring slot / barrier phase of the chunk being consumed
     uint32_t rphase = 0;
     auto res_request = [&]() {  // one thread
-      const int rm0 = tile_m0(pf_u), rn0 = (pf_u % n_tiles) * BLOCK_N;
+      const int rm0 = grp_m0(pf_mt), rn0 = pf_nt * BLOCK_N;
       mbar_arrive_expect_tx(&my_res_bar[pf_slot], 32 * 128);
       tma_load_2d_s(my_stage + pf_slot * kBuf, &tmap_res, &my_res_bar[pf_slot], rn0 + pf_c * CW, rm0 + q * 32);
     };
@@ -467,7 +490,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       pf_c += kSub;
       if (pf_c >= NC) {
         pf_c = half;
-        pf_u += unit_stride;
+        pos_next(pf_u, pf_mt, pf_nt);
       }
     };
     if (has_res) {
@@ -483,9 +506,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // would be paid in full (16 tiles x ~800 cycles = 7 us at batch 256).
     float pf_bias[NCWmax], pf_csum[NCWmax];
     float4 pf_s0 = make_float4(0.f, 0.f, 0.f, 0.f), pf_s1 = pf_s0;
-    auto prefetch_tile = [&](int t) {
+    auto prefetch_tile = [&](int t, int t_mt, int t_nt) {
       if (t >= num_units) return;
-      const int pm0 = tile_m0(t / S), pn0 = ((t / S) % n_tiles) * BLOCK_N;
+      const int pm0 = grp_m0(t_mt), pn0 = t_nt * BLOCK_N;
 #pragma unroll
       for (int ci = 0; ci < NCWmax; ++ci) {
         pf_bias[ci] = (ci < NCW && p.bias) ? __ldg(p.bias + pn0 + (half + kSub * ci) * CW + lane) : 0.0f;
@@ -498,7 +521,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         pf_s1 = __ldg(sp + 1);
       }
     };
-    prefetch_tile(unit0);
+    int cur_mt, cur_nt;  // position of the unit being processed
+    pos_of(unit0, cur_mt, cur_nt);
+    prefetch_tile(unit0, cur_mt, cur_nt);
 
     int tidx = 0;
     const int erole = (ew == 0) ? 2 : (ew == 4 ? 3 : -1);
@@ -510,8 +535,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       // register file (65,536 / 576 threads = 112) with half-width blocks and without the register-resident bias /
       // column-sum double buffers (four warps per scheduler hide the broadcast LDS instead).
       static_assert(MODE == kModeBf16 || MODE == kModeBf16Gelu, "16 epilogue warps: bf16-output modes only");
-      const int d_mt = unit_stride / n_tiles, d_nt = unit_stride % n_tiles;  // unit -> (m-tile, n-tile) without divisions
-      int mt = unit0 / n_tiles, nt = unit0 % n_tiles;                        // (S == 1 in the bf16 modes)
+      int mt = cur_mt, nt = cur_nt;  // (S == 1 in the bf16 modes)
       const uint32_t bias_s = smem_u32(my_bias), csum_s = ln_in ? smem_u32(my_csum) : bias_s;
       // GELU mode: the block below produces h = x / 2 straight away (bias, rstd and -mean * rstd halved: exact scalings),
       // which is what gelu_erf_fast2_half wants
@@ -636,9 +660,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
     } else
     for (int u = unit0; u < num_units; u += unit_stride, ++tidx) {
-      const int tile = u / S;
-      const int m0 = tile_m0(tile);
-      const int n0 = (tile % n_tiles) * BLOCK_N;
+      const int m0 = grp_m0(cur_mt);
+      const int n0 = cur_nt * BLOCK_N;
+      const int tile_nt = cur_nt;
+      int nxt_u = u, nxt_mt = cur_mt, nxt_nt = cur_nt;
+      pos_next(nxt_u, nxt_mt, nxt_nt);
+      cur_mt = nxt_mt;  // (m0 / n0 / tile_nt hold this tile's position from here on)
+      cur_nt = nxt_nt;
       if (erole >= 0 && lane == 0) stamp(erole, tidx, 0);
       // accumulator ready?  (the epilogue is normally the slower side, so yes) -> start the first TMEM read right away: it
       // streams in under the per-tile vector staging below instead of after it
@@ -672,7 +700,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         ln_rstd = rsqrtf(var + p.ln_eps);
         ln_nmr = -mean * ln_rstd;
       }
-      prefetch_tile(u + unit_stride);
+      prefetch_tile(nxt_u, nxt_mt, nxt_nt);
       uint64_t ln_sum2 = 0, ln_sq2 = 0;  // producer: this warp's share of the row statistics of the tile (packed pairs)
       __syncwarp();
 
@@ -895,7 +923,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
       }
       if (ln_out && row < p.M) {
-        const int slot = (tile % n_tiles) * 2 + half;
+        const int slot = tile_nt * 2 + half;
         float s0, s1, q0, q1;
         unpack2(ln_sum2, s0, s1);
         unpack2(ln_sq2, q0, q1);
