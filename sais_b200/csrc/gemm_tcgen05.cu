@@ -107,6 +107,7 @@ struct GemmParams {
   int stages;         // depth of the operand ring
   int stage_buf;      // bytes per epilogue staging buffer (4096 or 2048)
   int reverse;        // walk the m-tiles from the last to the first (kernels.h g_tile_reverse)
+  int l2_hints;       // A operand loads carry an evict-first L2 policy (activations are consumed once)
   int nbuf;           // staging buffers per epilogue warp (2..4)
   // LayerNorm folding (see the file comment)
   const float* ln_stats_in;  // consumer: [M][4][2] (sum, sumsq) partials of the K-wide input rows
@@ -313,7 +314,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               if (seg > 0) mbar_wait(&aempty_bar[kb], (seg - 1) & 1);
               if (elect_one()) {
                 if (crank == 0) mbar_arrive_expect_tx(&afull_bar[kb], Cfg::kABytes * CG);
-                tma_load_2d_cg2(a_res + kb * Cfg::kABytes, &tmap_a, leader_smem_u32(&afull_bar[kb]), kb * BLOCK_K, m0);
+                // (A rows are read once, by this CTA only: evict-first keeps them from displacing the output the next
+                // kernel starts on, kernels.h g_tile_reverse; opt-in: SAIS_L2_HINTS=1)
+                if (p.l2_hints)
+                  tma_load_2d_cg2_hint(a_res + kb * Cfg::kABytes, &tmap_a, leader_smem_u32(&afull_bar[kb]), kb * BLOCK_K, m0,
+                                       kEvictFirst);
+                else
+                  tma_load_2d_cg2(a_res + kb * Cfg::kABytes, &tmap_a, leader_smem_u32(&afull_bar[kb]), kb * BLOCK_K, m0);
               }
               __syncwarp();
             }
@@ -366,6 +373,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             } else {
               // both CTAs' loads complete on the LEADER's full barrier (its MMA thread is the only consumer)
               const uint32_t lbar = leader_smem_u32(&full_bar[stage]);
+              // (no evict-first hint here: the ring variant's A tile is read by every n-tile's CTA pair, and the second
+              // reader then misses — proj / fc2 5 us slower in situ)
               if (!skip_a) tma_load_2d_cg2(sa, &tmap_a, lbar, ka * BLOCK_K, m0);
               tma_load_2d_cg2(sb, &tmap_b, lbar, kw * BLOCK_K, n0 + int(crank) * (BLOCK_N / 2));
             }
@@ -1058,6 +1067,8 @@ int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
   if (env_stages >= 2 && env_stages < p.stages) p.stages = env_stages;
   p.stage_buf = wide ? kStageBufBytes : kStageBufBytes / 2;
   p.reverse = g_tile_reverse;
+  static const int env_hints = getenv("SAIS_L2_HINTS") ? atoi(getenv("SAIS_L2_HINTS")) : 0;  // tried: -11 % DRAM reads, no time gain
+  p.l2_hints = env_hints && a.M >= 4096;  // streaming-sized problems only
   const int units = ((m_tiles + cluster - 1) / cluster) * (p.N / BLOCK_N) * p.k_slices;
   int grid = units * cluster < num_sms() ? units * cluster : num_sms();
   grid -= grid % cluster;

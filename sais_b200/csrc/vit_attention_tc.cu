@@ -74,8 +74,9 @@ __host__ __device__ constexpr bool pair_uses_poly(int j, int kPoly) {
 template <bool kPInTmem, bool kTurns, int kPoly>
 __global__ void __launch_bounds__(kThreads, 1)
 vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out,
-                        __nv_bfloat16* __restrict__ out, int n_items, int reverse,
+                        __nv_bfloat16* __restrict__ out, int n_items, int flags,
                         long long* __restrict__ dbg) {
+  const int reverse = flags & 1, l2_hints = flags & 2;  // (kernels.h g_tile_reverse; evict-first loads)
   // dev knob (SAIS_ATTN_TIMELINE=<file>): CTA 0 records clock64() at every phase boundary, [role][item][event]
   auto stamp = [&](int role, int idx, int ev) {
     if (dbg != nullptr && blockIdx.x == 0 && idx < 16) dbg[(role * 16 + idx) * 8 + ev] = clock64();
@@ -140,9 +141,15 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
           uint8_t* dst = smem + slot * SLOT_BYTES;
           if (elect_one()) {
             mbar_arrive_expect_tx(&ld_full[slot], SLOT_BYTES);
-            tma_load_3d(dst, &tmap_qkv, &ld_full[slot], h * HD, 0, b);
-            tma_load_3d(dst + MAT_BYTES, &tmap_qkv, &ld_full[slot], 384 + h * HD, 0, b);
-            tma_load_3d(dst + 2 * MAT_BYTES, &tmap_qkv, &ld_full[slot], 768 + h * HD, 0, b);
+            if (l2_hints) {  // q / k / v slices are read exactly once: evict-first (opt-in: SAIS_L2_HINTS=1)
+              tma_load_3d_hint(dst, &tmap_qkv, &ld_full[slot], h * HD, 0, b, kEvictFirst);
+              tma_load_3d_hint(dst + MAT_BYTES, &tmap_qkv, &ld_full[slot], 384 + h * HD, 0, b, kEvictFirst);
+              tma_load_3d_hint(dst + 2 * MAT_BYTES, &tmap_qkv, &ld_full[slot], 768 + h * HD, 0, b, kEvictFirst);
+            } else {
+              tma_load_3d(dst, &tmap_qkv, &ld_full[slot], h * HD, 0, b);
+              tma_load_3d(dst + MAT_BYTES, &tmap_qkv, &ld_full[slot], 384 + h * HD, 0, b);
+              tma_load_3d(dst + 2 * MAT_BYTES, &tmap_qkv, &ld_full[slot], 768 + h * HD, 0, b);
+            }
           }
           __syncwarp();
         }
@@ -430,9 +437,10 @@ int launch_attn(const CUtensorMap& tm, const CUtensorMap& tm_out, sais_bf16* out
     attr_set = true;
   }
   const int grid = items < num_sms() ? items : num_sms();
+  static const int env_hints = getenv("SAIS_L2_HINTS") ? atoi(getenv("SAIS_L2_HINTS")) : 0;  // tried: -11 % DRAM reads, no time gain
   return check_cuda(launch_pdl(vit_attention_tc_kernel<kPInTmem, kTurns, kPoly>, dim3(grid), dim3(kThreads),
                                size_t(smem_bytes<kPInTmem>()), stream, 1, tm, tm_out,
-                               reinterpret_cast<__nv_bfloat16*>(out), items, g_tile_reverse, dbg),
+                               reinterpret_cast<__nv_bfloat16*>(out), items, (g_tile_reverse ? 1 : 0) | (env_hints ? 2 : 0), dbg),
                     "vit_attention_tc launch");
 }
 
