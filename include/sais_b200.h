@@ -118,6 +118,12 @@ int sais_gemm_bias_act(const SaisGemmArgs* args, sais_stream_t stream);
  * biases fp32, x fp32 [rows,384] updated in place (the add happens in L2 through a TMA reduce store). */
 int sais_vit_mlp(const sais_bf16* xn, const sais_bf16* fc1_w, const float* fc1_b, const sais_bf16* fc2_w,
                  const float* fc2_b, float* x, int64_t rows, sais_stream_t stream);
+/* Same with norm2 (Block.norm2, vision_transformer.py:103,111) folded in, as in SaisGemmArgs.ln_stats_in: xb holds the RAW
+ * bf16 copy of the residual stream, ln_stats its per-row (sum, sum of squares) partials [rows][4][2], fc1_wg = gamma-scaled
+ * fc1 weights, fc1_c their column sums, fc1_d = fc1(beta) + fc1_b:   x += fc2(GELU_erf(rstd (xb fc1_wg^T - mean c) + d)) + fc2_b. */
+int sais_vit_mlp_ln(const sais_bf16* xb, const float* ln_stats, float ln_eps, const sais_bf16* fc1_wg, const float* fc1_c,
+                    const float* fc1_d, const sais_bf16* fc2_w, const float* fc2_b, float* x, int64_t rows,
+                    sais_stream_t stream);
 
 /* Linear + residual add + the FOLLOWING LayerNorm in one kernel (N = 384 = one full row per tile):
  *   x <- x + A · Wᵀ + bias   (fp32 [M,384], in place);   xn <- LayerNorm(x; gamma, beta, eps) as bf16 [M,384].

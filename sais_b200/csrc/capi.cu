@@ -294,6 +294,16 @@ int sais_vit_mlp(const sais_bf16* xn, const sais_bf16* fc1_w, const float* fc1_b
   return vit_mlp_fused(xn, fc1_w, fc1_b, fc2_w, fc2_b, x, rows, static_cast<cudaStream_t>(stream));
 }
 
+int sais_vit_mlp_ln(const sais_bf16* xb, const float* ln_stats, float ln_eps, const sais_bf16* fc1_wg, const float* fc1_c,
+                    const float* fc1_d, const sais_bf16* fc2_w, const float* fc2_b, float* x, int64_t rows,
+                    sais_stream_t stream) {
+  if (!ln_stats || !fc1_c) {
+    set_last_error("vit_mlp_ln: ln_stats and fc1_c are required");
+    return kErrInvalidArg;
+  }
+  return vit_mlp_fused(xb, fc1_wg, fc1_d, fc2_w, fc2_b, x, rows, static_cast<cudaStream_t>(stream), ln_stats, fc1_c, ln_eps);
+}
+
 int sais_gemm_residual_layernorm(const sais_bf16* a, int64_t lda, const sais_bf16* w, int64_t ldw, const float* bias,
                                  float* x, const float* gamma, const float* beta, float eps, sais_bf16* xn,
                                  int64_t M, int64_t K, sais_stream_t stream) {
@@ -425,6 +435,8 @@ int sais_vit_forward(const SaisVitWeights* w, const void* input, int32_t input_k
     // of the other paths walk forward); SAIS_SNAKE=0 disables it for A/B runs.
     static const bool env_nosnake = getenv("SAIS_SNAKE") != nullptr && atoi(getenv("SAIS_SNAKE")) == 0;
     const bool snake = fold && !env_nosnake;
+    // fused MLP kernel (mlp_fused.cu) inside the folded path instead of the fc1 / fc2 GEMM pair; SAIS_MLP_FOLD=0 restores the pair
+    static const bool mlp_fold = !(getenv("SAIS_MLP_FOLD") != nullptr && atoi(getenv("SAIS_MLP_FOLD")) == 0);
     int dir = 1;  // rowstats_cast (like the patch GEMM before it) walks forward, so block 0's qkv starts from the end
     struct DirGuard { ~DirGuard() { g_tile_reverse = 0; } } dir_guard;  // never leaks into later calls on this thread
     auto next_dir = [&]() {
@@ -499,6 +511,20 @@ int sais_vit_forward(const SaisVitWeights* w, const void* input, int32_t input_k
       }
       if (!precise && env_mlp) {  // fc1 + GELU + fc2 + residual: the hidden activations stay on chip
         if ((rc = vit_mlp_fused(xn, bw.fc1_w, bw.fc1_b, bw.fc2_w, bw.fc2_b, x, tok, stream))) return rc;
+        continue;
+      }
+      if (fold && mlp_fold) {
+        // Folded path with the fused MLP: proj left the raw bf16 copy + row statistics, the MLP kernel applies norm2 in
+        // its first epilogue and adds its result to the residual stream in L2 (no 155 MB hidden tensor through HBM); the
+        // next block's qkv operand (bf16 copy + statistics of the updated stream) comes from rowstats_cast.
+        g_tile_reverse = 0;
+        if ((rc = vit_mlp_fused(xn, bw.fc1_wg, bw.fc1_d, bw.fc2_w, bw.fc2_b, x, tok, stream, stats, bw.fc1_c, 1e-6f)))
+          return rc;
+        if (!last) {
+          if ((rc = rowstats_cast(x, tok, xn, stats, stream))) return rc;
+          xn_ready = true;
+          dir = 1;  // rowstats_cast walks forward: the next qkv starts from the end
+        }
         continue;
       }
       // fc1 + GELU

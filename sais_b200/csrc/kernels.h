@@ -37,7 +37,8 @@ int pick_block_n(int64_t M, int64_t N);
 
 // mlp_fused.cu: x += fc2(GELU(fc1(xn) + b1)) + b2 over bf16 xn [rows,384], fp32 x [rows,384] (in place)
 int vit_mlp_fused(const sais_bf16* xn, const sais_bf16* w1, const float* b1, const sais_bf16* w2, const float* b2,
-                  float* x, int64_t rows, cudaStream_t stream);
+                  float* x, int64_t rows, cudaStream_t stream, const float* ln_stats = nullptr,
+                  const float* ln_colsum = nullptr, float ln_eps = 0.0f);
 
 // gemm_rowln.cu: x += A · Wᵀ + bias (fp32 [M,384], in place); xn = LayerNorm(x) as bf16 [M,384] (xn may be null)
 int gemm_residual_layernorm(const sais_bf16* a, int64_t lda, const sais_bf16* w, int64_t ldw, const float* bias,

@@ -54,6 +54,12 @@ static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 struct MlpParams {
   const float* b1;
   const float* b2;
+  // folded LayerNorm (gemm_tcgen05.cu, "LayerNorm folding"): xn holds the RAW bf16 rows, w1 = gamma-scaled weights, b1 = d;
+  // the first epilogue applies rstd * (S - mean * c) + d per row from the producer's (sum, sum of squares) partials
+  const float* ln_stats;   // [rows][4][2] or nullptr
+  const float* ln_colsum;  // [1536] c_n
+  float ln_eps;
+  int64_t rows;
   int num_tiles;    // 256-row tiles
   int full_units;   // leading units that are whole tiles
   int tail_split;   // remaining tiles are split this many ways along the hidden dimension (1, 2, 3, 4, 6, ...)
@@ -155,33 +161,39 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t tmem_base = *tmem_base_smem;
 
   if (warp == kProducerWarp) {
-    // ===================== TMA producer (one thread per CTA) =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp, warp-uniform; TMA instructions elected) =====================
+    {
       int stage = 0;
       uint32_t wphase = 0;
       uint32_t ui = 0;
       int pg = 0, pg2 = 0;  // chunk counters (timeline only)
       auto load_w1 = [&](int j) {
         mbar_wait(&w_empty[stage], wphase ^ 1);
-        stamp(3, pg, 0);
-        if (crank == 0) mbar_arrive_expect_tx(&w_full[stage], 2 * STAGE_BYTES);
+        if (lane == 0) stamp(3, pg, 0);
         const uint32_t lbar = leader_smem_u32(&w_full[stage]);
         uint8_t* dst = w_smem + stage * STAGE_BYTES;
+        if (elect_one()) {
+          if (crank == 0) mbar_arrive_expect_tx(&w_full[stage], 2 * STAGE_BYTES);
 #pragma unroll
-        for (int kb = 0; kb < KB; ++kb)
-          tma_load_2d_cg2(dst + kb * 4096, &tmap_w1, lbar, kb * 64, j * HC + int(crank) * (HC / 2));
+          for (int kb = 0; kb < KB; ++kb)
+            tma_load_2d_cg2(dst + kb * 4096, &tmap_w1, lbar, kb * 64, j * HC + int(crank) * (HC / 2));
+        }
+        __syncwarp();
         ++pg;
         if (++stage == NSTAGE) { stage = 0; wphase ^= 1; }
       };
       auto load_w2 = [&](int j) {
         mbar_wait(&w_empty[stage], wphase ^ 1);
-        stamp(3, pg2, 1);
-        if (crank == 0) mbar_arrive_expect_tx(&w_full[stage], 2 * STAGE_BYTES);
+        if (lane == 0) stamp(3, pg2, 1);
         const uint32_t lbar = leader_smem_u32(&w_full[stage]);
         uint8_t* dst = w_smem + stage * STAGE_BYTES;
+        if (elect_one()) {
+          if (crank == 0) mbar_arrive_expect_tx(&w_full[stage], 2 * STAGE_BYTES);
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
-          tma_load_2d_cg2(dst + h * 12288, &tmap_w2, lbar, j * HC, h * 192 + int(crank) * 96);
+          for (int h = 0; h < 2; ++h)
+            tma_load_2d_cg2(dst + h * 12288, &tmap_w2, lbar, j * HC, h * 192 + int(crank) * 96);
+        }
+        __syncwarp();
         ++pg2;
         if (++stage == NSTAGE) { stage = 0; wphase ^= 1; }
       };
@@ -189,12 +201,13 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const Unit un = decode_unit(p, u);
         const int m0 = un.tile * (2 * MT) + int(crank) * MT;
         mbar_wait(a_empty, (ui & 1) ^ 1);  // the previous unit's G1s have retired
-        if (crank == 0) mbar_arrive_expect_tx(a_full, 2 * A_BYTES);
-        {
+        if (elect_one()) {
+          if (crank == 0) mbar_arrive_expect_tx(a_full, 2 * A_BYTES);
           const uint32_t lbar = leader_smem_u32(a_full);
 #pragma unroll
           for (int kb = 0; kb < KB; ++kb) tma_load_2d_cg2(a_smem + kb * (MT * 128), &tmap_a, lbar, kb * 64, m0);
         }
+        __syncwarp();
         for (int jj = 0; jj <= un.nj; ++jj) {
           if (jj < un.nj) load_w1(un.j0 + jj);
           if (jj >= 1) load_w2(un.j0 + jj - 1);
@@ -202,8 +215,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
   } else if (warp == kMmaWarp) {
-    // ===================== MMA issuer (leader CTA, one thread) =====================
-    if (lane == 0 && crank == 0) {
+    // ===================== MMA issuer (leader CTA) =====================
+    // The whole warp walks the loop (warp-uniform control flow, descriptors in uniform registers); only the tcgen05
+    // instructions sit under elect_one() — issued from one divergent lane every MMA cost a ~200-cycle ELECT / R2UR
+    // waterfall (profiles/r01f_mma_issue.md), and this kernel issues 32 small MMAs per hidden chunk.
+    if (crank == 0) {
       constexpr uint32_t idesc1 = umma_idesc_bf16(2 * MT, HC);
       constexpr uint32_t idesc2 = umma_idesc_bf16(2 * MT, 192);
       int stage = 0;
@@ -216,55 +232,59 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const Unit un = decode_unit(p, u);
         mbar_wait(a_full, ui & 1);
         tc_fence_after();
-        stamp(2, ui, 0);
+        if (lane == 0) stamp(2, ui, 0);
         for (int jj = 0; jj <= un.nj; ++jj) {
           if (jj < un.nj) {  // ---- G1: S[b] = A · W1[j]ᵀ
             const uint32_t gg = g + jj, b = gg & 1;
             mbar_wait(&s_empty[b], ((gg >> 1) & 1) ^ 1);
-            stamp(0, gg, 0);
+            if (lane == 0) stamp(0, gg, 0);
             mbar_wait(&w_full[stage], wphase);
             tc_fence_after();
-            stamp(0, gg, 1);
+            if (lane == 0) stamp(0, gg, 1);
             const uint32_t w_s = smem_u32(w_smem + stage * STAGE_BYTES);
             const uint32_t d = tmem_base + kSCol + b * HC;
+            if (elect_one()) {
 #pragma unroll
-            for (int kb = 0; kb < KB; ++kb) {
-              const uint64_t da = umma_desc_sw128_kmajor(a_s + kb * (MT * 128));
-              const uint64_t db = umma_desc_sw128_kmajor(w_s + kb * 4096);
+              for (int kb = 0; kb < KB; ++kb) {
+                const uint64_t da = umma_desc_sw128_kmajor(a_s + kb * (MT * 128));
+                const uint64_t db = umma_desc_sw128_kmajor(w_s + kb * 4096);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_f16_cg2(d, da + 2 * k, db + 2 * k, idesc1, (kb | k) != 0);
+                for (int k = 0; k < 4; ++k) umma_f16_cg2(d, da + 2 * k, db + 2 * k, idesc1, (kb | k) != 0);
+              }
+              umma_commit_cg2_mcast(&w_empty[stage], uint16_t(0b11));
+              if (jj == un.nj - 1) umma_commit_cg2_mcast(a_empty, uint16_t(0b11));
+              umma_commit_cg2_mcast(&s_full[b], uint16_t(0b11));
             }
-            umma_commit_cg2_mcast(&w_empty[stage], uint16_t(0b11));
-            if (jj == un.nj - 1) umma_commit_cg2_mcast(a_empty, uint16_t(0b11));
-            umma_commit_cg2_mcast(&s_full[b], uint16_t(0b11));
+            __syncwarp();
             if (++stage == NSTAGE) { stage = 0; wphase ^= 1; }
           }
           if (jj >= 1) {  // ---- G2: acc += H[b] · W2[:, j]ᵀ
             const uint32_t gg = g + jj - 1, b = gg & 1;
             if (jj == 1) {
               mbar_wait(acc_empty, (ui & 1) ^ 1);  // the previous unit's output epilogue has drained acc
-              stamp(2, ui, 1);
+              if (lane == 0) stamp(2, ui, 1);
             }
             mbar_wait(&h_full[b], (gg >> 1) & 1);
-            stamp(0, gg, 2);
+            if (lane == 0) stamp(0, gg, 2);
             mbar_wait(&w_full[stage], wphase);
             tc_fence_after();
-            stamp(0, gg, 3);
+            if (lane == 0) stamp(0, gg, 3);
             const uint32_t w_s = smem_u32(w_smem + stage * STAGE_BYTES);
             const uint64_t da = umma_desc_sw128_kmajor(h_s + b * H_BYTES);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+              for (int k = 0; k < 4; ++k) {
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const uint64_t db = umma_desc_sw128_kmajor(w_s + h * 12288);
-                umma_f16_cg2(tmem_base + h * 192, da + 2 * k, db + 2 * k, idesc2, (jj > 1) || (k > 0));
+                for (int h = 0; h < 2; ++h) {
+                  const uint64_t db = umma_desc_sw128_kmajor(w_s + h * 12288);
+                  umma_f16_cg2(tmem_base + h * 192, da + 2 * k, db + 2 * k, idesc2, (jj > 1) || (k > 0));
+                }
               }
+              umma_commit_cg2_mcast(&w_empty[stage], uint16_t(0b11));
+              umma_commit_cg2_mcast(&h_empty[b], uint16_t(0b11));
+              if (jj == un.nj) umma_commit_cg2_mcast(acc_full, uint16_t(0b11));
             }
-            umma_commit_cg2_mcast(&w_empty[stage], uint16_t(0b11));
-            umma_commit_cg2_mcast(&h_empty[b], uint16_t(0b11));
-            if (jj == un.nj) {
-              umma_commit_cg2_mcast(acc_full, uint16_t(0b11));
-            }
+            __syncwarp();
             if (++stage == NSTAGE) { stage = 0; wphase ^= 1; }
           }
         }
@@ -285,14 +305,33 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     for (int u = pair; u < p.num_units; u += npairs, ++ui) {
       const Unit un = decode_unit(p, u);
       const int m0 = un.tile * (2 * MT) + int(crank) * MT;
+      // h = x / 2 is produced directly (bias, rstd and -mean * rstd halved: exact scalings) for gelu_erf_fast2_half;
+      // without the folded LayerNorm rstd = 1, mean = 0 and the column-sum pointer aliases the bias
+      float rs_h = 0.5f, nm_h = 0.0f;
+      if (p.ln_stats != nullptr) {
+        const int64_t r = int64_t(m0) + row;
+        const float4* sp = reinterpret_cast<const float4*>(p.ln_stats + (r < p.rows ? r : p.rows - 1) * 8);
+        const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
+        const float mean = ((s0.x + s0.z) + (s1.x + s1.z)) * (1.0f / float(DM));
+        const float var = fmaxf(((s0.y + s0.w) + (s1.y + s1.w)) * (1.0f / float(DM)) - mean * mean, 0.0f);
+        const float rstd = rsqrtf(var + p.ln_eps);
+        rs_h = 0.5f * rstd;
+        nm_h = -mean * rstd * 0.5f;
+      }
+      const uint64_t rs2 = pack2(rs_h, rs_h), nm2 = pack2(nm_h, nm_h);
+      const float* cs_base = p.ln_colsum != nullptr ? p.ln_colsum : p.b1;
       for (int jj = 0; jj < un.nj; ++jj) {
         const uint32_t gg = g + jj, b = gg & 1;
         const int j = un.j0 + jj;
-        float4 bias[8];
+        float4 bias[8], cs[8];
         {
           const float4* bp = reinterpret_cast<const float4*>(p.b1 + j * HC + half * 32);
+          const float4* cp = reinterpret_cast<const float4*>(cs_base + j * HC + half * 32);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) bias[i] = __ldg(bp + i);
+          for (int i = 0; i < 8; ++i) {
+            bias[i] = __ldg(bp + i);
+            cs[i] = __ldg(cp + i);
+          }
         }
         mbar_wait(&s_full[b], (gg >> 1) & 1);
         tc_fence_after();
@@ -305,10 +344,13 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float f0 = gelu_erf_fast(__uint_as_float(v[4 * i]) + bias[i].x);
-          const float f1 = gelu_erf_fast(__uint_as_float(v[4 * i + 1]) + bias[i].y);
-          const float f2 = gelu_erf_fast(__uint_as_float(v[4 * i + 2]) + bias[i].z);
-          const float f3 = gelu_erf_fast(__uint_as_float(v[4 * i + 3]) + bias[i].w);
+          float f0, f1, f2, f3;
+          unpack2(fma2(pack2u(v[4 * i], v[4 * i + 1]), rs2,
+                       fma2(nm2, pack2(cs[i].x, cs[i].y), pack2(0.5f * bias[i].x, 0.5f * bias[i].y))), f0, f1);
+          unpack2(fma2(pack2u(v[4 * i + 2], v[4 * i + 3]), rs2,
+                       fma2(nm2, pack2(cs[i].z, cs[i].w), pack2(0.5f * bias[i].z, 0.5f * bias[i].w))), f2, f3);
+          gelu_erf_fast2_half(f0, f1);
+          gelu_erf_fast2_half(f2, f3);
           pk[2 * i] = pack_bf16x2(f0, f1);
           pk[2 * i + 1] = pack_bf16x2(f2, f3);
         }
@@ -392,7 +434,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 }  // namespace
 
 int vit_mlp_fused(const sais_bf16* xn, const sais_bf16* w1, const float* b1, const sais_bf16* w2, const float* b2,
-                  float* x, int64_t rows, cudaStream_t stream) {
+                  float* x, int64_t rows, cudaStream_t stream, const float* ln_stats, const float* ln_colsum, float ln_eps) {
   if (rows == 0) return kOk;
   if (!xn || !w1 || !b1 || !w2 || !b2 || !x || rows < 0) {
     set_last_error("vit_mlp: bad arguments");
@@ -420,14 +462,26 @@ int vit_mlp_fused(const sais_bf16* xn, const sais_bf16* w1, const float* b1, con
   MlpParams p;
   p.b1 = b1;
   p.b2 = b2;
+  if ((ln_stats == nullptr) != (ln_colsum == nullptr) ||
+      ((reinterpret_cast<uintptr_t>(ln_stats) | reinterpret_cast<uintptr_t>(ln_colsum)) & 15)) {
+    set_last_error("vit_mlp: ln_stats and ln_colsum go together (16-byte aligned)");
+    return kErrInvalidArg;
+  }
+  p.ln_stats = ln_stats;
+  p.ln_colsum = ln_colsum;
+  p.ln_eps = ln_eps;
+  p.rows = rows;
   p.num_tiles = int((rows + 2 * MT - 1) / (2 * MT));
   const int pairs_max = num_sms() / 2;
   // whole tiles for the full rounds; the last partial round is split along the hidden dimension when that shortens
   // the makespan (cost model: a unit costs its chunks + ~3 chunk-times of A load / output epilogue)
-  static const int env_split = getenv("SAIS_MLP_TAIL_SPLIT") ? atoi(getenv("SAIS_MLP_TAIL_SPLIT")) : 0;
+  // Splitting the tail makes the result depend on the order in which the partial sums of a row meet in L2 (fp32 adds are
+  // not associative): run-to-run bit differences.  The default is therefore NO split (every output element receives exactly
+  // one reduce-add: deterministic, ~6 % slower at batch 256); SAIS_MLP_TAIL_SPLIT=0 selects the cost model below, N > 1 forces N.
+  static const int env_split = getenv("SAIS_MLP_TAIL_SPLIT") ? atoi(getenv("SAIS_MLP_TAIL_SPLIT")) : 1;
   const int rem = p.num_tiles % pairs_max;
   int split = 1;
-  if (rem > 0) {
+  if (rem > 0 && env_split == 0) {
     double best = NCHUNK + 3.0;
     const int cands[6] = {2, 3, 4, 6, 8, 12};
     for (int s : cands) {

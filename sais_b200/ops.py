@@ -91,6 +91,20 @@ def vit_mlp(xn, fc1_w, fc1_b, fc2_w, fc2_b, x):
     return x
 
 
+def vit_mlp_ln(xb, ln_stats, fc1_wg, fc1_c, fc1_d, fc2_w, fc2_b, x, ln_eps=1e-6):
+    """vit_mlp with norm2 folded in: xb = raw bf16 rows + ln_stats [rows,8] (rowstats_cast / a LayerNorm-producer GEMM),
+    (fc1_wg, fc1_c, fc1_d) = fold_layernorm(gamma, beta, fc1_w, fc1_b).  x fp32 [rows,384] updated IN PLACE."""
+    require_cuda(xb, "xb")
+    require_cuda(x, "x")
+    assert xb.dtype == torch.bfloat16 and x.dtype == torch.float32 and xb.is_contiguous() and x.is_contiguous()
+    assert fc1_wg.dtype == torch.bfloat16 and fc2_w.dtype == torch.bfloat16 and ln_stats.dtype == torch.float32
+    assert tuple(fc1_wg.shape) == (1536, 384) and tuple(fc2_w.shape) == (384, 1536) and xb.shape[1] == 384
+    assert tuple(ln_stats.shape) == (xb.shape[0], 8) and ln_stats.is_contiguous() and x.shape == xb.shape
+    check(lib().sais_vit_mlp_ln(ptr(xb), ptr(ln_stats), float(ln_eps), ptr(fc1_wg), ptr(fc1_c), ptr(fc1_d), ptr(fc2_w),
+                                ptr(fc2_b), ptr(x), xb.shape[0], current_stream()), "sais_vit_mlp_ln")
+    return x
+
+
 def gemm_residual_layernorm(a, w, bias, x, gamma=None, beta=None, eps=1e-6, want_ln=True):
     """x += a @ w.T + bias (fp32 [M,384], IN PLACE); returns (x, LayerNorm(x) as bf16 [M,384] or None)."""
     require_cuda(a, "a")

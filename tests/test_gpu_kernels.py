@@ -385,6 +385,31 @@ def test_vit_mlp_fused_matches_unfused_gemms(dev):
     assert torch.allclose(got, ref, atol=1e-4, rtol=1e-4), (got - ref).abs().max()
 
 
+@pytest.mark.parametrize("rows", [130, 1000, 197 * 96, 256 * 80 - 57])
+def test_vit_mlp_fused_layernorm_folded(dev, rows):
+    """fused MLP with norm2 folded in (sais_vit_mlp_ln): raw bf16 rows + row statistics in, against the same GEMM-pair
+    arithmetic (folded fc1 + GELU -> bf16 hidden -> fc2 + residual) and against LayerNorm -> Mlp in fp32."""
+    from sais_b200 import _lib, ops
+    x0 = rnd(rows, 384, seed=rows) * 1.7 + 0.4
+    x0[:, 5] *= 8.0  # an outlier channel, as trained ViTs have
+    gamma, beta = 1 + 0.2 * rnd(384, seed=1), 0.2 * rnd(384, seed=2)
+    w1, b1 = rnd(1536, 384, seed=3, std=1 / math.sqrt(384)), rnd(1536, seed=4, std=0.3)
+    w2, b2 = rnd(384, 1536, seed=5, std=1 / math.sqrt(1536)), rnd(384, seed=6, std=0.5)
+    wg, c, d = ops.fold_layernorm(gamma, beta, w1, b1)
+    xb, stats = ops.rowstats_cast(x0.to(dev))
+    w2d, b2d = w2.to(dev).bfloat16(), b2.to(dev)
+    res = rnd(rows, 384, seed=7).to(dev)
+    got = ops.vit_mlp_ln(xb, stats, wg.to(dev), c.to(dev), d.to(dev), w2d, b2d, res.clone())
+    # (a) the two-GEMM path on the same operands
+    hid = ops.gemm_bias_act(xb, wg.to(dev), d.to(dev), act=_lib.ACT_GELU_ERF, ln_stats_in=stats, ln_colsum=c.to(dev), ln_eps=1e-6)
+    ref2 = ops.gemm_bias_act(hid, w2d, b2d, residual=res, out_dtype=torch.float32)
+    assert torch.allclose(got, ref2, atol=1e-4, rtol=1e-4), (got - ref2).abs().max()
+    # (b) LayerNorm -> fc1 -> GELU -> fc2 + residual in fp32 / fp64 (differs by the bf16 roundings of x, W', hidden)
+    h = torch.nn.functional.gelu(O.layer_norm(x0, gamma, beta, 1e-6) @ w1.t() + b1)
+    ref = res.cpu() + h @ w2.t() + b2
+    assert float((got.cpu().double() - ref.double()).norm() / ref.double().norm()) < 5e-3
+
+
 # ------------------------------------------------------------------------------------------------ ViT attention
 def _vit_attn_ref(qkv, B):
     q, k, v = bf(qkv).view(B, 197, 3, 6, 64).permute(2, 0, 3, 1, 4)
