@@ -517,13 +517,13 @@ int sais_vit_forward(const SaisVitWeights* w, const void* input, int32_t input_k
         // Folded path with the fused MLP: proj left the raw bf16 copy + row statistics, the MLP kernel applies norm2 in
         // its first epilogue and adds its result to the residual stream in L2 (no 155 MB hidden tensor through HBM); the
         // next block's qkv operand (bf16 copy + statistics of the updated stream) comes from rowstats_cast.
-        g_tile_reverse = 0;
+        next_dir();
         if ((rc = vit_mlp_fused(xn, bw.fc1_wg, bw.fc1_d, bw.fc2_w, bw.fc2_b, x, tok, stream, stats, bw.fc1_c, 1e-6f)))
           return rc;
         if (!last) {
+          next_dir();
           if ((rc = rowstats_cast(x, tok, xn, stats, stream))) return rc;
           xn_ready = true;
-          dir = 1;  // rowstats_cast walks forward: the next qkv starts from the end
         }
         continue;
       }

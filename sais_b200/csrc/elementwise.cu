@@ -117,13 +117,14 @@ __global__ void __launch_bounds__(256) layernorm384_kernel(const float* __restri
 // stats[row] = {sum, sum of squares, 0, 0, 0, 0, 0, 0}  (slot 0 of the four partial slots the GEMM epilogues fill).
 __global__ void __launch_bounds__(256) rowstats_cast384_kernel(const float* __restrict__ x, int64_t rows,
                                                                __nv_bfloat16* __restrict__ xb,
-                                                               float* __restrict__ stats) {
+                                                               float* __restrict__ stats, int reverse) {
   pdl_trigger();
   pdl_wait();  // (PDL, common.cuh) no global access above this line
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t warps_total = int64_t(gridDim.x) * (blockDim.x >> 5);
-  for (int64_t row = warp_global; row < rows; row += warps_total) {
+  for (int64_t row0 = warp_global; row0 < rows; row0 += warps_total) {
+    const int64_t row = reverse ? rows - 1 - row0 : row0;  // (kernels.h g_tile_reverse: start on the rows written last)
     const float* xr = x + row * D;
     float s = 0.f, q = 0.f;
 #pragma unroll
@@ -455,7 +456,7 @@ int rowstats_cast(const float* x, int64_t rows, sais_bf16* xb, float* stats, cud
   const int64_t cap = int64_t(num_sms()) * 8;
   if (blocks > cap) blocks = cap;
   LaunchScope ls(kClsLayerNorm, stream, double(rows) * D * 6);
-  return check_cuda(launch_pdl(rowstats_cast384_kernel, dim3(unsigned(blocks)), dim3(256), size_t(0), stream, 1, x, rows, reinterpret_cast<__nv_bfloat16*>(xb), stats),
+  return check_cuda(launch_pdl(rowstats_cast384_kernel, dim3(unsigned(blocks)), dim3(256), size_t(0), stream, 1, x, rows, reinterpret_cast<__nv_bfloat16*>(xb), stats, g_tile_reverse),
                     "rowstats_cast launch");
 }
 

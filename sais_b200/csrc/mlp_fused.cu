@@ -60,6 +60,7 @@ struct MlpParams {
   const float* ln_colsum;  // [1536] c_n
   float ln_eps;
   int64_t rows;
+  int reverse;      // walk the row tiles from the last to the first (kernels.h g_tile_reverse)
   int num_tiles;    // 256-row tiles
   int full_units;   // leading units that are whole tiles
   int tail_split;   // remaining tiles are split this many ways along the hidden dimension (1, 2, 3, 4, 6, ...)
@@ -93,6 +94,7 @@ __device__ __forceinline__ Unit decode_unit(const MlpParams& p, int u) {
     r.nj = NCHUNK / p.tail_split;
     r.j0 = (v % p.tail_split) * r.nj;
   }
+  if (p.reverse) r.tile = p.num_tiles - 1 - r.tile;
   return r;
 }
 
@@ -154,6 +156,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     tmem_alloc_cg2(tmem_base_smem, kTmemCols);
     tmem_relinquish_cg2();
   }
+  // PDL (common.cuh): the set-up above overlapped the previous kernel's tail; no global access before this line
+  pdl_trigger();
+  pdl_wait();
   for (int i = threadIdx.x; i < DM; i += kThreads) b2_smem[i] = __ldg(p.b2 + i);
   tc_fence_before();
   cluster_sync_all();
@@ -471,6 +476,7 @@ int vit_mlp_fused(const sais_bf16* xn, const sais_bf16* w1, const float* b1, con
   p.ln_colsum = ln_colsum;
   p.ln_eps = ln_eps;
   p.rows = rows;
+  p.reverse = g_tile_reverse;
   p.num_tiles = int((rows + 2 * MT - 1) / (2 * MT));
   const int pairs_max = num_sms() / 2;
   // whole tiles for the full rounds; the last partial round is split along the hidden dimension when that shortens
@@ -508,8 +514,10 @@ int vit_mlp_fused(const sais_bf16* xn, const sais_bf16* w1, const float* b1, con
   }
   {
     LaunchScope ls(kClsGemm, stream, 4.0 * double(rows) * DM * HID);
-    mlp_fused_kernel<<<2 * pairs, kThreads, kSmemBytes, stream>>>(ta, tw1, tw2, tout, p);
-    rc = check_cuda(cudaGetLastError(), "mlp_fused_kernel launch");
+    // (cluster = 1 here: the kernel carries its own __cluster_dims__(2, 1, 1))
+    rc = check_cuda(launch_pdl(mlp_fused_kernel, dim3(2 * pairs), dim3(kThreads), size_t(kSmemBytes), stream, 1, ta, tw1, tw2,
+                               tout, p),
+                    "mlp_fused_kernel launch");
   }
   if (p.dbg) {
     static long long h[kDbgN];
