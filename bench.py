@@ -362,8 +362,9 @@ def main():
                            in_loop_note="clock64 / globaltimer of a probe kernel enqueued after every step of a separate "
                                         "20-step pass"),
             "roofline": {"bound": "tensor",
-                         "kernel": "gemm_tcgen05_kernel, bf16 (the 49 ViT GEMM launches of a step: patch, qkv, proj, "
-                                   "fc1, fc2)",
+                         "kernel": "GEMM class, bf16: gemm_tcgen05_kernel + mlp_fused_kernel (the %d tensor-core GEMM "
+                                   "launches of a step: patch, qkv, proj, fused fc1+GELU+fc2, CLS-row GEMMs of the "
+                                   "last block)" % round(n_c[0] / prof_steps),
                          "achieved": gemm_tflops, "peak": sustained, "unit": "TFLOP/s",
                          "frac": gemm_tflops / sustained, "frac_of_burst": gemm_tflops / burst, "peak_source": src,
                          "avg_launch_ms": gemm_ms, "flop_per_launch": work_c[0] / max(n_c[0], 1),

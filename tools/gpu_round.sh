@@ -18,7 +18,7 @@ echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/bench_under_ncu.log 2>&1; echo "ncu list rc=$?"
 echo "== ncu full: gemm (one block of the second forward) / attention, layernorm, patchify, rowstats"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 53 -c 8 -f -o $OUT/prof_gemm \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'gemm_tcgen05|mlp_fused' -s 68 -c 6 -f -o $OUT/prof_gemm \
     python tools/profile_step.py > $OUT/prof_gemm.log 2>&1; echo "ncu gemm rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'vit_attention_tc|layernorm384|normalize_patchify|rowstats_cast|vit_cls_attention' -s 8 -c 5 -f -o $OUT/prof_other \
     python tools/profile_step.py > $OUT/prof_other.log 2>&1; echo "ncu other rc=$?"

@@ -14,7 +14,7 @@ col = {h: i for i, h in enumerate(hdr)}
 scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 tot, n, per = 0.0, 0, []
 for r in data:
-    if "gemm_tcgen05" not in r[col["Kernel Name"]]:
+    if "gemm_tcgen05" not in r[col["Kernel Name"]] and "mlp_fused" not in r[col["Kernel Name"]]:
         continue
     b = sum(float(r[col[k]].replace(",", "")) * scale[units[col[k]]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
     per.append({"kernel": r[col["Kernel Name"]][-60:], "dram_bytes": b,
