@@ -32,6 +32,7 @@ def timeit(name, fn, bytes_=0, flops=0, iters=20):
 x = torch.randn(M, 384, device=dev)
 g, b = torch.ones(384, device=dev), torch.zeros(384, device=dev)
 timeit("layernorm", lambda: ops.layernorm(x, g, b, 1e-6), bytes_=M * 384 * 6)
+timeit("rowstats_cast", lambda: ops.rowstats_cast(x), bytes_=M * (384 * 6 + 32))  # (allocates its outputs: a little pessimistic)
 qkv = torch.randn(M, 1152, device=dev).bfloat16()
 timeit("vit_attn", lambda: ops.vit_attention(qkv, B), bytes_=M * 1536 * 2, flops=4.0 * B * 6 * 197 * 197 * 64)
 fr = torch.randint(0, 256, (B, 224, 224, 3), dtype=torch.uint8, device=dev)
