@@ -377,48 +377,56 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tc_fence_after();
       if (ew == 0 && lane == 0) stamp(2, ui, 2);
       const bool add_bias = (un.j0 == 0);
-      constexpr int NOC = (DM / 2) / 16;  // 12 chunks of 16 columns per warp
+      constexpr int NOC = (DM / 2) / 16;  // 12 chunks of 16 columns per warp, handled two at a time:
+      // both accumulator chunks are moved to registers and biased BEFORE waiting for the previous iteration's two stores to
+      // have read the staging tiles, so that wait (the TMA queue is busy with the next unit's operand loads) overlaps the
+      // math; one fence / commit per 32 columns.  The output epilogue is fully exposed.
       uint32_t v[16], w[16];
       tmem_ld_32x16(t_lane + half * 192, v);
+      tmem_ld_32x16(t_lane + half * 192 + 16, w);
 #pragma unroll 1
       for (int c = 0; c < NOC; c += 2) {
+        const int col = half * 192 + c * 16;
+        tmem_ld_wait_dep(v);
+        tmem_ld_wait_dep(w);
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          f[i] = __uint_as_float(v[i]);
+          f[16 + i] = __uint_as_float(w[i]);
+        }
+        if (c + 2 < NOC) {
+          tmem_ld_32x16(t_lane + col + 32, v);
+          tmem_ld_32x16(t_lane + col + 48, w);
+        } else {
+          tc_fence_before();
+          if (lane == 0) mbar_arrive_cluster(leader_smem_u32(acc_empty));  // acc fully read by this warp
+        }
+        if (add_bias) {
+          const float4* bp = reinterpret_cast<const float4*>(b2_smem + col);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 b4 = bp[i];
+            f[4 * i] += b4.x; f[4 * i + 1] += b4.y; f[4 * i + 2] += b4.z; f[4 * i + 3] += b4.w;
+          }
+        }
+        if (lane == 0) tma_store_wait_read<0>();  // the previous iteration's stores have read both staging tiles
+        __syncwarp();
 #pragma unroll
         for (int s2 = 0; s2 < 2; ++s2) {
-          uint32_t(&cur)[16] = s2 == 0 ? v : w;
-          uint32_t(&nxt)[16] = s2 == 0 ? w : v;
-          const int cc = c + s2;
-          const int col = half * 192 + cc * 16;
-          tmem_ld_wait_dep(cur);
-          if (cc + 1 < NOC) {
-            tmem_ld_32x16(t_lane + col + 16, nxt);
-          } else {
-            tc_fence_before();
-            if (lane == 0) mbar_arrive_cluster(leader_smem_u32(acc_empty));  // acc fully read by this warp
-          }
-          float f[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(cur[i]);
-          if (add_bias) {
-            const float4* bp = reinterpret_cast<const float4*>(b2_smem + col);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 b4 = bp[i];
-              f[4 * i] += b4.x; f[4 * i + 1] += b4.y; f[4 * i + 2] += b4.z; f[4 * i + 3] += b4.w;
-            }
-          }
           const uint32_t buf = my_stage + s2 * 2048;
-          if (lane == 0) tma_store_wait_read<1>();  // the store issued from this buffer two chunks ago has read it
-          __syncwarp();
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            sts128m(buf + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4), __float_as_uint(f[4 * i]),
-                    __float_as_uint(f[4 * i + 1]), __float_as_uint(f[4 * i + 2]), __float_as_uint(f[4 * i + 3]));
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_reduce_add_2d(&tmap_out, buf, col, m0 + q * 32);
-            tma_store_commit();
-          }
+            sts128m(buf + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4), __float_as_uint(f[16 * s2 + 4 * i]),
+                    __float_as_uint(f[16 * s2 + 4 * i + 1]), __float_as_uint(f[16 * s2 + 4 * i + 2]),
+                    __float_as_uint(f[16 * s2 + 4 * i + 3]));
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_reduce_add_2d(&tmap_out, my_stage, col, m0 + q * 32);
+          tma_reduce_add_2d(&tmap_out, my_stage + 2048, col + 16, m0 + q * 32);
+          tma_store_commit();
         }
       }
       if (lane == 0) tma_store_wait_read<0>();
