@@ -160,6 +160,37 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int dtype, uint64_t rows, u
   return kOk;
 }
 
+// fp32 [d2][d1][d0] view (pitches ld1, ld2 in elements), box {box0, box1, 1}, 128-byte swizzle (box0 * 4 <= 128)
+int make_tmap_f32_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld1,
+                     uint64_t ld2, uint32_t box0, uint32_t box1) {
+  static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  });
+  if (!encode) {
+    set_last_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+    return kErrDriver;
+  }
+  const cuuint64_t gdim[3] = {d0, d1, d2};
+  const cuuint64_t gstride[2] = {ld1 * 4, ld2 * 4};
+  const cuuint32_t box[3] = {box0, box1, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled(3d f32) failed (%d) dims=%llu,%llu,%llu box=%u,%u", int(r),
+                   (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, box0, box1);
+    return kErrDriver;
+  }
+  return kOk;
+}
+
 int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld1,
                       uint64_t ld2, uint32_t box0, uint32_t box1) {
   static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;

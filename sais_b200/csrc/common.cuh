@@ -541,6 +541,8 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int dtype, uint64_t rows, u
 
 // 3D bf16 tensor [d2][d1][d0] (d0 contiguous; ld1 / ld2 = pitches of d1 / d2 in elements), box {box0, box1, 1},
 // 128-byte swizzle (box0 * 2 bytes must be 128).  Out-of-range coordinates are zero-filled on load.
+int make_tmap_f32_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld1,
+                     uint64_t ld2, uint32_t box0, uint32_t box1);
 int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld1,
                       uint64_t ld2, uint32_t box0, uint32_t box1);
 

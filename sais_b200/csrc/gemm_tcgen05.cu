@@ -107,6 +107,8 @@ struct GemmParams {
   int stages;         // depth of the operand ring
   int stage_buf;      // bytes per epilogue staging buffer (4096 or 2048)
   int reverse;        // walk the m-tiles from the last to the first (kernels.h g_tile_reverse)
+  int remap_tma;      // patch-embed row remap through TMA: tmap_out / tmap_res are 3-D views [group][remap_group tokens][N] of
+                      // the output with 32-row / 4-row boxes (opt-in, SAIS_PATCH_TMA=1)
   int l2_hints;       // A operand loads carry an evict-first L2 policy (activations are consumed once)
   int nbuf;           // staging buffers per epilogue warp (2..4)
   // LayerNorm folding (see the file comment)
@@ -157,6 +159,12 @@ __device__ __forceinline__ void tma_reduce_add_2d_s(const CUtensorMap* m, uint32
   asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
                :
                : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_3d_s(const CUtensorMap* m, uint32_t smem_src, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
 __device__ __forceinline__ void tma_store_2d_s(const CUtensorMap* m, uint32_t smem_src, int32_t c0, int32_t c1) {
@@ -470,7 +478,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     float* my_csum = csum_smem + ew * (NCWmax * CW);
     const bool ln_in = (MODE == kModeBf16 || MODE == kModeBf16Gelu) && p.ln_stats_in != nullptr;
     const bool ln_out = (MODE == kModeF32) && p.ln_stats_out != nullptr;
-    const bool tma_epi = (MODE != kModeGeneric) || (p.remap_group == 0);
+    const bool tma_epi = (MODE != kModeGeneric) || (p.remap_group == 0) || (p.remap_tma != 0);
     const bool has_res = (MODE == kModeF32 || MODE == kModeGeneric) && tma_epi && (p.residual != nullptr);
     const bool f32_out = (MODE == kModeF32) || (MODE == kModeGeneric && p.out_f32 != nullptr);
 
@@ -685,6 +693,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + astage * BLOCK_N;
       const int row = m0 + q * 32 + lane;
 
+      const int remap_pidx = (MODE == kModeGeneric && p.remap_tma) ? row % p.remap_group : 0;
       uint32_t v[32];
       // dev knobs for timing experiments (results wrong): & 16 = no TMEM reads, & 32 = no staging / store (bf16 modes)
       const bool dbg_no_ld = (p.debug_nostore & 16) != 0, dbg_no_st = (p.debug_nostore & 32) != 0 && !has_res;
@@ -785,6 +794,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
         }
 
+        if (MODE == kModeGeneric && p.remap_tma) {
+          // patch-embed: + row_add[row % remap_group] (the position embedding of the token this GEMM row becomes)
+          const float* radd = p.row_add + int64_t(remap_pidx) * p.N + n;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 a4 = __ldg(reinterpret_cast<const float4*>(radd + j));
+            f[j] += a4.x; f[j + 1] += a4.y; f[j + 2] += a4.z; f[j + 3] += a4.w;
+          }
+        }
         if (tma_epi && dbg_no_st) {
           float acc = 0.f;  // keep the math alive
 #pragma unroll
@@ -873,7 +891,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               tma_store_wait_read<0>();
               res_request();
             }
-            if (!(p.debug_nostore & 1)) {
+            if (MODE == kModeGeneric && p.remap_tma) {
+              // GEMM rows g * G + i -> token i of group g in the 3-D view (its token axis starts at output row 1 of every
+              // group).  The 32 rows of a chunk may straddle two groups: the box of the first store is clipped at token G
+              // (upper-bound clipping is legal for stores; a NEGATIVE start coordinate is an illegal instruction,
+              // tools/tma3d_test.cu), the rows of the next group leave as 4-row boxes from their offset in the staging tile
+              // (G and the chunk start are multiples of 4).
+              const int G = p.remap_group, groups = p.M / G;
+              const int r0 = m0 + q * 32, g0 = r0 / G, p0 = r0 - g0 * G;
+              if (g0 < groups) tma_store_3d_s(&tmap_out, buf, n, p0, g0);
+              if (p0 + 32 > G && g0 + 1 < groups)
+                for (int i = G - p0; i < 32; i += 4) tma_store_3d_s(&tmap_res, buf + i * 128, n, i - (G - p0), g0 + 1);
+            } else if (!(p.debug_nostore & 1)) {
               if (MODE == kModeF32 && p.accumulate) tma_reduce_add_2d_s(&tmap_out, buf, n, m0 + q * 32);
               else tma_store_2d_s(&tmap_out, buf, n, m0 + q * 32);
               if (MODE == kModeGeneric && p.split_out) tma_store_2d_s(&tmap_out, buf + 2048, p.N + n, m0 + q * 32);
@@ -976,6 +1005,18 @@ int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
   tout = ta;
   tres = ta;
   tout2 = ta;
+  // patch-embed row remap through TMA stores instead of per-thread 16-byte stores (80 us in situ at batch 256 against 41 us
+  // for the shape through the TMA epilogue).  OPT-IN (SAIS_PATCH_TMA=1) until it has been validated on the GPU.
+  static const int env_patch_tma = getenv("SAIS_PATCH_TMA") ? atoi(getenv("SAIS_PATCH_TMA")) : 0;
+  const bool remap_tma = MODE == kModeGeneric && a.remap_group > 0 && a.out_f32 && !a.residual && !a.split_out && env_patch_tma &&
+                         a.M % a.remap_group == 0 && a.remap_group % 4 == 0;
+  if (remap_tma) {
+    const uint64_t groups = uint64_t(a.M / a.remap_group), gpitch = uint64_t(a.remap_group + 1) * uint64_t(a.ldo32);
+    rc = make_tmap_f32_3d(&tout, a.out_f32 + a.ldo32, uint64_t(a.N), uint64_t(a.remap_group), groups, uint64_t(a.ldo32), gpitch, CW, 32);
+    if (rc) return rc;
+    rc = make_tmap_f32_3d(&tres, a.out_f32 + a.ldo32, uint64_t(a.N), uint64_t(a.remap_group), groups, uint64_t(a.ldo32), gpitch, CW, 4);
+    if (rc) return rc;
+  }
   if (a.remap_group == 0) {
     if (a.out_f32)
       rc = make_tmap_2d(&tout, a.out_f32, kTmapF32, uint64_t(a.M), uint64_t(a.N), uint64_t(a.ldo32), 32, CW, 128);
@@ -1067,6 +1108,7 @@ int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
   if (env_stages >= 2 && env_stages < p.stages) p.stages = env_stages;
   p.stage_buf = wide ? kStageBufBytes : kStageBufBytes / 2;
   p.reverse = g_tile_reverse;
+  p.remap_tma = remap_tma ? 1 : 0;
   static const int env_hints = getenv("SAIS_L2_HINTS") ? atoi(getenv("SAIS_L2_HINTS")) : 0;  // tried: -11 % DRAM reads, no time gain
   p.l2_hints = env_hints && a.M >= 4096;  // streaming-sized problems only
   const int units = ((m_tiles + cluster - 1) / cluster) * (p.N / BLOCK_N) * p.k_slices;
