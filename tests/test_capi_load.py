@@ -55,6 +55,12 @@ def test_no_cpu_fallback():
         ops.layernorm(torch.zeros(4, 384), torch.ones(384), torch.zeros(384), 1e-6)
     with pytest.raises(SaisError):
         ops.prototype_score(torch.zeros(2, 256), torch.zeros(2, 256))
+    with pytest.raises(SaisError):  # fused MLP with the folded LayerNorm (the default MLP path of sais_vit_forward)
+        ops.vit_mlp_ln(torch.zeros(4, 384, dtype=torch.bfloat16), torch.zeros(4, 8), torch.zeros(1536, 384, dtype=torch.bfloat16),
+                       torch.zeros(1536), torch.zeros(1536), torch.zeros(384, 1536, dtype=torch.bfloat16), torch.zeros(384),
+                       torch.zeros(4, 384))
+    with pytest.raises(SaisError):
+        ops.rowstats_cast(torch.zeros(4, 384))
 
 
 def test_product_never_imports_oracle():
