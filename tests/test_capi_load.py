@@ -68,3 +68,31 @@ def test_product_never_imports_oracle():
         assert "oracle" not in py.read_text(), f"{py} references the oracle"
     for cu in (ROOT / "sais_b200" / "csrc").glob("*.cu*"):
         assert "oracle" not in cu.read_text()
+
+
+def test_hot_kernels_do_not_spill():
+    """Register-budget regression guard (ptxas -v logs written by the build): the 16-warp GELU epilogue only pays off without
+    spills — earlier 12 / 16-warp variants were capped at 128 / 96 registers and lost 20-60 us to local-memory traffic
+    (DESIGN.md 3.2).  A few bytes for loop-invariant values are tolerated; the fused MLP and the 8-warp kernels must be clean."""
+    import re
+    from pathlib import Path
+    build = Path(__file__).resolve().parents[1] / "sais_b200" / "csrc" / "build"
+    logs = {n: build / f"{n}.ptxas.log" for n in ("gemm_tcgen05", "mlp_fused")}
+    if not all(p.exists() for p in logs.values()):
+        pytest.skip("no ptxas logs (library not built in-tree)")
+
+    def spills(text):
+        out = {}
+        for m in re.finditer(r"Compiling entry function '(\S+)'.*?(\d+) bytes spill stores, (\d+) bytes spill loads", text, re.S):
+            out[m.group(1)] = (int(m.group(2)), int(m.group(3)))
+        return out
+
+    gemm = spills(logs["gemm_tcgen05"].read_text())
+    assert gemm, "no kernels found in the ptxas log"
+    lean = {k: v for k, v in gemm.items() if re.search(r"ELi16ELb[01]E", k)}   # EW = 16 instantiations
+    eight = {k: v for k, v in gemm.items() if re.search(r"ELi8ELb[01]E", k)}   # EW = 8 instantiations
+    assert lean and eight
+    assert max(v[0] for v in lean.values()) <= 64, {k[-40:]: v for k, v in lean.items() if v[0] > 64}
+    assert max(v[0] for v in eight.values()) <= 64, {k[-40:]: v for k, v in eight.items() if v[0] > 64}
+    mlp = spills(logs["mlp_fused"].read_text())
+    assert mlp and all(v == (0, 0) for v in mlp.values()), mlp
