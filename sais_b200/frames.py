@@ -74,6 +74,7 @@ def crop_resize(frames: torch.Tensor, height_frac: float = 0.8, width_frac: floa
         return out
     tmp = torch.empty((n, ch, 224, 3), dtype=torch.uint8, device=frames.device)
     th, tv = _device_table(cw, frames.device), _device_table(ch, frames.device)
-    check(lib().sais_crop_resize_u8(ptr(frames), n, h, w, top, left, ch, cw, ptr(th), ptr(tv), ptr(tmp), ptr(out),
-                                    current_stream()), "sais_crop_resize_u8")
+    with torch.cuda.device(frames.device):
+        check(lib().sais_crop_resize_u8(ptr(frames), n, h, w, top, left, ch, cw, ptr(th), ptr(tv), ptr(tmp), ptr(out),
+                                        current_stream()), "sais_crop_resize_u8")
     return out

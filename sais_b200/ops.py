@@ -10,6 +10,27 @@ import torch
 from . import _lib
 from ._lib import SaisGemmArgs, check, current_stream, lib, ptr, require_cuda
 
+import functools
+
+
+def _on_device_of_first_tensor(fn):
+    """Run ``fn`` with the CUDA device of its first tensor argument current: the library launches on
+    ``torch.cuda.current_stream()`` of the CURRENT device, so a model living on cuda:1 (``loadModel(rank=1)``) must not
+    launch on cuda:0's stream with cuda:1 pointers."""
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        for a in list(args) + list(kw.values()):
+            if isinstance(a, torch.Tensor):
+                if a.is_cuda:
+                    with torch.cuda.device(a.device):
+                        return fn(*args, **kw)
+                break
+        return fn(*args, **kw)  # CPU tensor: the op itself raises SaisError (no CPU path)
+
+    return wrapper
+
+
 _IMAGENET_MEAN = (0.485, 0.456, 0.406)  # extract_representations.py:161
 _IMAGENET_STD = (0.229, 0.224, 0.225)
 
@@ -22,6 +43,7 @@ def split_bf16(t):
     return torch.cat([hi, lo], dim=-1).contiguous()
 
 
+@_on_device_of_first_tensor
 def gemm_bias_act(a, w, bias=None, act=_lib.ACT_NONE, residual=None, out_dtype=torch.bfloat16, out=None,
                   row_add=None, remap_group=0, split3=False, split_out=False, ln_stats_in=None, ln_colsum=None,
                   ln_eps=1e-6, ln_stats_out=None, out2=None, k_slices=0):
@@ -61,6 +83,7 @@ def gemm_bias_act(a, w, bias=None, act=_lib.ACT_NONE, residual=None, out_dtype=t
     return out
 
 
+@_on_device_of_first_tensor
 def rowstats_cast(x):
     """fp32 [rows,384] -> (bf16 copy [rows,384], stats fp32 [rows,8] = {sum, sum of squares, 0...})."""
     require_cuda(x, "x")
@@ -77,6 +100,7 @@ def fold_layernorm(gamma, beta, weight, bias):
     return wg, wg.float().sum(dim=1).contiguous(), (weight.float() @ beta.float() + bias.float()).contiguous()
 
 
+@_on_device_of_first_tensor
 def vit_mlp(xn, fc1_w, fc1_b, fc2_w, fc2_b, x):
     """x += fc2(GELU(fc1(xn) + fc1_b)) + fc2_b in one kernel.  xn bf16 [rows,384]; weights bf16; x fp32 [rows,384],
     updated IN PLACE and returned."""
@@ -91,6 +115,7 @@ def vit_mlp(xn, fc1_w, fc1_b, fc2_w, fc2_b, x):
     return x
 
 
+@_on_device_of_first_tensor
 def vit_mlp_ln(xb, ln_stats, fc1_wg, fc1_c, fc1_d, fc2_w, fc2_b, x, ln_eps=1e-6):
     """vit_mlp with norm2 folded in: xb = raw bf16 rows + ln_stats [rows,8] (rowstats_cast / a LayerNorm-producer GEMM),
     (fc1_wg, fc1_c, fc1_d) = fold_layernorm(gamma, beta, fc1_w, fc1_b).  x fp32 [rows,384] updated IN PLACE."""
@@ -105,6 +130,7 @@ def vit_mlp_ln(xb, ln_stats, fc1_wg, fc1_c, fc1_d, fc2_w, fc2_b, x, ln_eps=1e-6)
     return x
 
 
+@_on_device_of_first_tensor
 def gemm_residual_layernorm(a, w, bias, x, gamma=None, beta=None, eps=1e-6, want_ln=True):
     """x += a @ w.T + bias (fp32 [M,384], IN PLACE); returns (x, LayerNorm(x) as bf16 [M,384] or None)."""
     require_cuda(a, "a")
@@ -119,6 +145,7 @@ def gemm_residual_layernorm(a, w, bias, x, gamma=None, beta=None, eps=1e-6, want
     return x, xn
 
 
+@_on_device_of_first_tensor
 def layernorm(x, gamma, beta, eps, out_f32=False, out_bf16=True, in_pitch=None, rows=None, split_out=False):
     require_cuda(x, "x")
     assert x.dtype == torch.float32
@@ -134,6 +161,7 @@ def layernorm(x, gamma, beta, eps, out_f32=False, out_bf16=True, in_pitch=None, 
     return of, ob
 
 
+@_on_device_of_first_tensor
 def normalize_patchify_u8(frames, split_out=False):
     """u8 [B,224,224,3] -> bf16 patches [B*196,768] with ImageNet normalisation ([B*196,1536] = [hi|lo] if split)."""
     require_cuda(frames, "frames")
@@ -147,6 +175,7 @@ def normalize_patchify_u8(frames, split_out=False):
     return out
 
 
+@_on_device_of_first_tensor
 def patchify_f32(frames, split_out=False):
     """fp32 [B,3,224,224] (already normalised) -> bf16 patches [B*196,768] ([B*196,1536] = [hi|lo] if split)."""
     require_cuda(frames, "frames")
@@ -157,6 +186,7 @@ def patchify_f32(frames, split_out=False):
     return out
 
 
+@_on_device_of_first_tensor
 def vit_attention(qkv, B, emit_probs=False):
     """qkv bf16 [B*197,1152] -> (out bf16 [B*197,384], probs fp32 [B,6,197,197] or None)."""
     require_cuda(qkv, "qkv")
@@ -167,6 +197,7 @@ def vit_attention(qkv, B, emit_probs=False):
     return out, probs
 
 
+@_on_device_of_first_tensor
 def vit_cls_attention(qkv, B):
     """qkv bf16 [B*197,1152] -> attention output of the CLS query only, bf16 [B,384] (last-block shortcut)."""
     require_cuda(qkv, "qkv")
@@ -176,6 +207,7 @@ def vit_cls_attention(qkv, B):
     return out
 
 
+@_on_device_of_first_tensor
 def temporal_attention(qkv, seq_offsets, key_pad=None, attn_offsets=None, max_S=None, attn_numel=0):
     """qkv fp32 [tokens,1152]; seq_offsets int32 [nseq+1] (device); returns (out bf16 [tokens,768] = [hi|lo] halves
     of the fp32 attention output, head-averaged attention maps flat fp32 or None)."""
@@ -190,6 +222,7 @@ def temporal_attention(qkv, seq_offsets, key_pad=None, attn_offsets=None, max_S=
     return out, attn
 
 
+@_on_device_of_first_tensor
 def clip_head(cls_a, cls_b, B, nsnip, lin_w, lin_b):
     require_cuda(cls_a, "cls_a")
     out = torch.empty((B, 256), device=cls_a.device, dtype=torch.float32)
@@ -198,6 +231,7 @@ def clip_head(cls_a, cls_b, B, nsnip, lin_w, lin_b):
     return out
 
 
+@_on_device_of_first_tensor
 def prototype_score(reps, protos, want_sims=False):
     """reps fp32 [B,D], protos fp32 [P,D] -> (probs [B,P], sims or None, pred int32 [B])."""
     require_cuda(reps, "reps")

@@ -7,8 +7,11 @@
 * :func:`frame_range` / :func:`gather_embeddings`: data-parallel by contiguous frame range, one process per GPU;
   the only exchange on the path is an NCCL all-gather of the per-rank ``[n/R,384]`` embeddings ahead of the
   temporal encoder.  ``gloo`` works too (CPU tensors) for the host-logic tests.
-* :func:`sliding_windows` / :func:`gather_windows`: window + TTA index arithmetic of the inference datasets
-  (``prepare_dataset.py:1711-1726, 2642-2651``) done with tensor ops so the gather stays on the device.
+* :func:`sliding_windows` / :func:`gather_windows`: dense window + TTA index arithmetic (step-recognition form,
+  ``prepare_dataset.py:469-473, 2324``) done with tensor ops so the gather stays on the device.
+* :func:`custom_gesture_windows` / :func:`custom_gesture_indices` / :func:`gather_ragged`: the ``Custom_Gestures``
+  inference sampling contract of ``main.sh:27`` (``prepare_dataset.py:1711-1726, 2642-2672``), pinned to the reference's
+  own statements by ``tests/golden/custom_gesture_windows.npz`` (``oracle/make_golden_windows.py``).
 * :class:`SaisPipeline`: frames -> ViT -> windows -> temporal head -> prototype scores, the whole path.
 """
 from __future__ import annotations
@@ -88,6 +91,82 @@ def full_mask(n: int, T: int, device) -> torch.Tensor:
     return torch.zeros((n, 1, T + 1), dtype=torch.bool, device=device)
 
 
+# --------------------------------------------------------------------------------------------- Custom_Gestures sampling
+def custom_gesture_windows(total_frames: int, duration_frames: int = 15, hop_frames: int = 15):
+    """Window list of the ``Custom_inference`` phase (prepare_dataset.py:1711-1726): 0.5 s windows with a 0.5 s hop at an
+    assumed 30 fps -> ``StartFrame = n * hop``, ``EndFrame = StartFrame + duration`` for
+    ``n < (total_frames - duration) // hop + 1``.  Returns ``(start_frames, end_frames)`` as int64 arrays."""
+    if duration_frames <= 0 or hop_frames <= 0:
+        raise ValueError("duration and hop must be positive")
+    nsamples = max((int(total_frames) - duration_frames) // hop_frames + 1, 0)
+    starts = np.arange(nsamples, dtype=np.int64) * hop_frames
+    return starts, starts + duration_frames
+
+
+def _wrap_rows(idx: np.ndarray, n: int, what: str) -> np.ndarray:
+    """numpy fancy-indexing semantics of ``reps[idx, :]``: negative rows count from the end, out-of-range rows raise."""
+    if idx.size and (idx.max(initial=0) >= n or idx.min(initial=0) < -n):
+        raise IndexError(f"{what} index out of range for {n} rows (as the reference's reps[indices,:] would raise)")
+    return np.where(idx < 0, idx + n, idx)
+
+
+def custom_gesture_indices(start_frames, end_frames, n_rgb: int, n_flow: int, tta_offsets: Sequence[int] = (0, 3, 6),
+                           flow_stride: int = 15):
+    """Row indices the ``Custom_Gestures`` inference dataset reads for every window and TTA view
+    (prepare_dataset.py:2642-2672), quirks included:
+
+    * ``startIdx = StartFrame - 1``, ``endIdx = EndFrame - 1`` — the first window starts at row **-1**, which numpy
+      wraps to the video's LAST embedding;
+    * RGB rows of view ``o``: ``arange(startIdx + o, endIdx, (endIdx - startIdx) // 10)`` — 15 / 12 / 9 rows for the
+      shipped 15-frame windows (same end, later start);
+    * flow rows: ``unique(rgb_rows // flow_stride)`` (floor division BEFORE the wrap, so row -1 maps to flow row -1 = the
+      last one), restricted to ``< n_flow`` — 0 to 2 rows per view.
+
+    Returns ``(rgb, flow)``: ``rgb[v]`` is an int64 matrix ``[W, L_v]``; ``flow[v]`` a list of W int64 arrays (ragged)."""
+    starts = np.asarray(start_frames, dtype=np.int64)
+    ends = np.asarray(end_frames, dtype=np.int64)
+    rgb, flow = [], []
+    for o in tta_offsets:
+        rows, frows = [], []
+        for s, e in zip(starts.tolist(), ends.tolist()):
+            s0, e0 = s - 1, e - 1
+            jump = (e0 - s0) // 10
+            if jump <= 0:
+                raise ValueError("windows shorter than 10 frames have no valid stride (reference: arange step 0)")
+            raw = np.arange(s0 + o, e0, jump, dtype=np.int64)
+            f = np.unique(raw // flow_stride)
+            f = f[f < n_flow]
+            rows.append(_wrap_rows(raw, n_rgb, "RGB"))
+            frows.append(_wrap_rows(f, n_flow, "flow") if f.size else f)
+        lens = {len(r) for r in rows}
+        if len(lens) > 1:
+            raise ValueError("windows of different lengths in one call")
+        rgb.append(np.stack(rows) if rows else np.zeros((0, 0), dtype=np.int64))
+        flow.append(frows)
+    return rgb, flow
+
+
+def gather_ragged(embeddings: torch.Tensor, rows: Sequence[np.ndarray]):
+    """Ragged row lists -> zero-padded ``[W,1,Lmax,384]`` + key-padding mask ``bool [W,1,Lmax+1]`` built like
+    ``createPaddingMask`` (prepare_dataset.py:2798-2806: ``mask[b,:,len_b+1:] = True``) + the lengths."""
+    W = len(rows)
+    lens = np.asarray([len(r) for r in rows], dtype=np.int64)
+    L = int(lens.max()) if W else 0
+    D = embeddings.shape[1]
+    out = torch.zeros((W, 1, L, D), dtype=embeddings.dtype, device=embeddings.device)
+    mask = torch.zeros((W, 1, L + 1), dtype=torch.bool)
+    if W and L:
+        idx = np.zeros((W, L), dtype=np.int64)
+        valid = np.zeros((W, L), dtype=bool)
+        for w, r in enumerate(rows):
+            idx[w, :len(r)] = r
+            valid[w, :len(r)] = True
+            mask[w, :, len(r) + 1:] = True
+        g = embeddings[torch.from_numpy(idx.reshape(-1)).to(embeddings.device)].view(W, L, D)
+        out[:, 0] = g * torch.from_numpy(valid).to(embeddings.device).unsqueeze(-1)
+    return out, mask.to(embeddings.device), lens
+
+
 # --------------------------------------------------------------------------------------------- feature extraction
 def _pin(frames):
     t = torch.from_numpy(frames) if isinstance(frames, np.ndarray) else frames
@@ -96,11 +175,64 @@ def _pin(frames):
     return t
 
 
+class HostFrameStager:
+    """Double-buffered host->device staging of uint8 frame batches, owned by the model object so that it outlives
+    a single :func:`extract_features` call.
+
+    Two device buffers ``[batch,224,224,3]``, a private copy stream and one (ready, freed) event pair per buffer.
+    Every copy into buffer ``k`` first waits for ``freed[k]`` — recorded on the compute stream after the forward that
+    last READ buffer ``k``, whichever call issued it — so back-to-back calls (the single-batch-per-call pattern of
+    ``bench.py``) can never overwrite frames a still-running forward is reading.  (Round 1 allocated the buffers per
+    call and handed them back to the caching allocator while the forward was in flight: a cross-call WAR race.)"""
+
+    def __init__(self, device, batch_size: int):
+        self.device = torch.device(device)
+        self.batch_size = int(batch_size)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.bufs = [torch.empty((self.batch_size, 224, 224, 3), dtype=torch.uint8, device=self.device) for _ in range(2)]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.freed = [torch.cuda.Event(), torch.cuda.Event()]
+        self.used = [False, False]  # freed[k] has been recorded at least once
+        self.turn = 0               # buffer the next batch goes to (persists across calls)
+
+    def stage(self, src: torch.Tensor) -> int:
+        """Enqueue the copy of ``src`` (host, <= batch_size frames) into the next buffer; returns the buffer index."""
+        k = self.turn
+        self.turn ^= 1
+        with torch.cuda.stream(self.copy_stream):
+            if self.used[k]:
+                self.copy_stream.wait_event(self.freed[k])
+            self.bufs[k][: src.shape[0]].copy_(src, non_blocking=True)
+            self.ready[k].record(self.copy_stream)
+        return k
+
+    def acquire(self, k: int, n: int, stream) -> torch.Tensor:
+        stream.wait_event(self.ready[k])
+        return self.bufs[k][:n]
+
+    def release(self, k: int, stream) -> None:
+        self.freed[k].record(stream)
+        self.used[k] = True
+
+
+def _stager_for(model, device, batch_size: int) -> HostFrameStager:
+    st = getattr(model, "_host_stager", None)
+    if st is None or st.device != torch.device(device) or st.batch_size < batch_size:
+        st = HostFrameStager(device, batch_size)
+        try:
+            object.__setattr__(model, "_host_stager", st)  # plain attribute, not a module / parameter
+        except Exception:
+            pass
+    return st
+
+
 @torch.no_grad()
 def extract_features(model, frames, batch_size: int = 256, device=None, precision: Optional[str] = None,
                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """``frames``: uint8 ``[n,224,224,3]`` (host, ideally pinned; or already on the device).  Returns fp32
-    ``[n,384]`` on the device.  Host batches are double-buffered: copy of batch i+1 overlaps compute of batch i."""
+    """``extractFeatures`` (extract_representations.py:351-378): walk the frames in batches, ``reps = model(inputs)``.
+    ``frames``: uint8 ``[n,224,224,3]`` (host, ideally pinned; or already on the device).  Returns fp32 ``[n,384]`` on
+    the device.  Host batches are double-buffered through the model's :class:`HostFrameStager`: the copy of batch
+    i+1 overlaps the ViT on batch i, within a call and across calls."""
     device = torch.device(device) if device is not None else next(model.parameters()).device
     frames = _pin(frames)
     n = frames.shape[0]
@@ -110,32 +242,22 @@ def extract_features(model, frames, batch_size: int = 256, device=None, precisio
         return out
     if frames.device.type == "cuda":
         for lo in range(0, n, batch_size):
-            out[lo:lo + batch_size] = model.forward_u8(frames[lo:lo + batch_size], precision=precision)
+            model.forward_u8(frames[lo:lo + batch_size], precision=precision, out=out[lo:lo + batch_size])
         return out
-    copy_stream = torch.cuda.Stream(device=device)
-    main = torch.cuda.current_stream(device)
-    bufs = [torch.empty((min(batch_size, n), 224, 224, 3), dtype=torch.uint8, device=device) for _ in range(2)]
-    ready = [torch.cuda.Event(), torch.cuda.Event()]
-    freed = [torch.cuda.Event(), torch.cuda.Event()]
-    starts = list(range(0, n, batch_size))
-
-    def issue(i):
-        lo = starts[i]
-        hi = min(lo + batch_size, n)
-        with torch.cuda.stream(copy_stream):
-            if i >= 2:
-                copy_stream.wait_event(freed[i % 2])  # the forward that read this buffer two batches ago
-            bufs[i % 2][: hi - lo].copy_(frames[lo:hi], non_blocking=True)
-            ready[i % 2].record(copy_stream)
-
-    issue(0)
-    for i, lo in enumerate(starts):
-        hi = min(lo + batch_size, n)
-        if i + 1 < len(starts):
-            issue(i + 1)
-        main.wait_event(ready[i % 2])
-        out[lo:hi] = model.forward_u8(bufs[i % 2][: hi - lo], precision=precision)
-        freed[i % 2].record(main)
+    with torch.cuda.device(device):
+        st = _stager_for(model, device, min(batch_size, n))
+        main = torch.cuda.current_stream(device)
+        starts = list(range(0, n, batch_size))
+        pending = st.stage(frames[0:min(batch_size, n)])
+        for i, lo in enumerate(starts):
+            hi = min(lo + batch_size, n)
+            k = pending
+            if i + 1 < len(starts):
+                nlo = starts[i + 1]
+                pending = st.stage(frames[nlo:min(nlo + batch_size, n)])
+            buf = st.acquire(k, hi - lo, main)
+            model.forward_u8(buf, precision=precision, out=out[lo:hi])
+            st.release(k, main)
     return out
 
 
@@ -143,16 +265,31 @@ def extract_features(model, frames, batch_size: int = 256, device=None, precisio
 class SaisPipeline:
     """frames (RGB + flow) -> per-frame embeddings -> windows (+TTA) -> temporal head -> prototype probabilities.
 
-    Mirrors the chain ``main.sh:21,24,27,30`` of the reference without the HDF5 / pickle hand-offs.  With
-    ``torch.distributed`` initialised, frames are sharded by contiguous frame range, embeddings are all-gathered,
+    Mirrors the chain ``main.sh:21,24,27,30`` of the reference without the HDF5 / pickle hand-offs.  Two window
+    samplers:
+
+    * ``sampling='custom_gestures'`` (what ``main.sh:27`` runs): the ``Custom_inference`` window list and the
+      ``Custom_Gestures`` index contract, :func:`custom_gesture_windows` / :func:`custom_gesture_indices` — window rows
+      start at ``StartFrame - 1`` (row -1 wraps), TTA views of 15 / 12 / 9 rows, flow rows ``unique(rows // flow_stride)``
+      below ``len(flow)``, ragged flow views padded with key-padding masks;
+    * ``sampling='plain'``: dense sliding windows over both streams with ``flow_stride == 1`` (the step-recognition form,
+      prepare_dataset.py:469-473, 2324; BASELINE config C4).
+
+    With ``torch.distributed`` initialised, frames are sharded by contiguous frame range, embeddings are all-gathered,
     and windows are sharded round-robin; :meth:`run_video` then returns this rank's windows only."""
 
     def __init__(self, vit, head, prototypes, window: int = 15, hop: int = 15, tta_offsets: Sequence[int] = (0, 3, 6),
-                 flow_stride: int = 1, batch_size: int = 256):
+                 flow_stride: Optional[int] = None, batch_size: int = 256, sampling: str = "plain"):
+        if sampling not in ("plain", "custom_gestures"):
+            raise ValueError("sampling must be 'plain' or 'custom_gestures'")
         self.vit, self.head = vit, head
         self.prototypes = scoring.stack_prototypes(prototypes)
         self.window, self.hop, self.tta = window, hop, tuple(tta_offsets)
-        self.flow_stride = flow_stride
+        self.sampling = sampling
+        self.flow_stride = int(flow_stride) if flow_stride is not None else (15 if sampling == "custom_gestures" else 1)
+        if sampling == "plain" and self.flow_stride != 1:
+            raise ValueError("sampling='plain' cuts RGB and flow windows alike (flow_stride must be 1); use "
+                             "sampling='custom_gestures' for the rows // flow_stride mapping")
         self.batch_size = batch_size
 
     @torch.no_grad()
@@ -162,18 +299,36 @@ class SaisPipeline:
         local = extract_features(self.vit, frames[lo:hi], self.batch_size, precision=precision)
         return gather_embeddings(local, n) if world > 1 else local
 
+    def num_windows(self, n_rgb: int, n_flow: int) -> int:
+        if self.sampling == "custom_gestures":
+            return int(custom_gesture_windows(n_rgb, self.window, self.hop)[0].shape[0])
+        return min(sliding_windows(n_rgb, self.window, self.hop)[0].shape[0],
+                   sliding_windows(n_flow, self.window, self.hop)[0].shape[0])
+
     @torch.no_grad()
     def score_windows(self, rgb_emb: torch.Tensor, flow_emb: torch.Tensor, window_ids: Optional[np.ndarray] = None):
         """Returns ``(pred [W], probs [W,P], attn [W,S,S], window_ids)`` for the requested windows."""
-        views = sliding_windows(rgb_emb.shape[0], self.window, self.hop, self.tta)
-        fviews = sliding_windows(flow_emb.shape[0], self.window, self.hop, self.tta)
-        nw = min(views[0].shape[0], fviews[0].shape[0])
+        nw = self.num_windows(rgb_emb.shape[0], flow_emb.shape[0])
         ids = np.arange(nw, dtype=np.int64) if window_ids is None else np.asarray(window_ids, dtype=np.int64)
         dev = rgb_emb.device
-        xs = [gather_windows(rgb_emb, v[ids]) for v in views]
-        fs = [gather_windows(flow_emb, v[ids]) for v in fviews]
-        xp = [full_mask(len(ids), x.shape[2], dev) for x in xs]
-        fp = [full_mask(len(ids), f.shape[2], dev) for f in fs]
+        if self.sampling == "custom_gestures":
+            starts, ends = custom_gesture_windows(rgb_emb.shape[0], self.window, self.hop)
+            rgb_idx, flow_rows = custom_gesture_indices(starts[ids], ends[ids], rgb_emb.shape[0], flow_emb.shape[0],
+                                                        self.tta, self.flow_stride)
+            xs = [gather_windows(rgb_emb, r) for r in rgb_idx]
+            xp = [full_mask(len(ids), x.shape[2], dev) for x in xs]
+            fs, fp = [], []
+            for rows in flow_rows:
+                f, m, _ = gather_ragged(flow_emb, rows)
+                fs.append(f)
+                fp.append(m)
+        else:
+            views = sliding_windows(rgb_emb.shape[0], self.window, self.hop, self.tta)
+            fviews = sliding_windows(flow_emb.shape[0], self.window, self.hop, self.tta)
+            xs = [gather_windows(rgb_emb, v[ids]) for v in views]
+            fs = [gather_windows(flow_emb, v[ids]) for v in fviews]
+            xp = [full_mask(len(ids), x.shape[2], dev) for x in xs]
+            fp = [full_mask(len(ids), f.shape[2], dev) for f in fs]
         if len(xs) == 1:
             out, attn = self.head(xs[0], fs[0], None, None, 'Prototypes', xp[0], fp[0], None)
         else:
@@ -190,6 +345,5 @@ class SaisPipeline:
         rank = dist.get_rank() if world > 1 else 0
         er = self.embed(rgb_frames, rank, world, precision)
         ef = self.embed(flow_frames, rank, world, precision)
-        nw = min(sliding_windows(er.shape[0], self.window, self.hop)[0].shape[0],
-                 sliding_windows(ef.shape[0], self.window, self.hop)[0].shape[0])
+        nw = self.num_windows(er.shape[0], ef.shape[0])
         return self.score_windows(er, ef, shard_items(nw, rank, world))

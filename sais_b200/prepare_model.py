@@ -152,6 +152,24 @@ def _merge_pos_tables(state_dict, prefix, local_metadata, strict, missing_keys, 
         state_dict.pop(k)
 
 
+def load_checkpoint_params(savepath):
+    """``params.zip`` as train.py:105-112 writes it (``copy.deepcopy(model['model'].state_dict())`` of the DDP-wrapped
+    model: every key carries a ``module.`` prefix, stripped like prepare_model.py:523-527 does; unprefixed keys are
+    accepted as well).  Returns the reference-named state dict on CPU."""
+    params = torch.load(os.path.join(savepath, 'params.zip'), map_location='cpu', weights_only=True)
+    return {(k.split('module.', 1)[1] if k.startswith('module.') else k): v for k, v in params.items()}
+
+
+def load_prototypes(savepath, device):
+    """``prototypes.zip``: a deep-copied ``nn.ParameterDict`` ``'0'..'P-1' -> [1,256]`` (train.py:87,110) — a pickled
+    module, which the default ``weights_only=True`` unpickler of torch >= 2.6 rejects.  The file is the user's own
+    checkpoint (trusted, exactly as in the reference, prepare_model.py:562)."""
+    prototypes = torch.load(os.path.join(savepath, 'prototypes.zip'), map_location=device, weights_only=False)
+    if not isinstance(prototypes, (dict, nn.ParameterDict)):
+        raise _lib.SaisError(f"prototypes.zip holds a {type(prototypes).__name__}, expected a (Parameter)dict")
+    return prototypes
+
+
 def loadModel(rank, world_size, savepath, data_type, nclasses, domain, rep_dim, encoder_type, task, fold, lr=0.001,
               modalities='RGB-Flow', freeze_encoder_params=True, self_attention=True, importance_loss=False,
               inference=False):
@@ -161,16 +179,16 @@ def loadModel(rank, world_size, savepath, data_type, nclasses, domain, rep_dim, 
                       freeze_encoder_params=freeze_encoder_params, self_attention=self_attention,
                       importance_loss=importance_loss)
     if inference:
-        params = torch.load(os.path.join(savepath, 'params.zip'), map_location='cpu')
-        params = {(k.split('module.', 1)[1] if k.startswith('module.') else k): v for k, v in params.items()}
-        model.load_state_dict(params)
+        model.load_state_dict(load_checkpoint_params(savepath))  # strict: a key mismatch raises, as in the reference
     device = torch.device(f'cuda:{rank}' if isinstance(rank, int) else rank)
+    if device.type != 'cuda':
+        raise _lib.SaisError("sais_b200.loadModel places the model on a CUDA device (there is no CPU path)")
     model.to(device)
     if not inference:
         prototypes = nn.ParameterDict({str(i): nn.Parameter(torch.rand(1, 256, device=device))
                                        for i in range(nclasses)})
     else:
-        prototypes = torch.load(os.path.join(savepath, 'prototypes.zip'), map_location=device)
+        prototypes = load_prototypes(savepath, device)
     params = list(model.parameters()) + list(prototypes.values())
     optimizer = torch.optim.SGD(params, lr=lr)
     return {'model': model, 'prototypes': prototypes}, optimizer, device

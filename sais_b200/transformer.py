@@ -187,6 +187,12 @@ class TransformerEncoder(nn.Module):
         """tokens [N,S,E] fp32 (batch-major) that already include CLS/pos -> (out[S,N,E], attn[N,S,S])."""
         from . import ops  # local import to avoid a cycle at package import time
 
+        with torch.cuda.device(tokens_nse.device):  # launches go to the current device's stream
+            return self._forward_tokens_on_device(tokens_nse, key_padding_mask)
+
+    def _forward_tokens_on_device(self, tokens_nse, key_padding_mask):
+        from . import ops
+
         N, S, E = tokens_nse.shape
         dev = tokens_nse.device
         zero_cls = torch.zeros(E, device=dev)

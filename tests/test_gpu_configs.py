@@ -166,3 +166,41 @@ def test_c5_thousand_ragged_clips_sharded_by_clip(dev, head_sd):
     r_probs, r_sim = O.prototype_probs(r_out, protos)
     safe = O.top2_margin(r_sim) > MARGIN
     assert safe.any() and torch.equal(preds[pick][safe], r_probs.argmax(1)[safe])
+
+
+# ------------------------------------------------------------------------------------------------ main.sh:27 sampling
+def test_custom_gestures_pipeline_against_oracle(dev, golden_dir, head_sd):
+    """`SaisPipeline(sampling='custom_gestures')` on the embeddings of one video: the windows / TTA rows / flow rows are the
+    reference's (golden fixture written from its own statements), ragged flow views are padded with key-padding masks,
+    and every sampled window equals the oracle head run on that window ALONE with the fixture's rows."""
+    from sais_b200 import pipeline
+    g = np.load(golden_dir / "custom_gesture_windows.npz")
+    ci = 1
+    n_rgb, n_flow = g["cases"][ci].tolist()  # 450 RGB rows, 30 flow rows
+    gen = torch.Generator().manual_seed(77)
+    rgb_emb, flow_emb = torch.randn(n_rgb, 384, generator=gen), torch.randn(n_flow, 384, generator=gen)
+    head = _head(head_sd, dev, "RGB-Flow")
+    protos = O.make_prototypes(2, seed=2)
+    pipe = pipeline.SaisPipeline(None, head, protos, window=15, hop=15, tta_offsets=(0, 3, 6), sampling="custom_gestures")
+    pred, probs, attn, ids = pipe.score_windows(rgb_emb.to(dev), flow_emb.to(dev))
+    nw = len(g[f"c{ci}_start"])
+    assert ids.shape[0] == nw == 30 and probs.shape == (nw, 2) and attn.shape == (nw, 16, 16)
+    flat = [g[f"c{ci}_flow{v}_flat"] for v in range(3)]
+    lens = [g[f"c{ci}_flow{v}_len"] for v in range(3)]
+    offs = [np.concatenate([[0], np.cumsum(l)]) for l in lens]
+    for w in (0, 1, 13, nw - 1):
+        xs = [rgb_emb[torch.from_numpy(g[f"c{ci}_rgb{v}"][w])].view(1, 1, -1, 384) for v in range(3)]
+        fs = [flow_emb[torch.from_numpy(flat[v][offs[v][w]:offs[v][w + 1]])].view(1, 1, -1, 384) for v in range(3)]
+        xp = [O.padding_mask([t.shape[2]], t.shape[2]) for t in xs]
+        fp = [O.padding_mask([t.shape[2]], t.shape[2]) for t in fs]
+        r_out, r_attn = O.full_model_forward(head_sd, xs, fs, xp, fp)
+        r_probs = torch.stack([O.prototype_probs(o, protos)[0] for o in r_out], 0).mean(0)
+        assert float((probs[w].cpu() - r_probs[0]).abs().max()) <= 1e-4, w
+        assert float((attn[w].cpu() - r_attn[0]).abs().max()) <= 1e-4, w
+    # sharding the windows over ranks reassembles to the same result
+    got = torch.empty_like(probs)
+    for r in range(4):
+        own = pipeline.shard_items(nw, r, 4)
+        _, pr, _, _ = pipe.score_windows(rgb_emb.to(dev), flow_emb.to(dev), own)
+        got[torch.from_numpy(own).to(dev)] = pr
+    assert float((got - probs).abs().max()) <= 1e-6

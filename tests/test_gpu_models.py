@@ -14,10 +14,6 @@ from oracle import sais_oracle as O  # noqa: E402
 COS_MIN, REL_MAX, ATTN_ABS, MARGIN = 0.999, 1e-2, 1e-3, 1e-3
 # fp32-equivalent (split-precision) mode: BASELINE.json's "<= 1e-4 in the fp32/tf32 mode"
 REL_MAX_FP32 = 1e-4
-# bf16 fast path with the deliberately sharp 'stress' weights (attention rows peaking at 0.88): the logits of block
-# 12 inherit the ~0.7% bf16 error of the residual stream, so its probabilities move by up to ~1e-2; the 1e-3 bound
-# is met by the bf16 path on the reference's own init distribution and by the fp32 mode on both.
-ATTN_ABS_BF16_STRESS = 2e-2
 
 
 @pytest.fixture(scope="module")
@@ -49,14 +45,24 @@ def test_vit_matches_oracle_and_golden(dev, golden_dir, name, style, wseed, n, i
     reps_u8 = model.forward_u8(fr.to(dev)).cpu()
     cos, rel = O.embedding_errors(reps_u8, torch.from_numpy(g["reps"]))
     assert cos >= COS_MIN and rel <= REL_MAX, (name, "u8", cos, rel)
-    # last-block attention probabilities
+    # last-block attention probabilities: the DEFAULT call of a bf16 module meets BASELINE.json's 1e-3 on every weight
+    # style (get_last_selfattention runs the fp32-equivalent path unless told otherwise)
     attn = model.get_last_selfattention(x.to(dev)).cpu()
     assert attn.shape == (n, 6, 197, 197)
-    tol = ATTN_ABS if style == "init" else ATTN_ABS_BF16_STRESS
-    assert np.abs(attn[:, :, 0, :].numpy() - g["attn_cls"]).max() <= tol
-    assert np.abs(attn[:, :, 100, :].numpy() - g["attn_row100"]).max() <= tol
-    assert np.abs(attn[0, 3].numpy() - g["attn_frame0_head3"]).max() <= tol
+    assert np.abs(attn[:, :, 0, :].numpy() - g["attn_cls"]).max() <= ATTN_ABS
+    assert np.abs(attn[:, :, 100, :].numpy() - g["attn_row100"]).max() <= ATTN_ABS
+    assert np.abs(attn[0, 3].numpy() - g["attn_frame0_head3"]).max() <= ATTN_ABS
     assert torch.allclose(attn.sum(-1), torch.ones(n, 6, 197), atol=1e-4)
+    # explicit opt-in to the bf16 fast path: rows still sum to one; its deviation is REPORTED, and
+    # asserted against the 1e-3 bound only where the bf16 residual stream can meet it (the reference's own init)
+    attn_b = model.get_last_selfattention(x.to(dev), precision="bf16").cpu()
+    assert torch.allclose(attn_b.sum(-1), torch.ones(n, 6, 197), atol=1e-4)
+    dev_b = max(np.abs(attn_b[:, :, 0, :].numpy() - g["attn_cls"]).max(),
+                np.abs(attn_b[:, :, 100, :].numpy() - g["attn_row100"]).max(),
+                np.abs(attn_b[0, 3].numpy() - g["attn_frame0_head3"]).max())
+    print(f"[bf16 attention-map deviation] {name} ({style}): max abs {dev_b:.3e}")
+    if style == "init":
+        assert dev_b <= ATTN_ABS
     toks = model.get_intermediate_layers(x.to(dev), 1)[0].cpu()
     cos, rel = O.embedding_errors(toks[:, :8], torch.from_numpy(g["tokens_first8"]))
     assert cos >= COS_MIN and rel <= 2 * REL_MAX, (name, "tokens", cos, rel)
@@ -211,3 +217,37 @@ def test_class_identity_end_to_end(dev):
         assert safe.any()
         assert torch.equal(pred.cpu()[safe], r_probs.argmax(1)[safe])
         assert (probs.cpu() - r_probs).abs().max() < 5e-3
+
+
+def test_loadmodel_inference_checkpoint_on_gpu(dev, tmp_path):
+    """prepare_model.loadModel(..., inference=True) (reference :517-570, caller train.py:38): reads params.zip with the
+    DDP 'module.' prefix and prototypes.zip holding an nn.ParameterDict, places the model on cuda:rank, and the loaded model
+    reproduces the oracle on the same weights."""
+    import copy
+    import torch.nn as nn
+    from sais_b200 import scoring
+    from sais_b200.prepare_model import loadModel
+    sd = O.make_head_weights(6, "stress")
+    from sais_b200.prepare_model import fullModel
+    m = fullModel(data_type='reps', nclasses=2, domain='NH_02', rep_dim=384, encoder_type='ViT')
+    own = m.state_dict()
+    for k, v in sd.items():
+        if k == "frame_pos_table":
+            for i in range(v.shape[0]):
+                own[f"frame_pos_embeddings.{i}"] = v[i:i + 1]
+        else:
+            own[k] = v
+    torch.save(copy.deepcopy({"module." + k: v for k, v in own.items()}), tmp_path / "params.zip")
+    protos = nn.ParameterDict({str(i): nn.Parameter(O.make_prototypes(2, seed=9)[i:i + 1].clone()) for i in range(2)})
+    torch.save(copy.deepcopy(protos), tmp_path / "prototypes.zip")
+    md, opt, device = loadModel(0, 1, str(tmp_path), 'reps', 2, 'NH_02', 384, 'ViT', 'Prototypes', 0, inference=True)
+    assert device == torch.device("cuda:0") and set(md) == {"model", "prototypes"}
+    x, pad, _ = O.make_clip_batch(5, 9, seed=12)
+    f, fpad, _ = O.make_clip_batch(5, 4, seed=13)
+    out, attn = md["model"](x.to(dev), f.to(dev), None, None, 'Prototypes', pad.to(dev), fpad.to(dev), None)
+    r_out, r_attn = O.full_model_forward(sd, x, f, pad, fpad)
+    cos, rel = O.embedding_errors(out.cpu(), r_out)
+    assert cos >= 1 - 1e-6 and rel <= REL_MAX_FP32 and float((attn.cpu() - r_attn).abs().max()) <= 1e-4
+    pred, probs = scoring.predict(out, md["prototypes"])
+    r_probs, _ = O.prototype_probs(r_out, O.make_prototypes(2, seed=9))
+    assert float((probs.cpu() - r_probs).abs().max()) <= 1e-5

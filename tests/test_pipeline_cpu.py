@@ -119,3 +119,53 @@ def test_extract_features_empty_video():
     """batch loop of extractFeatures (extract_representations.py:365-371) on a video with no frames."""
     frames = torch.zeros((0, 224, 224, 3), dtype=torch.uint8)
     assert pipeline.extract_features(_FakeVit(), frames, 8, device="cpu").shape == (0, 384)
+
+
+# ------------------------------------------------------------------------------------- Custom_Gestures sampling contract
+def test_custom_gesture_sampling_matches_reference_statements(golden_dir):
+    """Window list + per-view RGB / flow rows equal what the reference's own statements read
+    (prepare_dataset.py:1711-1726, 2642-2695 executed by oracle/make_golden_windows.py): StartFrame-1 with the row -1
+    wrap-around, TTA views of 15 / 12 / 9 rows, flow rows unique(rows // 15) below len(flow)."""
+    g = np.load(golden_dir / "custom_gesture_windows.npz")
+    for ci, (n_rgb, n_flow) in enumerate(g["cases"].tolist()):
+        starts, ends = pipeline.custom_gesture_windows(n_rgb)
+        assert np.array_equal(starts, g[f"c{ci}_start"]) and np.array_equal(ends, g[f"c{ci}_end"]), (n_rgb, n_flow)
+        rgb, flow = pipeline.custom_gesture_indices(starts, ends, n_rgb, n_flow)
+        for v in range(3):
+            want = g[f"c{ci}_rgb{v}"]
+            if len(starts) == 0:
+                assert rgb[v].shape[0] == 0
+                continue
+            assert np.array_equal(rgb[v], want), (ci, v)
+            lens = g[f"c{ci}_flow{v}_len"]
+            assert [len(f) for f in flow[v]] == lens.tolist(), (ci, v)
+            flat = np.concatenate(flow[v]) if len(flow[v]) else np.zeros(0, dtype=np.int64)
+            assert np.array_equal(flat, g[f"c{ci}_flow{v}_flat"]), (ci, v)
+    # spot checks of the quirks themselves (SURVEY.md A.3)
+    starts, ends = pipeline.custom_gesture_windows(100)
+    rgb, flow = pipeline.custom_gesture_indices(starts, ends, 100, 7)
+    assert rgb[0][0, 0] == 99 and rgb[0].shape == (6, 15) and rgb[1].shape == (6, 12) and rgb[2].shape == (6, 9)
+    assert flow[0][0].tolist() == [6, 0] and flow[1][0].tolist() == [0]
+    assert pipeline.custom_gesture_windows(14)[0].size == 0
+    with pytest.raises(IndexError):  # a window past the end of the embeddings raises like reps[indices,:] does
+        pipeline.custom_gesture_indices([90], [105], 100, 7)
+
+
+def test_gather_ragged_masks_like_create_padding_mask():
+    emb = torch.arange(10 * 384, dtype=torch.float32).view(10, 384)
+    rows = [np.array([9, 0]), np.array([3]), np.zeros(0, dtype=np.int64)]
+    out, mask, lens = pipeline.gather_ragged(emb, rows)
+    assert out.shape == (3, 1, 2, 384) and mask.shape == (3, 1, 3) and lens.tolist() == [2, 1, 0]
+    assert torch.equal(out[0, 0, 0], emb[9]) and torch.equal(out[0, 0, 1], emb[0]) and torch.equal(out[1, 0, 0], emb[3])
+    assert not out[1, 0, 1].any() and not out[2].any()  # zero padding
+    assert mask.tolist() == [[[False, False, False]], [[False, False, True]], [[False, True, True]]]
+    from sais_b200 import postprocess
+    assert torch.equal(mask, postprocess.create_padding_mask([2, 1, 0]))
+
+
+def test_pipeline_sampling_modes_are_validated():
+    with pytest.raises(ValueError):
+        pipeline.SaisPipeline(None, None, torch.zeros(2, 256), sampling="plain", flow_stride=15)
+    p = pipeline.SaisPipeline(None, None, torch.zeros(2, 256), sampling="custom_gestures")
+    assert p.flow_stride == 15 and p.num_windows(100, 7) == 6
+    assert pipeline.SaisPipeline(None, None, torch.zeros(2, 256), window=20, hop=10).num_windows(3600, 3600) == 359
