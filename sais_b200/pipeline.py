@@ -11,7 +11,7 @@
   ``prepare_dataset.py:469-473, 2324``) done with tensor ops so the gather stays on the device.
 * :func:`custom_gesture_windows` / :func:`custom_gesture_indices` / :func:`gather_ragged`: the ``Custom_Gestures``
   inference sampling contract of ``main.sh:27`` (``prepare_dataset.py:1711-1726, 2642-2672``), pinned to the reference's
-  own statements by ``tests/golden/custom_gesture_windows.npz`` (``oracle/make_golden_windows.py``).
+  own statements by the fixture ``tests/golden/custom_gesture_windows.npz``.
 * :class:`SaisPipeline`: frames -> ViT -> windows -> temporal head -> prototype scores, the whole path.
 """
 from __future__ import annotations
