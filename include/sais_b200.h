@@ -120,19 +120,14 @@ int sais_vit_mlp(const sais_bf16* xn, const sais_bf16* fc1_w, const float* fc1_b
                  const float* fc2_b, float* x, int64_t rows, sais_stream_t stream);
 /* Same with norm2 (Block.norm2, vision_transformer.py:103,111) folded in, as in SaisGemmArgs.ln_stats_in: xb holds the RAW
  * bf16 copy of the residual stream, ln_stats its per-row (sum, sum of squares) partials [rows][4][2], fc1_wg = gamma-scaled
- * fc1 weights, fc1_c their column sums, fc1_d = fc1(beta) + fc1_b:   x += fc2(GELU_erf(rstd (xb fc1_wg^T - mean c) + d)) + fc2_b. */
+ * fc1 weights, fc1_c their column sums, fc1_d = fc1(beta) + fc1_b:   x += fc2(GELU_erf(rstd (xb fc1_wg^T - mean c) + d)) + fc2_b.
+ * xb_out / stats_out (both or neither, may alias xb / ln_stats): the bf16 copy and row statistics of the UPDATED stream,
+ * i.e. exactly what sais_rowstats_cast(x) would produce afterwards (bit for bit) — the operand of the next block's folded
+ * qkv GEMM (Block.norm1, vision_transformer.py:99,108), written by the kernel's cast warps from L2 while the tensor pipe
+ * works on the next row tile, which saves a separate pass over the residual stream. */
 int sais_vit_mlp_ln(const sais_bf16* xb, const float* ln_stats, float ln_eps, const sais_bf16* fc1_wg, const float* fc1_c,
                     const float* fc1_d, const sais_bf16* fc2_w, const float* fc2_b, float* x, int64_t rows,
-                    sais_stream_t stream);
-
-/* Linear + residual add + the FOLLOWING LayerNorm in one kernel (N = 384 = one full row per tile):
- *   x <- x + A · Wᵀ + bias   (fp32 [M,384], in place);   xn <- LayerNorm(x; gamma, beta, eps) as bf16 [M,384].
- * Replaces `x = x + attn(...)` / `x = x + mlp(...)` plus the next `norm2(x)` / `norm1(x)` of Block.forward
- * (vision_transformer.py:103-108).  A bf16 [M,K] (pitch lda), W bf16 [384,K] (pitch ldw), K % 64 == 0.
- * xn == NULL skips the LayerNorm (gamma / beta may then be NULL). */
-int sais_gemm_residual_layernorm(const sais_bf16* a, int64_t lda, const sais_bf16* w, int64_t ldw, const float* bias,
-                                 float* x, const float* gamma, const float* beta, float eps, sais_bf16* xn,
-                                 int64_t M, int64_t K, sais_stream_t stream);
+                    sais_bf16* xb_out, float* stats_out, sais_stream_t stream);
 
 /* LayerNorm over the last dim (cols == 384) — nn.LayerNorm at vision_transformer.py:99,103,156
  * (eps 1e-6) and TransformerEncoderLayer.norm1/norm2 (eps 1e-5).  x: fp32, row pitch in_pitch

@@ -74,15 +74,42 @@ bool pdl_enabled() {
   return on;
 }
 
+namespace {
+constexpr int kMaxDevices = 64;
+int current_device_index() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+  return dev;
+}
+}  // namespace
+
 int num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-      sms = 148;
+  static std::atomic<int> sms[kMaxDevices];
+  const int dev = current_device_index();
+  int v = sms[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    sms[dev].store(v, std::memory_order_relaxed);
   }
-  return sms;
+  return v;
+}
+
+int ensure_dynamic_smem(const void* kernel, int bytes, const char* what) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, int> granted[kMaxDevices];  // per device: kernel -> bytes already opted in
+  const int dev = current_device_index();
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = granted[dev].find(kernel);
+  if (it != granted[dev].end() && it->second >= bytes) return kOk;
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) {
+      set_last_error("cudaFuncSetAttribute(%s, %d bytes): %s", what, bytes, cudaGetErrorString(e));
+      return kErrCuda;
+    }
+  }
+  granted[dev][kernel] = bytes;
+  return kOk;
 }
 
 namespace {
@@ -327,18 +354,13 @@ int sais_vit_mlp(const sais_bf16* xn, const sais_bf16* fc1_w, const float* fc1_b
 
 int sais_vit_mlp_ln(const sais_bf16* xb, const float* ln_stats, float ln_eps, const sais_bf16* fc1_wg, const float* fc1_c,
                     const float* fc1_d, const sais_bf16* fc2_w, const float* fc2_b, float* x, int64_t rows,
-                    sais_stream_t stream) {
+                    sais_bf16* xb_out, float* stats_out, sais_stream_t stream) {
   if (!ln_stats || !fc1_c) {
     set_last_error("vit_mlp_ln: ln_stats and fc1_c are required");
     return kErrInvalidArg;
   }
-  return vit_mlp_fused(xb, fc1_wg, fc1_d, fc2_w, fc2_b, x, rows, static_cast<cudaStream_t>(stream), ln_stats, fc1_c, ln_eps);
-}
-
-int sais_gemm_residual_layernorm(const sais_bf16* a, int64_t lda, const sais_bf16* w, int64_t ldw, const float* bias,
-                                 float* x, const float* gamma, const float* beta, float eps, sais_bf16* xn,
-                                 int64_t M, int64_t K, sais_stream_t stream) {
-  return gemm_residual_layernorm(a, lda, w, ldw, bias, x, gamma, beta, eps, xn, M, K, static_cast<cudaStream_t>(stream));
+  return vit_mlp_fused(xb, fc1_wg, fc1_d, fc2_w, fc2_b, x, rows, static_cast<cudaStream_t>(stream), ln_stats, fc1_c, ln_eps,
+                       xb_out, stats_out);
 }
 
 int sais_rowstats_cast(const float* x, int64_t rows, sais_bf16* xb, float* stats, sais_stream_t stream) {
@@ -441,33 +463,32 @@ int sais_vit_forward(const SaisVitWeights* w, const void* input, int32_t input_k
     if ((rc = gemm_bias_act(g, stream))) return rc;
     if ((rc = write_cls_rows(w->cls_pos0, Bc, x, stream))) return rc;
 
-    // Fast-path variants (A/B knobs):
-    //   default          : LayerNorm folded into the GEMMs (no LayerNorm kernels inside the blocks)
-    //   SAIS_LN_FOLD=0   : separate LayerNorm kernels
-    //   SAIS_ROWLN=1     : proj / fc2 + residual + LayerNorm in the full-row kernel (gemm_rowln.cu), unfolded consumers
-    //   SAIS_MLP_FUSED=1 : fc1 + GELU + fc2 + residual as one kernel (mlp_fused.cu); LayerNorms stay separate
+    // Fast path: LayerNorm folded into the GEMMs (no LayerNorm kernels inside the blocks), fused MLP kernel whose cast warps
+    // also produce the next block's qkv operand.  A/B knobs (read once per process; defaults are the product):
+    //   SAIS_LN_FOLD=0  separate LayerNorm kernels (what the split-precision mode always uses)
+    //   SAIS_MLP_FOLD=0 fc1 / fc2 GEMM pair instead of the fused MLP kernel
+    //   SAIS_MLP_CAST=0 stand-alone rowstats_cast pass after the fused MLP instead of its cast warps (bit-identical)
+    //   SAIS_SNAKE=0    every kernel walks its row tiles first-to-last
+    //   SAIS_LAST_BLOCK_FULL=1  last block on all rows
     static const bool env_nofold = getenv("SAIS_LN_FOLD") != nullptr && atoi(getenv("SAIS_LN_FOLD")) == 0;
-    static const bool env_rowln = getenv("SAIS_ROWLN") != nullptr && atoi(getenv("SAIS_ROWLN")) != 0;
-    static const bool env_mlp = getenv("SAIS_MLP_FUSED") != nullptr && atoi(getenv("SAIS_MLP_FUSED")) != 0;
     const bool have_folded = w->blocks[0].qkv_wg != nullptr;
-    const bool fold = !precise && have_folded && !env_nofold && !env_rowln && !env_mlp;
-    const bool rowln = !precise && env_rowln && !env_mlp;
+    const bool fold = !precise && have_folded && !env_nofold;
     bool xn_ready = false;  // xn already holds what the coming block's qkv GEMM consumes
     // last block on the CLS rows only (when neither all tokens nor the attention probabilities are requested)
     static const bool env_nocls = getenv("SAIS_LAST_BLOCK_FULL") != nullptr && atoi(getenv("SAIS_LAST_BLOCK_FULL")) != 0;
-    const bool cls_only = !precise && !out_probs && !out_tokens && !env_nocls && !env_rowln && !env_mlp;
+    const bool cls_only = !precise && !out_probs && !out_tokens && !env_nocls;
     bool cls_done = false;
     if (fold) {  // bf16 copy + row statistics of the embedded tokens: operand of block 0's folded qkv GEMM
       if ((rc = rowstats_cast(x, tok, xn, stats, stream))) return rc;
       xn_ready = true;
     }
-    // "snake" row order through the chain qkv -> attention -> proj -> fc1 -> fc2 -> qkv ... (kernels.h g_tile_reverse):
-    // each kernel starts on the rows its producer finished with.  Folded path only (the stand-alone LayerNorm kernels
-    // of the other paths walk forward); SAIS_SNAKE=0 disables it for A/B runs.
+    // "snake" row order through the chain qkv -> attention -> proj -> mlp -> qkv ... (kernels.h g_tile_reverse): each
+    // kernel starts on the rows its producer finished with.  Folded path only (the stand-alone LayerNorm kernels of the
+    // other path walk forward).
     static const bool env_nosnake = getenv("SAIS_SNAKE") != nullptr && atoi(getenv("SAIS_SNAKE")) == 0;
     const bool snake = fold && !env_nosnake;
-    // fused MLP kernel (mlp_fused.cu) inside the folded path instead of the fc1 / fc2 GEMM pair; SAIS_MLP_FOLD=0 restores the pair
     static const bool mlp_fold = !(getenv("SAIS_MLP_FOLD") != nullptr && atoi(getenv("SAIS_MLP_FOLD")) == 0);
+    static const bool mlp_cast = !(getenv("SAIS_MLP_CAST") != nullptr && atoi(getenv("SAIS_MLP_CAST")) == 0);
     int dir = 1;  // rowstats_cast (like the patch GEMM before it) walks forward, so block 0's qkv starts from the end
     struct DirGuard { ~DirGuard() { g_tile_reverse = 0; } } dir_guard;  // never leaks into later calls on this thread
     auto next_dir = [&]() {
@@ -524,36 +545,30 @@ int sais_vit_forward(const SaisVitWeights* w, const void* input, int32_t input_k
       else
         rc = vit_attention(static_cast<const sais_bf16*>(qkv), Bc, ao, probs, stream);
       if (rc) return rc;
-      if (rowln) {
-        // proj + residual + norm2 in one kernel
-        if ((rc = gemm_residual_layernorm(ao, Dm, bw.proj_w, Dm, bw.proj_b, x, bw.ln2_w, bw.ln2_b, 1e-6f, xn, tok, Dm,
-                                          stream)))
-          return rc;
-      } else {
-        // proj + residual (folded path: + bf16 copy and row statistics for fc1)
-        memset(&g, 0, sizeof(g));
-        g.a = ao; g.w = bw.proj_w; g.bias = bw.proj_b; g.residual = x; g.out_f32 = x;
-        g.M = tok; g.N = Dm; g.K = Dm; g.lda = Dm * s; g.ldw = Dm * s; g.ldr = Dm; g.ldo32 = Dm; g.split3 = precise;
-        if (fold) { g.ln_stats_out = stats; g.out2_bf16 = xn; g.ldo2 = Dm; }
-        next_dir();
-        if ((rc = gemm_bias_act(g, stream))) return rc;
-        // norm2
-        if (!fold && (rc = layernorm(x, Dm, bw.ln2_w, bw.ln2_b, 1e-6f, tok, nullptr, xn, stream, precise))) return rc;
-      }
-      if (!precise && env_mlp) {  // fc1 + GELU + fc2 + residual: the hidden activations stay on chip
-        if ((rc = vit_mlp_fused(xn, bw.fc1_w, bw.fc1_b, bw.fc2_w, bw.fc2_b, x, tok, stream))) return rc;
-        continue;
-      }
+      // proj + residual (folded path: + bf16 copy and row statistics for fc1)
+      memset(&g, 0, sizeof(g));
+      g.a = ao; g.w = bw.proj_w; g.bias = bw.proj_b; g.residual = x; g.out_f32 = x;
+      g.M = tok; g.N = Dm; g.K = Dm; g.lda = Dm * s; g.ldw = Dm * s; g.ldr = Dm; g.ldo32 = Dm; g.split3 = precise;
+      if (fold) { g.ln_stats_out = stats; g.out2_bf16 = xn; g.ldo2 = Dm; }
+      next_dir();
+      if ((rc = gemm_bias_act(g, stream))) return rc;
+      // norm2
+      if (!fold && (rc = layernorm(x, Dm, bw.ln2_w, bw.ln2_b, 1e-6f, tok, nullptr, xn, stream, precise))) return rc;
       if (fold && mlp_fold) {
-        // Folded path with the fused MLP: proj left the raw bf16 copy + row statistics, the MLP kernel applies norm2 in
-        // its first epilogue and adds its result to the residual stream in L2 (no 155 MB hidden tensor through HBM); the
-        // next block's qkv operand (bf16 copy + statistics of the updated stream) comes from rowstats_cast.
+        // Fused MLP: proj left the raw bf16 copy + row statistics, the MLP kernel applies norm2 in its first epilogue and
+        // adds its result to the residual stream in L2 (no 155 MB hidden tensor through HBM).  The next block's qkv
+        // operand (bf16 copy + statistics of the UPDATED stream) is written by the kernel's cast warps in place over
+        // xn / stats, one row tile behind the reduce-adds (mlp_fused.cu).
+        const bool cast_in_kernel = mlp_cast && !last;
         next_dir();
-        if ((rc = vit_mlp_fused(xn, bw.fc1_wg, bw.fc1_d, bw.fc2_w, bw.fc2_b, x, tok, stream, stats, bw.fc1_c, 1e-6f)))
+        if ((rc = vit_mlp_fused(xn, bw.fc1_wg, bw.fc1_d, bw.fc2_w, bw.fc2_b, x, tok, stream, stats, bw.fc1_c, 1e-6f,
+                                cast_in_kernel ? xn : nullptr, cast_in_kernel ? stats : nullptr)))
           return rc;
         if (!last) {
-          next_dir();
-          if ((rc = rowstats_cast(x, tok, xn, stats, stream))) return rc;
+          if (!cast_in_kernel) {
+            next_dir();
+            if ((rc = rowstats_cast(x, tok, xn, stats, stream))) return rc;
+          }
           xn_ready = true;
         }
         continue;
@@ -566,23 +581,14 @@ int sais_vit_forward(const SaisVitWeights* w, const void* input, int32_t input_k
       g.split3 = precise; g.split_out = precise;
       next_dir();
       if ((rc = gemm_bias_act(g, stream))) return rc;
-      if (rowln) {
-        // fc2 + residual + the next block's norm1 (the final norm reads the fp32 stream itself)
-        const SaisVitBlockWeights* nb = last ? nullptr : &w->blocks[l + 1];
-        if ((rc = gemm_residual_layernorm(hid, Hid, bw.fc2_w, Hid, bw.fc2_b, x, nb ? nb->ln1_w : nullptr,
-                                          nb ? nb->ln1_b : nullptr, 1e-6f, nb ? xn : nullptr, tok, Hid, stream)))
-          return rc;
-        xn_ready = !last;
-      } else {
-        // fc2 + residual (folded path: + bf16 copy and row statistics for the next block's qkv)
-        memset(&g, 0, sizeof(g));
-        g.a = hid; g.w = bw.fc2_w; g.bias = bw.fc2_b; g.residual = x; g.out_f32 = x;
-        g.M = tok; g.N = Dm; g.K = Hid; g.lda = Hid * s; g.ldw = Hid * s; g.ldr = Dm; g.ldo32 = Dm;
-        g.split3 = precise;
-        if (fold && !last) { g.ln_stats_out = stats; g.out2_bf16 = xn; g.ldo2 = Dm; xn_ready = true; }
-        next_dir();
-        if ((rc = gemm_bias_act(g, stream))) return rc;
-      }
+      // fc2 + residual (folded path: + bf16 copy and row statistics for the next block's qkv)
+      memset(&g, 0, sizeof(g));
+      g.a = hid; g.w = bw.fc2_w; g.bias = bw.fc2_b; g.residual = x; g.out_f32 = x;
+      g.M = tok; g.N = Dm; g.K = Hid; g.lda = Hid * s; g.ldw = Hid * s; g.ldr = Dm; g.ldo32 = Dm;
+      g.split3 = precise;
+      if (fold && !last) { g.ln_stats_out = stats; g.out2_bf16 = xn; g.ldo2 = Dm; xn_ready = true; }
+      next_dir();
+      if ((rc = gemm_bias_act(g, stream))) return rc;
     }
     // final norm: only the CLS rows are consumed (vision_transformer.py:213-214)
     if (!cls_done && (rc = layernorm(x, int64_t(Tk) * Dm, w->norm_w, w->norm_b, 1e-6f, Bc, out_cls + size_t(b0) * Dm,

@@ -546,7 +546,9 @@ int make_tmap_f32_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d
 int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld1,
                       uint64_t ld2, uint32_t box0, uint32_t box1);
 
-int num_sms();
+int num_sms();  // of the CURRENT device (cached per device)
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE function attribute: set it once per (device, kernel)
+int ensure_dynamic_smem(const void* kernel, int bytes, const char* what);
 
 // ----------------------------------------------------------------------------------------------
 // Programmatic dependent launch (PDL).  Every kernel of the library is launched through launch_pdl():

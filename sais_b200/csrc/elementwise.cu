@@ -3,6 +3,7 @@
 // 16-byte vector accesses, warp-shuffle reductions, no shared-memory staging where there is no reuse.
 #include "common.cuh"
 #include "kernels.h"
+#include "rowcast.cuh"
 
 namespace sais {
 
@@ -128,48 +129,7 @@ __global__ void __launch_bounds__(256) rowstats_cast384_kernel(const float* __re
   for (int64_t r0 = warp_global * 2; r0 < rows; r0 += warps_total * 2) {
     const bool two = (r0 + 1 < rows);
     const int64_t ra = reverse ? rows - 1 - r0 : r0;  // (kernels.h g_tile_reverse: start on the rows written last)
-    const int64_t rb = two ? (reverse ? ra - 1 : ra + 1) : ra;
-    float4 va[3], vb[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) va[i] = *reinterpret_cast<const float4*>(x + ra * D + i * 128 + lane * 4);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) vb[i] = *reinterpret_cast<const float4*>(x + rb * D + i * 128 + lane * 4);
-    float sa = 0.f, qa = 0.f, sb = 0.f, qb = 0.f;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const float4 v = va[i];
-      sa += (v.x + v.y) + (v.z + v.w);
-      qa = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, qa))));
-      uint2 o;
-      o.x = pack_bf16x2(v.x, v.y);
-      o.y = pack_bf16x2(v.z, v.w);
-      *reinterpret_cast<uint2*>(xb + ra * D + i * 128 + lane * 4) = o;
-    }
-    if (two) {
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const float4 v = vb[i];
-        sb += (v.x + v.y) + (v.z + v.w);
-        qb = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, qb))));
-        uint2 o;
-        o.x = pack_bf16x2(v.x, v.y);
-        o.y = pack_bf16x2(v.z, v.w);
-        *reinterpret_cast<uint2*>(xb + rb * D + i * 128 + lane * 4) = o;
-      }
-    }
-    sa = warp_sum(sa);
-    qa = warp_sum(qa);
-    sb = warp_sum(sb);
-    qb = warp_sum(qb);
-    if (lane < 2) {
-      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (lane == 0) { o.x = sa; o.y = qa; }
-      *reinterpret_cast<float4*>(stats + ra * 8 + lane * 4) = o;
-    } else if (lane < 4 && two) {
-      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (lane == 2) { o.x = sb; o.y = qb; }
-      *reinterpret_cast<float4*>(stats + rb * 8 + (lane - 2) * 4) = o;
-    }
+    rowcast_rows<2, false>(x, xb, stats, ra, reverse ? -1 : 1, two ? 2 : 1, lane);
   }
 }
 

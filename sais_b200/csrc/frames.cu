@@ -221,13 +221,9 @@ int sais_crop_resize_u8(const uint8_t* frames, int32_t N, int32_t H, int32_t W, 
     set_last_error("crop_resize_u8: crop width %d too large", cw);
     return kErrShape;
   }
-  static size_t attr_smem = 48 * 1024;
-  if (smem > attr_smem) {
-    int rc = check_cuda(cudaFuncSetAttribute(resize_horizontal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
-                        "cudaFuncSetAttribute(resize_horizontal)");
-    if (rc) return rc;
-    attr_smem = 200 * 1024;
-  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(resize_horizontal_kernel),
+                                   smem > 48 * 1024 ? 200 * 1024 : 48 * 1024, "resize_horizontal"))
+    return rc;
   const int64_t total_bytes = int64_t(N) * H * W * 3;
   const int64_t groups = int64_t(N) * ((ch + kRows - 1) / kRows);
   const int64_t cap = int64_t(num_sms()) * 16;

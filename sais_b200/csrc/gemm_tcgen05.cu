@@ -1036,14 +1036,9 @@ int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
     }
   }
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    rc = check_cuda(cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, MODE, CG, EW, ASTAT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         227 * 1024),
-                    "cudaFuncSetAttribute(gemm)");
-    if (rc) return rc;
-    attr_set = true;
-  }
+  if ((rc = ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_tcgen05_kernel<BLOCK_N, MODE, CG, EW, ASTAT>), 227 * 1024,
+                                "gemm_tcgen05")))
+    return rc;
   const bool wide = a.out_f32 != nullptr || a.split_out;  // 128-byte staging rows
   GemmParams p;
   p.bias = a.bias;

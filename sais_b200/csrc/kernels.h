@@ -36,14 +36,12 @@ extern thread_local int g_tile_reverse;
 int pick_block_n(int64_t M, int64_t N);
 
 // mlp_fused.cu: x += fc2(GELU(fc1(xn) + b1)) + b2 over bf16 xn [rows,384], fp32 x [rows,384] (in place)
+// xb_out / stats_out (both or neither; may alias xn / ln_stats): bf16 copy + row statistics of the UPDATED stream, written by
+// the kernel's cast warps — what rowstats_cast would produce from x afterwards, bit for bit
 int vit_mlp_fused(const sais_bf16* xn, const sais_bf16* w1, const float* b1, const sais_bf16* w2, const float* b2,
                   float* x, int64_t rows, cudaStream_t stream, const float* ln_stats = nullptr,
-                  const float* ln_colsum = nullptr, float ln_eps = 0.0f);
-
-// gemm_rowln.cu: x += A · Wᵀ + bias (fp32 [M,384], in place); xn = LayerNorm(x) as bf16 [M,384] (xn may be null)
-int gemm_residual_layernorm(const sais_bf16* a, int64_t lda, const sais_bf16* w, int64_t ldw, const float* bias,
-                            float* x, const float* gamma, const float* beta, float eps, sais_bf16* xn, int64_t M,
-                            int64_t K, cudaStream_t stream);
+                  const float* ln_colsum = nullptr, float ln_eps = 0.0f, sais_bf16* xb_out = nullptr,
+                  float* stats_out = nullptr);
 
 // elementwise.cu
 // out_plus (optional) = LayerNorm output + plus_vec[384]: the pre-loaded accumulator of an accumulate-mode GEMM

@@ -18,20 +18,32 @@
 // With ln_stats / ln_colsum the first epilogue also applies the block's norm2 (folded LayerNorm, gemm_tcgen05.cu): A then
 // holds the RAW bf16 rows of the residual stream and W1 / b1 the gamma-scaled weights / folded bias.
 //
-//   warps 0..7 : E1 and the output epilogue (two warps per TMEM lane quarter)
-//   warp 8     : TMA producer (A tile, then the W1/W2 chunk ring in exactly the order the MMAs consume it)
-//   warp 9     : TMEM allocator + MMA issuer (leader CTA of the pair only)
+//   warps 0..7  : E1 and the output epilogue (two warps per TMEM lane quarter)
+//   warps 8..9  : cast warps (optional outputs xb_out / stats_out, below)
+//   warp 10     : TMA producer (A tile, then the W1/W2 chunk ring in exactly the order the MMAs consume it)
+//   warp 11     : TMEM allocator + MMA issuer (leader CTA of the pair only)
 // Both role warps walk their loops with all 32 lanes (warp-uniform control flow) and elect one lane only around the TMA /
 // tcgen05 instructions: issued from a divergent single lane every MMA cost ~200 cycles of issue overhead (161 -> 115 us).
 // TMEM columns: acc [0,384) | S0 [384,448) | S1 [448,512).
-// Work units: (row tile, chunk range).  Whole tiles are dealt round-robin to the 74 pairs; the tiles of the last,
-// partial round are split `tail_split` ways along the hidden dimension (legal because the output is a reduce-add),
-// which removes most of the wave-quantisation loss (197 tiles on 74 pairs: 2.66 -> 3 rounds otherwise).
+// Work units: 256-row tiles, dealt round-robin to the 74 CTA pairs.  Every output element receives exactly one reduce-add,
+// so the result is deterministic (an earlier version split the tiles of the last partial round along the hidden
+// dimension: +1.4 % throughput, but partial sums then met in L2 in arbitrary order — run-to-run bit differences; removed).
+//
+// Cast warps (xb_out / stats_out): the NEXT block's LayerNorm-folded qkv GEMM consumes the bf16 copy and the per-row
+// (sum, sum of squares) of the UPDATED residual stream, which a reduce-add kernel never holds in registers.  Instead of a
+// separate pass over the stream (rowstats_cast384_kernel: 20 us per block at batch 256, 5.8 % of the step), two otherwise
+// idle warps per CTA re-read the rows of the unit that has just been reduced into L2 (L2 hits, ld.global.cg) while the
+// tensor pipe works on the next unit, and write the bf16 copy + statistics with the very same code
+// (rowcast.cuh: bit-identical to the stand-alone kernel).  Ordering: an epilogue warp's reduce-adds are complete
+// (cp.async.bulk.wait_group 0 + fence.proxy.async) before its arrival on cast_full; the wait is deferred to the second hidden
+// chunk of the following unit so that it never stalls the E1 pipeline.  The last unit of a CTA is cast by the eight
+// epilogue warps together (nothing is left to overlap it with).
 #include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.h"
+#include "rowcast.cuh"
 
 namespace sais {
 
@@ -44,13 +56,13 @@ constexpr int HC = 64;              // hidden chunk (N of G1, K of G2)
 constexpr int NCHUNK = HID / HC;    // 24
 constexpr int KB = DM / 64;         // 6 k-blocks of A
 constexpr int kEpiWarps = 8;
-constexpr int kThreads = 32 * (kEpiWarps + 2);
+constexpr int kCastWarps = 2;
+constexpr int kThreads = 32 * (kEpiWarps + kCastWarps + 2);
 constexpr int A_BYTES = KB * MT * 128;    // 98,304: six 128-row x 128-byte swizzled k-blocks
 constexpr int STAGE_BYTES = 24576;        // one W1 chunk half (6 x 32 rows x 128 B) or one W2 chunk half (2 x 96 rows x 128 B)
 constexpr int NSTAGE = 4;
 constexpr int H_BYTES = MT * 128;         // 16,384: H_j tile, 128 rows x 64 bf16
 constexpr int kTmemCols = 512;
-constexpr int kAccCols = DM;              // acc at column 0
 constexpr int kSCol = DM;                 // S0 at 384, S1 at 448
 constexpr int kTailBytes = 256 /*barriers*/ + DM * 4 /*b2*/;
 constexpr int kSmemBytes = 1024 + A_BYTES + NSTAGE * STAGE_BYTES + 2 * H_BYTES + kTailBytes;
@@ -66,10 +78,11 @@ struct MlpParams {
   float ln_eps;
   int64_t rows;
   int reverse;      // walk the row tiles from the last to the first (kernels.h g_tile_reverse)
-  int num_tiles;    // 256-row tiles
-  int full_units;   // leading units that are whole tiles
-  int tail_split;   // remaining tiles are split this many ways along the hidden dimension (1, 2, 3, 4, 6, ...)
-  int num_units;
+  int num_tiles;    // 256-row tiles = work units
+  // cast warps: bf16 copy + row statistics of the UPDATED stream (both or neither; may alias xn / ln_stats)
+  const float* x;
+  __nv_bfloat16* xb_out;
+  float* stats_out;
   long long* dbg;
 };
 
@@ -84,24 +97,8 @@ __device__ __forceinline__ void sts128m(uint32_t addr, uint32_t a, uint32_t b, u
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
 
-struct Unit {
-  int tile, j0, nj;
-};
-__device__ __forceinline__ Unit decode_unit(const MlpParams& p, int u) {
-  Unit r;
-  if (u < p.full_units) {
-    r.tile = u;
-    r.j0 = 0;
-    r.nj = NCHUNK;
-  } else {
-    const int v = u - p.full_units;
-    r.tile = p.full_units + v / p.tail_split;
-    r.nj = NCHUNK / p.tail_split;
-    r.j0 = (v % p.tail_split) * r.nj;
-  }
-  if (p.reverse) r.tile = p.num_tiles - 1 - r.tile;
-  return r;
-}
+__device__ __forceinline__ int unit_tile(const MlpParams& p, int u) { return p.reverse ? p.num_tiles - 1 - u : u; }
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w1,
@@ -123,7 +120,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* h_empty = bars + 16;  // [2]
   uint64_t* acc_full = bars + 18;
   uint64_t* acc_empty = bars + 19;  // leader's, 16 arrivals
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* cast_full = bars + 20;  // this CTA's, kEpiWarps arrivals: the unit's reduce-adds have completed
+  uint64_t* cast_done = bars + 21;  // this CTA's, kCastWarps arrivals: its rows have been cast
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 22);
   float* b2_smem = reinterpret_cast<float*>(bars + 32);  // [384]
 
   const int warp = threadIdx.x >> 5;
@@ -135,7 +134,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (p.dbg != nullptr && blockIdx.x == 0 && idx < 32 && ev < 4) p.dbg[(role * 32 + idx) * 4 + ev] = clock64();
   };
 
-  constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
+  constexpr int kCastWarp0 = kEpiWarps, kProducerWarp = kEpiWarps + kCastWarps, kMmaWarp = kProducerWarp + 1;
+  const bool do_cast = p.xb_out != nullptr;
   if (warp == kProducerWarp && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_w1);
@@ -155,6 +155,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     mbar_init(acc_full, 1);
     mbar_init(acc_empty, 2 * kEpiWarps);
+    mbar_init(cast_full, kEpiWarps);
+    mbar_init(cast_done, kCastWarps);
     fence_mbar_init();
   }
   if (warp == kMmaWarp) {
@@ -207,9 +209,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         ++pg2;
         if (++stage == NSTAGE) { stage = 0; wphase ^= 1; }
       };
-      for (int u = pair; u < p.num_units; u += npairs, ++ui) {
-        const Unit un = decode_unit(p, u);
-        const int m0 = un.tile * (2 * MT) + int(crank) * MT;
+      for (int u = pair; u < p.num_tiles; u += npairs, ++ui) {
+        const int m0 = unit_tile(p, u) * (2 * MT) + int(crank) * MT;
         mbar_wait(a_empty, (ui & 1) ^ 1);  // the previous unit's G1s have retired
         if (elect_one()) {
           if (crank == 0) mbar_arrive_expect_tx(a_full, 2 * A_BYTES);
@@ -218,9 +219,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           for (int kb = 0; kb < KB; ++kb) tma_load_2d_cg2(a_smem + kb * (MT * 128), &tmap_a, lbar, kb * 64, m0);
         }
         __syncwarp();
-        for (int jj = 0; jj <= un.nj; ++jj) {
-          if (jj < un.nj) load_w1(un.j0 + jj);
-          if (jj >= 1) load_w2(un.j0 + jj - 1);
+        for (int jj = 0; jj <= NCHUNK; ++jj) {
+          if (jj < NCHUNK) load_w1(jj);
+          if (jj >= 1) load_w2(jj - 1);
         }
       }
     }
@@ -238,13 +239,12 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t ui = 0;
       const uint32_t a_s = smem_u32(a_smem);
       const uint32_t h_s = smem_u32(h_smem);
-      for (int u = pair; u < p.num_units; u += npairs, ++ui) {
-        const Unit un = decode_unit(p, u);
+      for (int u = pair; u < p.num_tiles; u += npairs, ++ui) {
         mbar_wait(a_full, ui & 1);
         tc_fence_after();
         if (lane == 0) stamp(2, ui, 0);
-        for (int jj = 0; jj <= un.nj; ++jj) {
-          if (jj < un.nj) {  // ---- G1: S[b] = A · W1[j]ᵀ
+        for (int jj = 0; jj <= NCHUNK; ++jj) {
+          if (jj < NCHUNK) {  // ---- G1: S[b] = A · W1[j]ᵀ
             const uint32_t gg = g + jj, b = gg & 1;
             mbar_wait(&s_empty[b], ((gg >> 1) & 1) ^ 1);
             if (lane == 0) stamp(0, gg, 0);
@@ -262,7 +262,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 for (int k = 0; k < 4; ++k) umma_f16_cg2(d, da + 2 * k, db + 2 * k, idesc1, (kb | k) != 0);
               }
               umma_commit_cg2_mcast(&w_empty[stage], uint16_t(0b11));
-              if (jj == un.nj - 1) umma_commit_cg2_mcast(a_empty, uint16_t(0b11));
+              if (jj == NCHUNK - 1) umma_commit_cg2_mcast(a_empty, uint16_t(0b11));
               umma_commit_cg2_mcast(&s_full[b], uint16_t(0b11));
             }
             __syncwarp();
@@ -292,13 +292,33 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               }
               umma_commit_cg2_mcast(&w_empty[stage], uint16_t(0b11));
               umma_commit_cg2_mcast(&h_empty[b], uint16_t(0b11));
-              if (jj == un.nj) umma_commit_cg2_mcast(acc_full, uint16_t(0b11));
+              if (jj == NCHUNK) umma_commit_cg2_mcast(acc_full, uint16_t(0b11));
             }
             __syncwarp();
             if (++stage == NSTAGE) { stage = 0; wphase ^= 1; }
           }
         }
-        g += un.nj;
+        g += NCHUNK;
+      }
+    }
+  } else if (warp >= kCastWarp0) {
+    // ===================== cast warps: bf16 copy + row statistics of the unit reduced one unit ago =====================
+    if (do_cast) {
+      const int cw = warp - kCastWarp0;
+      constexpr int kRowsPerCastWarp = MT / kCastWarps;
+      uint32_t ui = 0;
+      for (int u = pair; u < p.num_tiles; u += npairs, ++ui) {
+        if (u + npairs >= p.num_tiles) break;  // the last unit is cast by the epilogue warps themselves
+        const int64_t r0 = int64_t(unit_tile(p, u)) * (2 * MT) + int(crank) * MT + cw * kRowsPerCastWarp;
+        mbar_wait(cast_full, ui & 1);
+#pragma unroll 1
+        for (int i = 0; i < kRowsPerCastWarp; i += 4) {
+          const int64_t left = p.rows - (r0 + i);
+          if (left <= 0) break;
+          rowcast_rows<4, true>(p.x, p.xb_out, p.stats_out, r0 + i, 1, left < 4 ? int(left) : 4, lane);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(cast_done);
       }
     }
   } else {
@@ -312,9 +332,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int sw = row & 7;
     const uint32_t my_stage = smem_u32(h_smem) + ew * 4096;  // output staging: 2 x (32 rows x 64 B), aliasing H
     uint32_t g = 0, ui = 0;
-    for (int u = pair; u < p.num_units; u += npairs, ++ui) {
-      const Unit un = decode_unit(p, u);
-      const int m0 = un.tile * (2 * MT) + int(crank) * MT;
+    bool cast_pending = false;  // the previous unit's reduce-adds have not been confirmed complete yet
+    for (int u = pair; u < p.num_tiles; u += npairs, ++ui) {
+      const int m0 = unit_tile(p, u) * (2 * MT) + int(crank) * MT;
       // h = x / 2 is produced directly (bias, rstd and -mean * rstd halved: exact scalings) for gelu_erf_fast2_half;
       // without the folded LayerNorm rstd = 1, mean = 0 and the column-sum pointer aliases the bias
       float rs_h = 0.5f, nm_h = 0.0f;
@@ -330,9 +350,21 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       const uint64_t rs2 = pack2(rs_h, rs_h), nm2 = pack2(nm_h, nm_h);
       const float* cs_base = p.ln_colsum != nullptr ? p.ln_colsum : p.b1;
-      for (int jj = 0; jj < un.nj; ++jj) {
+      for (int jj = 0; jj < NCHUNK; ++jj) {
         const uint32_t gg = g + jj, b = gg & 1;
-        const int j = un.j0 + jj;
+        const int j = jj;
+        if (jj == 2 && cast_pending) {
+          // hand the PREVIOUS unit's rows to the cast warps: by now (two hidden chunks later) this warp's reduce-adds have
+          // long completed, so the wait does not stall E1
+          if (lane == 0) {
+            tma_store_wait<0>();
+            fence_proxy_async_global();
+            if (ui >= 2) mbar_wait(cast_done, ui & 1);  // (never blocks in practice: the cast of unit ui - 2 is a unit old)
+            mbar_arrive(cast_full);
+          }
+          __syncwarp();
+          cast_pending = false;
+        }
         float4 bias[8], cs[8];
         {
           const float4* bp = reinterpret_cast<const float4*>(p.b1 + j * HC + half * 32);
@@ -375,13 +407,13 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (lane == 0) mbar_arrive_cluster(leader_smem_u32(&h_full[b]));
         if (ew == 0 && lane == 0) stamp(1, gg, 2);
       }
-      g += un.nj;
+      g += NCHUNK;
 
       // ---- output epilogue: acc (+ b2) -> swizzled staging -> TMA reduce-add into the residual stream
       mbar_wait(acc_full, ui & 1);
       tc_fence_after();
       if (ew == 0 && lane == 0) stamp(2, ui, 2);
-      const bool add_bias = (un.j0 == 0);
+      constexpr bool add_bias = true;
       constexpr int NOC = (DM / 2) / 16;  // 12 chunks of 16 columns per warp, handled two at a time:
       // both accumulator chunks are moved to registers and biased BEFORE waiting for the previous iteration's two stores to
       // have read the staging tiles, so that wait (the TMA queue is busy with the next unit's operand loads) overlaps the
@@ -434,9 +466,30 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           tma_store_commit();
         }
       }
-      if (lane == 0) tma_store_wait_read<0>();
+      const bool last_unit = (u + npairs >= p.num_tiles);
+      if (lane == 0) {
+        if (do_cast && last_unit) {
+          tma_store_wait<0>();  // complete, not just read: the rows are re-read below
+          fence_proxy_async_global();
+        } else {
+          tma_store_wait_read<0>();
+        }
+      }
       if (ew == 0 && lane == 0) stamp(2, ui, 3);
       epi_bar_sync();  // every warp's staging (which aliases H) has been read before any warp writes H again
+      cast_pending = do_cast && !last_unit;
+      if (do_cast && last_unit) {
+        // last unit of this CTA: nothing left to hide the cast under — all eight epilogue warps share its 128 rows
+        // (every warp's reduce-adds completed before the barrier above)
+        constexpr int kRowsPerWarp = MT / kEpiWarps;
+        const int64_t r0 = int64_t(m0) + ew * kRowsPerWarp;
+#pragma unroll 1
+        for (int i = 0; i < kRowsPerWarp; i += 4) {
+          const int64_t left = p.rows - (r0 + i);
+          if (left <= 0) break;
+          rowcast_rows<4, true>(p.x, p.xb_out, p.stats_out, r0 + i, 1, left < 4 ? int(left) : 4, lane);
+        }
+      }
     }
     if (lane == 0) tma_store_wait<0>();
   }
@@ -452,7 +505,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 }  // namespace
 
 int vit_mlp_fused(const sais_bf16* xn, const sais_bf16* w1, const float* b1, const sais_bf16* w2, const float* b2,
-                  float* x, int64_t rows, cudaStream_t stream, const float* ln_stats, const float* ln_colsum, float ln_eps) {
+                  float* x, int64_t rows, cudaStream_t stream, const float* ln_stats, const float* ln_colsum, float ln_eps,
+                  sais_bf16* xb_out, float* stats_out) {
   if (rows == 0) return kOk;
   if (!xn || !w1 || !b1 || !w2 || !b2 || !x || rows < 0) {
     set_last_error("vit_mlp: bad arguments");
@@ -463,6 +517,11 @@ int vit_mlp_fused(const sais_bf16* xn, const sais_bf16* w1, const float* b1, con
     set_last_error("vit_mlp: operands must be 16-byte aligned");
     return kErrInvalidArg;
   }
+  if ((xb_out == nullptr) != (stats_out == nullptr) ||
+      ((reinterpret_cast<uintptr_t>(xb_out) | reinterpret_cast<uintptr_t>(stats_out)) & 15)) {
+    set_last_error("vit_mlp: xb_out and stats_out go together (16-byte aligned)");
+    return kErrInvalidArg;
+  }
   CUtensorMap ta, tw1, tw2, tout;
   int rc = make_tmap_2d(&ta, xn, kTmapBf16, uint64_t(rows), DM, DM, MT, 64, 128);
   if (rc) return rc;
@@ -470,13 +529,7 @@ int vit_mlp_fused(const sais_bf16* xn, const sais_bf16* w1, const float* b1, con
   if ((rc = make_tmap_2d(&tw2, w2, kTmapBf16, DM, HID, HID, 96, 64, 128))) return rc;
   if ((rc = make_tmap_2d(&tout, x, kTmapF32, uint64_t(rows), DM, DM, 32, 16, 64))) return rc;
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    rc = check_cuda(cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes),
-                    "cudaFuncSetAttribute(mlp_fused)");
-    if (rc) return rc;
-    attr_set = true;
-  }
+  if ((rc = ensure_dynamic_smem(reinterpret_cast<const void*>(mlp_fused_kernel), kSmemBytes, "mlp_fused"))) return rc;
   MlpParams p;
   p.b1 = b1;
   p.b2 = b2;
@@ -491,32 +544,11 @@ int vit_mlp_fused(const sais_bf16* xn, const sais_bf16* w1, const float* b1, con
   p.rows = rows;
   p.reverse = g_tile_reverse;
   p.num_tiles = int((rows + 2 * MT - 1) / (2 * MT));
+  p.x = x;
+  p.xb_out = reinterpret_cast<__nv_bfloat16*>(xb_out);
+  p.stats_out = stats_out;
   const int pairs_max = num_sms() / 2;
-  // whole tiles for the full rounds; the last partial round is split along the hidden dimension when that shortens
-  // the makespan (cost model: a unit costs its chunks + ~3 chunk-times of A load / output epilogue)
-  // Splitting the tail makes the result depend on the order in which the partial sums of a row meet in L2 (fp32 adds are
-  // not associative): run-to-run bit differences.  The default is therefore NO split (every output element receives exactly
-  // one reduce-add: deterministic, ~6 % slower at batch 256); SAIS_MLP_TAIL_SPLIT=0 selects the cost model below, N > 1 forces N.
-  static const int env_split = getenv("SAIS_MLP_TAIL_SPLIT") ? atoi(getenv("SAIS_MLP_TAIL_SPLIT")) : 1;
-  const int rem = p.num_tiles % pairs_max;
-  int split = 1;
-  if (rem > 0 && env_split == 0) {
-    double best = NCHUNK + 3.0;
-    const int cands[6] = {2, 3, 4, 6, 8, 12};
-    for (int s : cands) {
-      const int rounds = (rem * s + pairs_max - 1) / pairs_max;
-      const double cost = rounds * (double(NCHUNK) / s + 3.0);
-      if (cost < best - 0.5) {
-        best = cost;
-        split = s;
-      }
-    }
-  }
-  if (env_split > 0 && NCHUNK % env_split == 0) split = env_split;
-  p.tail_split = split;
-  p.full_units = (split > 1) ? p.num_tiles - rem : p.num_tiles;
-  p.num_units = p.full_units + (p.num_tiles - p.full_units) * split;
-  const int pairs = p.num_units < pairs_max ? p.num_units : pairs_max;
+  const int pairs = p.num_tiles < pairs_max ? p.num_tiles : pairs_max;
 
   static const char* timeline = getenv("SAIS_MLP_TIMELINE");
   p.dbg = nullptr;
@@ -540,7 +572,7 @@ int vit_mlp_fused(const sais_bf16* xn, const sais_bf16* w1, const float* b1, con
     long long t0 = 0;
     for (long long v : h) if (v && (!t0 || v < t0)) t0 = v;
     if (FILE* f = fopen(timeline, "w")) {
-      fprintf(f, "# rows=%lld tiles=%d units=%d split=%d pairs=%d\n", (long long)rows, p.num_tiles, p.num_units, split, pairs);
+      fprintf(f, "# rows=%lld tiles=%d pairs=%d cast=%d\n", (long long)rows, p.num_tiles, pairs, int(xb_out != nullptr));
       const char* names[4] = {"mma(chunk: s_empty ok, w_full(W1) ok, h_full ok, w_full(W2) ok)",
                               "e1(chunk: s_full, h_empty, h_full arrive)",
                               "unit(mma a_full, mma acc_empty, out acc_full, out done)",

@@ -179,16 +179,9 @@ int launch_seq_attention(const float* qkv, const int32_t* seq_offsets, const uin
     set_last_error("seq_attention: max_S=%d needs %zu bytes of shared memory", max_S, sm);
     return kErrShape;
   }
-  static size_t attr_smem[2] = {0, 0};
   const void* fn = smem_kv ? reinterpret_cast<const void*>(seq_attention_f32_kernel<H, HD, true>)
                            : reinterpret_cast<const void*>(seq_attention_f32_kernel<H, HD, false>);
-  if (sm > attr_smem[smem_kv]) {
-    const size_t want = sm > 48 * 1024 ? 227 * 1024 : 48 * 1024;
-    int rc = check_cuda(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(want)),
-                        "cudaFuncSetAttribute(seq_attention)");
-    if (rc) return rc;
-    attr_smem[smem_kv] = want;
-  }
+  if (int rc = ensure_dynamic_smem(fn, sm > 48 * 1024 ? 227 * 1024 : 48 * 1024, "seq_attention")) return rc;
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_split);
   LaunchScope ls(cls, stream, 0.0);
   auto kern = smem_kv ? seq_attention_f32_kernel<H, HD, true> : seq_attention_f32_kernel<H, HD, false>;

@@ -341,18 +341,10 @@ int vit_attention(const sais_bf16* qkv, int B, sais_bf16* out, float* probs, cud
   // emitting variant (and SAIS_ATTN_LEGACY=1 for A/B comparisons)
   static const bool legacy = getenv("SAIS_ATTN_LEGACY") != nullptr && atoi(getenv("SAIS_ATTN_LEGACY")) != 0;
   if (probs == nullptr && !legacy) return vit_attention_tc(qkv, B, out, stream);
-  static bool attr_set = false;
-  if (!attr_set) {
-    int rc = check_cuda(cudaFuncSetAttribute(vit_attention_kernel<false>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem),
-                        "cudaFuncSetAttribute(vit_attention)");
-    if (rc) return rc;
-    rc = check_cuda(cudaFuncSetAttribute(vit_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kSmem),
-                    "cudaFuncSetAttribute(vit_attention probs)");
-    if (rc) return rc;
-    attr_set = true;
-  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(vit_attention_kernel<false>), kSmem, "vit_attention"))
+    return rc;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(vit_attention_kernel<true>), kSmem, "vit_attention probs"))
+    return rc;
   const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(qkv);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
   LaunchScope ls(kClsVitAttn, stream, 4.0 * double(B) * 6 * 197 * 197 * 64);

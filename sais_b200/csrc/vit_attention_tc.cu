@@ -428,14 +428,9 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
 template <bool kPInTmem, bool kTurns, int kPoly>
 int launch_attn(const CUtensorMap& tm, const CUtensorMap& tm_out, sais_bf16* out, int items, cudaStream_t stream,
                 long long* dbg) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    int rc = check_cuda(cudaFuncSetAttribute(vit_attention_tc_kernel<kPInTmem, kTurns, kPoly>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<kPInTmem>()),
-                        "cudaFuncSetAttribute(vit_attention_tc)");
-    if (rc) return rc;
-    attr_set = true;
-  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(vit_attention_tc_kernel<kPInTmem, kTurns, kPoly>),
+                                   smem_bytes<kPInTmem>(), "vit_attention_tc"))
+    return rc;
   const int grid = items < num_sms() ? items : num_sms();
   static const int env_hints = getenv("SAIS_L2_HINTS") ? atoi(getenv("SAIS_L2_HINTS")) : 0;  // tried: -11 % DRAM reads, no time gain
   return check_cuda(launch_pdl(vit_attention_tc_kernel<kPInTmem, kTurns, kPoly>, dim3(grid), dim3(kThreads),

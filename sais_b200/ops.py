@@ -116,33 +116,26 @@ def vit_mlp(xn, fc1_w, fc1_b, fc2_w, fc2_b, x):
 
 
 @_on_device_of_first_tensor
-def vit_mlp_ln(xb, ln_stats, fc1_wg, fc1_c, fc1_d, fc2_w, fc2_b, x, ln_eps=1e-6):
+def vit_mlp_ln(xb, ln_stats, fc1_wg, fc1_c, fc1_d, fc2_w, fc2_b, x, ln_eps=1e-6, xb_out=None, stats_out=None):
     """vit_mlp with norm2 folded in: xb = raw bf16 rows + ln_stats [rows,8] (rowstats_cast / a LayerNorm-producer GEMM),
-    (fc1_wg, fc1_c, fc1_d) = fold_layernorm(gamma, beta, fc1_w, fc1_b).  x fp32 [rows,384] updated IN PLACE."""
+    (fc1_wg, fc1_c, fc1_d) = fold_layernorm(gamma, beta, fc1_w, fc1_b).  x fp32 [rows,384] updated IN PLACE.
+    xb_out bf16 [rows,384] / stats_out fp32 [rows,8] (both or neither; may be xb / ln_stats themselves): receive
+    rowstats_cast(x_updated), produced inside the kernel."""
     require_cuda(xb, "xb")
     require_cuda(x, "x")
     assert xb.dtype == torch.bfloat16 and x.dtype == torch.float32 and xb.is_contiguous() and x.is_contiguous()
     assert fc1_wg.dtype == torch.bfloat16 and fc2_w.dtype == torch.bfloat16 and ln_stats.dtype == torch.float32
     assert tuple(fc1_wg.shape) == (1536, 384) and tuple(fc2_w.shape) == (384, 1536) and xb.shape[1] == 384
     assert tuple(ln_stats.shape) == (xb.shape[0], 8) and ln_stats.is_contiguous() and x.shape == xb.shape
+    if (xb_out is None) != (stats_out is None):
+        raise ValueError("xb_out and stats_out go together")
+    if xb_out is not None:
+        assert xb_out.dtype == torch.bfloat16 and xb_out.shape == xb.shape and xb_out.is_contiguous()
+        assert stats_out.dtype == torch.float32 and tuple(stats_out.shape) == (xb.shape[0], 8) and stats_out.is_contiguous()
     check(lib().sais_vit_mlp_ln(ptr(xb), ptr(ln_stats), float(ln_eps), ptr(fc1_wg), ptr(fc1_c), ptr(fc1_d), ptr(fc2_w),
-                                ptr(fc2_b), ptr(x), xb.shape[0], current_stream()), "sais_vit_mlp_ln")
+                                ptr(fc2_b), ptr(x), xb.shape[0], ptr(xb_out), ptr(stats_out), current_stream()),
+          "sais_vit_mlp_ln")
     return x
-
-
-@_on_device_of_first_tensor
-def gemm_residual_layernorm(a, w, bias, x, gamma=None, beta=None, eps=1e-6, want_ln=True):
-    """x += a @ w.T + bias (fp32 [M,384], IN PLACE); returns (x, LayerNorm(x) as bf16 [M,384] or None)."""
-    require_cuda(a, "a")
-    require_cuda(x, "x")
-    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.dtype == torch.float32
-    assert a.stride(-1) == 1 and w.stride(-1) == 1 and x.is_contiguous() and x.shape[1] == 384 and w.shape[0] == 384
-    M, K = a.shape
-    xn = torch.empty((M, 384), device=x.device, dtype=torch.bfloat16) if want_ln else None
-    check(lib().sais_gemm_residual_layernorm(ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(bias), ptr(x), ptr(gamma),
-                                             ptr(beta), float(eps), ptr(xn), M, K, current_stream()),
-          "sais_gemm_residual_layernorm")
-    return x, xn
 
 
 @_on_device_of_first_tensor

@@ -301,33 +301,6 @@ def test_gemm_layernorm_producer(dev, M, K):
     assert torch.allclose(st[:, 1], (got * got).sum(1), atol=2e-3, rtol=1e-5)
 
 
-# ------------------------------------------------------------------------------------------------ GEMM + residual + LN
-@pytest.mark.parametrize("M,K,want_ln", [(1, 384, True), (300, 384, True), (777, 1536, True), (256, 384, False),
-                                         (197 * 96, 384, True), (256 * 80 - 57, 1536, True), (5000, 1536, False)])
-def test_gemm_residual_layernorm(dev, M, K, want_ln):
-    """x += A W^T + b in place (proj / fc2) and xn = LayerNorm(x) from the same epilogue."""
-    from sais_b200 import ops
-    a = rnd(M, K, seed=M + K)
-    w = rnd(384, K, seed=K, std=1 / math.sqrt(K))
-    bias = rnd(384, seed=7, std=0.5)
-    x = rnd(M, 384, seed=9) * 2 + 0.3
-    gamma, beta = 1 + 0.1 * rnd(384, seed=1), 0.1 * rnd(384, seed=2)
-    xd = x.to(dev).clone()
-    _, xn = ops.gemm_residual_layernorm(a.to(dev).bfloat16(), w.to(dev).bfloat16(), bias.to(dev), xd,
-                                        gamma.to(dev) if want_ln else None, beta.to(dev) if want_ln else None,
-                                        eps=1e-6, want_ln=want_ln)
-    ref_x = _gemm_ref(a, w, bias, 0, x)
-    got_x = xd.cpu()
-    assert torch.allclose(got_x, ref_x, atol=2e-4, rtol=1e-4), (got_x - ref_x).abs().max()
-    if want_ln:
-        # LayerNorm of the kernel's own fp32 row (exact two-pass statistics), rounded once to bf16
-        ref_n = O.layer_norm(got_x, gamma, beta, 1e-6)
-        got_n = xn.cpu().float()
-        assert torch.allclose(got_n, ref_n, atol=2e-5 + 2 ** -8 * float(ref_n.abs().max()), rtol=2 ** -8)
-        assert (got_n - bf(ref_n)).abs().max() <= 2 ** -6  # at most one bf16 ulp of O(3) values
-        assert ((got_n - bf(ref_n)) != 0).float().mean() < 0.01
-
-
 @pytest.mark.parametrize("B,scale", [(1, 1.0), (5, 3.0)])
 def test_vit_cls_attention(dev, B, scale):
     """last-block shortcut: attention output of the CLS query row only == row 0 of the full attention."""
@@ -408,6 +381,40 @@ def test_vit_mlp_fused_layernorm_folded(dev, rows):
     h = torch.nn.functional.gelu(O.layer_norm(x0, gamma, beta, 1e-6) @ w1.t() + b1)
     ref = res.cpu() + h @ w2.t() + b2
     assert float((got.cpu().double() - ref.double()).norm() / ref.double().norm()) < 5e-3
+
+
+@pytest.mark.parametrize("rows", [1, 130, 256, 257, 1000, 197 * 96, 256 * 80 - 57, 197 * 256])
+@pytest.mark.parametrize("alias", [False, True])
+def test_vit_mlp_fused_cast_warps(dev, rows, alias):
+    """sais_vit_mlp_ln with xb_out / stats_out: the residual update itself is unchanged bit for bit, and the bf16 copy +
+    row statistics written by the kernel's cast warps equal sais_rowstats_cast of the UPDATED stream bit for bit — in
+    separate buffers and in place over the kernel's own inputs (how sais_vit_forward uses it).  Row counts cover one unit,
+    ragged last tiles, several units per CTA pair (197*256 rows = 197 tiles on 74 pairs) and the reverse walk."""
+    from sais_b200 import ops
+    x0 = rnd(rows, 384, seed=rows % 1000) * 1.7 + 0.4
+    gamma, beta = 1 + 0.2 * rnd(384, seed=1), 0.2 * rnd(384, seed=2)
+    w1, b1 = rnd(1536, 384, seed=3, std=1 / math.sqrt(384)), rnd(1536, seed=4, std=0.3)
+    w2, b2 = rnd(384, 1536, seed=5, std=1 / math.sqrt(1536)), rnd(384, seed=6, std=0.5)
+    wg, c, d = (t.to(dev) for t in ops.fold_layernorm(gamma, beta, w1, b1))
+    w2d, b2d = w2.to(dev).bfloat16(), b2.to(dev)
+    x_in = x0.to(dev)
+    xb, stats = ops.rowstats_cast(x_in)
+    want_x = ops.vit_mlp_ln(xb, stats, wg, c, d, w2d, b2d, x_in.clone())
+    want_xb, want_stats = ops.rowstats_cast(want_x)
+    for rep in range(2):  # twice: barrier phases / leftovers of a previous launch must not matter
+        xg = x_in.clone()
+        if alias:
+            xb_io, st_io = xb.clone(), stats.clone()
+            ops.vit_mlp_ln(xb_io, st_io, wg, c, d, w2d, b2d, xg, xb_out=xb_io, stats_out=st_io)
+        else:
+            xb_io = torch.full_like(xb, float("nan"))
+            st_io = torch.full_like(stats, float("nan"))
+            ops.vit_mlp_ln(xb, stats, wg, c, d, w2d, b2d, xg, xb_out=xb_io, stats_out=st_io)
+        assert torch.equal(xg, want_x), rep
+        assert torch.equal(xb_io.view(torch.int16), want_xb.view(torch.int16)), rep
+        assert torch.equal(st_io, want_stats), rep
+    with pytest.raises(ValueError):
+        ops.vit_mlp_ln(xb, stats, wg, c, d, w2d, b2d, x_in.clone(), xb_out=xb.clone())
 
 
 # ------------------------------------------------------------------------------------------------ ViT attention

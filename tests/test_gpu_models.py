@@ -251,3 +251,43 @@ def test_loadmodel_inference_checkpoint_on_gpu(dev, tmp_path):
     pred, probs = scoring.predict(out, md["prototypes"])
     r_probs, _ = O.prototype_probs(r_out, O.make_prototypes(2, seed=9))
     assert float((probs.cpu() - r_probs).abs().max()) <= 1e-5
+
+
+_VIT_VARIANT_SCRIPT = """
+import sys, torch
+sys.path.insert(0, '.')
+from oracle import sais_oracle as O
+import sais_b200.vision_transformer as vits
+dev = torch.device('cuda:0')
+m = vits.vit_small(patch_size=16)
+m.load_state_dict(O.make_vit_weights(0, 'stress'))
+m = m.to(dev).eval()
+g = torch.Generator().manual_seed(9)
+outs = []
+for n in (3, 70, 256):
+    fr = torch.randint(0, 256, (n, 224, 224, 3), dtype=torch.uint8, generator=g).to(dev)
+    outs.append(m.forward_u8(fr).cpu())
+    outs.append(m.get_intermediate_layers(O.normalize_frames(fr[:2].cpu()).to(dev), 1)[0].cpu())
+torch.save(outs, sys.argv[1])
+"""
+
+
+@pytest.mark.parametrize("knob", ["SAIS_MLP_CAST", "SAIS_SNAKE"])
+def test_vit_forward_variants_bit_identical(dev, tmp_path, knob):
+    """Whole-backbone A/B of two scheduling choices that must not change a single bit: the fused MLP's cast warps vs the
+    stand-alone rowstats_cast pass (SAIS_MLP_CAST=0), and the snake row order vs forward walks (SAIS_SNAKE=0) — at 3, 70
+    and 256 frames (one to several row tiles per CTA pair), CLS-only and all-token variants of the last block."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    res = {}
+    for flag in ("0", "1"):
+        env = dict(os.environ, PYTHONPATH=str(root))
+        env[knob] = flag
+        out = tmp_path / f"{knob}{flag}.pt"
+        subprocess.run([sys.executable, "-c", _VIT_VARIANT_SCRIPT, str(out)], check=True, env=env, cwd=root, timeout=600)
+        res[flag] = torch.load(out)
+    for a, b in zip(res["0"], res["1"]):
+        assert a.shape == b.shape and torch.equal(a, b), (a - b).abs().max()
