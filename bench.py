@@ -1,18 +1,23 @@
 #!/usr/bin/env python
-"""Benchmark of the SAIS inference hot path on B200 (contract: see the task description / DESIGN.md §Measurement).
+"""Benchmark of the SAIS inference hot path on B200 (contract: see the task description / DESIGN.md §6).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 One "step" = one pass of the hot path over one batch of synthetic input per rank:
   256 uint8 frames (128 RGB + 128 optical-flow, 224x224) -> frame normalisation + DINO ViT-S/16 (bf16 operands,
-  fp32 accumulate) -> [256,384] embeddings -> (N>1: NCCL all-gather of the frame-range shards) -> SAIS temporal
+  fp32 accumulate) -> [256,384] embeddings, written straight into this rank's slice of a persistent gather buffer ->
+  (N>1: in-place NCCL all-gather of the frame-range shards, asynchronous, overlapped with the head) -> SAIS temporal
   head on this rank's 8 clips x 16 frames (RGB + flow) -> prototype scores (P=2).
 This is BASELINE.json configs[1] (ViT-S/16, batch 256, 1xB200) with the SAIS head of the metric on top.
 
 value : frames/s with the u8 frames already resident in HBM (max over ranks, CUDA events, K steps).
 e2e   : same metric through the public API (sais_b200.pipeline.extract_features + fullModel + scoring) with the
         frames in PINNED HOST memory: H2D of every batch and D2H of embeddings + clip scores inside the timed region.
---impl reference : the reference's algorithm on the host CPU (oracle port, all cores) on a bounded sample.
+        Before timing, one e2e step is checked bit for bit against the resident step on the same frames.
+roofline : the DOMINANT KERNEL of the step (mlp_fused_kernel), CUDA events around every one of its launches.
+extra : the other BASELINE configs measured in the same run — C1 (10+10-frame clip), C3 (head, 512 clips x 30 frames),
+        C4 (60-min video, 3,600+3,600 frames, STRONG scaling over the ranks), C5 (1,000 ragged clips sharded by clip).
+--impl reference : the reference's algorithm on the host CPU (oracle port, all cores) on a bounded sample per step.
 """
 from __future__ import annotations
 
@@ -34,6 +39,11 @@ FLOP_PER_FRAME = 9_196_996_608  # every token through all 12 bl
 # vision_transformer.py:213-214): 196/197 of (QK^T + PV + proj + fc1 + fc2) of one block are never needed.
 FLOP_PER_FRAME_EXECUTED = FLOP_PER_FRAME - (29_805_312 * 2 + 58_097_664 + 2 * 232_390_656) * 196 // 197
 METRIC = "frames/sec (ViT-S/16 224^2 RGB+flow + SAIS head)"
+REF_FRAMES = 16  # frames per step of the CPU reference arm (8 RGB + 8 flow + head on 1 clip)
+# kernel classes of the library's CUDA-event profiler (include/sais_b200.h, sais_profile_end)
+CLASSES = ["gemm_other", "vit_attention", "layernorm_rowstats", "patchify", "temporal_attention", "misc",
+           "gemm_split3_head", "mlp_fused", "gemm_qkv", "gemm_proj"]
+TENSOR_CLASSES = {"gemm_other", "vit_attention", "gemm_split3_head", "mlp_fused", "gemm_qkv", "gemm_proj"}
 
 
 def load_peaks():
@@ -106,49 +116,13 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def cpu_reference_rate(seconds_budget=12.0, frames=16):
-    """Oracle port of the reference forward on the host CPU (fp32, all cores): ViT on `frames` frames (half RGB,
-    half flow) + temporal head + scoring.  Returns (frames/s, cores, sample description, seconds per pass)."""
+def make_reference_step(frames=REF_FRAMES):
+    """One bounded sample of the workload through the oracle port of the reference forward on the host CPU (fp32, all
+    cores): ViT on `frames` frames (half RGB, half flow) + temporal head on one clip + prototype scoring."""
     import torch
     from oracle import sais_oracle as O
 
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    vsd, hsd = O.make_vit_weights(0, "init"), O.make_head_weights(0, "init")
-    fr = O.make_frames_u8(frames, 5)
-    protos = O.make_prototypes(2)
-    T = frames // 2
-
-    def one_pass():
-        emb = O.vit_forward(vsd, O.normalize_frames(fr))
-        x, f = emb[:T].view(1, 1, T, 384), emb[T:].view(1, 1, T, 384)
-        pad = O.padding_mask([T], T)
-        out, _ = O.full_model_forward(hsd, x, f, pad, pad)
-        return O.prototype_probs(out, protos)[0]
-
-    one_pass()  # warm-up
-    times = []
-    t_end = time.perf_counter() + seconds_budget
-    while len(times) < 2 or time.perf_counter() < t_end:
-        t0 = time.perf_counter()
-        one_pass()
-        times.append(time.perf_counter() - t0)
-        if len(times) >= 50:
-            break
-    best = min(times)
-    sample = f"{frames} frames ({T} RGB + {T} flow) + head on 1 clip, best of {len(times)} passes, fp32 torch CPU"
-    return frames / best, cores, sample, best
-
-
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    import torch  # noqa: F401
-    frames = 16
-    from oracle import sais_oracle as O
-    cores = os.cpu_count() or 1
-    import torch
     torch.set_num_threads(cores)
     vsd, hsd = O.make_vit_weights(0, "init"), O.make_head_weights(0, "init")
     fr = O.make_frames_u8(frames, 5)
@@ -162,19 +136,42 @@ def run_reference(args):
         out, _ = O.full_model_forward(hsd, x, f, pad, pad)
         return O.prototype_probs(out, protos)[0]
 
-    steps = max(1, min(args.steps, 20))
-    warm = max(1, min(args.warmup, 2))
-    for _ in range(warm):
+    sample = (f"{frames} frames ({T} RGB + {T} flow) through the ViT + SAIS head on 1 clip + scoring per step, "
+              f"oracle port of the reference forward, fp32 torch CPU, {cores} threads")
+    return step, cores, sample
+
+
+def cpu_reference_rate(seconds_budget=12.0):
+    """(frames/s, cores, sample description) — best pass within the budget (reported baseline of the GPU arm's line)."""
+    step, cores, sample = make_reference_step()
+    step()  # warm-up
+    times = []
+    t_end = time.perf_counter() + seconds_budget
+    while len(times) < 2 or time.perf_counter() < t_end:
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+        if len(times) >= 50:
+            break
+    return REF_FRAMES / min(times), cores, sample + f" (best of {len(times)} passes)"
+
+
+def run_reference(args):
+    """--impl reference: EXACTLY --steps timed steps after --warmup warm-up steps, each a bounded sample (16 frames + 1
+    clip) of the GPU arm's workload; rank 0 alone runs and prints."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    step, cores, sample = make_reference_step()
+    for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
-    for _ in range(steps):
+    for _ in range(args.steps):
         step()
     dt = time.perf_counter() - t0
-    value = frames * steps / dt
-    sample = f"{frames} frames ({T} RGB + {T} flow) + SAIS head on 1 clip per step, fp32 torch CPU, {cores} threads"
+    value = REF_FRAMES * args.steps / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.gpus),
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
@@ -183,10 +180,10 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def gemm_traffic():
-    """DRAM bytes per bf16 GEMM launch from the committed ncu --set full capture (profiles/gemm_traffic.json, written
-    by tools/ncu_traffic.py from the same batch-256 step); null when no capture is committed."""
-    p = ROOT / "profiles" / "gemm_traffic.json"
+def kernel_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of the same batch-256 step
+    (profiles/mlp_traffic.json, written by tools/ncu_traffic.py); null when no capture is committed."""
+    p = ROOT / "profiles" / "mlp_traffic.json"
     if not p.exists():
         return {"traffic": None}
     d = json.loads(p.read_text())
@@ -198,7 +195,7 @@ def workload_config(n_gpus):
         "workload": "C2: DINO ViT-S/16 feature extraction, batch 256 u8 frames 224x224 (128 RGB + 128 flow) per GPU, "
                     "+ SAIS temporal head on 8 clips x 16 frames (RGB+flow) + 2 prototypes",
         "frames_per_gpu_per_step": FRAMES_PER_STEP, "clips_per_gpu_per_step": CLIPS_PER_STEP, "clip_frames": CLIP_T,
-        "sharding": "frame range per rank; all-gather of embeddings when n_gpus > 1",
+        "sharding": "frame range per rank; in-place all-gather of embeddings (overlapped with the head) when n_gpus > 1",
         "l2": "inputs rotate over 4 distinct 38.5 MB frame batches and the 426 MB per-step working set exceeds "
               "the 126 MB L2",
         "parallelism": f"dp{n_gpus}",
@@ -213,12 +210,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="sais_b200", choices=["sais_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C1 / C3 / C4 / C5 legs")
     ap.add_argument("--chunk", type=int, default=256, help="ViT frames per workspace chunk")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
+        args.warmup = max(args.warmup, 1)
         run_reference(args)
         return
+    args.warmup = max(args.warmup, 3)
 
     import torch
     import torch.distributed as dist
@@ -234,7 +233,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     import sais_b200.vision_transformer as vits
-    from sais_b200 import _lib, pipeline, scoring
+    from sais_b200 import _lib, pipeline, postprocess, scoring
     from sais_b200.prepare_model import fullModel
 
     lib = _lib.lib()
@@ -253,37 +252,59 @@ def main():
     dev_batches = [hb.to(dev) for hb in host_batches]
     pad = pipeline.full_mask(CLIPS_PER_STEP, CLIP_T, dev)
     n_global = FRAMES_PER_STEP * world
+    gatherer = pipeline.EmbeddingGatherer(n_global, 384, rank, world, dev)
 
-    def head_and_score(emb_all):
+    def head_and_score(own):
         # this rank's clips: 8 RGB clips from the first half of its frame range, 8 flow clips from the second half
-        lo = rank * FRAMES_PER_STEP
-        x = emb_all[lo:lo + CLIPS_PER_STEP * CLIP_T].view(CLIPS_PER_STEP, 1, CLIP_T, 384)
-        f = emb_all[lo + 128:lo + 128 + CLIPS_PER_STEP * CLIP_T].view(CLIPS_PER_STEP, 1, CLIP_T, 384)
+        x = own[:CLIPS_PER_STEP * CLIP_T].view(CLIPS_PER_STEP, 1, CLIP_T, 384)
+        f = own[128:128 + CLIPS_PER_STEP * CLIP_T].view(CLIPS_PER_STEP, 1, CLIP_T, 384)
         out, attn = head(x, f, None, None, 'Prototypes', pad, pad, None)
         pred, probs = scoring.predict(out, protos)
         return out, probs, pred
 
     def step_resident(i):
-        emb = vit.forward_u8(dev_batches[i % nbuf])
-        emb_all = pipeline.gather_embeddings(emb, n_global) if world > 1 else emb
-        return head_and_score(emb_all)
+        own = gatherer.own_slice(i)               # the final-LN kernel writes at rank * count of the gather buffer
+        vit.forward_u8(dev_batches[i % nbuf], out=own)
+        gatherer.gather_async(i)                  # in place, on NCCL's stream; the head below reads own rows only
+        return own, head_and_score(own)
 
     emb_host = torch.empty((FRAMES_PER_STEP, 384), dtype=torch.float32).pin_memory()
     probs_host = torch.empty((CLIPS_PER_STEP, 2), dtype=torch.float32).pin_memory()
-    emb_dev = torch.empty((FRAMES_PER_STEP, 384), dtype=torch.float32, device=dev)
 
     def step_e2e(i):
-        emb = pipeline.extract_features(vit, host_batches[i % nbuf], batch_size=FRAMES_PER_STEP, device=dev,
-                                        out=emb_dev)
-        emb_all = pipeline.gather_embeddings(emb, n_global) if world > 1 else emb
-        out, probs, pred = head_and_score(emb_all)
-        emb_host.copy_(emb, non_blocking=True)
+        own = gatherer.own_slice(i)
+        pipeline.extract_features(vit, host_batches[i % nbuf], batch_size=FRAMES_PER_STEP, device=dev, out=own)
+        gatherer.gather_async(i)
+        out, probs, pred = head_and_score(own)
+        emb_host.copy_(own, non_blocking=True)
         probs_host.copy_(probs, non_blocking=True)
+        return own, (out, probs, pred)
 
     def barrier():
+        gatherer.wait_all()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    # ---- parity gate of the e2e path: host-frame step == resident step on the same frames, bit for bit
+    for i in range(2):
+        own_r, (out_r, probs_r, _) = step_resident(i)
+        keep = (own_r.clone(), out_r.clone(), probs_r.clone())
+        barrier()
+        own_e, (out_e, probs_e, _) = step_e2e(i)
+        barrier()
+        if not (torch.equal(own_e, keep[0]) and torch.equal(emb_host, keep[0].cpu())):
+            raise SystemExit("bench: e2e embeddings differ from the device-resident step")
+        if not (torch.allclose(out_e, keep[1], rtol=1e-5, atol=1e-6) and torch.allclose(probs_host, keep[2].cpu(), atol=1e-6)):
+            raise SystemExit("bench: e2e clip vectors / probabilities differ from the device-resident step")
+        if world > 1:  # the gathered buffer holds every rank's rows: compare a checksum of rank r's slice with rank r's own
+            full = gatherer.buffer(i)
+            sums = full.view(world, -1).double().sum(1)
+            mine = sums[rank].clone()
+            allsums = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allsums, mine)
+            if not torch.equal(torch.stack(allsums), sums):
+                raise SystemExit("bench: gathered embeddings differ from the owners' rows")
 
     def timed(fn, steps, warmup, sampler=None):
         for i in range(warmup):
@@ -296,6 +317,7 @@ def main():
         e0.record()
         for i in range(steps):
             fn(warmup + i)
+        gatherer.wait_all()  # every gather of the timed steps completes inside the timed region
         e1.record()
         barrier()
         clocks = sampler.stop() if sampler else None
@@ -310,7 +332,7 @@ def main():
 
     # roofline leg: same steps with every launch bracketed by CUDA events, per kernel class
     import ctypes as C
-    ncls = 7
+    ncls = len(CLASSES)
     ms_c, work_c, n_c = (C.c_double * ncls)(), (C.c_double * ncls)(), (C.c_int64 * ncls)()
     prof_steps = min(args.steps, 10)
     barrier()
@@ -334,16 +356,36 @@ def main():
     ghz = ((pr[:, 3] - pr[:, 1]) / (pr[:, 2] - pr[:, 0]).clamp(min=1.0)).tolist()
     ghz_sorted = sorted(ghz)
 
+    extra = {}
+    if not args.no_extra:
+        extra = run_extra_configs(torch, dist, dev, rank, world, vit, head, pipeline, postprocess, scoring, barrier)
+
     if rank == 0:
         burst, sustained, hbm, src = load_peaks()
         value = n_global * args.steps / (ms * 1e-3)
         e2e = n_global * args.steps / (ms_e2e * 1e-3)
-        gemm_ms = ms_c[0] / max(n_c[0], 1)
-        gemm_tflops = (work_c[0] / 1e12) / (ms_c[0] * 1e-3) if ms_c[0] > 0 else 0.0
-        classes = ["gemm", "vit_attention", "layernorm", "patchify", "temporal_attention", "misc", "gemm_split3_head"]
         total_prof = sum(ms_c) or 1.0
-        shares = {c: {"ms_per_step": ms_c[i] / prof_steps, "launches_per_step": n_c[i] / prof_steps,
-                      "share": ms_c[i] / total_prof} for i, c in enumerate(classes)}
+        shares = {}
+        for i, c in enumerate(CLASSES):
+            if n_c[i] == 0:
+                continue
+            d = {"ms_per_step": ms_c[i] / prof_steps, "launches_per_step": n_c[i] / prof_steps,
+                 "share": ms_c[i] / total_prof, "avg_launch_us": 1e3 * ms_c[i] / n_c[i]}
+            if c in TENSOR_CLASSES:
+                d["tflops"] = work_c[i] / 1e12 / (ms_c[i] * 1e-3)
+            else:
+                d["gbs"] = work_c[i] / 1e9 / (ms_c[i] * 1e-3)
+            shares[c] = d
+        # the regime decides the denominator: the timed region runs at (near) max clock -> burst peak, else sustained
+        ghz_med = ghz_sorted[len(ghz_sorted) // 2]
+        max_ghz = ((clocks or {}).get("sm_max_mhz") or 1965) / 1e3
+        use_burst = ghz_med >= 0.95 * max_ghz
+        peak, peak_kind = (burst, "bf16_tflops (burst)") if use_burst else (sustained, "bf16_tflops_sustained")
+        k = CLASSES.index("mlp_fused")
+        mlp_ms = ms_c[k] / max(n_c[k], 1)
+        mlp_flop = work_c[k] / max(n_c[k], 1)
+        mlp_tflops = mlp_flop / 1e12 / (mlp_ms * 1e-3) if mlp_ms > 0 else 0.0
+        tok = FRAMES_PER_STEP * 197
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -351,32 +393,162 @@ def main():
             "flop_per_frame": {"reference_forward": FLOP_PER_FRAME, "executed": FLOP_PER_FRAME_EXECUTED,
                                "note": "last block evaluated on the CLS rows only (dead rows of the reference "
                                        "forward are not computed); fractions below use the EXECUTED flops"},
-            "tc_frac_of_measured_sustained": value / world * FLOP_PER_FRAME_EXECUTED / (sustained * 1e12),
-            "tc_frac_of_measured_burst": value / world * FLOP_PER_FRAME_EXECUTED / (burst * 1e12),
+            "step_tc_frac": {"of_burst": value / world * FLOP_PER_FRAME_EXECUTED / (burst * 1e12),
+                             "of_sustained": value / world * FLOP_PER_FRAME_EXECUTED / (sustained * 1e12),
+                             "target": 0.60},
             "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": FRAMES_PER_STEP * 224 * 224 * 3,
-                    "d2h_bytes_per_step": FRAMES_PER_STEP * 384 * 4 + CLIPS_PER_STEP * 2 * 4},
+                    "d2h_bytes_per_step": FRAMES_PER_STEP * 384 * 4 + CLIPS_PER_STEP * 2 * 4,
+                    "verified": "one e2e step == resident step bit for bit before timing"},
             "gpu_launches": int(launches),
-            "clocks": dict(clocks or {}, sm_ghz_in_loop_median=ghz_sorted[len(ghz_sorted) // 2], sm_ghz_in_loop_min=ghz_sorted[0],
+            "clocks": dict(clocks or {}, sm_ghz_in_loop_median=ghz_med, sm_ghz_in_loop_min=ghz_sorted[0],
                            sm_ghz_in_loop_max=ghz_sorted[-1],
                            in_loop_note="clock64 / globaltimer of a probe kernel enqueued after every step of a separate "
                                         "20-step pass"),
             "roofline": {"bound": "tensor",
-                         "kernel": "GEMM class, bf16: gemm_tcgen05_kernel + mlp_fused_kernel (the %d tensor-core GEMM "
-                                   "launches of a step: patch, qkv, proj, fused fc1+GELU+fc2, CLS-row GEMMs of the "
-                                   "last block)" % round(n_c[0] / prof_steps),
-                         "achieved": gemm_tflops, "peak": sustained, "unit": "TFLOP/s",
-                         "frac": gemm_tflops / sustained, "frac_of_burst": gemm_tflops / burst, "peak_source": src,
-                         "avg_launch_ms": gemm_ms, "flop_per_launch": work_c[0] / max(n_c[0], 1),
-                         **gemm_traffic()},
+                         "kernel": "mlp_fused_kernel (fc1 + GELU + fc2 + residual, %d launches per step, %.1f %% of the "
+                                   "step's kernel time)" % (round(n_c[k] / prof_steps), 100 * ms_c[k] / total_prof),
+                         "achieved": mlp_tflops, "peak": peak, "unit": "TFLOP/s", "frac": mlp_tflops / peak,
+                         "peak_kind": peak_kind, "peak_source": src, "frac_of_burst": mlp_tflops / burst,
+                         "frac_of_sustained": mlp_tflops / sustained,
+                         "avg_launch_ms": mlp_ms, "flop_per_launch": mlp_flop,
+                         "algorithmic_bytes_per_launch": tok * (768 + 32 + 1536 * 2 + 768 + 32) + 2 * 2 * 1536 * 384,
+                         "algorithmic_bytes_note": "per launch: bf16 rows + statistics in, fp32 residual read-modify-write, "
+                                                   "bf16 copy + statistics out (cast warps), weights once",
+                         **kernel_traffic()},
             "kernel_classes": shares,
+            "extra_configs": extra,
         }
         if not args.no_cpu_baseline:
-            v, cores, sample, _ = cpu_reference_rate()
+            v, cores, sample = cpu_reference_rate()
             line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ other BASELINE configs
+def run_extra_configs(torch, dist, dev, rank, world, vit, head, pipeline, postprocess, scoring, barrier):
+    """C1 / C3 on every rank (rank 0 reports), C4 strong scaling and C5 sharded by clip over all ranks.  Device-timed with
+    CUDA events, max over ranks; each leg: 1-2 warm-up passes + a few timed ones (bounded, ~2 s in total at N = 1)."""
+    out = {}
+
+    def time_passes(fn, warm, reps):
+        for _ in range(warm):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    protos2 = torch.randn(2, 256, device=dev, generator=g)
+    protos3 = torch.randn(3, 256, device=dev, generator=g)
+
+    # ---- C1: one 10-frame RGB + flow clip (20 ViT frames + head, S = 11), single GPU semantics on every rank
+    c1_frames = torch.randint(0, 256, (20, 224, 224, 3), dtype=torch.uint8, device=dev, generator=g)
+    pad10 = pipeline.full_mask(1, 10, dev)
+
+    def c1():
+        e = vit.forward_u8(c1_frames)
+        o, _ = head(e[:10].view(1, 1, 10, 384), e[10:].view(1, 1, 10, 384), None, None, 'Prototypes', pad10, pad10, None)
+        return scoring.predict(o, protos2)
+
+    ms = time_passes(c1, 3, 20)
+    out["C1_clip_10+10_frames"] = {"ms_per_clip": ms, "frames_per_s": 20 / (ms * 1e-3), "n_gpus": 1,
+                                   "note": "latency-bound: 20 frames is 0.08 of one ViT row-tile round"}
+
+    # ---- C3: temporal head alone, 512 clips x 30 frames (RGB + flow), attention maps out
+    x = torch.randn(512, 1, 30, 384, device=dev, generator=g)
+    f = torch.randn(512, 1, 30, 384, device=dev, generator=g)
+    pad30 = pipeline.full_mask(512, 30, dev)
+
+    def c3():
+        o, a = head(x, f, None, None, 'Prototypes', pad30, pad30, None)
+        return scoring.predict(o, protos2)
+
+    ms = time_passes(c3, 2, 10)
+    flop = 512 * 1.0847e9
+    out["C3_temporal_512x30"] = {"ms_per_batch": ms, "clips_per_s": 512 / (ms * 1e-3), "n_gpus": 1,
+                                 "tflops_fp32_equivalent": flop / 1e12 / (ms * 1e-3),
+                                 "note": "split-precision (3 bf16 MMAs per product): executed tensor work is 3x this"}
+
+    # ---- C4: 60-minute 1 fps video, 3,600 RGB + 3,600 flow frames, STRONG scaling: frame ranges over the ranks,
+    # all-gather of both [3600,384] streams, windows 20 / hop 10 x TTA {0,3,6}, P = 3, windows sharded round-robin
+    n = 3600
+    lo, hi = pipeline.frame_range(n, rank, world)
+    pool = torch.randint(0, 256, (512, 224, 224, 3), dtype=torch.uint8, device=dev, generator=g)  # frames of the shard
+
+    def shard_frames(k):  # contiguous 256-frame chunks cut from the pool: no copies inside the timed region
+        return pool[(k * 256) % 512: (k * 256) % 512 + 256]
+
+    pipe = pipeline.SaisPipeline(vit, head, protos3, window=20, hop=10, tta_offsets=(0, 3, 6), batch_size=256)
+    g_rgb = pipeline.EmbeddingGatherer(n, 384, rank, world, dev, frame_ranges=True)
+    g_flow = pipeline.EmbeddingGatherer(n, 384, rank, world, dev, frame_ranges=True)
+
+    def c4():
+        for gat in (g_rgb, g_flow):
+            own = gat.own_slice(0)
+            k = 0
+            for b0 in range(0, hi - lo, 256):
+                nb = min(256, hi - lo - b0)
+                vit.forward_u8(shard_frames(k)[:nb], out=own[b0:b0 + nb])
+                k += 1
+            gat.gather_async(0)
+        g_rgb.wait_all()
+        g_flow.wait_all()
+        nw = pipe.num_windows(n, n)
+        return pipe.score_windows(g_rgb.buffer(0), g_flow.buffer(0), pipeline.shard_items(nw, rank, world))
+
+    ms = time_passes(c4, 1, 3)
+    out["C4_60min_video"] = {"ms_per_video": ms, "frames_per_s": 2 * n / (ms * 1e-3), "n_gpus": world,
+                             "scaling": "strong", "frames": 2 * n, "windows": 359, "tta_views": 3}
+
+    # ---- C5: 1,000 clips of 8-64 RGB frames (+ ceil(len/2) flow frames), sharded by clip id mod world: ViT over the
+    # shard's frames, padded batches of 32 clips through the head, all-gather of the [n_own,256] clip vectors
+    import numpy as np
+    rng = np.random.default_rng(3)
+    lens = rng.integers(8, 65, 1000)
+    own_ids = np.arange(rank, 1000, world)
+    rl = lens[own_ids]
+    fl = (rl + 1) // 2
+    nr, nf = int(rl.sum()), int(fl.sum())
+    emb = torch.empty((nr + nf, 384), dtype=torch.float32, device=dev)
+    r_off = np.concatenate([[0], np.cumsum(rl)])
+    f_off = nr + np.concatenate([[0], np.cumsum(fl)])
+    width = (1000 + world - 1) // world
+    vec_own = torch.zeros((width, 256), dtype=torch.float32, device=dev)
+    vec_all = torch.empty((world * width, 256), dtype=torch.float32, device=dev)
+
+    def c5():
+        k = 0
+        for b0 in range(0, nr + nf, 256):
+            nb = min(256, nr + nf - b0)
+            vit.forward_u8(shard_frames(k)[:nb], out=emb[b0:b0 + nb])
+            k += 1
+        for b0 in range(0, len(own_ids), 32):
+            ids = range(b0, min(b0 + 32, len(own_ids)))
+            xs, xp, _ = postprocess.pad_collate([emb[r_off[i]:r_off[i + 1]].unsqueeze(0) for i in ids])
+            fs, fp, _ = postprocess.pad_collate([emb[f_off[i]:f_off[i + 1]].unsqueeze(0) for i in ids])
+            o, _ = head(xs, fs, None, None, 'Prototypes', xp, fp, None)
+            vec_own[b0:b0 + len(ids)] = o
+        if world > 1:
+            dist.all_gather_into_tensor(vec_all, vec_own)
+            return scoring.predict(vec_all, protos2)
+        return scoring.predict(vec_own, protos2)
+
+    ms = time_passes(c5, 1, 2)
+    tot = int((lens + (lens + 1) // 2).sum())
+    out["C5_1000_clips"] = {"ms_per_sweep": ms, "clips_per_s": 1000 / (ms * 1e-3), "frames_per_s": tot / (ms * 1e-3),
+                            "n_gpus": world, "scaling": "strong", "frames": tot}
+    return out
 
 
 if __name__ == "__main__":

@@ -57,10 +57,11 @@ int sais_clock_probe(int64_t* out4, int32_t spin_iters, sais_stream_t stream);
 
 /* Optional per-kernel-class CUDA-event profiler (bench.py's roofline leg).  Between begin and end every
  * launch is bracketed by events on its stream; end synchronises the device and returns, per class
- * (0 bf16 GEMM, 1 ViT attention, 2 LayerNorm / row statistics, 3 patchify, 4 temporal attention, 5 misc,
- * 6 split-precision GEMM of the temporal head / fp32 mode): summed milliseconds, summed algorithmic work (flops for
- * classes 0, 1 and 6, bytes otherwise) and launch counts.  All arrays are HOST. */
-#define SAIS_NUM_KERNEL_CLASSES 7
+ * (0 other bf16 GEMMs, 1 ViT attention, 2 LayerNorm / row statistics, 3 patchify, 4 temporal attention, 5 misc,
+ * 6 split-precision GEMM of the temporal head / fp32 mode, 7 fused ViT MLP kernel, 8 ViT qkv GEMM, 9 ViT proj GEMM):
+ * summed milliseconds, summed algorithmic work (flops for classes 0, 1, 6, 7, 8, 9; bytes otherwise) and launch counts.
+ * All arrays are HOST. */
+#define SAIS_NUM_KERNEL_CLASSES 10
 void sais_profile_begin(void);
 int sais_profile_end(double* ms_per_class, double* work_per_class, int64_t* launches_per_class, int32_t n_classes);
 

@@ -1111,8 +1111,11 @@ int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
   const int units = ((m_tiles + cluster - 1) / cluster) * (p.N / BLOCK_N) * p.k_slices;
   int grid = units * cluster < num_sms() ? units * cluster : num_sms();
   grid -= grid % cluster;
-  LaunchScope ls(a.split3 ? kClsGemmSplit : kClsGemm, stream,
-                 2.0 * double(a.M) * double(a.N) * double(a.K) * (a.split3 ? 3 : 1));
+  const int cls = a.split3 ? kClsGemmSplit
+                  : (a.M >= 4096 && a.N == 1152 && a.K == 384 && a.out_bf16) ? kClsGemmQkv
+                  : (a.M >= 4096 && a.N == 384 && a.K == 384 && a.out_f32) ? kClsGemmProj
+                                                                          : kClsGemm;
+  LaunchScope ls(cls, stream, 2.0 * double(a.M) * double(a.N) * double(a.K) * (a.split3 ? 3 : 1));
   const size_t smem_bytes = ASTAT ? size_t(Cfg::smem_bytes_astat(wide, nbuf, csum)) : size_t(Cfg::smem_bytes(wide, nbuf, p.xb_buf, csum));
   rc = check_cuda(launch_pdl(gemm_tcgen05_kernel<BLOCK_N, MODE, CG, EW, ASTAT>, dim3(grid), dim3(32 * (2 + EW)), smem_bytes, stream,
                              cluster, ta, tb, tout, tres, tout2, p),

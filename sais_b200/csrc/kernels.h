@@ -12,6 +12,9 @@ namespace sais {
 enum LaunchClass : int {
   kClsGemm = 0, kClsVitAttn, kClsLayerNorm, kClsPatchify, kClsTemporalAttn, kClsMisc,
   kClsGemmSplit,  // split-precision (3-pass) GEMM launches: the temporal head and the fp32-equivalent ViT mode
+  kClsMlpFused,   // mlp_fused_kernel (the dominant kernel of a step; work = 4 * rows * 384 * 1536 flop)
+  kClsGemmQkv,    // bf16 qkv GEMM of the ViT blocks (M >= 4096, N = 1152, K = 384)
+  kClsGemmProj,   // fp32-output proj GEMM + residual of the ViT blocks (M >= 4096, N = 384, K = 384)
   kNumClasses
 };
 

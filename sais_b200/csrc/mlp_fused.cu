@@ -558,7 +558,7 @@ int vit_mlp_fused(const sais_bf16* xn, const sais_bf16* w1, const float* b1, con
     if (p.dbg) cudaMemsetAsync(p.dbg, 0, kDbgN * sizeof(long long), stream);
   }
   {
-    LaunchScope ls(kClsGemm, stream, 4.0 * double(rows) * DM * HID);
+    LaunchScope ls(kClsMlpFused, stream, 4.0 * double(rows) * DM * HID);
     // (cluster = 1 here: the kernel carries its own __cluster_dims__(2, 1, 1))
     rc = check_cuda(launch_pdl(mlp_fused_kernel, dim3(2 * pairs), dim3(kThreads), size_t(kSmemBytes), stream, 1, ta, tw1, tw2,
                                tout, p),

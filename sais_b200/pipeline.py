@@ -4,9 +4,10 @@
   frames in batches, ``reps = model(inputs)``, collect ``[n_frames,384]``.  Here the frames are raw ``uint8`` HWC
   images in (pinned) host memory; the next batch's host->device copy runs on a side stream while the current batch
   is in the ViT (the reference's DataLoader is ``num_workers=0``, :178).
-* :func:`frame_range` / :func:`gather_embeddings`: data-parallel by contiguous frame range, one process per GPU;
-  the only exchange on the path is an NCCL all-gather of the per-rank ``[n/R,384]`` embeddings ahead of the
-  temporal encoder.  ``gloo`` works too (CPU tensors) for the host-logic tests.
+* :func:`frame_range` / :func:`gather_embeddings` / :class:`EmbeddingGatherer`: data-parallel by contiguous frame
+  range, one process per GPU; the only exchange on the path is an NCCL all-gather of the per-rank ``[n/R,384]``
+  embeddings ahead of the temporal encoder — in place into a persistent buffer the ViT writes to, and
+  asynchronous so that the head / next batch overlap it.  ``gloo`` works too (CPU tensors) for the host-logic tests.
 * :func:`sliding_windows` / :func:`gather_windows`: dense window + TTA index arithmetic (step-recognition form,
   ``prepare_dataset.py:469-473, 2324``) done with tensor ops so the gather stays on the device.
 * :func:`custom_gesture_windows` / :func:`custom_gesture_indices` / :func:`gather_ragged`: the ``Custom_Gestures``
@@ -62,6 +63,65 @@ def gather_embeddings(local: torch.Tensor, n_frames: int, group=None) -> torch.T
     out = torch.empty((world * width,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, padded, group=group)
     return torch.cat([out[r * width: r * width + (hi - lo)] for r, (lo, hi) in enumerate(sizes)], 0)
+
+
+class EmbeddingGatherer:
+    """The one exchange step of the path, without allocations or copies: a persistent ``[R * width, D]``
+    buffer per slot in which rank ``r`` owns rows ``[r * width, r * width + n_r)``.  The ViT's final-LayerNorm kernel writes
+    this rank's embeddings straight into :meth:`own_slice` (``forward_u8(..., out=...)``), :meth:`gather_async` issues the
+    IN-PLACE all-gather (send buffer = this rank's slice of the receive buffer) asynchronously on the process group's
+    own stream, so whatever the caller enqueues next on the compute stream — the temporal head over the rank's own clips,
+    the next batch's ViT — overlaps the collective; :meth:`buffer` / :meth:`wait_all` join it.  ``depth`` slots rotate so
+    that step ``i + 1`` can write while the gather of step ``i`` is still in flight (a slot is re-used only after its
+    pending gather has been joined).  Rows are split evenly (``ceil(n / R)`` per rank) unless ``frame_ranges=True``
+    (then exactly as :func:`frame_range` does; ragged splits are compacted by :meth:`buffer`)."""
+
+    def __init__(self, n_rows: int, dim: int, rank: int, world: int, device, frame_ranges: bool = False, depth: int = 2,
+                 dtype=torch.float32, group=None):
+        self.n, self.dim, self.rank, self.world, self.group = int(n_rows), int(dim), int(rank), int(world), group
+        if frame_ranges:
+            self.ranges = [frame_range(self.n, r, world) for r in range(world)]
+        else:
+            w = (self.n + world - 1) // world
+            self.ranges = [(min(r * w, self.n), min((r + 1) * w, self.n)) for r in range(world)]
+        self.width = max(hi - lo for lo, hi in self.ranges) if world else 0
+        self.even = all(hi - lo == self.width for lo, hi in self.ranges)
+        self.slots = [torch.zeros((world * self.width, dim), dtype=dtype, device=device) for _ in range(depth)]
+        self.pending = [None] * depth
+
+    def _join(self, k):
+        if self.pending[k] is not None:
+            self.pending[k].wait()  # stream-level: the current stream waits for the collective, the host does not
+            self.pending[k] = None
+
+    def own_slice(self, i: int) -> torch.Tensor:
+        """This rank's rows of slot ``i % depth`` (joins that slot's previous gather first: WAR)."""
+        k = i % len(self.slots)
+        self._join(k)
+        lo, hi = self.ranges[self.rank]
+        return self.slots[k][self.rank * self.width: self.rank * self.width + (hi - lo)]
+
+    def gather_async(self, i: int) -> None:
+        if self.world == 1:
+            return
+        import torch.distributed as dist
+        k = i % len(self.slots)
+        buf = self.slots[k]
+        mine = buf[self.rank * self.width: (self.rank + 1) * self.width]
+        self.pending[k] = dist.all_gather_into_tensor(buf, mine, group=self.group, async_op=True)
+
+    def buffer(self, i: int) -> torch.Tensor:
+        """All ``n`` rows of slot ``i % depth`` in frame order (joins its gather)."""
+        k = i % len(self.slots)
+        self._join(k)
+        if self.even:
+            return self.slots[k][: self.n]
+        return torch.cat([self.slots[k][r * self.width: r * self.width + (hi - lo)]
+                          for r, (lo, hi) in enumerate(self.ranges)], 0)
+
+    def wait_all(self) -> None:
+        for k in range(len(self.slots)):
+            self._join(k)
 
 
 # --------------------------------------------------------------------------------------------- windows / TTA

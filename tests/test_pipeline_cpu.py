@@ -169,3 +169,50 @@ def test_pipeline_sampling_modes_are_validated():
     p = pipeline.SaisPipeline(None, None, torch.zeros(2, 256), sampling="custom_gestures")
     assert p.flow_stride == 15 and p.num_windows(100, 7) == 6
     assert pipeline.SaisPipeline(None, None, torch.zeros(2, 256), window=20, hop=10).num_windows(3600, 3600) == 359
+
+
+def _gatherer_worker(rank, world, port, n_rows, frame_ranges, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        gat = pipeline.EmbeddingGatherer(n_rows, 384, rank, world, "cpu", frame_ranges=frame_ranges)
+        ok = True
+        for step in range(5):  # slots rotate; every step's rows differ
+            full = torch.arange(n_rows * 384, dtype=torch.float32).view(n_rows, 384) + 1000.0 * step
+            lo, hi = gat.ranges[rank]
+            own = gat.own_slice(step)
+            assert own.shape == (hi - lo, 384)
+            own.copy_(full[lo:hi])          # stands in for forward_u8(..., out=own)
+            gat.gather_async(step)
+            got = gat.buffer(step)
+            ok = ok and torch.equal(got, full)
+        gat.wait_all()
+        covered = sorted(gat.ranges)
+        ok = ok and covered[0][0] == 0 and covered[-1][1] == n_rows and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_rows,frame_ranges", [(64, False), (61, True), (61, False)])
+def test_embedding_gatherer_in_place_world2_gloo(n_rows, frame_ranges):
+    """The in-place, asynchronous all-gather of bench.py / C4 (persistent slots, the owner writes its slice, gather joins on
+    demand) on CPU tensors over gloo, world size 2: even split, frame_range split and a ragged ceil split."""
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gatherer_worker, args=(r, 2, port, n_rows, frame_ranges, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert sorted(q.get() for _ in range(2)) == [(0, True), (1, True)]
+
+
+def test_embedding_gatherer_single_rank_is_a_plain_buffer():
+    gat = pipeline.EmbeddingGatherer(10, 384, 0, 1, "cpu")
+    own = gat.own_slice(0)
+    own.fill_(3.0)
+    gat.gather_async(0)
+    assert gat.buffer(0).data_ptr() == own.data_ptr() and gat.buffer(0).shape == (10, 384)

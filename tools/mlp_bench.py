@@ -37,8 +37,25 @@ def unfused():
 
 
 flops = 4.0 * M * 384 * 1536
-ms_f = timeit(lambda: ops.vit_mlp(xn, w1, b1, w2, b2, x))
+gamma, beta = 1 + 0.1 * torch.randn(384, device=dev), 0.1 * torch.randn(384, device=dev)
+wg, c, d = ops.fold_layernorm(gamma, beta, w1.float(), b1)
+xb, stats = ops.rowstats_cast(x)
+xb2, stats2 = xb.clone(), stats.clone()
+
+
+def folded_then_cast():
+    ops.vit_mlp_ln(xb, stats, wg, c, d, w2, b2, x)
+    ops.rowstats_cast(x)
+
+
 ms_u = timeit(unfused)
+ms_f = timeit(lambda: ops.vit_mlp(xn, w1, b1, w2, b2, x))
+ms_l = timeit(lambda: ops.vit_mlp_ln(xb, stats, wg, c, d, w2, b2, x))
+ms_s = timeit(folded_then_cast)
+ms_c = timeit(lambda: ops.vit_mlp_ln(xb2, stats2, wg, c, d, w2, b2, x, xb_out=xb2, stats_out=stats2))  # (timeline: last call)
 print(f"frames={frames} rows={M}")
-print(f"mlp fused    {ms_f*1e3:8.1f} us  {flops/ms_f/1e9:8.1f} TFLOP/s")
-print(f"mlp 2-gemm   {ms_u*1e3:8.1f} us  {flops/ms_u/1e9:8.1f} TFLOP/s")
+print(f"mlp 2-gemm                   {ms_u*1e3:8.1f} us  {flops/ms_u/1e9:8.1f} TFLOP/s")
+print(f"mlp fused                    {ms_f*1e3:8.1f} us  {flops/ms_f/1e9:8.1f} TFLOP/s")
+print(f"mlp fused + LN fold          {ms_l*1e3:8.1f} us  {flops/ms_l/1e9:8.1f} TFLOP/s")
+print(f"  ... + rowstats_cast kernel {ms_s*1e3:8.1f} us")
+print(f"mlp fused + LN fold + cast warps {ms_c*1e3:8.1f} us  {flops/ms_c/1e9:8.1f} TFLOP/s")
