@@ -141,6 +141,16 @@ int sais_layernorm(const float* x, int64_t in_pitch, const float* gamma, const f
  * of 384 (x: [rows,384]; xb: bf16 [rows,384]; stats: fp32 [rows,8]). */
 int sais_rowstats_cast(const float* x, int64_t rows, sais_bf16* xb, float* stats, sais_stream_t stream);
 
+/* JPEG front-end (replaces the host-side PIL decode of dino-main/main_dino.py:295-301,313 /
+ * extract_representations.py:178 for RGB frames and for the `flows_%08d.jpg` optical-flow frames of :246-261).
+ *   sais_jpeg_info: HOST helper, parses the frame header of one JPEG stream: hw2_host = {height, width}.  No CUDA context.
+ *   sais_jpeg_decode_batch: n same-sized JPEG streams (HOST pointers / lengths) -> out_device u8 [n,H,W,3] interleaved RGB,
+ *   one batched nvJPEG decode enqueued on `stream` (entropy decode + IDCT are nvJPEG's; results can differ from libjpeg's
+ *   by a few levels per pixel, see tests/test_frames.py for the measured bound). */
+int sais_jpeg_info(const uint8_t* data, size_t len, int32_t* hw2_host);
+int sais_jpeg_decode_batch(const uint8_t* const* data_host, const size_t* lengths_host, int32_t n, int32_t H, int32_t W,
+                           uint8_t* out_device, sais_stream_t stream);
+
 /* Frame front-end: centre crop + Pillow-exact antialiased bilinear resize to 224 x 224.
  * Replaces, for decoded uint8 frames, `transforms.CenterCrop((height_frac*height, width_frac*width))`
  * (dino-main/main_dino.py:298-301; fractions from getCropDims :317-322) and `transforms.Resize((224,224))`

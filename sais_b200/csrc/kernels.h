@@ -72,8 +72,8 @@ int vit_attention(const sais_bf16* qkv, int B, sais_bf16* out, float* probs, cud
 // last block, CLS query only: qkv bf16 [B*197,1152] -> out_cls bf16 [B,384]
 int vit_cls_attention(const sais_bf16* qkv, int B, sais_bf16* out_cls, cudaStream_t stream);
 
-// vit_attention_tc.cu (tcgen05 path, no probabilities)
-int vit_attention_tc(const sais_bf16* qkv, int B, sais_bf16* out, cudaStream_t stream);
+// vit_attention_tc.cu (tcgen05 kernel; probs: optional fp32 [B,6,197,197] softmax probabilities)
+int vit_attention_tc(const sais_bf16* qkv, int B, sais_bf16* out, float* probs, cudaStream_t stream);
 
 // temporal_attention.cu
 // fp32 qkv in, bf16 [hi | lo] (row pitch 2*384) out

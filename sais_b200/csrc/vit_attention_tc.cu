@@ -10,9 +10,12 @@
 //                        (tcgen05.st) where the second MMA reads it as its A operand, so probabilities touch
 //                        neither shared memory nor HBM; finally O / sum -> bf16 -> global.
 // TMEM map per row tile mt (256-column window): S fp32 [0,208) -> P bf16x2 [0,104) + O fp32 [128,192).
-// kPInTmem = false keeps P in a 128B-swizzled K-major smem tile instead (one buffer shared by the two row tiles;
-// slower, kept as the conservative fallback: SAIS_ATTN_PSMEM=1).
-// The probabilities-emitting variant (get_last_selfattention) stays on the register-level kernel in vit_attention.cu.
+// kEmitProbs (get_last_selfattention with precision='bf16', vision_transformer.py:216-223): the softmax warps also write
+// the normalised probabilities exp(s - max) / sum as fp32 [B,6,197,197]; the row sum is then taken in an extra pass over
+// the logits before the exp pass, so that what is stored is already normalised (a visualiser path: one block, no timing
+// pressure).  The exp pass of the two row tiles of an item alternates per lane quarter (`turn` barriers): one tile's
+// exponentials hide the other's MMA round trips.  (Experiments that did not pay — P through shared memory, no turns,
+// part of the exponentials as a polynomial on the FMA pipe — were removed from the product; DESIGN.md 3.4 has the numbers.)
 #include <cstdio>
 #include <cstdlib>
 
@@ -29,54 +32,22 @@ constexpr int HD = 64;
 constexpr int KEYS = 208;                  // keys padded to a multiple of 16 (UMMA N / K granularity)
 constexpr int MAT_BYTES = KEYS * 128;      // one of Q / K / V in smem: 208 rows x 128 B (SWIZZLE_128B)
 constexpr int SLOT_BYTES = 3 * MAT_BYTES;  // Q, K, V of one item
-constexpr int P_BYTES = 4 * 128 * 128;     // smem P tile (fallback): 128 rows x 256 keys bf16 = 4 k-blocks of 16 KB
 constexpr int kThreads = 11 * 32;  // 8 softmax warps + loader + one MMA-issuing warp per row-tile window
 constexpr int kTmemCols = 512;             // row tile 0 at column 0, row tile 1 at column 256
-constexpr int kDefaultPoly = 0;           // see ex2_poly2 (SAIS_ATTN_POLY overrides)
 constexpr int kOCol = 128;                 // O accumulator inside the row tile's window
 
 constexpr int kOutStage = 8 * 4096;        // per softmax warp: 32 rows x 128 B staging tile for the TMA store of O
-template <bool kPInTmem>
-constexpr int smem_bytes() {
-  return 2 * SLOT_BYTES + (kPInTmem ? 16384 /*overrun pad for the 2nd Q row tile*/ + kOutStage : P_BYTES) + 1024 + 256;
-}
+constexpr int kSmemBytes = 2 * SLOT_BYTES + 16384 /*overrun pad for the 2nd Q row tile*/ + kOutStage + 1024 + 256;
 
 __device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// 2^x for x <= 0 on the FMA pipe (packed fp32x2): Cody-Waite split x = n + f with n = round(x), f in [-0.5, 0.5], a
-// degree-3 minimax polynomial for 2^f (max relative error 8.0e-5, far below the bf16 rounding of P) and n added into
-// the exponent field.  The exp pass of the softmax is bound by the MUFU pipe (16 ex2 / clk / SM); evaluating kPoly of
-// every 8 element pairs here instead takes that share off the MUFU at ~5.5 issue slots per element.
-__device__ __forceinline__ void ex2_poly2(float x0, float x1, float& p0, float& p1) {
-  const uint64_t x = pack2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
-  const uint64_t t = add2(x, pack2(12582912.0f, 12582912.0f));  // 1.5 * 2^23: the sum's low mantissa bits hold round(x)
-  const uint64_t r = add2(t, pack2(-12582912.0f, -12582912.0f));
-  const uint64_t f = fma2(r, pack2(-1.0f, -1.0f), x);
-  uint64_t q = fma2(f, pack2(0.05519810691475868f, 0.05519810691475868f), pack2(0.24267712235450745f, 0.24267712235450745f));
-  q = fma2(q, f, pack2(0.6932618021965027f, 0.6932618021965027f));
-  q = fma2(q, f, pack2(0.9999227523803711f, 0.9999227523803711f));
-  float t0, t1, q0, q1;
-  unpack2(t, t0, t1);
-  unpack2(q, q0, q1);
-  p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
-  p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
-}
-// which of every 8 consecutive element pairs go to the polynomial (spread out so MUFU and FMA work interleave)
-__host__ __device__ constexpr bool pair_uses_poly(int j, int kPoly) {
-  return kPoly == 0 ? false
-         : kPoly == 2 ? ((j & 3) == 1)
-         : kPoly == 3 ? ((j & 7) == 1 || (j & 7) == 4 || (j & 7) == 6)
-                      : ((j & 1) == 1);
-}
-
-template <bool kPInTmem, bool kTurns, int kPoly>
+template <bool kEmitProbs>
 __global__ void __launch_bounds__(kThreads, 1)
 vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out,
-                        __nv_bfloat16* __restrict__ out, int n_items, int flags,
-                        long long* __restrict__ dbg) {
-  const int reverse = flags & 1, l2_hints = flags & 2;  // (kernels.h g_tile_reverse; evict-first loads)
+                        float* __restrict__ probs, int n_items, int flags, long long* __restrict__ dbg) {
+  const int reverse = flags & 1;  // (kernels.h g_tile_reverse)
   // dev knob (SAIS_ATTN_TIMELINE=<file>): CTA 0 records clock64() at every phase boundary, [role][item][event]
   auto stamp = [&](int role, int idx, int ev) {
     if (dbg != nullptr && blockIdx.x == 0 && idx < 16) dbg[(role * 16 + idx) * 8 + ev] = clock64();
@@ -84,8 +55,8 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* p_smem = smem + 2 * SLOT_BYTES;
-  uint8_t* o_stage = p_smem + 16384;  // (P-in-TMEM build only)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + (kPInTmem ? 16384 + kOutStage : P_BYTES));
+  uint8_t* o_stage = p_smem + 16384;  // (16 KB pad: the second Q row tile's UMMA descriptor may run past row 207)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + 16384 + kOutStage);
   uint64_t* ld_full = bars;       // [2] item slot loaded
   uint64_t* ld_empty = bars + 2;  // [2] item slot free again
   uint64_t* s_full = bars + 4;    // [2] S[mt] in TMEM
@@ -141,15 +112,9 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
           uint8_t* dst = smem + slot * SLOT_BYTES;
           if (elect_one()) {
             mbar_arrive_expect_tx(&ld_full[slot], SLOT_BYTES);
-            if (l2_hints) {  // q / k / v slices are read exactly once: evict-first (opt-in: SAIS_L2_HINTS=1)
-              tma_load_3d_hint(dst, &tmap_qkv, &ld_full[slot], h * HD, 0, b, kEvictFirst);
-              tma_load_3d_hint(dst + MAT_BYTES, &tmap_qkv, &ld_full[slot], 384 + h * HD, 0, b, kEvictFirst);
-              tma_load_3d_hint(dst + 2 * MAT_BYTES, &tmap_qkv, &ld_full[slot], 768 + h * HD, 0, b, kEvictFirst);
-            } else {
-              tma_load_3d(dst, &tmap_qkv, &ld_full[slot], h * HD, 0, b);
-              tma_load_3d(dst + MAT_BYTES, &tmap_qkv, &ld_full[slot], 384 + h * HD, 0, b);
-              tma_load_3d(dst + 2 * MAT_BYTES, &tmap_qkv, &ld_full[slot], 768 + h * HD, 0, b);
-            }
+            tma_load_3d(dst, &tmap_qkv, &ld_full[slot], h * HD, 0, b);
+            tma_load_3d(dst + MAT_BYTES, &tmap_qkv, &ld_full[slot], 384 + h * HD, 0, b);
+            tma_load_3d(dst + 2 * MAT_BYTES, &tmap_qkv, &ld_full[slot], 768 + h * HD, 0, b);
           }
           __syncwarp();
         }
@@ -164,8 +129,6 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
           const uint32_t q_s = smem_u32(smem + slot * SLOT_BYTES);
           const uint32_t k_s = q_s + MAT_BYTES, v_s = q_s + 2 * MAT_BYTES;
           mbar_wait(&ld_full[slot], (idx >> 1) & 1);
-          // (no-turns build) the second window starts half an item late so that the two windows' softmax passes interleave
-          if (!kTurns && w == 1 && idx == 0) __nanosleep(1800);
           if (lane == 0) stamp(2 + w, idx, 0);
           mbar_wait(&t_free[w], (idx & 1) ^ 1);  // window drained by the softmax warps
           tc_fence_after();
@@ -184,17 +147,11 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
           mbar_wait(&p_full[w], idx & 1);
           tc_fence_after();
           if (lane == 0) stamp(2 + w, idx, 3);
-          const uint32_t p_s = smem_u32(p_smem);
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < KEYS / 16; ++ks) {
               const uint64_t db = umma_desc_sw128_mnmajor(v_s + ks * 2048, 0);
-              if (kPInTmem) {
-                umma_f16_ts(win + kOCol, win + ks * 8, db, idesc_o, ks != 0);
-              } else {
-                const uint64_t da = umma_desc_sw128_kmajor(p_s + (ks >> 2) * 16384 + (ks & 3) * 32);
-                umma_f16(win + kOCol, da, db, idesc_o, ks != 0);
-              }
+              umma_f16_ts(win + kOCol, win + ks * 8, db, idesc_o, ks != 0);
             }
             umma_commit(&o_full[w]);
             umma_commit(&ld_empty[slot]);  // this window's reads of the slot have retired (barrier counts both windows)
@@ -210,7 +167,6 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
     const int row = mt * 128 + q * 32 + lane;  // query row inside the frame
     const bool warp_has_rows = (mt * 128 + q * 32) < T;
     const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + mt * 256;
-    const uint32_t p_row = smem_u32(p_smem) + (q * 32 + lane) * 128;
     const int sw = lane & 7;
     const float sl2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
 
@@ -252,43 +208,52 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
         }
         const float mb = m * sl2;
         if (st_on) stamp(mt, it, 2);
-        if (!kPInTmem) {
-          // the single smem P buffer is shared by the two row tiles: wait until the tensor core has finished reading
-          // the previous tile's probabilities (tile 0 follows tile 1 of the previous item, tile 1 follows tile 0)
-          if (mt == 0) {
-            if (it > 0) mbar_wait(&o_full[1], (it - 1) & 1);
-          } else {
-            mbar_wait(&o_full[0], ph);
-          }
-        }
         // The exp pass is MUFU-bound (208 ex2 per row at 4 /clk per scheduler) and the two warps of a scheduler (row tile
         // 0 and 1 of the same lane quarter) would otherwise run it at the same time at half speed each and leave the
         // MUFU idle while both wait for their MMAs: take turns, so one tile's exponentials hide the other's MMA round trips.
-        if (kTurns) mbar_wait(&turn[mt * 4 + q], (mt == 0) ? (ph ^ 1) : ph);
+        mbar_wait(&turn[mt * 4 + q], (mt == 0) ? (ph ^ 1) : ph);
+        // (probabilities requested) the row sum first, with the very exponentials pass 2 evaluates, so that pass 2 can
+        // store exp / sum directly
+        float inv_emit = 0.f;
+        float* prow = nullptr;
+        if (kEmitProbs) {
+          float se = 0.f;
+          uint32_t v[32];
+#pragma unroll 1
+          for (int c = 0; c < 6; ++c) {
+            tmem_ld_32x32(t_row + c * 32, v);
+            tmem_ld_wait_dep(v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              se += ex2_approx(fmaf(__uint_as_float(v[2 * j]), sl2, -mb)) + ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), sl2, -mb));
+          }
+          tmem_ld_32x16(t_row + 192, v);
+          tmem_ld_wait_dep(v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float p0 = (2 * j < T - 192) ? ex2_approx(fmaf(__uint_as_float(v[2 * j]), sl2, -mb)) : 0.0f;
+            const float p1 = (2 * j + 1 < T - 192) ? ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), sl2, -mb)) : 0.0f;
+            se += p0 + p1;
+          }
+          inv_emit = 1.0f / se;
+          if (row < T) prow = probs + ((int64_t(b) * HEADS + h) * T + row) * T;
+        }
         // pass 2: p = exp2((s - max) * scale), row sum, bf16 P
         float sum = 0.f;
         auto softmax_chunk = [&](const uint32_t(&v)[32], int c) {
           uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            float p0, p1;
-            if (pair_uses_poly(j, kPoly)) {
-              ex2_poly2(fmaf(__uint_as_float(v[2 * j]), sl2, -mb), fmaf(__uint_as_float(v[2 * j + 1]), sl2, -mb), p0, p1);
-            } else {
-              p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), sl2, -mb));
-              p1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), sl2, -mb));
-            }
+            const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), sl2, -mb));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), sl2, -mb));
             sum += p0 + p1;
             pk[j] = pack_bf16x2(p0, p1);
+            if (kEmitProbs && prow != nullptr) {  // (rows are 788 bytes apart: 4-byte stores; not a hot path)
+              prow[c * 32 + 2 * j] = p0 * inv_emit;
+              prow[c * 32 + 2 * j + 1] = p1 * inv_emit;
+            }
           }
-          if (kPInTmem) {
-            tmem_st_32x16(t_row + c * 16, pk);  // over logits this thread has already consumed
-          } else {
-            const uint32_t kb_base = p_row + (c >> 1) * 16384;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              sts128u(kb_base + ((((c & 1) * 4 + j) ^ sw) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-          }
+          tmem_st_32x16(t_row + c * 16, pk);  // over logits this thread has already consumed
         };
         {
           uint32_t v[32], w[32];
@@ -312,29 +277,23 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
             const float p1 = (2 * j + 1 < T - 192) ? ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), sl2, -mb)) : 0.0f;
             sum += p0 + p1;
             pk[j] = pack_bf16x2(p0, p1);
+            if (kEmitProbs && prow != nullptr) {
+              if (2 * j < T - 192) prow[192 + 2 * j] = p0 * inv_emit;
+              if (2 * j + 1 < T - 192) prow[192 + 2 * j + 1] = p1 * inv_emit;
+            }
           }
-          if (kPInTmem) {
-            tmem_st_32x8(t_row + 96, pk);
-          } else {
-            const uint32_t kb_base = p_row + 3 * 16384;
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-              sts128u(kb_base + ((j ^ sw) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-          }
+          tmem_st_32x8(t_row + 96, pk);
         }
         row_sum = sum;
-        if (kTurns && lane == 0) mbar_arrive(&turn[(mt ^ 1) * 4 + q]);
-        if (kPInTmem) tmem_st_wait();
+        if (lane == 0) mbar_arrive(&turn[(mt ^ 1) * 4 + q]);
+        tmem_st_wait();
       } else {
-        if (kTurns) {  // rows 224..255 do not exist: pass the turn straight on
-          mbar_wait(&turn[mt * 4 + q], (mt == 0) ? (ph ^ 1) : ph);
-          if (lane == 0) mbar_arrive(&turn[(mt ^ 1) * 4 + q]);
-        }
-        // keep the barrier protocol, skip the math (their P rows stay stale/unused)
-        if (!kPInTmem) mbar_wait(&o_full[0], ph);
+        // rows 224..255 do not exist: pass the turn straight on, keep the barrier protocol, skip the math (their P rows
+        // stay stale / unused)
+        mbar_wait(&turn[mt * 4 + q], (mt == 0) ? (ph ^ 1) : ph);
+        if (lane == 0) mbar_arrive(&turn[(mt ^ 1) * 4 + q]);
       }
       tc_fence_before();
-      if (!kPInTmem) fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[mt]);
       if (st_on) stamp(mt, it, 3);
@@ -345,7 +304,6 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
       if (st_on) stamp(mt, it, 4);
       if (warp_has_rows) {
         const float inv = 1.0f / row_sum;
-        __nv_bfloat16* op = out + (int64_t(b) * T + row) * 384 + h * HD;
         uint32_t v[32], w[32];
         tmem_ld_32x32(t_row + kOCol, v);
         tmem_ld_32x32(t_row + kOCol + 32, w);
@@ -356,7 +314,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_free[mt]);
-        if (kPInTmem) {
+        {
           // O tile of this warp (32 rows x 64) -> swizzled staging -> one TMA store; rows beyond token 196 are
           // clipped by the [frame, token, 384] tensor map
           const uint32_t st = smem_u32(o_stage) + warp * 4096 + lane * 128;
@@ -386,25 +344,6 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
                          : "memory");
             tma_store_commit();
           }
-        } else if (row < T) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(v[8 * j]) * inv, __uint_as_float(v[8 * j + 1]) * inv);
-            o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]) * inv, __uint_as_float(v[8 * j + 3]) * inv);
-            o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]) * inv, __uint_as_float(v[8 * j + 5]) * inv);
-            o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) * inv, __uint_as_float(v[8 * j + 7]) * inv);
-            *reinterpret_cast<uint4*>(op + j * 8) = o;
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(w[8 * j]) * inv, __uint_as_float(w[8 * j + 1]) * inv);
-            o.y = pack_bf16x2(__uint_as_float(w[8 * j + 2]) * inv, __uint_as_float(w[8 * j + 3]) * inv);
-            o.z = pack_bf16x2(__uint_as_float(w[8 * j + 4]) * inv, __uint_as_float(w[8 * j + 5]) * inv);
-            o.w = pack_bf16x2(__uint_as_float(w[8 * j + 6]) * inv, __uint_as_float(w[8 * j + 7]) * inv);
-            *reinterpret_cast<uint4*>(op + 32 + j * 8) = o;
-          }
         }
       }
       if (!warp_has_rows) {
@@ -414,7 +353,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
       }
       if (st_on) stamp(mt, it, 5);
     }
-    if (kPInTmem && lane == 0) tma_store_wait<0>();
+    if (lane == 0) tma_store_wait<0>();
   }
 
   tc_fence_before();
@@ -425,23 +364,21 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
   }
 }
 
-template <bool kPInTmem, bool kTurns, int kPoly>
-int launch_attn(const CUtensorMap& tm, const CUtensorMap& tm_out, sais_bf16* out, int items, cudaStream_t stream,
+template <bool kEmitProbs>
+int launch_attn(const CUtensorMap& tm, const CUtensorMap& tm_out, float* probs, int items, cudaStream_t stream,
                 long long* dbg) {
-  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(vit_attention_tc_kernel<kPInTmem, kTurns, kPoly>),
-                                   smem_bytes<kPInTmem>(), "vit_attention_tc"))
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(vit_attention_tc_kernel<kEmitProbs>), kSmemBytes,
+                                   "vit_attention_tc"))
     return rc;
   const int grid = items < num_sms() ? items : num_sms();
-  static const int env_hints = getenv("SAIS_L2_HINTS") ? atoi(getenv("SAIS_L2_HINTS")) : 0;  // tried: -11 % DRAM reads, no time gain
-  return check_cuda(launch_pdl(vit_attention_tc_kernel<kPInTmem, kTurns, kPoly>, dim3(grid), dim3(kThreads),
-                               size_t(smem_bytes<kPInTmem>()), stream, 1, tm, tm_out,
-                               reinterpret_cast<__nv_bfloat16*>(out), items, (g_tile_reverse ? 1 : 0) | (env_hints ? 2 : 0), dbg),
+  return check_cuda(launch_pdl(vit_attention_tc_kernel<kEmitProbs>, dim3(grid), dim3(kThreads), size_t(kSmemBytes), stream, 1,
+                               tm, tm_out, probs, items, g_tile_reverse ? 1 : 0, dbg),
                     "vit_attention_tc launch");
 }
 
 }  // namespace
 
-int vit_attention_tc(const sais_bf16* qkv, int B, sais_bf16* out, cudaStream_t stream) {
+int vit_attention_tc(const sais_bf16* qkv, int B, sais_bf16* out, float* probs, cudaStream_t stream) {
   if (B == 0) return kOk;
   CUtensorMap tm;
   int rc = make_tmap_bf16_3d(&tm, qkv, /*d0=*/1152, /*d1=*/T, /*d2=*/uint64_t(B), /*ld1=*/1152,
@@ -451,7 +388,6 @@ int vit_attention_tc(const sais_bf16* qkv, int B, sais_bf16* out, cudaStream_t s
   rc = make_tmap_bf16_3d(&tm_out, out, /*d0=*/384, /*d1=*/T, /*d2=*/uint64_t(B), /*ld1=*/384, /*ld2=*/uint64_t(T) * 384,
                          /*box0=*/HD, /*box1=*/32);
   if (rc) return rc;
-  static const bool p_smem = getenv("SAIS_ATTN_PSMEM") != nullptr && atoi(getenv("SAIS_ATTN_PSMEM")) != 0;
   static const char* timeline = getenv("SAIS_ATTN_TIMELINE");
   long long* dbg = nullptr;
   if (timeline) {
@@ -460,15 +396,8 @@ int vit_attention_tc(const sais_bf16* qkv, int B, sais_bf16* out, cudaStream_t s
   }
   {
     LaunchScope ls(kClsVitAttn, stream, 4.0 * double(B) * 6 * 197 * 197 * 64);
-    static const bool no_turns = getenv("SAIS_ATTN_NOTURNS") != nullptr && atoi(getenv("SAIS_ATTN_NOTURNS")) != 0;
-    // pairs of every 8 whose exponential runs on the FMA pipe instead of the MUFU (SAIS_ATTN_POLY=0|2|3|4)
-    static const int poly = getenv("SAIS_ATTN_POLY") ? atoi(getenv("SAIS_ATTN_POLY")) : kDefaultPoly;
-    rc = p_smem ? launch_attn<false, false, 0>(tm, tm_out, out, B * HEADS, stream, dbg)
-         : no_turns ? launch_attn<true, false, 0>(tm, tm_out, out, B * HEADS, stream, dbg)
-         : poly == 2 ? launch_attn<true, true, 2>(tm, tm_out, out, B * HEADS, stream, dbg)
-         : poly == 3 ? launch_attn<true, true, 3>(tm, tm_out, out, B * HEADS, stream, dbg)
-         : poly == 4 ? launch_attn<true, true, 4>(tm, tm_out, out, B * HEADS, stream, dbg)
-                     : launch_attn<true, true, 0>(tm, tm_out, out, B * HEADS, stream, dbg);
+    rc = probs ? launch_attn<true>(tm, tm_out, probs, B * HEADS, stream, dbg)
+               : launch_attn<false>(tm, tm_out, nullptr, B * HEADS, stream, dbg);
   }
   if (dbg) {
     long long h[4 * 16 * 8];

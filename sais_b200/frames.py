@@ -9,13 +9,17 @@ Reference call sites:
 
 Here both run on the GPU over a whole batch of decoded ``uint8 [N,H,W,3]`` frames (``sais_crop_resize_u8``,
 ``csrc/frames.cu``), bit-identical to Pillow; the result feeds ``VisionTransformer.forward_u8`` (which fuses
-ToTensor + Normalize + patch layout).  JPEG decoding itself is plumbing (``torchvision.io.decode_jpeg(device='cuda')``
-= nvJPEG, or any decoder that yields uint8 HWC frames).  No CPU path: CPU tensors raise ``SaisError``.
+ToTensor + Normalize + patch layout).  :func:`decode_jpegs` / :func:`load_frames` put the JPEG decode in front of it
+(one batched nvJPEG call straight into the ``[N,H,W,3]`` buffer the crop-resize kernel reads; the reference decodes with
+Pillow on the host, ``main_dino.py:313`` via ``ImageFolder``).  The optical-flow stream takes the same route: RAFT's output
+is stored by the reference as ``flows_%08d.jpg`` images (``extract_representations.py:246-261``), so externally supplied
+flow frames are JPEG inputs like the RGB ones — :func:`flow_frame_name` gives the reference's file name for frame ``n``.
+No CPU path: CPU tensors raise ``SaisError``.
 """
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, Tuple
+from typing import Dict, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -78,3 +82,53 @@ def crop_resize(frames: torch.Tensor, height_frac: float = 0.8, width_frac: floa
         check(lib().sais_crop_resize_u8(ptr(frames), n, h, w, top, left, ch, cw, ptr(th), ptr(tv), ptr(tmp), ptr(out),
                                         current_stream()), "sais_crop_resize_u8")
     return out
+
+
+# --------------------------------------------------------------------------------------------- JPEG front-end
+def jpeg_size(data: bytes) -> Tuple[int, int]:
+    """(height, width) from the frame header of one JPEG stream (host-only parse, no CUDA context)."""
+    buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+    hw = (C.c_int32 * 2)()
+    check(lib().sais_jpeg_info(C.cast(buf, C.c_void_p), len(data), hw), "sais_jpeg_info")
+    return int(hw[0]), int(hw[1])
+
+
+@torch.no_grad()
+def decode_jpegs(streams: Sequence[bytes], device, out: torch.Tensor = None) -> torch.Tensor:
+    """Same-sized JPEG streams (``bytes``, as read from the frame files) -> ``uint8 [N,H,W,3]`` RGB on ``device``."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        from ._lib import SaisError
+        raise SaisError("decode_jpegs decodes on a CUDA device (there is no CPU path)")
+    n = len(streams)
+    if n == 0:
+        return torch.empty((0, 0, 0, 3), dtype=torch.uint8, device=device)
+    h, w = jpeg_size(streams[0])
+    if out is None:
+        out = torch.empty((n, h, w, 3), dtype=torch.uint8, device=device)
+    elif tuple(out.shape) != (n, h, w, 3) or out.dtype != torch.uint8 or not out.is_contiguous() or out.device != device:
+        raise ValueError(f"out must be a contiguous uint8 [{n},{h},{w},3] tensor on {device}")
+    bufs = [(C.c_uint8 * len(d)).from_buffer_copy(d) for d in streams]
+    ptrs = (C.c_void_p * n)(*[C.cast(b, C.c_void_p) for b in bufs])
+    lens = (C.c_size_t * n)(*[len(d) for d in streams])
+    with torch.cuda.device(device):
+        check(lib().sais_jpeg_decode_batch(C.cast(ptrs, C.c_void_p), C.cast(lens, C.c_void_p), n, h, w, ptr(out),
+                                           current_stream()), "sais_jpeg_decode_batch")
+        # nvJPEG reads the host bit streams while the decode is in flight: keep them alive until the stream has passed it
+        torch.cuda.current_stream(device).synchronize()
+    return out
+
+
+@torch.no_grad()
+def load_frames(streams: Sequence[bytes], device, dataset: str = "") -> torch.Tensor:
+    """JPEG streams -> decoded -> centre-cropped (``getCropDims``) -> resized ``uint8 [N,224,224,3]``: everything the
+    reference's dataset + transform pipeline does to a frame before ``ToTensor`` (main_dino.py:295-313)."""
+    frames = decode_jpegs(streams, device)
+    hf, wf = get_crop_dims(dataset)
+    return crop_resize(frames, hf, wf)
+
+
+def flow_frame_name(nflow: int) -> str:
+    """File name the reference gives the optical-flow image of frame pair ``nflow`` (saveFlows,
+    extract_representations.py:253-254): ``flows_`` + the index zero-padded to 8 digits + ``.jpg``."""
+    return "flows_" + "0" * (8 - len(str(int(nflow)))) + str(int(nflow)) + ".jpg"

@@ -143,3 +143,76 @@ def test_gpu_frames_to_embeddings(dev):
     a = model.forward_u8(F.crop_resize(torch.from_numpy(imgs).to(dev)))
     b = model.forward_u8(torch.from_numpy(FO.crop_resize_frames(imgs)).to(dev))
     assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------------ JPEG front-end
+def _smooth_frame(h, w, seed):
+    """video-like content: smooth gradients + blobs + mild noise (pure noise is the worst case of any JPEG codec)"""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    img = np.stack([128 + 100 * np.sin(xx / (20 + 7 * c) + seed) * np.cos(yy / (31 + 5 * c)) for c in range(3)], -1)
+    for _ in range(6):
+        cy, cx, r = rng.uniform(0, h), rng.uniform(0, w), rng.uniform(10, 60)
+        img += rng.uniform(-60, 60, 3) * np.exp(-(((yy - cy) ** 2 + (xx - cx) ** 2) / (2 * r * r)))[..., None]
+    img += rng.normal(0, 2.0, img.shape)
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def _encode(img, **kw):
+    import io
+    from PIL import Image
+    b = io.BytesIO()
+    Image.fromarray(img).save(b, "JPEG", **kw)
+    return b.getvalue()
+
+
+def test_jpeg_header_parse_matches_pillow():
+    """sais_jpeg_info (host-only SOF parse) on baseline / progressive / subsampled / grey-free streams; garbage is refused"""
+    import io
+    from PIL import Image
+    from sais_b200 import SaisError, frames as F
+    for (h, w), kw in [((48, 64), dict(quality=90)), ((1080, 1920), dict(quality=75, subsampling=2)),
+                       ((355, 501), dict(quality=95, subsampling=0)), ((97, 131), dict(quality=80, progressive=True)),
+                       ((224, 224), dict(quality=85, optimize=True))]:
+        data = _encode(_smooth_frame(h, w, h + w), **kw)
+        assert F.jpeg_size(data) == (h, w) == Image.open(io.BytesIO(data)).size[::-1]
+    with pytest.raises(SaisError):
+        F.jpeg_size(b"\x89PNG\r\n\x1a\n" + b"\0" * 32)
+    with pytest.raises(SaisError):
+        F.jpeg_size(b"\xff\xd8\xff\xda\x00\x02" + b"\0" * 16)  # scan without a frame header
+    assert F.flow_frame_name(0) == "flows_00000000.jpg" and F.flow_frame_name(123456) == "flows_00123456.jpg"
+    with pytest.raises(SaisError):
+        F.decode_jpegs([_encode(_smooth_frame(32, 32, 1))], "cpu")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("h,w,kw", [(360, 640, dict(quality=90, subsampling=0)), (360, 640, dict(quality=90, subsampling=2)),
+                                    (1080, 1920, dict(quality=85, subsampling=2)), (481, 853, dict(quality=95, subsampling=1))])
+def test_jpeg_decode_batch_against_pillow(dev, h, w, kw):
+    """Batched nvJPEG decode into the [N,H,W,3] buffer vs Pillow's decode of the same streams (what the reference's
+    ImageFolder loader yields).  Two JPEG decoders are not bit-identical (IDCT rounding, chroma upsampling filter): the
+    bound asserted here is the one stated in include/sais_b200.h — mean |diff| <= 1 level, 99.9 % of the bytes within 4
+    levels — and the measured figures are printed for BASELINE.md.  After crop + resize the frames agree within 3 levels."""
+    import io
+    from PIL import Image
+    from sais_b200 import frames as F
+    n = 5
+    streams = [_encode(_smooth_frame(h, w, 10 * i + h), **kw) for i in range(n)]
+    got = F.decode_jpegs(streams, dev)
+    assert got.shape == (n, h, w, 3) and got.dtype == torch.uint8
+    ref = np.stack([np.asarray(Image.open(io.BytesIO(s)).convert("RGB")) for s in streams])
+    d = np.abs(got.cpu().numpy().astype(np.int16) - ref.astype(np.int16))
+    print(f"[jpeg decode vs Pillow] {h}x{w} {kw}: mean {d.mean():.3f} max {d.max()} p99.9 {np.percentile(d, 99.9):.1f}")
+    assert d.mean() <= 1.0 and np.percentile(d, 99.9) <= 4
+    # a second call with another batch size re-initialises the batched state; a mismatching frame size is refused
+    again = F.decode_jpegs(streams[:2], dev)
+    assert torch.equal(again, got[:2])
+    from sais_b200 import SaisError
+    with pytest.raises(SaisError):
+        F.decode_jpegs([streams[0], _encode(_smooth_frame(h // 2, w, 3))], dev)
+    # the whole front-end: decode -> centre crop 0.8 -> resize 224 (bit-exact given the decoded bytes)
+    out = F.load_frames(streams, dev)
+    assert torch.equal(out, F.crop_resize(got))
+    ref_small = FO.crop_resize_frames(ref)
+    d2 = np.abs(out.cpu().numpy().astype(np.int16) - ref_small.astype(np.int16))
+    assert d2.max() <= 3 and d2.mean() <= 0.6, (d2.max(), d2.mean())
