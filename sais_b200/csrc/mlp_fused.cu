@@ -62,6 +62,7 @@ constexpr int A_BYTES = KB * MT * 128;    // 98,304: six 128-row x 128-byte swiz
 constexpr int STAGE_BYTES = 24576;        // one W1 chunk half (6 x 32 rows x 128 B) or one W2 chunk half (2 x 96 rows x 128 B)
 constexpr int NSTAGE = 4;
 constexpr int H_BYTES = MT * 128;         // 16,384: H_j tile, 128 rows x 64 bf16
+constexpr int kPfFirst = 6;               // hidden chunk at which the producer starts prefetching the unit's residual rows
 constexpr int kTmemCols = 512;
 constexpr int kSCol = DM;                 // S0 at 384, S1 at 448
 constexpr int kTailBytes = 256 /*barriers*/ + DM * 4 /*b2*/;
@@ -92,6 +93,13 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t
                : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1)
                : "memory");
 }
+// bring a box of a tensor into L2 without touching shared memory (the x tile the unit's reduce-adds will hit)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void sts128m(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -103,7 +111,7 @@ __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w1,
                  const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_out,
-                 const MlpParams p) {
+                 const __grid_constant__ CUtensorMap tmap_xpf, const MlpParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_smem = smem;
@@ -141,6 +149,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     tma_prefetch_desc(&tmap_w1);
     tma_prefetch_desc(&tmap_w2);
     tma_prefetch_desc(&tmap_out);
+    tma_prefetch_desc(&tmap_xpf);
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(&w_full[s], 1);
       mbar_init(&w_empty[s], 1);
@@ -222,6 +231,15 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int jj = 0; jj <= NCHUNK; ++jj) {
           if (jj < NCHUNK) load_w1(jj);
           if (jj >= 1) load_w2(jj - 1);
+          // L2 prefetch of this unit's 128 x 384 fp32 residual rows, one 128 x 32 box per hidden chunk in the middle of the
+          // unit.  All CTAs reach their output epilogue at about the same time (equal units, lock step): without this the
+          // reduce-adds of 148 CTAs (28 MB) all miss L2 at once and the epilogue runs at HBM speed (measured 15-20 k cycles
+          // against ~9 k for the bytes it moves through the SM's L2 port); prefetched, the reads are spread over the hidden
+          // loop and the reduce-adds hit.
+          if (jj >= kPfFirst && jj < kPfFirst + DM / 32) {
+            if (elect_one()) tma_prefetch_l2_2d(&tmap_xpf, (jj - kPfFirst) * 32, m0);
+            __syncwarp();
+          }
         }
       }
     }
@@ -316,6 +334,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const int64_t left = p.rows - (r0 + i);
           if (left <= 0) break;
           rowcast_rows<4, true>(p.x, p.xb_out, p.stats_out, r0 + i, 1, left < 4 ? int(left) : 4, lane);
+          // paced: 16 batches of 4 rows spread over most of a unit (~28 us).  Back to back they pull 192 KB + push 96 KB
+          // through the SM's L2 port within a few microseconds, on top of the operand stream — measured as a 15 % slower
+          // hidden loop while the cast ran.
+          __nanosleep(1000);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(cast_done);
@@ -528,6 +550,8 @@ int vit_mlp_fused(const sais_bf16* xn, const sais_bf16* w1, const float* b1, con
   if ((rc = make_tmap_2d(&tw1, w1, kTmapBf16, HID, DM, DM, HC / 2, 64, 128))) return rc;
   if ((rc = make_tmap_2d(&tw2, w2, kTmapBf16, DM, HID, HID, 96, 64, 128))) return rc;
   if ((rc = make_tmap_2d(&tout, x, kTmapF32, uint64_t(rows), DM, DM, 32, 16, 64))) return rc;
+  CUtensorMap txpf;  // L2-prefetch view of x: 128-row x 32-column boxes
+  if ((rc = make_tmap_2d(&txpf, x, kTmapF32, uint64_t(rows), DM, DM, MT, 32, 128))) return rc;
 
   if ((rc = ensure_dynamic_smem(reinterpret_cast<const void*>(mlp_fused_kernel), kSmemBytes, "mlp_fused"))) return rc;
   MlpParams p;
@@ -561,7 +585,7 @@ int vit_mlp_fused(const sais_bf16* xn, const sais_bf16* w1, const float* b1, con
     LaunchScope ls(kClsMlpFused, stream, 4.0 * double(rows) * DM * HID);
     // (cluster = 1 here: the kernel carries its own __cluster_dims__(2, 1, 1))
     rc = check_cuda(launch_pdl(mlp_fused_kernel, dim3(2 * pairs), dim3(kThreads), size_t(kSmemBytes), stream, 1, ta, tw1, tw2,
-                               tout, p),
+                               tout, txpf, p),
                     "mlp_fused_kernel launch");
   }
   if (p.dbg) {
