@@ -212,6 +212,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the C1 / C3 / C4 / C5 legs")
     ap.add_argument("--chunk", type=int, default=256, help="ViT frames per workspace chunk")
+    ap.add_argument("--head-stream", type=int, default=0,
+                    help="1: run the temporal head + scoring of step i on a second (high-priority) stream, overlapped with "
+                         "the ViT of step i+1 (software pipelining across steps; every step's work stays inside the timed region)")
     args = ap.parse_args()
     if args.impl == "reference":
         args.warmup = max(args.warmup, 1)
@@ -262,25 +265,59 @@ def main():
         pred, probs = scoring.predict(out, protos)
         return out, probs, pred
 
+    side = torch.cuda.Stream(device=dev, priority=-1) if args.head_stream else None
+    head_done = [None, None]
+
+    def run_head(i, own):
+        """head + scoring of step i; with --head-stream on the side stream, ordered after the ViT of step i and before the
+        ViT of step i + 2 overwrites the same gather slot"""
+        if side is None:
+            return head_and_score(own)
+        main = torch.cuda.current_stream(dev)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        side.wait_event(ev)
+        with torch.cuda.stream(side):
+            res = head_and_score(own)
+            done = torch.cuda.Event()
+            done.record(side)
+        head_done[i % 2] = done
+        return res
+
+    def claim_slot(i):
+        own = gatherer.own_slice(i)
+        if side is not None and head_done[i % 2] is not None:
+            torch.cuda.current_stream(dev).wait_event(head_done[i % 2])  # the head that read this slot two steps ago
+        return own
+
     def step_resident(i):
-        own = gatherer.own_slice(i)               # the final-LN kernel writes at rank * count of the gather buffer
+        own = claim_slot(i)                       # the final-LN kernel writes at rank * count of the gather buffer
         vit.forward_u8(dev_batches[i % nbuf], out=own)
         gatherer.gather_async(i)                  # in place, on NCCL's stream; the head below reads own rows only
-        return own, head_and_score(own)
+        return own, run_head(i, own)
 
     emb_host = torch.empty((FRAMES_PER_STEP, 384), dtype=torch.float32).pin_memory()
     probs_host = torch.empty((CLIPS_PER_STEP, 2), dtype=torch.float32).pin_memory()
 
     def step_e2e(i):
-        own = gatherer.own_slice(i)
+        own = claim_slot(i)
         pipeline.extract_features(vit, host_batches[i % nbuf], batch_size=FRAMES_PER_STEP, device=dev, out=own)
         gatherer.gather_async(i)
-        out, probs, pred = head_and_score(own)
         emb_host.copy_(own, non_blocking=True)
-        probs_host.copy_(probs, non_blocking=True)
+        out, probs, pred = run_head(i, own)
+        if side is None:
+            probs_host.copy_(probs, non_blocking=True)
+        else:
+            with torch.cuda.stream(side):
+                probs_host.copy_(probs, non_blocking=True)
         return own, (out, probs, pred)
 
+    def join_side():
+        if side is not None:
+            torch.cuda.current_stream(dev).wait_stream(side)
+
     def barrier():
+        join_side()
         gatherer.wait_all()
         if world > 1:
             dist.barrier()
@@ -318,7 +355,8 @@ def main():
         e0.record()
         for i in range(steps):
             fn(warmup + i)
-        gatherer.wait_all()  # every gather of the timed steps completes inside the timed region
+        join_side()          # every head of the timed steps ...
+        gatherer.wait_all()  # ... and every gather completes inside the timed region
         e1.record()
         barrier()
         clocks = sampler.stop() if sampler else None
@@ -390,7 +428,8 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(world),
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": dict(workload_config(world), head_stream=bool(args.head_stream)),
             "flop_per_frame": {"reference_forward": FLOP_PER_FRAME, "executed": FLOP_PER_FRAME_EXECUTED,
                                "note": "last block evaluated on the CLS rows only (dead rows of the reference "
                                        "forward are not computed); fractions below use the EXECUTED flops"},

@@ -13,7 +13,8 @@ from pathlib import Path
 
 _PKG_DIR = Path(__file__).resolve().parent
 _CSRC = _PKG_DIR / "csrc"
-LIB_PATH = _PKG_DIR / "libsais_b200.so"
+# (dev: SAIS_B200_LIB points at an alternative build of the same C ABI, e.g. for A/B timing of a kernel rewrite)
+LIB_PATH = Path(os.environ["SAIS_B200_LIB"]).resolve() if os.environ.get("SAIS_B200_LIB") else _PKG_DIR / "libsais_b200.so"
 
 VIT_DEPTH = 12
 TMP_LAYERS = 4
