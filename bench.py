@@ -326,8 +326,8 @@ def main():
     # ---- parity gate of the e2e path: host-frame step == resident step on the same frames, bit for bit
     for i in range(2):
         own_r, (out_r, probs_r, _) = step_resident(i)
+        barrier()  # (the head may run on the side stream: join before reading its results)
         keep = (own_r.clone(), out_r.clone(), probs_r.clone())
-        barrier()
         own_e, (out_e, probs_e, _) = step_e2e(i)
         barrier()
         if not (torch.equal(own_e, keep[0]) and torch.equal(emb_host, keep[0].cpu())):

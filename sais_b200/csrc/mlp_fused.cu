@@ -6,18 +6,12 @@
 // writes and re-reads the [rows,1536] hidden matrix through HBM (6,144 B/row) and pulls 128x256-tile operands
 // through L2 at ~2x the ~45 B/clk/SM the L2 can deliver.  Here a CTA PAIR (2-CTA cluster, tcgen05 cta_group::2) owns
 // 256 rows: the LayerNorm'd rows A[256,384] stay resident in shared memory, the hidden dimension is walked in
-// chunks of 128, and per chunk j
-//     G1(j):  S_j[256,128]  = A · W1[j]ᵀ                 (24 MMAs 256x128x16, accumulator S in TMEM)
-//     E1(j):  H_j           = bf16(GELU(S_j + b1[j]))     (epilogue warps, TMEM -> registers -> two swizzled smem k-blocks)
-//     G2(j):  acc[256,384] += H_j · W2[:, j]ᵀ             (16 MMAs 256x192x16, accumulator acc in TMEM)
-// issued as G1(j), G2(j-1), G1(j+1), ...: S is single-buffered (acc 384 + S 128 = all 512 TMEM columns) and that is enough,
-// because the epilogue warps move S to registers within a few hundred cycles of s_full and release it while the pipe is
-// busy with G2(j-1) for ~1.5 k cycles; E1(j)'s GELU + stores then have G2(j-1) + G1(j+1) (~3 k cycles) to finish.
-// Why 128 and not 64 (round 1): an N = 64 MMA is bound by the 128 B/clk shared-memory port (4 KB of A + 1 KB of W per 32
-// tensor cycles: 45 cycles measured) — at N = 128 the same A bytes feed twice the columns (6 KB per 64 cycles), which
-// takes the hidden loop from 123 to ~98 B/clk of shared-memory traffic and G1 from 45 to 32 cycles per 64 columns.
-// Only the weights stream (each CTA loads half of every W1/W2 chunk; the pair exchanges operand halves in hardware),
-// 96 KB per chunk per CTA through a ring of three 24 KB stages.  The finished
+// chunks of 64, and per chunk j
+//     G1(j):  S_j[256,64]   = A · W1[j]ᵀ                 (24 MMAs 256x64x16,  accumulator S in TMEM, double buffered)
+//     E1(j):  H_j           = bf16(GELU(S_j + b1[j]))     (epilogue warps, TMEM -> registers -> swizzled smem tile)
+//     G2(j):  acc[256,384] += H_j · W2[:, j]ᵀ             (8 MMAs 256x192x16, accumulator acc in TMEM)
+// with the tensor pipe running G1(j+1) while the epilogue warps do E1(j).  Only the weights stream (each CTA loads
+// half of every W1/W2 chunk; the pair exchanges operand halves in hardware), 48 KB per chunk per CTA.  The finished
 // accumulator (+ b2) is added to the fp32 residual stream IN L2 by a TMA reduce-add store, so the residual is never
 // loaded into the SM at all.
 //
@@ -30,7 +24,7 @@
 //   warp 11     : TMEM allocator + MMA issuer (leader CTA of the pair only)
 // Both role warps walk their loops with all 32 lanes (warp-uniform control flow) and elect one lane only around the TMA /
 // tcgen05 instructions: issued from a divergent single lane every MMA cost ~200 cycles of issue overhead (161 -> 115 us).
-// TMEM columns: acc [0,384) | S [384,512).  H: three 16 KB k-block buffers (128 rows x 64 hidden), rotated.
+// TMEM columns: acc [0,384) | S0 [384,448) | S1 [448,512).
 // Work units: 256-row tiles, dealt round-robin to the 74 CTA pairs.  Every output element receives exactly one reduce-add,
 // so the result is deterministic (an earlier version split the tiles of the last partial round along the hidden
 // dimension: +1.4 % throughput, but partial sums then met in L2 in arbitrary order — run-to-run bit differences; removed).
@@ -58,23 +52,21 @@ namespace {
 constexpr int MT = 128;             // rows per CTA (256 per pair)
 constexpr int DM = 384;             // model dim (K of fc1, N of fc2)
 constexpr int HID = 1536;           // hidden dim
-constexpr int HC = 128;             // hidden chunk (N of G1; two K = 64 k-blocks of G2)
-constexpr int NCHUNK = HID / HC;    // 12
+constexpr int HC = 64;              // hidden chunk (N of G1, K of G2)
+constexpr int NCHUNK = HID / HC;    // 24
 constexpr int KB = DM / 64;         // 6 k-blocks of A
 constexpr int kEpiWarps = 8;
 constexpr int kCastWarps = 2;
 constexpr int kThreads = 32 * (kEpiWarps + kCastWarps + 2);
 constexpr int A_BYTES = KB * MT * 128;    // 98,304: six 128-row x 128-byte swizzled k-blocks
-constexpr int STAGE_BYTES = 24576;        // three k-blocks of a W1 chunk half (3 x 64 rows x 128 B) or one k-block of a W2
-                                          // chunk half (2 x 96 rows x 128 B)
-constexpr int NSTAGE = 3;
-constexpr int H_BYTES = MT * 128;         // 16,384: one H k-block, 128 rows x 64 bf16
-constexpr int NHBUF = 3;
-constexpr int kPfFirst = 2;               // hidden chunk at which the producer starts prefetching the unit's residual rows
+constexpr int STAGE_BYTES = 24576;        // one W1 chunk half (6 x 32 rows x 128 B) or one W2 chunk half (2 x 96 rows x 128 B)
+constexpr int NSTAGE = 4;
+constexpr int H_BYTES = MT * 128;         // 16,384: H_j tile, 128 rows x 64 bf16
+constexpr int kPfFirst = 6;               // hidden chunk at which the producer starts prefetching the unit's residual rows
 constexpr int kTmemCols = 512;
-constexpr int kSCol = DM;                 // S at columns [384, 512)
+constexpr int kSCol = DM;                 // S0 at 384, S1 at 448
 constexpr int kTailBytes = 256 /*barriers*/ + DM * 4 /*b2*/;
-constexpr int kSmemBytes = 1024 + A_BYTES + NSTAGE * STAGE_BYTES + NHBUF * H_BYTES + kTailBytes;
+constexpr int kSmemBytes = 1024 + A_BYTES + NSTAGE * STAGE_BYTES + 2 * H_BYTES + kTailBytes;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
 struct MlpParams {
@@ -88,6 +80,7 @@ struct MlpParams {
   int64_t rows;
   int reverse;      // walk the row tiles from the last to the first (kernels.h g_tile_reverse)
   int num_tiles;    // 256-row tiles = work units
+  int stagger_ns;   // (experiment) odd CTA pairs start this many nanoseconds late
   // cast warps: bf16 copy + row statistics of the UPDATED stream (both or neither; may alias xn / ln_stats)
   const float* x;
   __nv_bfloat16* xb_out;
@@ -125,15 +118,15 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint8_t* a_smem = smem;
   uint8_t* w_smem = smem + A_BYTES;
   uint8_t* h_smem = w_smem + NSTAGE * STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(h_smem + NHBUF * H_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(h_smem + 2 * H_BYTES);
   uint64_t* w_full = bars;            // [NSTAGE] (leader's copy is the one that counts)
-  uint64_t* w_empty = bars + 4;       // [NSTAGE]
+  uint64_t* w_empty = bars + NSTAGE;  // [NSTAGE]
   uint64_t* a_full = bars + 8;
   uint64_t* a_empty = bars + 9;
-  uint64_t* s_full = bars + 10;
-  uint64_t* s_empty = bars + 11;  // leader's, 16 arrivals (every epilogue warp of both CTAs)
-  uint64_t* h_full = bars + 12;   // [NHBUF] leader's, 8 arrivals (the four warps of one column half, both CTAs)
-  uint64_t* h_empty = bars + 15;  // [NHBUF]
+  uint64_t* s_full = bars + 10;   // [2]
+  uint64_t* s_empty = bars + 12;  // [2] leader's, 16 arrivals
+  uint64_t* h_full = bars + 14;   // [2] leader's, 16 arrivals
+  uint64_t* h_empty = bars + 16;  // [2]
   uint64_t* acc_full = bars + 18;
   uint64_t* acc_empty = bars + 19;  // leader's, 16 arrivals
   uint64_t* cast_full = bars + 20;  // this CTA's, kEpiWarps arrivals: the unit's reduce-adds have completed
@@ -164,10 +157,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
-    mbar_init(s_full, 1);
-    mbar_init(s_empty, 2 * kEpiWarps);
-    for (int s = 0; s < NHBUF; ++s) {
-      mbar_init(&h_full[s], kEpiWarps);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], 2 * kEpiWarps);
+      mbar_init(&h_full[s], 2 * kEpiWarps);
       mbar_init(&h_empty[s], 1);
     }
     mbar_init(acc_full, 1);
@@ -184,6 +177,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   pdl_trigger();
   pdl_wait();
   for (int i = threadIdx.x; i < DM; i += kThreads) b2_smem[i] = __ldg(p.b2 + i);
+  if (p.stagger_ns > 0 && (pair & 1)) {  // (experiment: does de-synchronising the pairs' drain / compute phases pay?)
+    for (int left = p.stagger_ns; left > 0; left -= 1000) __nanosleep(left < 1000 ? left : 1000);
+  }
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
@@ -196,41 +192,35 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t wphase = 0;
       uint32_t ui = 0;
       int pg = 0, pg2 = 0;  // chunk counters (timeline only)
-      auto load_w1 = [&](int j) {  // W1 rows of hidden chunk j (this CTA's 64 of 128): two stages of three k-blocks
-#pragma unroll 1
-        for (int st = 0; st < 2; ++st) {
-          mbar_wait(&w_empty[stage], wphase ^ 1);
-          if (lane == 0 && st == 0) stamp(3, pg, 0);
-          const uint32_t lbar = leader_smem_u32(&w_full[stage]);
-          uint8_t* dst = w_smem + stage * STAGE_BYTES;
-          if (elect_one()) {
-            if (crank == 0) mbar_arrive_expect_tx(&w_full[stage], 2 * STAGE_BYTES);
+      auto load_w1 = [&](int j) {
+        mbar_wait(&w_empty[stage], wphase ^ 1);
+        if (lane == 0) stamp(3, pg, 0);
+        const uint32_t lbar = leader_smem_u32(&w_full[stage]);
+        uint8_t* dst = w_smem + stage * STAGE_BYTES;
+        if (elect_one()) {
+          if (crank == 0) mbar_arrive_expect_tx(&w_full[stage], 2 * STAGE_BYTES);
 #pragma unroll
-            for (int k3 = 0; k3 < 3; ++k3)
-              tma_load_2d_cg2(dst + k3 * 8192, &tmap_w1, lbar, (st * 3 + k3) * 64, j * HC + int(crank) * (HC / 2));
-          }
-          __syncwarp();
-          if (++stage == NSTAGE) { stage = 0; wphase ^= 1; }
+          for (int kb = 0; kb < KB; ++kb)
+            tma_load_2d_cg2(dst + kb * 4096, &tmap_w1, lbar, kb * 64, j * HC + int(crank) * (HC / 2));
         }
+        __syncwarp();
         ++pg;
+        if (++stage == NSTAGE) { stage = 0; wphase ^= 1; }
       };
-      auto load_w2 = [&](int j) {  // W2 columns of hidden chunk j: one stage per K = 64 k-block (both output halves)
-#pragma unroll 1
-        for (int sub = 0; sub < 2; ++sub) {
-          mbar_wait(&w_empty[stage], wphase ^ 1);
-          if (lane == 0 && sub == 0) stamp(3, pg2, 1);
-          const uint32_t lbar = leader_smem_u32(&w_full[stage]);
-          uint8_t* dst = w_smem + stage * STAGE_BYTES;
-          if (elect_one()) {
-            if (crank == 0) mbar_arrive_expect_tx(&w_full[stage], 2 * STAGE_BYTES);
+      auto load_w2 = [&](int j) {
+        mbar_wait(&w_empty[stage], wphase ^ 1);
+        if (lane == 0) stamp(3, pg2, 1);
+        const uint32_t lbar = leader_smem_u32(&w_full[stage]);
+        uint8_t* dst = w_smem + stage * STAGE_BYTES;
+        if (elect_one()) {
+          if (crank == 0) mbar_arrive_expect_tx(&w_full[stage], 2 * STAGE_BYTES);
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
-              tma_load_2d_cg2(dst + h * 12288, &tmap_w2, lbar, (2 * j + sub) * 64, h * 192 + int(crank) * 96);
-          }
-          __syncwarp();
-          if (++stage == NSTAGE) { stage = 0; wphase ^= 1; }
+          for (int h = 0; h < 2; ++h)
+            tma_load_2d_cg2(dst + h * 12288, &tmap_w2, lbar, j * HC, h * 192 + int(crank) * 96);
         }
+        __syncwarp();
         ++pg2;
+        if (++stage == NSTAGE) { stage = 0; wphase ^= 1; }
       };
       for (int u = pair; u < p.num_tiles; u += npairs, ++ui) {
         const int m0 = unit_tile(p, u) * (2 * MT) + int(crank) * MT;
@@ -245,16 +235,13 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int jj = 0; jj <= NCHUNK; ++jj) {
           if (jj < NCHUNK) load_w1(jj);
           if (jj >= 1) load_w2(jj - 1);
-          // L2 prefetch of this unit's 128 x 384 fp32 residual rows, two 128 x 32 boxes per hidden chunk in the middle of the
+          // L2 prefetch of this unit's 128 x 384 fp32 residual rows, one 128 x 32 box per hidden chunk in the middle of the
           // unit.  All CTAs reach their output epilogue at about the same time (equal units, lock step): without this the
           // reduce-adds of 148 CTAs (28 MB) all miss L2 at once and the epilogue runs at HBM speed (measured 15-20 k cycles
           // against ~9 k for the bytes it moves through the SM's L2 port); prefetched, the reads are spread over the hidden
           // loop and the reduce-adds hit.
-          if (jj >= kPfFirst && jj < kPfFirst + DM / 64) {
-            if (elect_one()) {
-              tma_prefetch_l2_2d(&tmap_xpf, (jj - kPfFirst) * 64, m0);
-              tma_prefetch_l2_2d(&tmap_xpf, (jj - kPfFirst) * 64 + 32, m0);
-            }
+          if (jj >= kPfFirst && jj < kPfFirst + DM / 32) {
+            if (elect_one()) tma_prefetch_l2_2d(&tmap_xpf, (jj - kPfFirst) * 32, m0);
             __syncwarp();
           }
         }
@@ -270,7 +257,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       constexpr uint32_t idesc2 = umma_idesc_bf16(2 * MT, 192);
       int stage = 0;
       uint32_t wphase = 0;
-      uint32_t g = 0;  // hidden chunks issued so far by this pair (barrier phases; H k-block index = 2 g + sub)
+      uint32_t g = 0;  // chunks issued so far by this pair (selects S / H buffers and their barrier phases)
       uint32_t ui = 0;
       const uint32_t a_s = smem_u32(a_smem);
       const uint32_t h_s = smem_u32(h_smem);
@@ -279,66 +266,58 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         tc_fence_after();
         if (lane == 0) stamp(2, ui, 0);
         for (int jj = 0; jj <= NCHUNK; ++jj) {
-          if (jj < NCHUNK) {  // ---- G1: S = A · W1[j]ᵀ   (N = 128, two ring stages of three k-blocks)
-            const uint32_t gg = g + jj;
-            mbar_wait(s_empty, (gg & 1) ^ 1);  // E1(gg - 1) has moved S to registers
+          if (jj < NCHUNK) {  // ---- G1: S[b] = A · W1[j]ᵀ
+            const uint32_t gg = g + jj, b = gg & 1;
+            mbar_wait(&s_empty[b], ((gg >> 1) & 1) ^ 1);
             if (lane == 0) stamp(0, gg, 0);
-            const uint32_t d = tmem_base + kSCol;
-#pragma unroll 1
-            for (int st = 0; st < 2; ++st) {
-              mbar_wait(&w_full[stage], wphase);
-              tc_fence_after();
-              if (lane == 0 && st == 0) stamp(0, gg, 1);
-              const uint32_t w_s = smem_u32(w_smem + stage * STAGE_BYTES);
-              if (elect_one()) {
+            mbar_wait(&w_full[stage], wphase);
+            tc_fence_after();
+            if (lane == 0) stamp(0, gg, 1);
+            const uint32_t w_s = smem_u32(w_smem + stage * STAGE_BYTES);
+            const uint32_t d = tmem_base + kSCol + b * HC;
+            if (elect_one()) {
 #pragma unroll
-                for (int k3 = 0; k3 < 3; ++k3) {
-                  const uint64_t da = umma_desc_sw128_kmajor(a_s + (st * 3 + k3) * (MT * 128));
-                  const uint64_t db = umma_desc_sw128_kmajor(w_s + k3 * 8192);
+              for (int kb = 0; kb < KB; ++kb) {
+                const uint64_t da = umma_desc_sw128_kmajor(a_s + kb * (MT * 128));
+                const uint64_t db = umma_desc_sw128_kmajor(w_s + kb * 4096);
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) umma_f16_cg2(d, da + 2 * k, db + 2 * k, idesc1, (st | k3 | k) != 0);
-                }
-                umma_commit_cg2_mcast(&w_empty[stage], uint16_t(0b11));
-                if (st == 1) {
-                  if (jj == NCHUNK - 1) umma_commit_cg2_mcast(a_empty, uint16_t(0b11));
-                  umma_commit_cg2_mcast(s_full, uint16_t(0b11));
-                }
+                for (int k = 0; k < 4; ++k) umma_f16_cg2(d, da + 2 * k, db + 2 * k, idesc1, (kb | k) != 0);
               }
-              __syncwarp();
-              if (++stage == NSTAGE) { stage = 0; wphase ^= 1; }
+              umma_commit_cg2_mcast(&w_empty[stage], uint16_t(0b11));
+              if (jj == NCHUNK - 1) umma_commit_cg2_mcast(a_empty, uint16_t(0b11));
+              umma_commit_cg2_mcast(&s_full[b], uint16_t(0b11));
             }
+            __syncwarp();
+            if (++stage == NSTAGE) { stage = 0; wphase ^= 1; }
           }
-          if (jj >= 1) {  // ---- G2: acc += H · W2[:, j - 1]ᵀ   (two K = 64 k-blocks, one ring stage each)
-#pragma unroll 1
-            for (int sub = 0; sub < 2; ++sub) {
-              const uint32_t kg = 2 * (g + jj - 1) + sub, hb = kg % NHBUF, hn = kg / NHBUF;
-              if (jj == 1 && sub == 0) {
-                mbar_wait(acc_empty, (ui & 1) ^ 1);  // the previous unit's output epilogue has drained acc
-                if (lane == 0) stamp(2, ui, 1);
-              }
-              mbar_wait(&h_full[hb], hn & 1);
-              if (lane == 0 && sub == 0) stamp(0, g + jj - 1, 2);
-              mbar_wait(&w_full[stage], wphase);
-              tc_fence_after();
-              if (lane == 0 && sub == 0) stamp(0, g + jj - 1, 3);
-              const uint32_t w_s = smem_u32(w_smem + stage * STAGE_BYTES);
-              const uint64_t da = umma_desc_sw128_kmajor(h_s + hb * H_BYTES);
-              if (elect_one()) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-#pragma unroll
-                  for (int h = 0; h < 2; ++h) {
-                    const uint64_t db = umma_desc_sw128_kmajor(w_s + h * 12288);
-                    umma_f16_cg2(tmem_base + h * 192, da + 2 * k, db + 2 * k, idesc2, (jj > 1) || (sub > 0) || (k > 0));
-                  }
-                }
-                umma_commit_cg2_mcast(&w_empty[stage], uint16_t(0b11));
-                umma_commit_cg2_mcast(&h_empty[hb], uint16_t(0b11));
-                if (jj == NCHUNK && sub == 1) umma_commit_cg2_mcast(acc_full, uint16_t(0b11));
-              }
-              __syncwarp();
-              if (++stage == NSTAGE) { stage = 0; wphase ^= 1; }
+          if (jj >= 1) {  // ---- G2: acc += H[b] · W2[:, j]ᵀ
+            const uint32_t gg = g + jj - 1, b = gg & 1;
+            if (jj == 1) {
+              mbar_wait(acc_empty, (ui & 1) ^ 1);  // the previous unit's output epilogue has drained acc
+              if (lane == 0) stamp(2, ui, 1);
             }
+            mbar_wait(&h_full[b], (gg >> 1) & 1);
+            if (lane == 0) stamp(0, gg, 2);
+            mbar_wait(&w_full[stage], wphase);
+            tc_fence_after();
+            if (lane == 0) stamp(0, gg, 3);
+            const uint32_t w_s = smem_u32(w_smem + stage * STAGE_BYTES);
+            const uint64_t da = umma_desc_sw128_kmajor(h_s + b * H_BYTES);
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const uint64_t db = umma_desc_sw128_kmajor(w_s + h * 12288);
+                  umma_f16_cg2(tmem_base + h * 192, da + 2 * k, db + 2 * k, idesc2, (jj > 1) || (k > 0));
+                }
+              }
+              umma_commit_cg2_mcast(&w_empty[stage], uint16_t(0b11));
+              umma_commit_cg2_mcast(&h_empty[b], uint16_t(0b11));
+              if (jj == NCHUNK) umma_commit_cg2_mcast(acc_full, uint16_t(0b11));
+            }
+            __syncwarp();
+            if (++stage == NSTAGE) { stage = 0; wphase ^= 1; }
           }
         }
         g += NCHUNK;
@@ -372,12 +351,12 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ===================== epilogue warps 0..7 =====================
     const int ew = warp;
     const int q = ew & 3;      // TMEM lane quarter
-    const int half = ew >> 2;  // column half (E1: 64 of the chunk's 128 = one H k-block; output: 192 of 384)
+    const int half = ew >> 2;  // column half (E1: 32 of 64; output: 192 of 384)
     const int row = q * 32 + lane;
     const uint32_t t_lane = tmem_base + (uint32_t(q * 32) << 16);
     const uint32_t h_row = smem_u32(h_smem) + row * 128;
     const int sw = row & 7;
-    const uint32_t my_stage = smem_u32(h_smem) + ew * 4096;  // output staging: 2 x (32 rows x 64 B), aliasing H
+    const uint32_t my_stage = smem_u32(h_smem) + ew * 4096;  // output staging: 32 rows x 128 B (swizzled), aliasing H
     uint32_t g = 0, ui = 0;
     bool cast_pending = false;  // the previous unit's reduce-adds have not been confirmed complete yet
     for (int u = pair; u < p.num_tiles; u += npairs, ++ui) {
@@ -398,10 +377,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const uint64_t rs2 = pack2(rs_h, rs_h), nm2 = pack2(nm_h, nm_h);
       const float* cs_base = p.ln_colsum != nullptr ? p.ln_colsum : p.b1;
       for (int jj = 0; jj < NCHUNK; ++jj) {
-        const uint32_t gg = g + jj;
-        const uint32_t kg = 2 * gg + half, hbuf = kg % NHBUF, hn = kg / NHBUF;  // this warp's H k-block, its buffer / use count
-        if (jj == 1 && cast_pending) {
-          // hand the PREVIOUS unit's rows to the cast warps: by now (one hidden chunk later) this warp's reduce-adds have
+        const uint32_t gg = g + jj, b = gg & 1;
+        const int j = jj;
+        if (jj == 2 && cast_pending) {
+          // hand the PREVIOUS unit's rows to the cast warps: by now (two hidden chunks later) this warp's reduce-adds have
           // long completed, so the wait does not stall E1
           if (lane == 0) {
             tma_store_wait<0>();
@@ -412,25 +391,25 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           __syncwarp();
           cast_pending = false;
         }
-        const float* bcol = p.b1 + jj * HC + half * 64;
-        const float* ccol = cs_base + jj * HC + half * 64;
         float4 bias[8], cs[8];
+        {
+          const float4* bp = reinterpret_cast<const float4*>(p.b1 + j * HC + half * 32);
+          const float4* cp = reinterpret_cast<const float4*>(cs_base + j * HC + half * 32);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          bias[i] = __ldg(reinterpret_cast<const float4*>(bcol) + i);
-          cs[i] = __ldg(reinterpret_cast<const float4*>(ccol) + i);
+          for (int i = 0; i < 8; ++i) {
+            bias[i] = __ldg(bp + i);
+            cs[i] = __ldg(cp + i);
+          }
         }
-        mbar_wait(s_full, gg & 1);
+        mbar_wait(&s_full[b], (gg >> 1) & 1);
         tc_fence_after();
         if (ew == 0 && lane == 0) stamp(1, gg, 0);
-        uint32_t v[32], w[32];
-        tmem_ld_32x32(t_lane + kSCol + half * 64, v);
-        tmem_ld_32x32(t_lane + kSCol + half * 64 + 32, w);
+        uint32_t v[32];
+        tmem_ld_32x32(t_lane + kSCol + b * HC + half * 32, v);
         tmem_ld_wait_dep(v);
-        tmem_ld_wait_dep(w);
         tc_fence_before();
-        if (lane == 0) mbar_arrive_cluster(leader_smem_u32(s_empty));  // S is in registers: G1(gg + 1) may overwrite it
-        uint32_t pk[32];
+        if (lane == 0) mbar_arrive_cluster(leader_smem_u32(&s_empty[b]));  // S[b] may be overwritten by G1(gg + 2)
+        uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           float f0, f1, f2, f3;
@@ -443,32 +422,15 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           pk[2 * i] = pack_bf16x2(f0, f1);
           pk[2 * i + 1] = pack_bf16x2(f2, f3);
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {  // second 32 columns: their vectors are fetched now (L1 hits), the registers are reused
-          bias[i] = __ldg(reinterpret_cast<const float4*>(bcol + 32) + i);
-          cs[i] = __ldg(reinterpret_cast<const float4*>(ccol + 32) + i);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float f0, f1, f2, f3;
-          unpack2(fma2(pack2u(w[4 * i], w[4 * i + 1]), rs2,
-                       fma2(nm2, pack2(cs[i].x, cs[i].y), pack2(0.5f * bias[i].x, 0.5f * bias[i].y))), f0, f1);
-          unpack2(fma2(pack2u(w[4 * i + 2], w[4 * i + 3]), rs2,
-                       fma2(nm2, pack2(cs[i].z, cs[i].w), pack2(0.5f * bias[i].z, 0.5f * bias[i].w))), f2, f3);
-          gelu_erf_fast2_half(f0, f1);
-          gelu_erf_fast2_half(f2, f3);
-          pk[16 + 2 * i] = pack_bf16x2(f0, f1);
-          pk[16 + 2 * i + 1] = pack_bf16x2(f2, f3);
-        }
-        mbar_wait(&h_empty[hbuf], (hn & 1) ^ 1);  // the G2 that read this buffer three k-blocks ago has retired
+        mbar_wait(&h_empty[b], ((gg >> 1) & 1) ^ 1);  // G2(gg - 2) has finished reading H[b]
         if (ew == 0 && lane == 0) stamp(1, gg, 1);
-        const uint32_t hb = h_row + hbuf * H_BYTES;
+        const uint32_t hb = h_row + b * H_BYTES;
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          sts128m(hb + ((i ^ sw) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        for (int i = 0; i < 4; ++i)
+          sts128m(hb + (((half * 4 + i) ^ sw) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(leader_smem_u32(&h_full[hbuf]));
+        if (lane == 0) mbar_arrive_cluster(leader_smem_u32(&h_full[b]));
         if (ew == 0 && lane == 0) stamp(1, gg, 2);
       }
       g += NCHUNK;
@@ -511,22 +473,18 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             f[4 * i] += b4.x; f[4 * i + 1] += b4.y; f[4 * i + 2] += b4.z; f[4 * i + 3] += b4.w;
           }
         }
-        if (lane == 0) tma_store_wait_read<0>();  // the previous iteration's stores have read both staging tiles
+        if (lane == 0) tma_store_wait_read<0>();  // the previous iteration's store has read the staging tile
         __syncwarp();
+        // one 32-row x 128-byte box (128-byte swizzle) per 32 columns: half as many TMA requests as two 64-byte-wide boxes
+        // — the drain was paced by the TMA unit's request rate (192 KB in ~16 k cycles = 12 B/clk), not by the L2 port
 #pragma unroll
-        for (int s2 = 0; s2 < 2; ++s2) {
-          const uint32_t buf = my_stage + s2 * 2048;
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            sts128m(buf + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4), __float_as_uint(f[16 * s2 + 4 * i]),
-                    __float_as_uint(f[16 * s2 + 4 * i + 1]), __float_as_uint(f[16 * s2 + 4 * i + 2]),
-                    __float_as_uint(f[16 * s2 + 4 * i + 3]));
-        }
+        for (int i = 0; i < 8; ++i)
+          sts128m(my_stage + lane * 128 + ((i ^ (lane & 7)) << 4), __float_as_uint(f[4 * i]), __float_as_uint(f[4 * i + 1]),
+                  __float_as_uint(f[4 * i + 2]), __float_as_uint(f[4 * i + 3]));
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
           tma_reduce_add_2d(&tmap_out, my_stage, col, m0 + q * 32);
-          tma_reduce_add_2d(&tmap_out, my_stage + 2048, col + 16, m0 + q * 32);
           tma_store_commit();
         }
       }
@@ -591,7 +549,7 @@ int vit_mlp_fused(const sais_bf16* xn, const sais_bf16* w1, const float* b1, con
   if (rc) return rc;
   if ((rc = make_tmap_2d(&tw1, w1, kTmapBf16, HID, DM, DM, HC / 2, 64, 128))) return rc;
   if ((rc = make_tmap_2d(&tw2, w2, kTmapBf16, DM, HID, HID, 96, 64, 128))) return rc;
-  if ((rc = make_tmap_2d(&tout, x, kTmapF32, uint64_t(rows), DM, DM, 32, 16, 64))) return rc;
+  if ((rc = make_tmap_2d(&tout, x, kTmapF32, uint64_t(rows), DM, DM, 32, 32, 128))) return rc;
   CUtensorMap txpf;  // L2-prefetch view of x: 128-row x 32-column boxes
   if ((rc = make_tmap_2d(&txpf, x, kTmapF32, uint64_t(rows), DM, DM, MT, 32, 128))) return rc;
 
@@ -610,6 +568,8 @@ int vit_mlp_fused(const sais_bf16* xn, const sais_bf16* w1, const float* b1, con
   p.rows = rows;
   p.reverse = g_tile_reverse;
   p.num_tiles = int((rows + 2 * MT - 1) / (2 * MT));
+  static const int env_stagger = getenv("SAIS_MLP_STAGGER_NS") ? atoi(getenv("SAIS_MLP_STAGGER_NS")) : 0;
+  p.stagger_ns = env_stagger;
   p.x = x;
   p.xb_out = reinterpret_cast<__nv_bfloat16*>(xb_out);
   p.stats_out = stats_out;
