@@ -212,6 +212,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the C1 / C3 / C4 / C5 legs")
     ap.add_argument("--chunk", type=int, default=256, help="ViT frames per workspace chunk")
+    ap.add_argument("--vit-sms", type=int, default=0,
+                    help="with --head-stream 1: SMs the ViT kernels may occupy (even; 0 = all); the rest are left to the head")
     ap.add_argument("--head-stream", type=int, default=0,
                     help="1: run the temporal head + scoring of step i on a second (high-priority) stream, overlapped with "
                          "the ViT of step i+1 (software pipelining across steps; every step's work stays inside the timed region)")
@@ -290,9 +292,12 @@ def main():
             torch.cuda.current_stream(dev).wait_event(head_done[i % 2])  # the head that read this slot two steps ago
         return own
 
+    vit_limit = _lib.sm_limit(args.vit_sms if (args.head_stream and args.vit_sms) else 0)
+
     def step_resident(i):
         own = claim_slot(i)                       # the final-LN kernel writes at rank * count of the gather buffer
-        vit.forward_u8(dev_batches[i % nbuf], out=own)
+        with vit_limit:
+            vit.forward_u8(dev_batches[i % nbuf], out=own)
         gatherer.gather_async(i)                  # in place, on NCCL's stream; the head below reads own rows only
         return own, run_head(i, own)
 
@@ -301,7 +306,8 @@ def main():
 
     def step_e2e(i):
         own = claim_slot(i)
-        pipeline.extract_features(vit, host_batches[i % nbuf], batch_size=FRAMES_PER_STEP, device=dev, out=own)
+        with vit_limit:
+            pipeline.extract_features(vit, host_batches[i % nbuf], batch_size=FRAMES_PER_STEP, device=dev, out=own)
         gatherer.gather_async(i)
         emb_host.copy_(own, non_blocking=True)
         out, probs, pred = run_head(i, own)
@@ -429,7 +435,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": dict(workload_config(world), head_stream=bool(args.head_stream)),
+            "config": dict(workload_config(world), head_stream=bool(args.head_stream), vit_sms=args.vit_sms or "all"),
             "flop_per_frame": {"reference_forward": FLOP_PER_FRAME, "executed": FLOP_PER_FRAME_EXECUTED,
                                "note": "last block evaluated on the CLS rows only (dead rows of the reference "
                                        "forward are not computed); fractions below use the EXECUTED flops"},

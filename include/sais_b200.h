@@ -49,6 +49,14 @@ const char* sais_last_error(void);
 /* number of kernels this library has launched since load (for bench.py's gpu_launches) */
 int64_t sais_launch_count(void);
 
+/* Spatial partitioning of the GPU between two streams of this library's kernels.  Every persistent kernel sizes its grid
+ * from the SM count; with a limit set (an even number below the device's count, 0 = no limit) the kernels LAUNCHED while it is
+ * in force occupy at most that many SMs and leave the rest to kernels launched on another stream without it.  Used to run
+ * the latency-bound temporal head of batch i (~30 small dependent kernels, 0.3 ms on an otherwise idle GPU) on 4 reserved
+ * SMs concurrently with the ViT of batch i + 1 instead of after it.  Process-wide, read at launch time; returns the
+ * previous limit (>= 0) or a negative error code. */
+int sais_set_sm_limit(int32_t n_sms);
+
 /* Measurement aid: a one-thread kernel enqueued on `stream` that records {globaltimer ns, SM cycle counter} before and
  * after a chain of spin_iters dependent FMAs into out4 (device int64[4]): (out4[3]-out4[1]) / (out4[2]-out4[0]) is the
  * effective SM clock in GHz at that point of the stream — what the kernels around it actually ran at (NVML sampling

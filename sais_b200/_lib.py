@@ -67,6 +67,7 @@ SIGNATURES = {
     "sais_version": (C.c_int, []),
     "sais_last_error": (C.c_char_p, []),
     "sais_launch_count": (C.c_int64, []),
+    "sais_set_sm_limit": (C.c_int, [C.c_int32]),
     "sais_clock_probe": (C.c_int, [_p, C.c_int32, _p]),
     "sais_profile_begin": (None, []),
     "sais_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
@@ -133,6 +134,24 @@ def lib() -> C.CDLL:
         fn.argtypes = args
     _lib = handle
     return handle
+
+
+class sm_limit:
+    """``with sm_limit(144): vit.forward_u8(...)`` — kernels launched inside occupy at most that many SMs
+    (``sais_set_sm_limit``); the rest stay free for kernels launched on another stream outside the block."""
+
+    def __init__(self, n_sms: int):
+        self.n, self.prev = int(n_sms), 0
+
+    def __enter__(self):
+        self.prev = lib().sais_set_sm_limit(self.n)
+        if self.prev < 0:
+            check(self.prev, "sais_set_sm_limit")
+        return self
+
+    def __exit__(self, *exc):
+        lib().sais_set_sm_limit(self.prev)
+        return False
 
 
 def check(rc: int, what: str = "") -> None:

@@ -83,6 +83,10 @@ int current_device_index() {
 }
 }  // namespace
 
+namespace {
+std::atomic<int> g_sm_limit{0};  // 0 = every SM of the device (sais_set_sm_limit)
+}
+
 int num_sms() {
   static std::atomic<int> sms[kMaxDevices];
   const int dev = current_device_index();
@@ -91,6 +95,8 @@ int num_sms() {
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
     sms[dev].store(v, std::memory_order_relaxed);
   }
+  const int lim = g_sm_limit.load(std::memory_order_relaxed);
+  if (lim > 0 && lim < v) v = lim;
   return v;
 }
 
@@ -310,6 +316,14 @@ int sais_clock_probe(int64_t* out4, int32_t spin_iters, sais_stream_t stream_) {
   return check_cuda(launch_pdl(clock_probe_kernel, dim3(1), dim3(1), size_t(0), stream, 1,
                                reinterpret_cast<long long*>(out4), int(spin_iters)),
                     "clock_probe launch");
+}
+
+int sais_set_sm_limit(int32_t n_sms) {
+  if (n_sms < 0 || (n_sms & 1)) {
+    set_last_error("set_sm_limit: need 0 (all SMs) or an even count (CTA pairs)");
+    return kErrInvalidArg;
+  }
+  return g_sm_limit.exchange(n_sms, std::memory_order_relaxed);
 }
 
 int sais_version(void) { return 100; }

@@ -80,7 +80,6 @@ struct MlpParams {
   int64_t rows;
   int reverse;      // walk the row tiles from the last to the first (kernels.h g_tile_reverse)
   int num_tiles;    // 256-row tiles = work units
-  int stagger_ns;   // (experiment) odd CTA pairs start this many nanoseconds late
   // cast warps: bf16 copy + row statistics of the UPDATED stream (both or neither; may alias xn / ln_stats)
   const float* x;
   __nv_bfloat16* xb_out;
@@ -177,9 +176,6 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   pdl_trigger();
   pdl_wait();
   for (int i = threadIdx.x; i < DM; i += kThreads) b2_smem[i] = __ldg(p.b2 + i);
-  if (p.stagger_ns > 0 && (pair & 1)) {  // (experiment: does de-synchronising the pairs' drain / compute phases pay?)
-    for (int left = p.stagger_ns; left > 0; left -= 1000) __nanosleep(left < 1000 ? left : 1000);
-  }
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
@@ -568,8 +564,6 @@ int vit_mlp_fused(const sais_bf16* xn, const sais_bf16* w1, const float* b1, con
   p.rows = rows;
   p.reverse = g_tile_reverse;
   p.num_tiles = int((rows + 2 * MT - 1) / (2 * MT));
-  static const int env_stagger = getenv("SAIS_MLP_STAGGER_NS") ? atoi(getenv("SAIS_MLP_STAGGER_NS")) : 0;
-  p.stagger_ns = env_stagger;
   p.x = x;
   p.xb_out = reinterpret_cast<__nv_bfloat16*>(xb_out);
   p.stats_out = stats_out;
