@@ -281,6 +281,19 @@ int sais_temporal_forward(const SaisTemporalWeights* w_host, const float* x_fram
 int sais_clip_head(const float* cls_a, const float* cls_b, int32_t B, int32_t nsnip, const float* lin_w,
                    const float* lin_b, float* out, sais_stream_t stream);
 
+/* MIL pathway of fullModel.forward (task='MIL', prepare_model.py:359-363; getClipReps :451-466, MIL_Head :468-488,
+ * calcAttention / obtainVideoRep / obtainVideoScore :131-149).
+ *   sais_add_pos_rows: out[r,:] = x[r,:] + pos[r % period,:] over fp32 rows of 384 (the clip positional embeddings).
+ *   sais_mil_head: enc_out fp32 [B,nsnip,384] = output of the clip-level encoder (batch-major, before the ReLU);
+ *     att_a / att_b: the gated-attention pair [256,384] + [256]; att_c_w [ncls,256], att_c_b [ncls]: attentionModules;
+ *     final_w [ncls,384], final_b [ncls]: finalModules.  Writes reps_out [B,nsnip,384] = relu(enc_out), logits [B,ncls] and
+ *     attn_out [ncls,B,nsnip] (softmax over the snippets).  1 <= nsnip <= 64, 1 <= ncls <= 3. */
+int sais_add_pos_rows(const float* x, const float* pos, int64_t rows, int32_t period, float* out, sais_stream_t stream);
+int sais_mil_head(const float* enc_out, int32_t B, int32_t nsnip, int32_t ncls, const float* att_a_w, const float* att_a_b,
+                  const float* att_b_w, const float* att_b_b, const float* att_c_w, const float* att_c_b,
+                  const float* final_w, const float* final_b, float* reps_out, float* logits, float* attn_out,
+                  sais_stream_t stream);
+
 /* Prototype scoring (prepare_miscellaneous.py:102-125, process_inference_results.py:76-91):
  * probs = softmax-free exp(cos)/sum exp(cos); pred = argmax.  reps fp32 [B,D], protos fp32 [P,D], P <= 64. */
 int sais_prototype_score(const float* reps, const float* protos, int32_t B, int32_t P, int32_t D, float* probs,

@@ -96,6 +96,8 @@ SIGNATURES = {
     "sais_temporal_forward": (C.c_int, [C.POINTER(SaisTemporalWeights), _p, _p, _p, _p, C.c_int32, C.c_int32,
                                         C.c_int32, _p, C.c_size_t, _p, _p, _p, _p]),
     "sais_clip_head": (C.c_int, [_p, _p, C.c_int32, C.c_int32, _p, _p, _p, _p]),
+    "sais_add_pos_rows": (C.c_int, [_p, _p, C.c_int64, C.c_int32, _p, _p]),
+    "sais_mil_head": (C.c_int, [_p, C.c_int32, C.c_int32, C.c_int32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "sais_prototype_score": (C.c_int, [_p, _p, C.c_int32, C.c_int32, C.c_int32, _p, _p, _p, _p]),
 }
 

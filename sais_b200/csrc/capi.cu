@@ -736,6 +736,18 @@ int sais_clip_head(const float* cls_a, const float* cls_b, int32_t B, int32_t ns
   return clip_head(cls_a, cls_b, B, nsnip, lin_w, lin_b, out, static_cast<cudaStream_t>(stream));
 }
 
+int sais_add_pos_rows(const float* x, const float* pos, int64_t rows, int32_t period, float* out, sais_stream_t stream) {
+  return add_pos_rows(x, pos, rows, period, out, static_cast<cudaStream_t>(stream));
+}
+
+int sais_mil_head(const float* enc_out, int32_t B, int32_t nsnip, int32_t ncls, const float* att_a_w, const float* att_a_b,
+                  const float* att_b_w, const float* att_b_b, const float* att_c_w, const float* att_c_b,
+                  const float* final_w, const float* final_b, float* reps_out, float* logits, float* attn_out,
+                  sais_stream_t stream) {
+  return mil_head(enc_out, B, nsnip, ncls, att_a_w, att_a_b, att_b_w, att_b_b, att_c_w, att_c_b, final_w, final_b, reps_out,
+                  logits, attn_out, static_cast<cudaStream_t>(stream));
+}
+
 int sais_prototype_score(const float* reps, const float* protos, int32_t B, int32_t P, int32_t D, float* probs,
                          float* sims, int32_t* pred, sais_stream_t stream) {
   return prototype_score(reps, protos, B, P, D, probs, sims, pred, static_cast<cudaStream_t>(stream));

@@ -530,6 +530,143 @@ int clip_head(const float* cls_a, const float* cls_b, int B, int nsnip, const fl
                     "clip_head launch");
 }
 
+// ----------------------------------------------------------------------------------------------
+// MIL pathway (fullModel.forward task='MIL', prepare_model.py:359-363, 451-488).
+//   add_pos_rows : tokens[b, s, :] = x[b, s, :] + pos[s, :]  — getClipReps' clip positional embeddings (:455-457)
+//   mil_head     : ReLU of the clip encoder's output, then per class c the gated attention of calcAttention (:131-139):
+//                  a = tanh(A r), g = sigmoid(B r), score_s = w_c . (a * g) + b_c, att = softmax over the snippets,
+//                  video_rep = sum_s att_s r_s (:141-144), logit_c = f_c . video_rep + f_c0 (:146-149).
+// One CTA per batch element; everything fp32 (a few thousand MACs per snippet: latency, not throughput).
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) add_pos_rows_kernel(const float* __restrict__ x, const float* __restrict__ pos,
+                                                           int64_t rows, int period, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+  const int64_t total = rows * (D / 4);
+  for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = e / (D / 4);
+    const int k4 = int(e - r * (D / 4));
+    const float4 a = reinterpret_cast<const float4*>(x)[e];
+    const float4 b = __ldg(reinterpret_cast<const float4*>(pos + (r % period) * D) + k4);
+    reinterpret_cast<float4*>(out)[e] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  }
+}
+
+constexpr int kMilGate = 256;
+constexpr int kMilMaxClasses = 3;  // attentionModules / finalModules hold three heads (prepare_model.py:84-101)
+
+__global__ void __launch_bounds__(256) mil_head_kernel(const float* __restrict__ enc_out, int nsnip, int ncls,
+                                                       const float* __restrict__ wa, const float* __restrict__ ba,
+                                                       const float* __restrict__ wb, const float* __restrict__ bb,
+                                                       const float* __restrict__ wc, const float* __restrict__ bc,
+                                                       const float* __restrict__ wf, const float* __restrict__ bf,
+                                                       float* __restrict__ reps_out, float* __restrict__ logits,
+                                                       float* __restrict__ attn_out, int B) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) float mil_s[];
+  float* reps = mil_s;                       // [nsnip][D]   relu(enc_out)
+  float* gated = reps + size_t(nsnip) * D;   // [nsnip][256] tanh(A r) * sigmoid(B r)
+  float* score = gated + size_t(nsnip) * kMilGate;  // [kMilMaxClasses][nsnip]
+  float* vrep = score + kMilMaxClasses * nsnip;     // [D]
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int e = threadIdx.x; e < nsnip * D; e += blockDim.x) {
+    const float v = fmaxf(enc_out[int64_t(b) * nsnip * D + e], 0.f);
+    reps[e] = v;
+    reps_out[int64_t(b) * nsnip * D + e] = v;
+  }
+  __syncthreads();
+  // gated attention features: warp w takes gate outputs w, w + 8, ... ; weight rows live in registers across the snippets
+  for (int o = warp; o < kMilGate; o += 8) {
+    float ra[12], rb[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      ra[i] = __ldg(wa + int64_t(o) * D + i * 32 + lane);
+      rb[i] = __ldg(wb + int64_t(o) * D + i * 32 + lane);
+    }
+    const float ba_o = __ldg(ba + o), bb_o = __ldg(bb + o);
+    for (int s = 0; s < nsnip; ++s) {
+      float da = 0.f, db = 0.f;
+#pragma unroll
+      for (int i = 0; i < 12; ++i) {
+        const float r = reps[s * D + i * 32 + lane];
+        da = fmaf(ra[i], r, da);
+        db = fmaf(rb[i], r, db);
+      }
+      da = warp_sum(da);
+      db = warp_sum(db);
+      if (lane == 0) gated[s * kMilGate + o] = tanhf(da + ba_o) * (1.0f / (1.0f + expf(-(db + bb_o))));
+    }
+  }
+  __syncthreads();
+  // per-class snippet scores
+  for (int e = warp; e < ncls * nsnip; e += 8) {
+    const int c = e / nsnip, s = e - c * nsnip;
+    float d = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMilGate / 32; ++i) d = fmaf(__ldg(wc + c * kMilGate + i * 32 + lane), gated[s * kMilGate + i * 32 + lane], d);
+    d = warp_sum(d);
+    if (lane == 0) score[c * nsnip + s] = d + __ldg(bc + c);
+  }
+  __syncthreads();
+  for (int c = 0; c < ncls; ++c) {
+    // softmax over the snippets (every thread computes the same max / sum: nsnip is small)
+    float m = -INFINITY;
+    for (int s = 0; s < nsnip; ++s) m = fmaxf(m, score[c * nsnip + s]);
+    float sum = 0.f;
+    for (int s = 0; s < nsnip; ++s) sum += expf(score[c * nsnip + s] - m);
+    const float inv = 1.0f / sum;
+    for (int s = threadIdx.x; s < nsnip; s += blockDim.x)
+      attn_out[(int64_t(c) * B + b) * nsnip + s] = expf(score[c * nsnip + s] - m) * inv;
+    for (int k = threadIdx.x; k < D; k += blockDim.x) {
+      float acc = 0.f;
+      for (int s = 0; s < nsnip; ++s) acc = fmaf(expf(score[c * nsnip + s] - m) * inv, reps[s * D + k], acc);
+      vrep[k] = acc;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      float d = 0.f;
+#pragma unroll
+      for (int i = 0; i < 12; ++i) d = fmaf(__ldg(wf + c * D + i * 32 + lane), vrep[i * 32 + lane], d);
+      d = warp_sum(d);
+      if (lane == 0) logits[int64_t(b) * ncls + c] = d + __ldg(bf + c);
+    }
+    __syncthreads();
+  }
+}
+
+int add_pos_rows(const float* x, const float* pos, int64_t rows, int period, float* out, cudaStream_t stream) {
+  if (rows == 0) return kOk;
+  if (!x || !pos || !out || rows < 0 || period <= 0) {
+    set_last_error("add_pos_rows: bad arguments");
+    return kErrInvalidArg;
+  }
+  const int64_t total = rows * (D / 4);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > int64_t(num_sms()) * 8) blocks = int64_t(num_sms()) * 8;
+  LaunchScope ls(kClsMisc, stream, double(rows) * D * 8);
+  return check_cuda(launch_pdl(add_pos_rows_kernel, dim3(unsigned(blocks)), dim3(256), size_t(0), stream, 1, x, pos, rows, period, out),
+                    "add_pos_rows launch");
+}
+
+int mil_head(const float* enc_out, int B, int nsnip, int ncls, const float* wa, const float* ba, const float* wb,
+             const float* bb, const float* wc, const float* bc, const float* wf, const float* bf, float* reps_out,
+             float* logits, float* attn_out, cudaStream_t stream) {
+  if (B == 0) return kOk;
+  if (!enc_out || !wa || !ba || !wb || !bb || !wc || !bc || !wf || !bf || !reps_out || !logits || !attn_out || B < 0 ||
+      nsnip <= 0 || nsnip > 64 || ncls <= 0 || ncls > kMilMaxClasses) {
+    set_last_error("mil_head: bad arguments (need 1 <= nsnippets <= 64, 1 <= classes <= 3)");
+    return kErrInvalidArg;
+  }
+  const size_t smem = (size_t(nsnip) * (D + kMilGate) + kMilMaxClasses * size_t(nsnip) + D) * sizeof(float);
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(mil_head_kernel), int(smem), "mil_head")) return rc;
+  LaunchScope ls(kClsMisc, stream, double(B) * nsnip * D * 8);
+  return check_cuda(launch_pdl(mil_head_kernel, dim3(B), dim3(256), smem, stream, 1, enc_out, nsnip, ncls, wa, ba, wb, bb, wc, bc,
+                               wf, bf, reps_out, logits, attn_out, B),
+                    "mil_head launch");
+}
+
 int prototype_score(const float* reps, const float* protos, int B, int P, int Dd, float* probs, float* sims,
                     int32_t* pred, cudaStream_t stream) {
   if (B == 0) return kOk;

@@ -65,6 +65,10 @@ int clip_head(const float* cls_a, const float* cls_b, int B, int nsnip, const fl
               float* out, cudaStream_t stream);
 int prototype_score(const float* reps, const float* protos, int B, int P, int D, float* probs, float* sims,
                     int32_t* pred, cudaStream_t stream);
+int add_pos_rows(const float* x, const float* pos, int64_t rows, int period, float* out, cudaStream_t stream);
+int mil_head(const float* enc_out, int B, int nsnip, int ncls, const float* wa, const float* ba, const float* wb,
+             const float* bb, const float* wc, const float* bc, const float* wf, const float* bf, float* reps_out,
+             float* logits, float* attn_out, cudaStream_t stream);
 
 // vit_attention.cu
 int vit_attention(const sais_bf16* qkv, int B, sais_bf16* out, float* probs, cudaStream_t stream);

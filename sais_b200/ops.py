@@ -238,3 +238,35 @@ def prototype_score(reps, protos, want_sims=False):
     check(lib().sais_prototype_score(ptr(reps), ptr(protos), B, P, D, ptr(probs), ptr(sims), ptr(pred),
                                      current_stream()), "sais_prototype_score")
     return probs, sims, pred
+
+
+@_on_device_of_first_tensor
+def add_pos_rows(x, pos):
+    """x fp32 [..., S, 384] + pos fp32 [S, 384] broadcast over the leading dims (clip positional embeddings)."""
+    require_cuda(x, "x")
+    x = x.contiguous().float()
+    pos = pos.contiguous().float()
+    assert x.shape[-1] == 384 and pos.shape[-1] == 384 and x.shape[-2] == pos.shape[0]
+    out = torch.empty_like(x)
+    check(lib().sais_add_pos_rows(ptr(x), ptr(pos), x.numel() // 384, pos.shape[0], ptr(out), current_stream()),
+          "sais_add_pos_rows")
+    return out
+
+
+@_on_device_of_first_tensor
+def mil_head(enc_out, att_a, att_b, att_c_w, att_c_b, final_w, final_b):
+    """enc_out fp32 [B,nsnip,384] (clip encoder output before the ReLU); att_a / att_b: (weight [256,384], bias [256]);
+    att_c_w [ncls,256], att_c_b [ncls], final_w [ncls,384], final_b [ncls].
+    Returns (reps [B,nsnip,384], logits [B,ncls], attention [ncls,B,nsnip])."""
+    require_cuda(enc_out, "enc_out")
+    enc_out = enc_out.contiguous().float()
+    B, ns, E = enc_out.shape
+    ncls = att_c_w.shape[0]
+    f = lambda t: t.detach().contiguous().float()
+    ws = [f(att_a[0]), f(att_a[1]), f(att_b[0]), f(att_b[1]), f(att_c_w), f(att_c_b), f(final_w), f(final_b)]
+    reps = torch.empty_like(enc_out)
+    logits = torch.empty((B, ncls), device=enc_out.device, dtype=torch.float32)
+    attn = torch.empty((ncls, B, ns), device=enc_out.device, dtype=torch.float32)
+    check(lib().sais_mil_head(ptr(enc_out), B, ns, ncls, *[ptr(w) for w in ws], ptr(reps), ptr(logits), ptr(attn),
+                              current_stream()), "sais_mil_head")
+    return reps, logits, attn

@@ -12,7 +12,9 @@ prototype scoring are fused fp32 kernels.
 
 Differences from the reference, all deliberate: inputs are NOT mutated in place (:192 does ``x += pos``); the
 unused timm ViT-B ``encoder`` (:40) is not instantiated (``encoder.*`` keys in a checkpoint are ignored); only
-``data_type='reps'``, ``encoder_type='ViT'``, ``self_attention=True``, ``task='Prototypes'`` are implemented.
+``data_type='reps'``, ``encoder_type='ViT'``, ``self_attention=True`` are implemented, with ``task='Prototypes'`` (the
+``main.sh`` path) and ``task='MIL'`` (:359-363, 451-488).  ``task='ClassificationHead'`` needs ``self.cls_head``, which the
+reference creates only for ``data_type='raw'`` (:52-53) — unreachable with representations as input, so not provided.
 """
 from __future__ import annotations
 
@@ -67,8 +69,10 @@ class fullModel(nn.Module):  # noqa: N801 — reference class name
         """x, f: fp32 [B,nsnip,T,384] (or lists of 3 TTA views); xpad, fpad: bool [B,nsnip,T+1], True = padded
         key, index 0 (CLS) never padded.  Returns ``(snip_sequence [B,256] or list, snip_attn [B*nsnip,T+1,T+1])``
         where ``snip_attn`` belongs to view 0 of the RGB stream (flow stream for modalities='Flow')."""
+        if task == 'MIL':
+            return self._forward_mil(x, xpad)
         if task != 'Prototypes':
-            raise NotImplementedError("only task='Prototypes' is on the SAIS inference hot path")
+            raise NotImplementedError("task must be 'Prototypes' or 'MIL' (ClassificationHead needs data_type='raw')")
         if self.training:
             raise _lib.SaisError("sais_b200.fullModel is inference-only; call .eval()")
         is_list = isinstance(x, list) if self.modalities != 'Flow' else isinstance(f, list)
@@ -120,6 +124,39 @@ class fullModel(nn.Module):  # noqa: N801 — reference class name
                 cls_b = cls[b0:b0 + bn]
             outs.append(ops.clip_head(cls_a, cls_b, B, nsnip, lin_w, lin_b))
         return (outs if is_list else outs[0]), snip_attn
+
+    @torch.no_grad()
+    def _forward_mil(self, x, xpad):
+        """task='MIL' (:286-295, 344-351, 359-363, 442-443): frame-level encoder per snippet -> clip-level encoder over the
+        snippets' CLS vectors (+ clip positional embeddings, no CLS token, no mask) -> ReLU -> attention-based MIL head.
+        Returns ``(snip_sequence [nsnip,B,384], snip_reps [B,nsnip,384], output_logits [B,nclasses], attention_dict)`` like
+        the reference; the flow stream does not enter these outputs there either (``MIL_Head(snip_reps, flow_reps=None)``)."""
+        if self.training:
+            raise _lib.SaisError("sais_b200.fullModel is inference-only; call .eval()")
+        if isinstance(x, list):
+            raise NotImplementedError("task='MIL' takes a single view (the reference's list form never reaches getClipReps)")
+        if self.nclasses > 3:
+            raise NotImplementedError("attentionModules / finalModules hold three heads (prepare_model.py:84-101)")
+        _lib.require_cuda(x, "x")
+        B, nsnip, T, E = x.shape
+        n = B * nsnip
+        if xpad is None:
+            key_pad = torch.zeros(n * (T + 1), dtype=torch.uint8, device=x.device)
+        else:
+            p = xpad.reshape(n * (T + 1)).to(x.device)
+            key_pad = p.view(torch.uint8) if p.dtype == torch.bool else p.to(torch.uint8)
+        cls, _, _, _ = self.transEncoderFrame.run_packed(x.reshape(n * T, E).float(), [T + 1] * n, key_pad, [False] * n,
+                                                         self.frame_cls, self.frame_pos_table)
+        tokens = ops.add_pos_rows(cls.view(B, nsnip, E), self.clip_pos_table[:nsnip].detach())  # getClipReps :455-457
+        enc, _ = self.transEncoderClip._forward_tokens(tokens, None)                            # [nsnip,B,E], no ReLU yet
+        att_c_w = torch.cat([self.attentionModules[str(c)].weight for c in range(self.nclasses)], 0)
+        att_c_b = torch.cat([self.attentionModules[str(c)].bias for c in range(self.nclasses)], 0)
+        fin_w = torch.cat([self.finalModules[str(c)].weight for c in range(self.nclasses)], 0)
+        fin_b = torch.cat([self.finalModules[str(c)].bias for c in range(self.nclasses)], 0)
+        reps, logits, attn = ops.mil_head(enc.permute(1, 0, 2).contiguous(),
+                                          (self.attentionA.weight, self.attentionA.bias),
+                                          (self.attentionB.weight, self.attentionB.bias), att_c_w, att_c_b, fin_w, fin_b)
+        return tokens.permute(1, 0, 2).contiguous(), reps, logits, {c: attn[c] for c in range(self.nclasses)}
 
     def train(self, mode=True):
         if mode:

@@ -291,3 +291,42 @@ def test_vit_forward_variants_bit_identical(dev, tmp_path, knob):
         res[flag] = torch.load(out)
     for a, b in zip(res["0"], res["1"]):
         assert a.shape == b.shape and torch.equal(a, b), (a - b).abs().max()
+
+
+def test_mil_task_matches_oracle_and_golden(dev, golden_dir):
+    """fullModel.forward(task='MIL') — SURVEY §8f row 4 "other heads": frame-level encoder per snippet, clip-level
+    transEncoderClip over the snippet CLS vectors, gated-attention MIL head — against the oracle and the executed
+    reference's outputs (tests/golden/mil.npz)."""
+    from oracle import make_golden_mil as MM
+    from sais_b200.prepare_model import fullModel
+    g = np.load(golden_dir / "mil.npz")
+    for name, wseed, ncls, B, ns, tr, tf, iseed in MM.MIL_CASES:
+        sd = O.make_mil_weights(wseed, "stress", ncls)
+        m = fullModel(data_type='reps', nclasses=ncls, domain='NH_02', rep_dim=384, encoder_type='ViT', modalities='RGB-Flow')
+        own = m.state_dict()
+        for k, v in sd.items():
+            if k in ("frame_pos_table", "clip_pos_table"):
+                pre = "frame_pos_embeddings." if k.startswith("frame") else "clip_pos_embeddings."
+                for i in range(v.shape[0]):
+                    own[pre + str(i)] = v[i:i + 1]
+            else:
+                own[k] = v
+        m.load_state_dict(own, strict=True)
+        m = m.to(dev).eval()
+        x, f, xp, fp = MM.mil_inputs(B, ns, tr, tf, iseed)
+        keep = x.clone()
+        x_dev = x.to(dev)
+        seq, reps, logits, attn = m(x_dev, f.to(dev), None, None, 'MIL', xp.to(dev), fp.to(dev), None)
+        assert torch.equal(x_dev.cpu(), keep), "inputs must not be mutated"
+        r_seq, r_reps, r_logits, r_attn = O.mil_forward(sd, x, f, xp, fp, ncls)
+        assert seq.shape == (ns, B, 384) and reps.shape == (B, ns, 384) and logits.shape == (B, ncls) and len(attn) == ncls
+        for got, ref, gold, tol in ((seq, r_seq, g[f"{name}_seq"], 2e-4), (reps, r_reps, g[f"{name}_reps"], 5e-4),
+                                    (logits, r_logits, g[f"{name}_logits"], 5e-4)):
+            scale = float(ref.abs().max())
+            assert float((got.cpu() - ref).abs().max()) <= tol * max(scale, 1.0), name
+            assert float(np.abs(got.cpu().numpy() - gold).max()) <= tol * max(scale, 1.0), name
+        for c in range(ncls):
+            assert float((attn[c].cpu() - r_attn[c]).abs().max()) <= 1e-4
+            assert float(np.abs(attn[c].cpu().numpy() - g[f"{name}_attn"][c]).max()) <= 1e-4
+    with pytest.raises(NotImplementedError):
+        m(x.to(dev), f.to(dev), None, None, 'ClassificationHead', xp.to(dev), fp.to(dev), None)

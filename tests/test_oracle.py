@@ -70,3 +70,21 @@ def test_padding_mask_contract():
     assert m.shape == (2, 1, 6)
     assert not m[:, :, 0].any()                      # CLS never padded
     assert m[0, 0].tolist() == [False] * 4 + [True] * 2 and not m[1].any()
+
+
+def test_mil_oracle_matches_reference_golden(golden_dir):
+    """MIL pathway (getClipReps + MIL_Head, prepare_model.py:359-363, 451-488): the restatement equals the executed
+    reference (tests/golden/mil.npz, written by oracle/make_golden_mil.py) on both cases."""
+    from oracle import make_golden_mil as MM
+    g = np.load(golden_dir / "mil.npz")
+    for name, wseed, ncls, B, ns, tr, tf, iseed in MM.MIL_CASES:
+        sd = O.make_mil_weights(wseed, "stress", ncls)
+        x, f, xp, fp = MM.mil_inputs(B, ns, tr, tf, iseed)
+        seq, reps, logits, attn = O.mil_forward(sd, x, f, xp, fp, ncls)
+        assert seq.shape == (ns, B, 384) and reps.shape == (B, ns, 384) and logits.shape == (B, ncls)
+        assert np.abs(seq.numpy() - g[f"{name}_seq"]).max() <= 1e-5
+        assert np.abs(reps.numpy() - g[f"{name}_reps"]).max() <= 2e-4
+        assert np.abs(logits.numpy() - g[f"{name}_logits"]).max() <= 2e-4
+        for c in range(ncls):
+            assert np.abs(attn[c].numpy() - g[f"{name}_attn"][c]).max() <= 1e-5
+            assert torch.allclose(attn[c].sum(1), torch.ones(B), atol=1e-6)
