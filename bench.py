@@ -7,7 +7,9 @@ One "step" = one pass of the hot path over one batch of synthetic input per rank
   256 uint8 frames (128 RGB + 128 optical-flow, 224x224) -> frame normalisation + DINO ViT-S/16 (bf16 operands,
   fp32 accumulate) -> [256,384] embeddings, written straight into this rank's slice of a persistent gather buffer ->
   (N>1: in-place NCCL all-gather of the frame-range shards, asynchronous, overlapped with the head) -> SAIS temporal
-  head on this rank's 8 clips x 16 frames (RGB + flow) -> prototype scores (P=2).
+  head on this rank's 8 clips x 16 frames (RGB + flow) -> prototype scores (P=2).  The head + scoring of step i run on a
+  second stream underneath the ViT of step i + 1 (pipeline.SideStream; --head-stream 0 for one stream); every step's work
+  completes inside the timed region.
 This is BASELINE.json configs[1] (ViT-S/16, batch 256, 1xB200) with the SAIS head of the metric on top.
 
 value : frames/s with the u8 frames already resident in HBM (max over ranks, CUDA events, K steps).
@@ -214,9 +216,10 @@ def main():
     ap.add_argument("--chunk", type=int, default=256, help="ViT frames per workspace chunk")
     ap.add_argument("--vit-sms", type=int, default=0,
                     help="with --head-stream 1: SMs the ViT kernels may occupy (even; 0 = all); the rest are left to the head")
-    ap.add_argument("--head-stream", type=int, default=0,
-                    help="1: run the temporal head + scoring of step i on a second (high-priority) stream, overlapped with "
-                         "the ViT of step i+1 (software pipelining across steps; every step's work stays inside the timed region)")
+    ap.add_argument("--head-stream", type=int, default=1,
+                    help="1 (default): run the temporal head + scoring of step i on a second (high-priority) stream, under the "
+                         "ViT of step i+1 (pipeline.SideStream: software pipelining across steps; every step's work stays "
+                         "inside the timed region); 0: one stream")
     args = ap.parse_args()
     if args.impl == "reference":
         args.warmup = max(args.warmup, 1)
@@ -267,29 +270,19 @@ def main():
         pred, probs = scoring.predict(out, protos)
         return out, probs, pred
 
-    side = torch.cuda.Stream(device=dev, priority=-1) if args.head_stream else None
-    head_done = [None, None]
+    side = pipeline.SideStream(dev) if args.head_stream else None
 
     def run_head(i, own):
-        """head + scoring of step i; with --head-stream on the side stream, ordered after the ViT of step i and before the
-        ViT of step i + 2 overwrites the same gather slot"""
+        """head + scoring of step i; by default on the side stream, ordered after the ViT of step i (and joined before the
+        ViT of step i + 2 overwrites the gather slot it reads)"""
         if side is None:
             return head_and_score(own)
-        main = torch.cuda.current_stream(dev)
-        ev = torch.cuda.Event()
-        ev.record(main)
-        side.wait_event(ev)
-        with torch.cuda.stream(side):
-            res = head_and_score(own)
-            done = torch.cuda.Event()
-            done.record(side)
-        head_done[i % 2] = done
-        return res
+        return side.run(i, head_and_score, own)
 
     def claim_slot(i):
         own = gatherer.own_slice(i)
-        if side is not None and head_done[i % 2] is not None:
-            torch.cuda.current_stream(dev).wait_event(head_done[i % 2])  # the head that read this slot two steps ago
+        if side is not None:
+            side.guard(i)  # the head that read this slot two steps ago
         return own
 
     vit_limit = _lib.sm_limit(args.vit_sms if (args.head_stream and args.vit_sms) else 0)
@@ -314,13 +307,13 @@ def main():
         if side is None:
             probs_host.copy_(probs, non_blocking=True)
         else:
-            with torch.cuda.stream(side):
+            with torch.cuda.stream(side.stream):
                 probs_host.copy_(probs, non_blocking=True)
         return own, (out, probs, pred)
 
     def join_side():
         if side is not None:
-            torch.cuda.current_stream(dev).wait_stream(side)
+            side.join()
 
     def barrier():
         join_side()

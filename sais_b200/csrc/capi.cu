@@ -288,7 +288,6 @@ namespace sais {
 namespace {
 // one thread: SM cycle counter and nanosecond timer before / after a fixed-length dependent FMA chain
 __global__ void clock_probe_kernel(long long* out4, int spin) {
-  pdl_trigger();
   pdl_wait();
   unsigned long long ns0, ns1;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));

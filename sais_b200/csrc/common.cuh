@@ -551,17 +551,22 @@ int num_sms();  // of the CURRENT device (cached per device)
 int ensure_dynamic_smem(const void* kernel, int bytes, const char* what);
 
 // ----------------------------------------------------------------------------------------------
-// Programmatic dependent launch (PDL).  Every kernel of the library is launched through launch_pdl():
-// with the stream-serialization attribute set, the NEXT kernel of the stream may be scheduled while this
-// one is still running (as soon as every CTA of this grid has executed pdl_trigger() or exited), so its
-// launch latency and its prologue (mbarrier init, TMEM allocation, tensor-map prefetch) hide under this
-// kernel's tail.  The contract every kernel keeps: pdl_wait() — which returns once ALL prerequisite grids
-// have completed and flushed — precedes the first global-memory access of any kind (reads of data a
-// predecessor wrote, and writes a predecessor may still read), so results are identical to plain stream
-// order.  SAIS_PDL=0 drops the attribute (both instructions are then no-ops).
+// Programmatic dependent launch (PDL).  Every kernel of the library is launched through launch_pdl(): with the
+// stream-serialization attribute set, the NEXT kernel of the stream is launched as soon as every CTA of this grid has
+// exited — before this grid's memory flush has completed — so its launch latency and its prologue (mbarrier init, TMEM
+// allocation, tensor-map prefetch) overlap the flush instead of following it.  The contract every kernel keeps:
+// pdl_wait() — which returns once ALL prerequisite grids have completed and flushed — precedes the first global-memory
+// access of any kind (reads of data a predecessor wrote, and writes a predecessor may still read), so results are
+// identical to plain stream order.  SAIS_PDL=0 drops the attribute (the instruction is then a no-op).
+//
+// Deliberately NO early `griddepcontrol.launch_dependents`: round 1 issued it at the top of every kernel, which lets the
+// dependent grid's CTAs occupy every SM the moment it becomes idle and spin there in pdl_wait().  That bought nothing
+// measurable over the implicit trigger at CTA exit (79.9 k vs 79.4 k frames/s) but it squatted on exactly the SMs a second
+// stream could use: the fused MLP leaves 50 SMs idle for a third of its run time (197 row tiles on 74 CTA pairs), and
+// with those SMs free the temporal head of batch i (a chain of ~35 small kernels on a high-priority stream,
+// pipeline.SideStream) runs underneath the ViT of batch i + 1: 80.5 k -> 84.3 k frames/s (profiles/r02_pdl_trigger.md).
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 bool pdl_enabled();
 
 template <typename... KArgs, typename... Args>

@@ -26,7 +26,6 @@ __global__ void __launch_bounds__(256) layernorm384_kernel(const float* __restri
                                                            __nv_bfloat16* __restrict__ out_bf16, int split,
                                                            float* __restrict__ out_plus,
                                                            const float* __restrict__ plus_vec) {
-  pdl_trigger();
   pdl_wait();  // (PDL, common.cuh) no global access above this line
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -119,7 +118,6 @@ __global__ void __launch_bounds__(256) layernorm384_kernel(const float* __restri
 __global__ void __launch_bounds__(256) rowstats_cast384_kernel(const float* __restrict__ x, int64_t rows,
                                                                __nv_bfloat16* __restrict__ xb,
                                                                float* __restrict__ stats, int reverse) {
-  pdl_trigger();
   pdl_wait();  // (PDL, common.cuh) no global access above this line
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -148,7 +146,6 @@ struct NormConsts {
 __global__ void __launch_bounds__(256) normalize_patchify_u8_kernel(const uint8_t* __restrict__ frames, int B,
                                                                     NormConsts nc,
                                                                     __nv_bfloat16* __restrict__ patches, int split) {
-  pdl_trigger();
   pdl_wait();  // (PDL, common.cuh) no global access above this line
   const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t total = int64_t(B) * 224 * 14;
@@ -192,7 +189,6 @@ __global__ void __launch_bounds__(256) normalize_patchify_u8_kernel(const uint8_
 // fp32 NCHW (already normalised, what the reference model is called with) -> bf16 patch matrix.
 __global__ void __launch_bounds__(256) patchify_f32_kernel(const float* __restrict__ frames, int B,
                                                            __nv_bfloat16* __restrict__ patches, int split) {
-  pdl_trigger();
   pdl_wait();  // (PDL, common.cuh) no global access above this line
   const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t total = int64_t(B) * 3 * 224 * 14;
@@ -226,7 +222,6 @@ __global__ void __launch_bounds__(256) patchify_f32_kernel(const float* __restri
 
 // seq_offsets[i] = i * stride (packed-sequence offsets of equally long sequences, built on device)
 __global__ void fill_offsets_kernel(int32_t* __restrict__ offs, int n, int stride) {
-  pdl_trigger();
   pdl_wait();  // (PDL, common.cuh) no global access above this line
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) offs[t] = t * stride;
@@ -234,7 +229,6 @@ __global__ void fill_offsets_kernel(int32_t* __restrict__ offs, int n, int strid
 
 // x[b, 0, :] = cls_token + pos_embed[0]   (vision_transformer.py:201-205)
 __global__ void write_cls_rows_kernel(const float* __restrict__ cls_pos0, int B, float* __restrict__ x) {
-  pdl_trigger();
   pdl_wait();  // (PDL, common.cuh) no global access above this line
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= B * (D / 4)) return;
@@ -254,7 +248,6 @@ __global__ void __launch_bounds__(128) temporal_prep_kernel(const float* __restr
                                                             __nv_bfloat16* __restrict__ tok_bf16,
                                                             float* __restrict__ tok_plus,
                                                             const float* __restrict__ plus_vec) {
-  pdl_trigger();
   pdl_wait();  // (PDL, common.cuh) no global access above this line
   const int i = blockIdx.x;
   const int t0 = seq_offsets[i];
@@ -290,7 +283,6 @@ __global__ void __launch_bounds__(128) temporal_prep_kernel(const float* __restr
 // out_cls[i] = relu(tokens[seq_offsets[i]])   (prepare_model.py:215,220)
 __global__ void gather_cls_relu_kernel(const float* __restrict__ tok, const int32_t* __restrict__ seq_offsets,
                                        int nseq, float* __restrict__ out_cls) {
-  pdl_trigger();
   pdl_wait();  // (PDL, common.cuh) no global access above this line
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nseq * (D / 4)) return;
@@ -311,7 +303,6 @@ __global__ void __launch_bounds__(256) clip_head_kernel(const float* __restrict_
                                                         const float* __restrict__ cls_b, int B, int nsnip,
                                                         const float* __restrict__ W, const float* __restrict__ bias,
                                                         float* __restrict__ out) {
-  pdl_trigger();
   pdl_wait();  // (PDL, common.cuh) no global access above this line
   __shared__ float v[kClipsPerBlock][D];
   const int b0 = blockIdx.x * kClipsPerBlock;
@@ -361,7 +352,6 @@ __global__ void __launch_bounds__(128) prototype_score_kernel(const float* __res
                                                               const float* __restrict__ protos, int B, int P, int Dd,
                                                               float* __restrict__ probs, float* __restrict__ sims,
                                                               int32_t* __restrict__ pred) {
-  pdl_trigger();
   pdl_wait();  // (PDL, common.cuh) no global access above this line
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -540,7 +530,6 @@ int clip_head(const float* cls_a, const float* cls_b, int B, int nsnip, const fl
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) add_pos_rows_kernel(const float* __restrict__ x, const float* __restrict__ pos,
                                                            int64_t rows, int period, float* __restrict__ out) {
-  pdl_trigger();
   pdl_wait();
   const int64_t total = rows * (D / 4);
   for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += int64_t(gridDim.x) * blockDim.x) {
@@ -562,7 +551,6 @@ __global__ void __launch_bounds__(256) mil_head_kernel(const float* __restrict__
                                                        const float* __restrict__ wf, const float* __restrict__ bf,
                                                        float* __restrict__ reps_out, float* __restrict__ logits,
                                                        float* __restrict__ attn_out, int B) {
-  pdl_trigger();
   pdl_wait();
   extern __shared__ __align__(16) float mil_s[];
   float* reps = mil_s;                       // [nsnip][D]   relu(enc_out)

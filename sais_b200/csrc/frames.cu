@@ -39,7 +39,6 @@ __global__ void __launch_bounds__(kRowBytes) resize_horizontal_kernel(const uint
                                                                       int N, int H, int W, int top, int left, int ch, int cw,
                                                                       const int32_t* __restrict__ table, int row_pitch,
                                                                       uint8_t* __restrict__ tmp) {
-  pdl_trigger();
   pdl_wait();  // (PDL, common.cuh) no global access above this line
   extern __shared__ __align__(16) uint8_t rows_s[];  // [kRows][row_pitch]
   const int t = threadIdx.x;
@@ -95,7 +94,6 @@ __global__ void __launch_bounds__(kRowBytes) resize_horizontal_kernel(const uint
 __global__ void __launch_bounds__(kRowBytes / 4) resize_vertical_kernel(const uint8_t* __restrict__ tmp, int N, int ch,
                                                                         const int32_t* __restrict__ table,
                                                                         uint8_t* __restrict__ out) {
-  pdl_trigger();
   pdl_wait();  // (PDL, common.cuh) no global access above this line
   const int t = threadIdx.x;
   for (int64_t row = blockIdx.x; row < int64_t(N) * kOut; row += gridDim.x) {

@@ -269,7 +269,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
   // PDL: the set-up above overlapped the previous kernel's tail; nothing before this line touched global memory
-  pdl_trigger();
   pdl_wait();
   if (p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {  // effective SM clock of this launch: cycles vs nanoseconds
     unsigned long long ns;

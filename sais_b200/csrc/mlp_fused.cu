@@ -173,7 +173,6 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     tmem_relinquish_cg2();
   }
   // PDL (common.cuh): the set-up above overlapped the previous kernel's tail; no global access before this line
-  pdl_trigger();
   pdl_wait();
   for (int i = threadIdx.x; i < DM; i += kThreads) b2_smem[i] = __ldg(p.b2 + i);
   tc_fence_before();

@@ -44,7 +44,6 @@ seq_attention_f32_kernel(const float* __restrict__ qkv, const int32_t* __restric
                          const uint8_t* __restrict__ key_pad, const int64_t* __restrict__ attn_offsets, int max_S,
                          float scale, __nv_bfloat16* __restrict__ out_split, float* __restrict__ attn_mean,
                          float* __restrict__ probs_per_head) {
-  pdl_trigger();
   pdl_wait();  // (PDL, common.cuh) no global access above this line
   using Cfg = AttnCfg<H, HD>;
   constexpr int E = Cfg::E, LD = Cfg::LD;

@@ -28,7 +28,6 @@ constexpr int OUT_LD = 384;
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) vit_cls_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int B,
                                                                 __nv_bfloat16* __restrict__ out_cls) {
-  pdl_trigger();
   pdl_wait();  // (PDL, common.cuh) no global access above this line
   // One CTA (4 warps) per (frame, head).  lane = (key group kg = lane / 8, 16-byte chunk dc = lane % 8): one warp
   // instruction covers four whole 128-byte K (or V) rows, fully coalesced; warp w takes keys 16 i + 4 w + kg, i < 13, and

@@ -89,7 +89,6 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
-  pdl_trigger();
   pdl_wait();  // (PDL) set-up done under the previous kernel's tail; global memory only from here on
 
   if (warp >= 8) {

@@ -124,6 +124,44 @@ class EmbeddingGatherer:
             self._join(k)
 
 
+class SideStream:
+    """Software pipelining of the two stages across batches: run the latency-bound stage of batch ``i`` (the temporal head
+    + prototype scoring: a chain of ~35 small dependent kernels, ~0.3 ms on an idle GPU) on a second, high-priority CUDA
+    stream underneath the throughput-bound stage of batch ``i + 1`` (the ViT, whose persistent kernels leave SMs idle at
+    their tails — the fused MLP runs 197 row tiles on 74 CTA pairs, so 50 SMs idle for a third of every launch).
+
+    ``run(fn, *args)`` orders ``fn`` after everything enqueued so far on the current stream and returns its result
+    immediately (tensors it returns belong to the side stream); ``guard(slot)`` makes the current stream wait for the
+    ``run`` that last used ``slot`` (call it before overwriting what that run reads); ``join()`` makes the current stream
+    wait for all side work.  Works because the library's kernels do not trigger their dependents early (csrc/common.cuh,
+    "Programmatic dependent launch"): idle SMs stay free for the other stream."""
+
+    def __init__(self, device, slots: int = 2):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device, priority=-1)
+        self.done = [None] * slots
+
+    def run(self, slot: int, fn, *args, **kw):
+        main = torch.cuda.current_stream(self.device)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.stream.wait_event(ev)
+        with torch.cuda.stream(self.stream):
+            res = fn(*args, **kw)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        self.done[slot % len(self.done)] = done
+        return res
+
+    def guard(self, slot: int) -> None:
+        d = self.done[slot % len(self.done)]
+        if d is not None:
+            torch.cuda.current_stream(self.device).wait_event(d)
+
+    def join(self) -> None:
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+
+
 # --------------------------------------------------------------------------------------------- windows / TTA
 def sliding_windows(n_frames: int, window: int, hop: int, tta_offsets: Sequence[int] = (0,)) -> List[np.ndarray]:
     """Frame-index matrices, one per TTA view: view ``o`` of window ``w`` covers ``[start_w + o, start_w + window)``
