@@ -214,8 +214,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the C1 / C3 / C4 / C5 legs")
     ap.add_argument("--chunk", type=int, default=256, help="ViT frames per workspace chunk")
-    ap.add_argument("--vit-sms", type=int, default=0,
-                    help="with --head-stream 1: SMs the ViT kernels may occupy (even; 0 = all); the rest are left to the head")
+    ap.add_argument("--vit-sms", type=int, default=140,
+                    help="with --head-stream 1: SMs the ViT's persistent kernels may occupy (even; 0 = all), the rest are left "
+                         "to the concurrent head (sais_set_sm_limit).  140 of 148 costs the ViT almost nothing at batch 256 — "
+                         "1,536 attention items = 11 rounds on 140 CTAs as on 148, 197 MLP row tiles = 3 rounds on 70 CTA "
+                         "pairs as on 74 — and measured +3.3 %% frames/s")
     ap.add_argument("--head-stream", type=int, default=1,
                     help="1 (default): run the temporal head + scoring of step i on a second (high-priority) stream, under the "
                          "ViT of step i+1 (pipeline.SideStream: software pipelining across steps; every step's work stays "
