@@ -305,13 +305,14 @@ def main():
         with vit_limit:
             pipeline.extract_features(vit, host_batches[i % nbuf], batch_size=FRAMES_PER_STEP, device=dev, out=own)
         gatherer.gather_async(i)
-        emb_host.copy_(own, non_blocking=True)
         out, probs, pred = run_head(i, own)
-        if side is None:
+        # device->host reads of the step's results: embeddings + clip probabilities (on the side stream when there is one,
+        # so the next batch's ViT does not queue behind two small PCIe transfers)
+        with torch.cuda.stream(side.stream if side is not None else torch.cuda.current_stream(dev)):
+            emb_host.copy_(own, non_blocking=True)
             probs_host.copy_(probs, non_blocking=True)
-        else:
-            with torch.cuda.stream(side.stream):
-                probs_host.copy_(probs, non_blocking=True)
+            if side is not None:
+                side.mark(i)
         return own, (out, probs, pred)
 
     def join_side():

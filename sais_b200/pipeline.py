@@ -153,6 +153,12 @@ class SideStream:
         self.done[slot % len(self.done)] = done
         return res
 
+    def mark(self, slot: int) -> None:
+        """Re-record ``slot``'s completion point after more work was enqueued on the side stream for it."""
+        done = torch.cuda.Event()
+        done.record(self.stream)
+        self.done[slot % len(self.done)] = done
+
     def guard(self, slot: int) -> None:
         d = self.done[slot % len(self.done)]
         if d is not None:
