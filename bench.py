@@ -7,16 +7,17 @@ One "step" = one pass of the hot path over one batch of synthetic input per rank
   256 uint8 frames (128 RGB + 128 optical-flow, 224x224) -> frame normalisation + DINO ViT-S/16 (bf16 operands,
   fp32 accumulate) -> [256,384] embeddings, written straight into this rank's slice of a persistent gather buffer ->
   (N>1: in-place NCCL all-gather of the frame-range shards, asynchronous, overlapped with the head) -> SAIS temporal
-  head on this rank's 8 clips x 16 frames (RGB + flow) -> prototype scores (P=2).  The head + scoring of step i run on a
-  second stream underneath the ViT of step i + 1 (pipeline.SideStream; --head-stream 0 for one stream); every step's work
-  completes inside the timed region.
+  head on this rank's 8 clips x 16 frames (RGB + flow) -> prototype scores (P=2).  Consecutive steps alternate between two
+  pipeline lanes (CUDA streams, pipeline.Lanes; --lanes 1 for a single stream): one batch's kernel tails and head are
+  filled by the other batch's kernels.  Every step's work completes inside the timed region.
 This is BASELINE.json configs[1] (ViT-S/16, batch 256, 1xB200) with the SAIS head of the metric on top.
 
 value : frames/s with the u8 frames already resident in HBM (max over ranks, CUDA events, K steps).
 e2e   : same metric through the public API (sais_b200.pipeline.extract_features + fullModel + scoring) with the
         frames in PINNED HOST memory: H2D of every batch and D2H of embeddings + clip scores inside the timed region.
         Before timing, one e2e step is checked bit for bit against the resident step on the same frames.
-roofline : the DOMINANT KERNEL of the step (mlp_fused_kernel), CUDA events around every one of its launches.
+roofline : the DOMINANT KERNEL of the step (mlp_fused_kernel), CUDA events around every one of its launches (separate
+        single-lane pass, so that a launch's time is its own).
 extra : the other BASELINE configs measured in the same run — C1 (10+10-frame clip), C3 (head, 512 clips x 30 frames),
         C4 (60-min video, 3,600+3,600 frames, STRONG scaling over the ranks), C5 (1,000 ragged clips sharded by clip).
 --impl reference : the reference's algorithm on the host CPU (oracle port, all cores) on a bounded sample per step.
@@ -24,6 +25,7 @@ extra : the other BASELINE configs measured in the same run — C1 (10+10-frame 
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import sys
@@ -214,15 +216,18 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the C1 / C3 / C4 / C5 legs")
     ap.add_argument("--chunk", type=int, default=256, help="ViT frames per workspace chunk")
-    ap.add_argument("--vit-sms", type=int, default=140,
+    ap.add_argument("--vit-sms", type=int, default=0,
                     help="with --head-stream 1: SMs the ViT's persistent kernels may occupy (even; 0 = all), the rest are left "
                          "to the concurrent head (sais_set_sm_limit).  140 of 148 costs the ViT almost nothing at batch 256 — "
                          "1,536 attention items = 11 rounds on 140 CTAs as on 148, 197 MLP row tiles = 3 rounds on 70 CTA "
                          "pairs as on 74 — and measured +3.3 %% frames/s")
-    ap.add_argument("--head-stream", type=int, default=1,
-                    help="1 (default): run the temporal head + scoring of step i on a second (high-priority) stream, under the "
-                         "ViT of step i+1 (pipeline.SideStream: software pipelining across steps; every step's work stays "
-                         "inside the timed region); 0: one stream")
+    ap.add_argument("--lanes", type=int, default=2,
+                    help="pipeline lanes (pipeline.Lanes): consecutive steps go to consecutive CUDA streams, so one batch's kernel "
+                         "tails and head are filled by the other batch's kernels (default 2)")
+    ap.add_argument("--head-stream", type=int, default=0,
+                    help="1: run the temporal head + scoring of a step on a separate high-priority stream "
+                         "(pipeline.SideStream) instead of on the step's lane; with --lanes 1 --vit-sms 140 this is the "
+                         "single-lane way of hiding the head (88.6 k frames/s); with two lanes it is not needed")
     args = ap.parse_args()
     if args.impl == "reference":
         args.warmup = max(args.warmup, 1)
@@ -263,7 +268,11 @@ def main():
     dev_batches = [hb.to(dev) for hb in host_batches]
     pad = pipeline.full_mask(CLIPS_PER_STEP, CLIP_T, dev)
     n_global = FRAMES_PER_STEP * world
-    gatherer = pipeline.EmbeddingGatherer(n_global, 384, rank, world, dev)
+    # pipeline lanes: consecutive steps go to consecutive CUDA streams (pipeline.Lanes); result slot i % depth belongs to
+    # lane i % n_lanes, so nothing is shared between lanes but the (read-only) weights
+    lanes = pipeline.Lanes(dev, args.lanes)
+    depth = len(lanes) if len(lanes) > 1 else 2
+    gatherer = pipeline.EmbeddingGatherer(n_global, 384, rank, world, dev, depth=depth)
 
     def head_and_score(own):
         # this rank's clips: 8 RGB clips from the first half of its frame range, 8 flow clips from the second half
@@ -273,11 +282,11 @@ def main():
         pred, probs = scoring.predict(out, protos)
         return out, probs, pred
 
-    side = pipeline.SideStream(dev) if args.head_stream else None
+    side = pipeline.SideStream(dev, slots=depth) if args.head_stream else None
 
     def run_head(i, own):
-        """head + scoring of step i; by default on the side stream, ordered after the ViT of step i (and joined before the
-        ViT of step i + 2 overwrites the gather slot it reads)"""
+        """head + scoring of step i: on the step's lane, or (--head-stream 1) on a high-priority side stream ordered after
+        the lane's ViT and joined before the slot it reads is overwritten"""
         if side is None:
             return head_and_score(own)
         return side.run(i, head_and_score, own)
@@ -285,37 +294,39 @@ def main():
     def claim_slot(i):
         own = gatherer.own_slice(i)
         if side is not None:
-            side.guard(i)  # the head that read this slot two steps ago
+            side.guard(i)  # the head that read this slot `depth` steps ago
         return own
 
     vit_limit = _lib.sm_limit(args.vit_sms if (args.head_stream and args.vit_sms) else 0)
 
     def step_resident(i):
-        own = claim_slot(i)                       # the final-LN kernel writes at rank * count of the gather buffer
-        with vit_limit:
-            vit.forward_u8(dev_batches[i % nbuf], out=own)
-        gatherer.gather_async(i)                  # in place, on NCCL's stream; the head below reads own rows only
-        return own, run_head(i, own)
+        with lanes.lane(i):
+            own = claim_slot(i)                   # the final-LN kernel writes at rank * count of the gather buffer
+            with vit_limit:
+                vit.forward_u8(dev_batches[i % nbuf], out=own)
+            gatherer.gather_async(i)              # in place, on NCCL's stream; the head below reads own rows only
+            return own, run_head(i, own)
 
-    emb_host = torch.empty((FRAMES_PER_STEP, 384), dtype=torch.float32).pin_memory()
-    probs_host = torch.empty((CLIPS_PER_STEP, 2), dtype=torch.float32).pin_memory()
+    emb_host = [torch.empty((FRAMES_PER_STEP, 384), dtype=torch.float32).pin_memory() for _ in range(depth)]
+    probs_host = [torch.empty((CLIPS_PER_STEP, 2), dtype=torch.float32).pin_memory() for _ in range(depth)]
 
     def step_e2e(i):
-        own = claim_slot(i)
-        with vit_limit:
-            pipeline.extract_features(vit, host_batches[i % nbuf], batch_size=FRAMES_PER_STEP, device=dev, out=own)
-        gatherer.gather_async(i)
-        out, probs, pred = run_head(i, own)
-        # device->host reads of the step's results: embeddings + clip probabilities (on the side stream when there is one,
-        # so the next batch's ViT does not queue behind two small PCIe transfers)
-        with torch.cuda.stream(side.stream if side is not None else torch.cuda.current_stream(dev)):
-            emb_host.copy_(own, non_blocking=True)
-            probs_host.copy_(probs, non_blocking=True)
-            if side is not None:
-                side.mark(i)
-        return own, (out, probs, pred)
+        with lanes.lane(i):
+            own = claim_slot(i)
+            with vit_limit:
+                pipeline.extract_features(vit, host_batches[i % nbuf], batch_size=FRAMES_PER_STEP, device=dev, out=own)
+            gatherer.gather_async(i)
+            out, probs, pred = run_head(i, own)
+            # device->host reads of the step's results: embeddings + clip probabilities, behind the head on its stream
+            with torch.cuda.stream(side.stream if side is not None else torch.cuda.current_stream(dev)):
+                emb_host[i % depth].copy_(own, non_blocking=True)
+                probs_host[i % depth].copy_(probs, non_blocking=True)
+                if side is not None:
+                    side.mark(i)
+            return own, (out, probs, pred)
 
     def join_side():
+        lanes.join()
         if side is not None:
             side.join()
 
@@ -333,10 +344,10 @@ def main():
         keep = (own_r.clone(), out_r.clone(), probs_r.clone())
         own_e, (out_e, probs_e, _) = step_e2e(i)
         barrier()
-        if not (torch.equal(own_e, keep[0]) and torch.equal(emb_host, keep[0].cpu())):
+        if not (torch.equal(own_e, keep[0]) and torch.equal(emb_host[i % depth], keep[0].cpu())):
             raise SystemExit("bench: e2e embeddings differ from the device-resident step")
         # (the small-batch head accumulates its split-K partials in L2 in arrival order: last-bit run-to-run differences)
-        if not (torch.allclose(out_e, keep[1], rtol=1e-3, atol=1e-4) and torch.allclose(probs_host, keep[2].cpu(), atol=1e-4)):
+        if not (torch.allclose(out_e, keep[1], rtol=1e-3, atol=1e-4) and torch.allclose(probs_host[i % depth], keep[2].cpu(), atol=1e-4)):
             raise SystemExit("bench: e2e clip vectors / probabilities differ from the device-resident step")
         if world > 1:  # the gathered buffer holds every rank's rows: compare a checksum of rank r's slice with rank r's own
             full = gatherer.buffer(i)
@@ -356,9 +367,10 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = lib.sais_launch_count()
         e0.record()
+        lanes.fork()         # the lanes start behind e0
         for i in range(steps):
             fn(warmup + i)
-        join_side()          # every head of the timed steps ...
+        join_side()          # every lane / head of the timed steps ...
         gatherer.wait_all()  # ... and every gather completes inside the timed region
         e1.record()
         barrier()
@@ -380,7 +392,7 @@ def main():
     barrier()
     lib.sais_profile_begin()
     for i in range(prof_steps):
-        step_resident(i)
+        step_resident(i * len(lanes))  # one lane only: per-kernel times must not include the other lane's kernels
     _lib.check(lib.sais_profile_end(ms_c, work_c, n_c, ncls), "sais_profile_end")
     barrier()
 
@@ -392,7 +404,9 @@ def main():
         step_resident(i)
     for i in range(probe_steps):
         step_resident(i)
-        _lib.check(lib.sais_clock_probe(probe[i].data_ptr(), 4000, torch.cuda.current_stream().cuda_stream), "clock_probe")
+        with lanes.lane(i):
+            _lib.check(lib.sais_clock_probe(probe[i].data_ptr(), 4000, torch.cuda.current_stream(dev).cuda_stream),
+                       "clock_probe")
     barrier()
     pr = probe.cpu().double()
     ghz = ((pr[:, 3] - pr[:, 1]) / (pr[:, 2] - pr[:, 0]).clamp(min=1.0)).tolist()
@@ -400,7 +414,7 @@ def main():
 
     extra = {}
     if not args.no_extra:
-        extra = run_extra_configs(torch, dist, dev, rank, world, vit, head, pipeline, postprocess, scoring, barrier)
+        extra = run_extra_configs(torch, dist, dev, rank, world, vit, head, pipeline, postprocess, scoring, barrier, lanes)
 
     if rank == 0:
         burst, sustained, hbm, src = load_peaks()
@@ -432,7 +446,8 @@ def main():
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": dict(workload_config(world), head_stream=bool(args.head_stream), vit_sms=args.vit_sms or "all"),
+            "config": dict(workload_config(world), lanes=len(lanes), head_stream=bool(args.head_stream),
+                           vit_sms=args.vit_sms or "all"),
             "flop_per_frame": {"reference_forward": FLOP_PER_FRAME, "executed": FLOP_PER_FRAME_EXECUTED,
                                "note": "last block evaluated on the CLS rows only (dead rows of the reference "
                                        "forward are not computed); fractions below use the EXECUTED flops"},
@@ -471,7 +486,7 @@ def main():
 
 
 # ------------------------------------------------------------------------------------------------ other BASELINE configs
-def run_extra_configs(torch, dist, dev, rank, world, vit, head, pipeline, postprocess, scoring, barrier):
+def run_extra_configs(torch, dist, dev, rank, world, vit, head, pipeline, postprocess, scoring, barrier, lanes):
     """C1 / C3 on every rank (rank 0 reports), C4 strong scaling and C5 sharded by clip over all ranks.  Device-timed with
     CUDA events, max over ranks; each leg: 1-2 warm-up passes + a few timed ones (bounded, ~2 s in total at N = 1)."""
     out = {}
@@ -537,14 +552,17 @@ def run_extra_configs(torch, dist, dev, rank, world, vit, head, pipeline, postpr
     g_flow = pipeline.EmbeddingGatherer(n, 384, rank, world, dev, frame_ranges=True)
 
     def c4():
-        for gat in (g_rgb, g_flow):
-            own = gat.own_slice(0)
-            k = 0
-            for b0 in range(0, hi - lo, 256):
-                nb = min(256, hi - lo - b0)
-                vit.forward_u8(shard_frames(k)[:nb], out=own[b0:b0 + nb])
-                k += 1
-            gat.gather_async(0)
+        lanes.fork()
+        for li, gat in enumerate((g_rgb, g_flow)):  # the RGB and the flow frames of the shard: one pipeline lane each
+            with lanes.lane(li):
+                own = gat.own_slice(0)
+                k = 0
+                for b0 in range(0, hi - lo, 256):
+                    nb = min(256, hi - lo - b0)
+                    vit.forward_u8(shard_frames(k)[:nb], out=own[b0:b0 + nb])
+                    k += 1
+                gat.gather_async(0)
+        lanes.join()
         g_rgb.wait_all()
         g_flow.wait_all()
         nw = pipe.num_windows(n, n)
@@ -571,11 +589,14 @@ def run_extra_configs(torch, dist, dev, rank, world, vit, head, pipeline, postpr
     vec_all = torch.empty((world * width, 256), dtype=torch.float32, device=dev)
 
     def c5():
+        lanes.fork()
         k = 0
-        for b0 in range(0, nr + nf, 256):
+        for b0 in range(0, nr + nf, 256):  # 256-frame chunks of the shard alternate between the lanes
             nb = min(256, nr + nf - b0)
-            vit.forward_u8(shard_frames(k)[:nb], out=emb[b0:b0 + nb])
+            with lanes.lane(k):
+                vit.forward_u8(shard_frames(k)[:nb], out=emb[b0:b0 + nb])
             k += 1
+        lanes.join()
         for b0 in range(0, len(own_ids), 32):
             ids = range(b0, min(b0 + 32, len(own_ids)))
             xs, xp, _ = postprocess.pad_collate([emb[r_off[i]:r_off[i + 1]].unsqueeze(0) for i in ids])

@@ -106,10 +106,16 @@ class TransformerEncoder(nn.Module):
         return self._packed
 
     def _workspace(self, total_tokens, device):
+        """One workspace per (device, CUDA stream) — see VisionTransformer._workspace."""
         need = lib().sais_temporal_workspace_bytes(total_tokens)
-        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=device)
-        return self._ws, need
+        if self._ws is None:
+            self._ws = {}
+        key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.uint8, device=device)
+            self._ws[key] = ws
+        return ws, need
 
     # ------------------------------------------------------------------ packed entry point
     @torch.no_grad()

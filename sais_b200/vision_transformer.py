@@ -171,10 +171,17 @@ class VisionTransformer(nn.Module):
         return w, keep
 
     def _workspace(self, chunk, device, precise):
+        """One workspace per (device, CUDA stream): forwards issued on different streams (pipeline.Lanes) may overlap in
+        time and must not share scratch buffers; forwards on one stream are ordered and reuse theirs."""
         need = lib().sais_vit_workspace_bytes(chunk, int(precise))
-        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=device)
-        return self._ws, need
+        if self._ws is None:
+            self._ws = {}
+        key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.uint8, device=device)
+            self._ws[key] = ws
+        return ws, need
 
     # ------------------------------------------------------------------ forward paths
     def _run(self, x, kind, want_probs=False, want_tokens=False, precision=None, out=None):
