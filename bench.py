@@ -221,9 +221,9 @@ def main():
                          "to the concurrent head (sais_set_sm_limit).  140 of 148 costs the ViT almost nothing at batch 256 — "
                          "1,536 attention items = 11 rounds on 140 CTAs as on 148, 197 MLP row tiles = 3 rounds on 70 CTA "
                          "pairs as on 74 — and measured +3.3 %% frames/s")
-    ap.add_argument("--lanes", type=int, default=2,
+    ap.add_argument("--lanes", type=int, default=3,
                     help="pipeline lanes (pipeline.Lanes): consecutive steps go to consecutive CUDA streams, so one batch's kernel "
-                         "tails and head are filled by the other batch's kernels (default 2)")
+                         "tails and head are filled by the other batches' kernels (default 3)")
     ap.add_argument("--head-stream", type=int, default=0,
                     help="1: run the temporal head + scoring of a step on a separate high-priority stream "
                          "(pipeline.SideStream) instead of on the step's lane; with --lanes 1 --vit-sms 140 this is the "

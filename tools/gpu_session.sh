@@ -11,7 +11,8 @@
 #   kernels                  tools/gemm_bench.py, mlp_bench.py, kernel_bench.py, head_bench.py, frames_bench.py
 #   timeline                 SAIS_MLP_TIMELINE / SAIS_ATTN_TIMELINE dumps of CTA 0 (tools/mlp_bench.py, kernel_bench.py)
 #   ncu_list                 launch list of two bench steps (gpu__time_duration)        -> launches.csv
-#   ncu_full:<kernel regex>  ncu --set full of three launches of the matching kernels   -> prof_<n>.ncu-rep
+#   ncu_full:<regex>[:skip]  ncu --set full of three launches of the matching kernels (after `skip` of them, default 12)
+#                            of tools/profile_step.py (two ViT forwards at batch 256)   -> prof_<n>.ncu-rep
 #   py:<script> [args]       any other tool script under tools/
 #   sh:<command>             any shell command (logged to sh_<n>.log)
 TAG=${1:-r02}; shift
@@ -52,9 +53,9 @@ PY
               SAIS_ATTN_TIMELINE=$OUT/timeline_attention.txt timeout 300 python tools/kernel_bench.py 256 > /dev/null 2>&1
               ls -la $OUT/timeline_* ;;
     ncu_list) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/launches.csv \
-                python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extra > $OUT/bench_under_ncu.log 2>&1; echo "rc=$?" ;;
-    ncu_full) NFULL=$((NFULL+1))
-              timeout 900 ncu --set full --clock-control none --import-source on -k regex:"$ARG" -s 24 -c 3 -f -o $OUT/prof_$NFULL \
+                python bench.py --steps 2 --warmup 3 --lanes 1 --no-cpu-baseline --no-extra > $OUT/bench_under_ncu.log 2>&1; echo "rc=$?" ;;
+    ncu_full) NFULL=$((NFULL+1)); RX=${ARG%%:*}; SKIP=12; [[ "$ARG" == *:* ]] && SKIP=${ARG#*:}
+              timeout 900 ncu --set full --clock-control none --import-source on -k regex:"$RX" -s $SKIP -c 3 -f -o $OUT/prof_$NFULL \
                 python tools/profile_step.py > $OUT/prof_$NFULL.log 2>&1; echo "rc=$?" ;;
     py)     timeout 600 python tools/$ARG > "$OUT/$(echo $ARG | tr ' /' '__').log" 2>&1; echo "rc=$?"; tail -30 "$OUT/$(echo $ARG | tr ' /' '__').log" ;;
     sh)     NSH=$((NSH+1)); timeout 600 bash -c "$ARG" > $OUT/sh_$NSH.log 2>&1; echo "rc=$?"; tail -12 $OUT/sh_$NSH.log ;;
