@@ -272,7 +272,8 @@ def main():
     # lane i % n_lanes, so nothing is shared between lanes but the (read-only) weights
     lanes = pipeline.Lanes(dev, args.lanes)
     depth = len(lanes) if len(lanes) > 1 else 2
-    gatherer = pipeline.EmbeddingGatherer(n_global, 384, rank, world, dev, depth=depth)
+    xgroup = pipeline.low_footprint_group() if world > 1 else None   # one-CTA NCCL collectives for the exchange
+    gatherer = pipeline.EmbeddingGatherer(n_global, 384, rank, world, dev, depth=depth, group=xgroup)
 
     def head_and_score(own):
         # this rank's clips: 8 RGB clips from the first half of its frame range, 8 flow clips from the second half
@@ -354,7 +355,7 @@ def main():
             sums = full.view(world, -1).double().sum(1)
             mine = sums[rank].clone()
             allsums = [torch.zeros_like(mine) for _ in range(world)]
-            dist.all_gather(allsums, mine)
+            dist.all_gather(allsums, mine)  # (default group: also checks the two communicators agree on the ranks)
             if not torch.equal(torch.stack(allsums), sums):
                 raise SystemExit("bench: gathered embeddings differ from the owners' rows")
 
@@ -414,7 +415,7 @@ def main():
 
     extra = {}
     if not args.no_extra:
-        extra = run_extra_configs(torch, dist, dev, rank, world, vit, head, pipeline, postprocess, scoring, barrier, lanes)
+        extra = run_extra_configs(torch, dist, dev, rank, world, vit, head, pipeline, postprocess, scoring, barrier, lanes, xgroup)
 
     if rank == 0:
         burst, sustained, hbm, src = load_peaks()
@@ -486,7 +487,7 @@ def main():
 
 
 # ------------------------------------------------------------------------------------------------ other BASELINE configs
-def run_extra_configs(torch, dist, dev, rank, world, vit, head, pipeline, postprocess, scoring, barrier, lanes):
+def run_extra_configs(torch, dist, dev, rank, world, vit, head, pipeline, postprocess, scoring, barrier, lanes, xgroup=None):
     """C1 / C3 on every rank (rank 0 reports), C4 strong scaling and C5 sharded by clip over all ranks.  Device-timed with
     CUDA events, max over ranks; each leg: 1-2 warm-up passes + a few timed ones (bounded, ~2 s in total at N = 1)."""
     out = {}
@@ -548,8 +549,8 @@ def run_extra_configs(torch, dist, dev, rank, world, vit, head, pipeline, postpr
         return pool[(k * 256) % 512: (k * 256) % 512 + 256]
 
     pipe = pipeline.SaisPipeline(vit, head, protos3, window=20, hop=10, tta_offsets=(0, 3, 6), batch_size=256)
-    g_rgb = pipeline.EmbeddingGatherer(n, 384, rank, world, dev, frame_ranges=True)
-    g_flow = pipeline.EmbeddingGatherer(n, 384, rank, world, dev, frame_ranges=True)
+    g_rgb = pipeline.EmbeddingGatherer(n, 384, rank, world, dev, frame_ranges=True, group=xgroup)
+    g_flow = pipeline.EmbeddingGatherer(n, 384, rank, world, dev, frame_ranges=True, group=xgroup)
 
     def c4():
         lanes.fork()
@@ -604,7 +605,7 @@ def run_extra_configs(torch, dist, dev, rank, world, vit, head, pipeline, postpr
             o, _ = head(xs, fs, None, None, 'Prototypes', xp, fp, None)
             vec_own[b0:b0 + len(ids)] = o
         if world > 1:
-            dist.all_gather_into_tensor(vec_all, vec_own)
+            dist.all_gather_into_tensor(vec_all, vec_own, group=xgroup)
             return scoring.predict(vec_all, protos2)
         return scoring.predict(vec_own, protos2)
 
