@@ -549,8 +549,10 @@ def run_extra_configs(torch, dist, dev, rank, world, vit, head, pipeline, postpr
         return pool[(k * 256) % 512: (k * 256) % 512 + 256]
 
     pipe = pipeline.SaisPipeline(vit, head, protos3, window=20, hop=10, tta_offsets=(0, 3, 6), batch_size=256)
-    g_rgb = pipeline.EmbeddingGatherer(n, 384, rank, world, dev, frame_ranges=True, group=xgroup)
-    g_flow = pipeline.EmbeddingGatherer(n, 384, rank, world, dev, frame_ranges=True, group=xgroup)
+    # (default communicator here: one 5.5 MB exchange per stream and video, nothing to overlap it with — bandwidth matters,
+    # the one-CTA group cost 1 ms per video at N = 8)
+    g_rgb = pipeline.EmbeddingGatherer(n, 384, rank, world, dev, frame_ranges=True)
+    g_flow = pipeline.EmbeddingGatherer(n, 384, rank, world, dev, frame_ranges=True)
 
     def c4():
         lanes.fork()
@@ -605,7 +607,7 @@ def run_extra_configs(torch, dist, dev, rank, world, vit, head, pipeline, postpr
             o, _ = head(xs, fs, None, None, 'Prototypes', xp, fp, None)
             vec_own[b0:b0 + len(ids)] = o
         if world > 1:
-            dist.all_gather_into_tensor(vec_all, vec_own, group=xgroup)
+            dist.all_gather_into_tensor(vec_all, vec_own)
             return scoring.predict(vec_all, protos2)
         return scoring.predict(vec_own, protos2)
 
