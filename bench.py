@@ -523,6 +523,18 @@ def run_extra_configs(torch, dist, dev, rank, world, vit, head, pipeline, postpr
     ms = time_passes(c1, 3, 20)
     out["C1_clip_10+10_frames"] = {"ms_per_clip": ms, "frames_per_s": 20 / (ms * 1e-3), "n_gpus": 1,
                                    "note": "latency-bound: 20 frames is 0.08 of one ViT row-tile round"}
+    # the same clip step as ONE CUDA-graph launch (pipeline.CapturedStep): ~120 kernel launches -> 1
+    try:
+        def c1_step(frames):
+            e = vit.forward_u8(frames)
+            o, _ = head(e[:10].view(1, 1, 10, 384), e[10:].view(1, 1, 10, 384), None, None, 'Prototypes', pad10, pad10, None)
+            return scoring.predict(o, protos2)
+
+        graphed = pipeline.CapturedStep(c1_step, c1_frames)
+        ms_g = time_passes(lambda: graphed(c1_frames), 3, 20)
+        out["C1_clip_10+10_frames"].update({"ms_per_clip_cuda_graph": ms_g, "frames_per_s_cuda_graph": 20 / (ms_g * 1e-3)})
+    except Exception as ex:  # reported, never fatal for the headline
+        out["C1_clip_10+10_frames"]["cuda_graph_error"] = f"{type(ex).__name__}: {str(ex)[:160]}"
 
     # ---- C3: temporal head alone, 512 clips x 30 frames (RGB + flow), attention maps out
     x = torch.randn(512, 1, 30, 384, device=dev, generator=g)

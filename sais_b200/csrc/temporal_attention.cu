@@ -162,6 +162,203 @@ seq_attention_f32_kernel(const float* __restrict__ qkv, const int32_t* __restric
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Tensor-core variant for the temporal head (4 heads x 96, S <= 80): warp-level TF32 MMAs on [hi | lo] operand splits
+// ("3xTF32": hi*hi + lo*hi + hi*lo with hi = tf32(x), lo = x - hi; the dropped lo*lo term and the representation error are
+// both 2^-22 relative, i.e. fp32-grade like the scalar kernel above — a bf16 split would be 2^-17, visible at the 2e-5
+// tolerance this kernel is tested to).
+//
+// Why warp-level mma.sync and not tcgen05 here: one (sequence, head) problem is S x S x 96 with S = 11..65 rows, a small
+// fraction of the 128-row UMMA tile.  Packing consecutive sequences into one 128-row tile makes the logits block-diagonal
+// (3/4 of the MMA work wasted at S = 31, on top of the 3x of the split) and needs a staging pass that converts the fp32
+// q|k|v rows to operand tiles in shared memory first; the 16-row warp tile pads S = 31 to 32 and takes its operand
+// fragments straight from the fp32 rows in L2.  The work is a few GFLOP per launch either way; what the scalar kernel
+// above lost was shared-memory bandwidth (one LDS.128 per 4 FMA).
+//
+// CTA = (16-row block, sequence); warp = head; g = lane / 4, t = lane % 4 (the m16n8k8 fragment coordinates).  Per warp:
+//   S = Q Kt  : per 8-dim k-step the Q fragment (rows r0 + g, r0 + g + 8; dims t, t + 4) and, per 8-key tile, the K fragment
+//               (key g; dims t, t + 4): the four lanes of a quad read one 32-byte sector of a row
+//   softmax   : exact, in the accumulator layout (row statistics across the 4 lanes of a quad); padded / out-of-range keys
+//               get -inf and come out as exactly 0
+//   head mean : the four warps park their normalised rows in shared memory and sum them in a fixed head order
+//   O = P V   : the probability accumulators ARE the A fragments of the second MMA: the summation index of an MMA can be
+//               permuted freely as long as A and B agree, so slot k = t stands for key 2t and slot k = t + 4 for key 2t + 1
+//               of the 8-key tile — exactly the two columns a lane's accumulators hold; V fragments are (key 2t, 2t + 1; dim g)
+// Output: bf16 [hi | lo] halves for the split-precision out-proj GEMM, as above.
+__device__ __forceinline__ void mma_tf32_1688(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  lo = __float_as_uint(x - __uint_as_float(hi));  // exact; the MMA reads its upper 19 bits
+}
+
+template <int MAXNT>
+__global__ void __launch_bounds__(128)
+seq_attention_mma_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ seq_offsets,
+                         const uint8_t* __restrict__ key_pad, const int64_t* __restrict__ attn_offsets, float scale,
+                         __nv_bfloat16* __restrict__ out_split, float* __restrict__ attn_mean) {
+  constexpr int H = 4, HD = 96, E = H * HD, LD = 3 * E;
+  constexpr int SP = MAXNT * 8 + 4;  // smem row pitch of the parked probabilities
+  __shared__ float probs_s[H][16][SP];
+  pdl_wait();  // (PDL, common.cuh) no global access above this line
+  const int i = blockIdx.y;
+  const int t0 = seq_offsets[i];
+  const int S = seq_offsets[i + 1] - t0;
+  const int r0 = blockIdx.x * 16;
+  if (r0 >= S) return;
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int NT = (S + 7) >> 3;  // 8-key tiles in use (warp-uniform)
+  const float* base = qkv + int64_t(t0) * LD + h * HD;
+
+  // ---- S = Q Kt
+  float sacc[MAXNT][4];
+#pragma unroll
+  for (int nt = 0; nt < MAXNT; ++nt) sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
+  const bool qa = (r0 + g) < S, qb = (r0 + g + 8) < S;
+  const float* qpa = base + int64_t(r0 + g) * LD + t;
+  const float* qpb = qpa + 8 * LD;
+#pragma unroll
+  for (int ks = 0; ks < HD / 8; ++ks) {
+    uint32_t ah[4], al[4];
+    split_tf32(qa ? qpa[ks * 8] : 0.f, ah[0], al[0]);
+    split_tf32(qb ? qpb[ks * 8] : 0.f, ah[1], al[1]);
+    split_tf32(qa ? qpa[ks * 8 + 4] : 0.f, ah[2], al[2]);
+    split_tf32(qb ? qpb[ks * 8 + 4] : 0.f, ah[3], al[3]);
+#pragma unroll
+    for (int nt = 0; nt < MAXNT; ++nt) {
+      if (nt < NT) {
+        const int key = nt * 8 + g;
+        const float* kp = base + E + int64_t(key) * LD + ks * 8 + t;
+        const bool kv = key < S;
+        uint32_t bh0, bl0, bh1, bl1;
+        split_tf32(kv ? kp[0] : 0.f, bh0, bl0);
+        split_tf32(kv ? kp[4] : 0.f, bh1, bl1);
+        mma_tf32_1688(sacc[nt], al, bh0, bh1);
+        mma_tf32_1688(sacc[nt], ah, bl0, bl1);
+        mma_tf32_1688(sacc[nt], ah, bh0, bh1);
+      }
+    }
+  }
+
+  // ---- exact softmax over the keys of this sequence (rows g and g + 8 of the block; columns nt * 8 + 2t, + 1)
+  const uint8_t* pad = key_pad ? key_pad + t0 : nullptr;
+  float ma = -INFINITY, mb = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < MAXNT; ++nt) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int key = nt * 8 + 2 * t + c;
+      const bool ok = nt < NT && key < S && !(pad && pad[key]);
+      sacc[nt][c] = ok ? sacc[nt][c] * scale : -INFINITY;
+      sacc[nt][2 + c] = ok ? sacc[nt][2 + c] * scale : -INFINITY;
+      ma = fmaxf(ma, sacc[nt][c]);
+      mb = fmaxf(mb, sacc[nt][2 + c]);
+    }
+  }
+  ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 1));
+  ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 2));
+  mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 1));
+  mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 2));
+  float sa = 0.f, sb = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < MAXNT; ++nt) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const float pa = expf(sacc[nt][c] - ma), pb = expf(sacc[nt][2 + c] - mb);
+      sacc[nt][c] = pa;
+      sacc[nt][2 + c] = pb;
+      sa += pa;
+      sb += pb;
+    }
+  }
+  sa += __shfl_xor_sync(0xffffffffu, sa, 1);
+  sa += __shfl_xor_sync(0xffffffffu, sa, 2);
+  sb += __shfl_xor_sync(0xffffffffu, sb, 1);
+  sb += __shfl_xor_sync(0xffffffffu, sb, 2);
+  const float ia = 1.0f / sa, ib = 1.0f / sb;
+#pragma unroll
+  for (int nt = 0; nt < MAXNT; ++nt) {
+    sacc[nt][0] *= ia; sacc[nt][1] *= ia;
+    sacc[nt][2] *= ib; sacc[nt][3] *= ib;
+  }
+
+  // ---- head-averaged map of this row block (heads summed in a fixed order: deterministic)
+  const int64_t aoff = (attn_mean != nullptr && attn_offsets != nullptr) ? attn_offsets[i] : -1;  // block-uniform
+  if (aoff >= 0) {
+#pragma unroll
+    for (int nt = 0; nt < MAXNT; ++nt) {
+      *reinterpret_cast<float2*>(&probs_s[h][g][nt * 8 + 2 * t]) = make_float2(sacc[nt][0], sacc[nt][1]);
+      *reinterpret_cast<float2*>(&probs_s[h][g + 8][nt * 8 + 2 * t]) = make_float2(sacc[nt][2], sacc[nt][3]);
+    }
+    __syncthreads();
+    const int rows = min(16, S - r0);
+    for (int e = threadIdx.x; e < rows * S; e += 128) {
+      const int r = e / S, j = e - r * S;
+      const float a = ((probs_s[0][r][j] + probs_s[1][r][j]) + probs_s[2][r][j]) + probs_s[3][r][j];
+      attn_mean[aoff + int64_t(r0 + r) * S + j] = a * (1.0f / H);
+    }
+  }
+
+  // ---- O = P V  (k slot t <-> key 2t, slot t + 4 <-> key 2t + 1 of the tile)
+  float oacc[HD / 8][4];
+#pragma unroll
+  for (int dt = 0; dt < HD / 8; ++dt) oacc[dt][0] = oacc[dt][1] = oacc[dt][2] = oacc[dt][3] = 0.f;
+  const float* vbase = base + 2 * E + g;
+#pragma unroll
+  for (int nt = 0; nt < MAXNT; ++nt) {
+    if (nt < NT) {
+      uint32_t ph[4], pl[4];
+      split_tf32(sacc[nt][0], ph[0], pl[0]);  // (row g,     key 2t)
+      split_tf32(sacc[nt][2], ph[1], pl[1]);  // (row g + 8, key 2t)
+      split_tf32(sacc[nt][1], ph[2], pl[2]);  // (row g,     key 2t + 1)
+      split_tf32(sacc[nt][3], ph[3], pl[3]);  // (row g + 8, key 2t + 1)
+      const int k0 = nt * 8 + 2 * t;
+      const float* v0 = vbase + int64_t(k0) * LD;
+      const bool e0 = k0 < S, e1 = k0 + 1 < S;
+#pragma unroll
+      for (int dt = 0; dt < HD / 8; ++dt) {
+        uint32_t bh0, bl0, bh1, bl1;
+        split_tf32(e0 ? v0[dt * 8] : 0.f, bh0, bl0);
+        split_tf32(e1 ? v0[LD + dt * 8] : 0.f, bh1, bl1);
+        mma_tf32_1688(oacc[dt], pl, bh0, bh1);
+        mma_tf32_1688(oacc[dt], ph, bl0, bl1);
+        mma_tf32_1688(oacc[dt], ph, bh0, bh1);
+      }
+    }
+  }
+  __nv_bfloat16* oa = out_split + int64_t(t0 + r0 + g) * (2 * E) + h * HD + 2 * t;
+  __nv_bfloat16* ob = oa + int64_t(8) * (2 * E);
+#pragma unroll
+  for (int dt = 0; dt < HD / 8; ++dt) {
+    if (qa) {
+      const uint32_t hi = pack_bf16x2(oacc[dt][0], oacc[dt][1]);
+      *reinterpret_cast<uint32_t*>(oa + dt * 8) = hi;
+      *reinterpret_cast<uint32_t*>(oa + E + dt * 8) = pack_bf16x2(oacc[dt][0] - bf16_lo(hi), oacc[dt][1] - bf16_hi(hi));
+    }
+    if (qb) {
+      const uint32_t hi = pack_bf16x2(oacc[dt][2], oacc[dt][3]);
+      *reinterpret_cast<uint32_t*>(ob + dt * 8) = hi;
+      *reinterpret_cast<uint32_t*>(ob + E + dt * 8) = pack_bf16x2(oacc[dt][2] - bf16_lo(hi), oacc[dt][3] - bf16_hi(hi));
+    }
+  }
+}
+
+template <int MAXNT>
+int launch_seq_attention_mma(const float* qkv, const int32_t* seq_offsets, const uint8_t* key_pad,
+                             const int64_t* attn_offsets, int nseq, int max_S, float scale, sais_bf16* out_split,
+                             float* attn_mean, cudaStream_t stream) {
+  LaunchScope ls(kClsTemporalAttn, stream, 0.0);
+  return check_cuda(launch_pdl(seq_attention_mma_kernel<MAXNT>, dim3((max_S + 15) / 16, nseq), dim3(128), size_t(0), stream,
+                               1, qkv, seq_offsets, key_pad, attn_offsets, scale,
+                               reinterpret_cast<__nv_bfloat16*>(out_split), attn_mean),
+                    "seq_attention_mma launch");
+}
+
 template <int H, int HD>
 int launch_seq_attention(const float* qkv, const int32_t* seq_offsets, const uint8_t* key_pad,
                          const int64_t* attn_offsets, int nseq, int max_S, float scale, sais_bf16* out_split,
@@ -194,9 +391,21 @@ int launch_seq_attention(const float* qkv, const int32_t* seq_offsets, const uin
 int temporal_attention(const float* qkv, const int32_t* seq_offsets, const uint8_t* key_pad,
                        const int64_t* attn_offsets, int nseq, int max_S, sais_bf16* out_split, float* attn_out,
                        cudaStream_t stream) {
-  return launch_seq_attention<4, 96>(qkv, seq_offsets, key_pad, attn_offsets, nseq, max_S,
-                                     0.10206207261596575f /* 96^-0.5 */, out_split, attn_out, nullptr,
-                                     kClsTemporalAttn, stream);
+  constexpr float scale = 0.10206207261596575f;  // 96^-0.5
+  if (max_S <= 80 && nseq <= 65535) {  // the temporal head's range (clips of 10..65 tokens): tensor-core kernel
+    if (nseq == 0) return kOk;
+    if (!qkv || !seq_offsets || !out_split || nseq < 0 || max_S <= 0) {
+      set_last_error("seq_attention: bad arguments");
+      return kErrInvalidArg;
+    }
+    if (max_S <= 32)
+      return launch_seq_attention_mma<4>(qkv, seq_offsets, key_pad, attn_offsets, nseq, max_S, scale, out_split, attn_out, stream);
+    if (max_S <= 48)
+      return launch_seq_attention_mma<6>(qkv, seq_offsets, key_pad, attn_offsets, nseq, max_S, scale, out_split, attn_out, stream);
+    return launch_seq_attention_mma<10>(qkv, seq_offsets, key_pad, attn_offsets, nseq, max_S, scale, out_split, attn_out, stream);
+  }
+  return launch_seq_attention<4, 96>(qkv, seq_offsets, key_pad, attn_offsets, nseq, max_S, scale, out_split, attn_out,
+                                     nullptr, kClsTemporalAttn, stream);
 }
 
 int vit_attention_precise(const float* qkv, const int32_t* seq_offsets, int B, sais_bf16* out_split, float* probs,

@@ -14,6 +14,8 @@
   inference sampling contract of ``main.sh:27`` (``prepare_dataset.py:1711-1726, 2642-2672``), pinned to the reference's
   own statements by the fixture ``tests/golden/custom_gesture_windows.npz``.
 * :class:`SaisPipeline`: frames -> ViT -> windows -> temporal head -> prototype scores, the whole path.
+* :class:`CapturedStep`: a fixed-geometry step (e.g. one clip: ViT + head + scoring) captured once as a CUDA graph and
+  replayed with a single launch — for the latency-bound, one-clip-at-a-time end of the path.
 """
 from __future__ import annotations
 
@@ -223,6 +225,59 @@ class Lanes:
         cur = torch.cuda.current_stream(self.device)
         for st in self.streams:
             cur.wait_stream(st)
+
+
+class CapturedStep:
+    """One fixed-geometry step of the path as a CUDA graph: ``fn(*inputs)`` is run a few times, captured once, and every
+    later call is a single ``cudaGraphLaunch`` instead of the ~85 (ViT) + ~35 (temporal head) kernel launches it contains.
+
+    What it is for: the latency-bound end of the path — one clip at a time (BASELINE config C1: 10 + 10 frames through the
+    ViT, the head and the scoring is ~120 launches of a few microseconds each, so the GPU waits for the host's launch
+    calls).  Throughput-bound steps (batch 256) gain nothing: their launches are already hidden behind the kernels.
+
+    The kernels' programmatic-dependent-launch attributes are captured as programmatic graph edges, so the replay keeps the
+    same overlap as the stream version; results are the eager path's (same kernels, same order, same workspaces).
+    Contract (the usual one for graphs): tensor arguments are copied into the static input tensors captured with the graph
+    (same shapes / dtypes as the examples), non-tensor arguments are frozen at capture, and the returned tensors are the
+    graph's static outputs — overwritten by the next call, so ``clone()`` what must survive it.  ``fn`` must be free of
+    host synchronisation and of host->device copies once warm (true for ``forward_u8``, ``fullModel.forward`` and
+    ``scoring.predict`` on a geometry they have seen: offset tables and packed weights are cached)."""
+
+    def __init__(self, fn, *example_inputs, warmup: int = 2):
+        tensors = [t for t in example_inputs if torch.is_tensor(t)]
+        if not tensors or tensors[0].device.type != "cuda":
+            raise ValueError("CapturedStep needs at least one CUDA tensor argument")
+        self.device = tensors[0].device
+        self.fn = fn
+        self.static_in = [t.clone() if torch.is_tensor(t) else t for t in example_inputs]
+        cur = torch.cuda.current_stream(self.device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.stream.wait_stream(cur)
+        with torch.cuda.device(self.device), torch.no_grad():
+            with torch.cuda.stream(self.stream):
+                # warm-up on the capture stream itself: per-stream workspaces, geometry tables and per-device function
+                # attributes exist before the capture starts (nothing inside it allocates outside the graph's pool)
+                for _ in range(max(int(warmup), 1)):
+                    fn(*self.static_in)
+            cur.wait_stream(self.stream)
+            torch.cuda.synchronize(self.device)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=self.stream):
+                self.static_out = fn(*self.static_in)
+        self.replays = 0
+
+    def __call__(self, *inputs):
+        if len(inputs) != len(self.static_in):
+            raise ValueError(f"expected {len(self.static_in)} arguments")
+        for dst, src in zip(self.static_in, inputs):
+            if torch.is_tensor(dst):
+                if not torch.is_tensor(src) or src.shape != dst.shape or src.dtype != dst.dtype:
+                    raise ValueError("CapturedStep inputs must keep the captured shapes and dtypes")
+                if src.data_ptr() != dst.data_ptr():
+                    dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        self.replays += 1
+        return self.static_out
 
 
 # --------------------------------------------------------------------------------------------- windows / TTA

@@ -92,30 +92,36 @@ def save_h5(results_dir: str, model_type: str, reps, labels: Sequence[str], kind
     """The HDF5 hand-off between feature extraction and the head, exactly as ``saveH5`` writes it
     (extract_representations.py:389-407): one float32 dataset ``[n_frames,384]`` per video label, rows in frame order,
     in ``<model_type>_RepsAndLabels.h5`` (``_FlowRepsAndLabels.h5`` for optical-flow frames).  ``reps``: ``[n,384]``
-    tensor / array, ``labels``: the per-frame video label.  Needs ``h5py`` (a dependency of the reference scripts);
-    raises ImportError with that hint when it is not installed."""
-    try:
-        import h5py
-    except ImportError as e:  # pragma: no cover - depends on the environment
-        raise ImportError("save_h5 / load_h5 need h5py, as the reference's own saveH5 does") from e
+    tensor / array, ``labels``: the per-frame video label.  Written with ``h5py`` when it is installed (a dependency of
+    the reference scripts) and otherwise with the built-in writer (:mod:`sais_b200.h5lite`: the same contiguous
+    version-0-superblock layout libhdf5 produces for this call, so ``h5py.File(path)[label][idx, :]`` reads it back)."""
     reps = reps.detach().cpu().numpy() if isinstance(reps, torch.Tensor) else np.asarray(reps)
     labels = np.asarray(list(labels))
     suffix = {"rgb": "%s_RepsAndLabels.h5", "flow": "%s_FlowRepsAndLabels.h5", "seg": "%s_SegRepsAndLabels.h5"}[kind]
     os.makedirs(results_dir, exist_ok=True)
     path = os.path.join(results_dir, suffix % model_type)
-    with h5py.File(path, "w") as hf:
-        for label in np.unique(labels):
-            hf.create_dataset(str(label), data=reps[np.where(labels == label)[0]].astype(np.float32))
+    per_label = {str(label): reps[np.where(labels == label)[0]].astype(np.float32) for label in np.unique(labels)}
+    try:
+        import h5py
+    except ImportError:
+        from . import h5lite
+        h5lite.write(path, per_label)
+        return path
+    with h5py.File(path, "w") as hf:  # pragma: no cover - depends on the environment
+        for label, rows in per_label.items():
+            hf.create_dataset(label, data=rows)
     return path
 
 
 def load_h5(path: str) -> Dict[str, np.ndarray]:
-    """``{video label: [n_frames,384] float32}`` as prepare_dataset.py:317-319, 2658-2667 reads it."""
+    """``{video label: [n_frames,384] float32}`` as prepare_dataset.py:317-319, 2658-2667 reads it (``h5py`` when installed,
+    :mod:`sais_b200.h5lite` otherwise)."""
     try:
         import h5py
-    except ImportError as e:  # pragma: no cover
-        raise ImportError("save_h5 / load_h5 need h5py, as the reference's own saveH5 does") from e
-    with h5py.File(path, "r") as hf:
+    except ImportError:
+        from . import h5lite
+        return h5lite.read(path)
+    with h5py.File(path, "r") as hf:  # pragma: no cover
         return {k: np.asarray(hf[k]) for k in hf.keys()}
 
 

@@ -99,3 +99,33 @@ def test_forward_u8_out_argument(dev, vit):
     assert torch.equal(buf[2:7], vit.forward_u8(fr)) and not buf[:2].any() and not buf[7:].any()
     with pytest.raises(SaisError):
         vit.forward_u8(fr, out=buf[:4])
+
+
+def test_captured_step_replays_the_eager_clip_path(dev, vit):
+    """pipeline.CapturedStep: one C1-shaped clip (10 RGB + 10 flow frames -> ViT -> temporal head -> prototype scores)
+    captured as a CUDA graph; replays on new frames equal the eager path (ViT embeddings bit for bit; the small-batch head
+    adds its split-K partials in L2 in arrival order, so the clip vector carries the same 1e-3 bound as bench.py's e2e gate)."""
+    from sais_b200 import pipeline, scoring
+    from test_gpu_models import _head
+
+    head = _head(O.make_head_weights(0), dev, 'RGB-Flow')
+    protos = torch.randn(2, 256, generator=torch.Generator().manual_seed(9)).to(dev)
+    pad = pipeline.full_mask(1, 10, dev)
+
+    def clip_step(frames):
+        e = vit.forward_u8(frames)
+        out, attn = head(e[:10].view(1, 1, 10, 384), e[10:].view(1, 1, 10, 384), None, None, 'Prototypes', pad, pad, None)
+        pred, probs = scoring.predict(out, protos)
+        return e, out, attn, pred, probs
+
+    step = pipeline.CapturedStep(clip_step, _host_frames(20, 500).to(dev))
+    for seed in (501, 502, 503):
+        fr = _host_frames(20, seed).to(dev)
+        want = [t.clone() for t in clip_step(fr)]
+        got = [t.clone() for t in step(fr)]
+        assert torch.equal(got[0], want[0])
+        assert torch.allclose(got[1], want[1], atol=1e-3, rtol=1e-3)
+        assert torch.allclose(got[2], want[2], atol=1e-4)
+        assert torch.equal(got[3], want[3]) and torch.allclose(got[4], want[4], atol=1e-4)
+    assert step.replays == 3
+    torch.cuda.synchronize()

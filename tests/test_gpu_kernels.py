@@ -474,7 +474,8 @@ def _tmp_attn_ref(qkv, lens_S, pads):
     return torch.cat(outs), attns
 
 
-@pytest.mark.parametrize("lens_S", [[11], [31] * 5, [16, 13, 10, 3, 3, 2], [65, 40], [200, 31]])
+@pytest.mark.parametrize("lens_S", [[11], [31] * 5, [16, 13, 10, 3, 3, 2], [65, 40], [200, 31], [48, 47, 33, 1],
+                                    [80, 79, 64, 17], [32, 16, 17, 8, 9], [81, 5]])
 def test_temporal_attention(dev, lens_S):
     from sais_b200 import ops
     total = sum(lens_S)

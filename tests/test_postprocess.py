@@ -1,5 +1,7 @@
 """CPU: window post-processing and clip collation (host logic either side of the temporal head) against the
 reference-pinned oracle (oracle/post_oracle.py) and the golden outputs of the reference's own functions."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -98,10 +100,67 @@ def test_reps_and_labels_round_trip(tmp_path):
 
 
 def test_h5_round_trip(tmp_path):
-    pytest.importorskip("h5py")  # not in this image; the reference requires it (requirements.txt)
+    """saveH5 / the h5py reads of prepare_dataset.py through the package (h5py when installed, else sais_b200.h5lite)."""
     reps = torch.randn(7, 384)
     labels = ["vidA"] * 3 + ["vidB"] * 4
     path = PP.save_h5(str(tmp_path), "ViT_SelfSupervised_ImageNet", reps, labels)
     assert path.endswith("ViT_SelfSupervised_ImageNet_RepsAndLabels.h5")
     back = PP.load_h5(path)
     assert set(back) == {"vidA", "vidB"} and np.array_equal(back["vidB"], reps[3:].numpy())
+    assert back["vidA"].dtype == np.float32 and back["vidA"].shape == (3, 384)
+    fpath = PP.save_h5(str(tmp_path), "ViT_SelfSupervised_ImageNet", reps, labels, kind="flow")
+    assert fpath.endswith("ViT_SelfSupervised_ImageNet_FlowRepsAndLabels.h5")
+
+
+_LIBHDF5_FILE = os.path.join(os.path.dirname(__import__("scipy").__file__), "io", "matlab", "tests", "data",
+                             "testhdf5_7.4_GLNX86.mat")
+
+
+@pytest.mark.skipif(not os.path.exists(_LIBHDF5_FILE), reason="SciPy's MATLAB-7.3 (HDF5) test file is not installed")
+def test_h5lite_reads_a_libhdf5_file():
+    """The reader against a file libhdf5 itself wrote (MATLAB 7.3 = HDF5 behind a 512-byte user block): version-0
+    superblock with a base address, symbol-table group, B-tree / SNOD / local heap, version-1 object header with six
+    messages, float64 dataset.  SciPy's own test expects exactly linspace(0, 2 pi, 9) in 'testdouble'."""
+    from sais_b200 import h5lite
+
+    d = h5lite.describe(_LIBHDF5_FILE)
+    assert d["base"] == 512 and d["members"] == ["testdouble"] and (d["leaf_k"], d["int_k"]) == (4, 16)
+    got = h5lite.read(_LIBHDF5_FILE)["testdouble"]
+    assert got.dtype == np.float64 and got.shape == (9, 1)
+    assert np.array_equal(got.ravel(), np.linspace(0, 2 * np.pi, 9))
+
+
+def test_h5lite_writer_layout_and_round_trip(tmp_path):
+    """The writer through the libhdf5-pinned reader: many videos (more than one default symbol-table node holds), names in
+    strcmp order, dtypes, empty datasets; message encodings compared byte for byte with what libhdf5 wrote in the file above."""
+    import struct
+    from sais_b200 import h5lite
+
+    rng = np.random.default_rng(0)
+    data = {f"P-{i:03d}_video{'_long_suffix' * (i % 3)}": rng.standard_normal((1 + i % 5, 384)).astype(np.float32)
+            for i in range(300)}
+    data["zzz_empty"] = np.zeros((0, 384), dtype=np.float32)
+    data["Upper"] = np.arange(6, dtype=np.int64).reshape(2, 3)
+    data["doubles"] = np.linspace(0, 2 * np.pi, 9).reshape(9, 1)
+    path = str(tmp_path / "many.h5")
+    h5lite.write(path, data)
+    back = h5lite.read(path)
+    assert set(back) == set(data)
+    for k, v in data.items():
+        assert back[k].dtype == v.dtype and back[k].shape == v.shape and np.array_equal(back[k], v), k
+    d = h5lite.describe(path)
+    assert d["members"] == sorted(data, key=lambda s: s.encode()) and d["base"] == 0 and d["root_cache_type"] == 1
+    assert d["eof"] == os.path.getsize(path) and d["leaf_k"] * 2 >= len(data)
+    with pytest.raises(h5lite.H5LiteError):
+        h5lite.write(str(tmp_path / "bad.h5"), {"a/b": np.zeros(3, np.float32)})
+    with pytest.raises(h5lite.H5LiteError):
+        h5lite.read(__file__)
+    if os.path.exists(_LIBHDF5_FILE):
+        # same float64 [9,1] dataset as the libhdf5-written file: datatype and dataspace messages must be byte-identical
+        theirs = h5lite._Reader(open(_LIBHDF5_FILE, "rb").read())
+        ours = h5lite._Reader(open(path, "rb").read())
+        t_msgs = dict(theirs._messages(dict(theirs.group_members(theirs.root_entry["ohdr"]))["testdouble"]))
+        o_msgs = dict(ours._messages(dict(ours.group_members(ours.root_entry["ohdr"]))["doubles"]))
+        assert o_msgs[0x0003] == t_msgs[0x0003] and o_msgs[0x0001] == t_msgs[0x0001] and o_msgs[0x0005] == t_msgs[0x0005]
+        addr, size = struct.unpack_from("<QQ", o_msgs[0x0008], 2)
+        assert o_msgs[0x0008][:2] == b"\x03\x01" and size == 72 and addr % 8 == 0

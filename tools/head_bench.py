@@ -36,12 +36,12 @@ for clips, T in ((8, 16), (512, 30)):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
-    ncls = 7
+    ncls = 10
     ms_c, work_c, n_c = (C.c_double * ncls)(), (C.c_double * ncls)(), (C.c_int64 * ncls)()
     lib.sais_profile_begin()
     for _ in range(5):
         step()
     lib.sais_profile_end(ms_c, work_c, n_c, ncls)
-    names = ["gemm", "vit_attn", "layernorm", "patchify", "temporal_attn", "misc", "gemm_split3"]
+    names = ["gemm", "vit_attn", "layernorm", "patchify", "temporal_attn", "misc", "gemm_split3", "mlp_fused", "gemm_qkv", "gemm_proj"]
     per = ", ".join(f"{n} {ms_c[i]/5*1e3:.0f}us/{n_c[i]//5}" for i, n in enumerate(names) if n_c[i])
     print(f"head {clips} clips x {T} frames (RGB+flow): {ms*1e3:8.1f} us/step  {clips/ms*1e3:9.0f} clips/s | {per}")
