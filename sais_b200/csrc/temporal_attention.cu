@@ -175,15 +175,20 @@ seq_attention_f32_kernel(const float* __restrict__ qkv, const int32_t* __restric
 // fragments straight from the fp32 rows in L2.  The work is a few GFLOP per launch either way; what the scalar kernel
 // above lost was shared-memory bandwidth (one LDS.128 per 4 FMA).
 //
-// CTA = (16-row block, sequence); warp = head; g = lane / 4, t = lane % 4 (the m16n8k8 fragment coordinates).  Per warp:
-//   S = Q Kt  : per 8-dim k-step the Q fragment (rows r0 + g, r0 + g + 8; dims t, t + 4) and, per 8-key tile, the K fragment
-//               (key g; dims t, t + 4): the four lanes of a quad read one 32-byte sector of a row
+// CTA = (16-row block, sequence); warp = head; g = lane / 4, t = lane % 4 (the m16n8k8 fragment coordinates).
+// The summation index of an MMA, and the column index of its B / D operands, can be permuted freely as long as both
+// operands (resp. the consumer of D) agree — used three times so that EVERY global access is a contiguous 16-byte load or
+// store and the code is branch-free (all loads of a phase issue back to back; out-of-range keys are predicated to zero):
+//   S = Q Kt  : k slot (step ks, k = t) stands for dim 24t + 2ks and slot (ks, k = t + 4) for dim 24t + 2ks + 1: a lane owns
+//               dims [24t, 24t + 24) of its Q rows (r0 + g, r0 + g + 8) and of key nt * 8 + g — six float4 loads per row,
+//               the four lanes of a quad read one whole 384-byte head row
 //   softmax   : exact, in the accumulator layout (row statistics across the 4 lanes of a quad); padded / out-of-range keys
 //               get -inf and come out as exactly 0
 //   head mean : the four warps park their normalised rows in shared memory and sum them in a fixed head order
-//   O = P V   : the probability accumulators ARE the A fragments of the second MMA: the summation index of an MMA can be
-//               permuted freely as long as A and B agree, so slot k = t stands for key 2t and slot k = t + 4 for key 2t + 1
-//               of the 8-key tile — exactly the two columns a lane's accumulators hold; V fragments are (key 2t, 2t + 1; dim g)
+//   O = P V   : the probability accumulators ARE the A fragments of the second MMA: k slot t stands for key 2t, slot t + 4
+//               for key 2t + 1 of the 8-key tile — exactly the two columns a lane's accumulators hold; B column g of dim
+//               tile dt stands for dim 12g + dt, so a lane reads 12 contiguous floats of V rows 2t and 2t + 1, and its
+//               output columns (2t, 2t + 1) of the 12 dim tiles are the contiguous dims [24t, 24t + 24) of rows g, g + 8
 // Output: bf16 [hi | lo] halves for the split-precision out-proj GEMM, as above.
 __device__ __forceinline__ void mma_tf32_1688(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -197,7 +202,7 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
 }
 
 template <int MAXNT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, MAXNT <= 4 ? 4 : 2)
 seq_attention_mma_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ seq_offsets,
                          const uint8_t* __restrict__ key_pad, const int64_t* __restrict__ attn_offsets, float scale,
                          __nv_bfloat16* __restrict__ out_split, float* __restrict__ attn_mean) {
@@ -212,7 +217,6 @@ seq_attention_mma_kernel(const float* __restrict__ qkv, const int32_t* __restric
   if (r0 >= S) return;
   const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int NT = (S + 7) >> 3;  // 8-key tiles in use (warp-uniform)
   const float* base = qkv + int64_t(t0) * LD + h * HD;
 
   // ---- S = Q Kt
@@ -220,24 +224,36 @@ seq_attention_mma_kernel(const float* __restrict__ qkv, const int32_t* __restric
 #pragma unroll
   for (int nt = 0; nt < MAXNT; ++nt) sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
   const bool qa = (r0 + g) < S, qb = (r0 + g + 8) < S;
-  const float* qpa = base + int64_t(r0 + g) * LD + t;
-  const float* qpb = qpa + 8 * LD;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 qra[6], qrb[6];  // dims [24t, 24t + 24) of rows r0 + g, r0 + g + 8
+  {
+    const float4* qpa = reinterpret_cast<const float4*>(base + int64_t(r0 + g) * LD + 24 * t);
+    const float4* qpb = reinterpret_cast<const float4*>(base + int64_t(r0 + g + 8) * LD + 24 * t);
 #pragma unroll
-  for (int ks = 0; ks < HD / 8; ++ks) {
-    uint32_t ah[4], al[4];
-    split_tf32(qa ? qpa[ks * 8] : 0.f, ah[0], al[0]);
-    split_tf32(qb ? qpb[ks * 8] : 0.f, ah[1], al[1]);
-    split_tf32(qa ? qpa[ks * 8 + 4] : 0.f, ah[2], al[2]);
-    split_tf32(qb ? qpb[ks * 8 + 4] : 0.f, ah[3], al[3]);
+    for (int c = 0; c < 6; ++c) {
+      qra[c] = qa ? __ldg(qpa + c) : zero4;
+      qrb[c] = qb ? __ldg(qpb + c) : zero4;
+    }
+  }
 #pragma unroll
-    for (int nt = 0; nt < MAXNT; ++nt) {
-      if (nt < NT) {
-        const int key = nt * 8 + g;
-        const float* kp = base + E + int64_t(key) * LD + ks * 8 + t;
-        const bool kv = key < S;
-        uint32_t bh0, bl0, bh1, bl1;
-        split_tf32(kv ? kp[0] : 0.f, bh0, bl0);
-        split_tf32(kv ? kp[4] : 0.f, bh1, bl1);
+  for (int nt = 0; nt < MAXNT; ++nt) {
+    const int key = nt * 8 + g;
+    const bool kv = key < S;
+    const float4* kp = reinterpret_cast<const float4*>(base + E + int64_t(key) * LD + 24 * t);
+    float4 kr[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) kr[c] = kv ? __ldg(kp + c) : zero4;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {  // k-step ks = 2c + hh covers dims 24t + 4c + 2hh, + 1
+        uint32_t ah[4], al[4], bh0, bl0, bh1, bl1;
+        split_tf32(hh ? qra[c].z : qra[c].x, ah[0], al[0]);
+        split_tf32(hh ? qrb[c].z : qrb[c].x, ah[1], al[1]);
+        split_tf32(hh ? qra[c].w : qra[c].y, ah[2], al[2]);
+        split_tf32(hh ? qrb[c].w : qrb[c].y, ah[3], al[3]);
+        split_tf32(hh ? kr[c].z : kr[c].x, bh0, bl0);
+        split_tf32(hh ? kr[c].w : kr[c].y, bh1, bl1);
         mma_tf32_1688(sacc[nt], al, bh0, bh1);
         mma_tf32_1688(sacc[nt], ah, bl0, bl1);
         mma_tf32_1688(sacc[nt], ah, bh0, bh1);
@@ -253,7 +269,7 @@ seq_attention_mma_kernel(const float* __restrict__ qkv, const int32_t* __restric
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       const int key = nt * 8 + 2 * t + c;
-      const bool ok = nt < NT && key < S && !(pad && pad[key]);
+      const bool ok = key < S && !(pad && pad[key]);
       sacc[nt][c] = ok ? sacc[nt][c] * scale : -INFINITY;
       sacc[nt][2 + c] = ok ? sacc[nt][2 + c] * scale : -INFINITY;
       ma = fmaxf(ma, sacc[nt][c]);
@@ -304,46 +320,60 @@ seq_attention_mma_kernel(const float* __restrict__ qkv, const int32_t* __restric
     }
   }
 
-  // ---- O = P V  (k slot t <-> key 2t, slot t + 4 <-> key 2t + 1 of the tile)
+  // ---- O = P V  (k slot t <-> key 2t, slot t + 4 <-> key 2t + 1 of the tile; B / D column g of tile dt <-> dim 12g + dt)
   float oacc[HD / 8][4];
 #pragma unroll
   for (int dt = 0; dt < HD / 8; ++dt) oacc[dt][0] = oacc[dt][1] = oacc[dt][2] = oacc[dt][3] = 0.f;
-  const float* vbase = base + 2 * E + g;
 #pragma unroll
   for (int nt = 0; nt < MAXNT; ++nt) {
-    if (nt < NT) {
-      uint32_t ph[4], pl[4];
-      split_tf32(sacc[nt][0], ph[0], pl[0]);  // (row g,     key 2t)
-      split_tf32(sacc[nt][2], ph[1], pl[1]);  // (row g + 8, key 2t)
-      split_tf32(sacc[nt][1], ph[2], pl[2]);  // (row g,     key 2t + 1)
-      split_tf32(sacc[nt][3], ph[3], pl[3]);  // (row g + 8, key 2t + 1)
-      const int k0 = nt * 8 + 2 * t;
-      const float* v0 = vbase + int64_t(k0) * LD;
-      const bool e0 = k0 < S, e1 = k0 + 1 < S;
+    uint32_t ph[4], pl[4];
+    split_tf32(sacc[nt][0], ph[0], pl[0]);  // (row g,     key 2t)
+    split_tf32(sacc[nt][2], ph[1], pl[1]);  // (row g + 8, key 2t)
+    split_tf32(sacc[nt][1], ph[2], pl[2]);  // (row g,     key 2t + 1)
+    split_tf32(sacc[nt][3], ph[3], pl[3]);  // (row g + 8, key 2t + 1)
+    const int k0 = nt * 8 + 2 * t;
+    const float4* v0 = reinterpret_cast<const float4*>(base + 2 * E + int64_t(k0) * LD + 12 * g);
+    const float4* v1 = reinterpret_cast<const float4*>(base + 2 * E + int64_t(k0 + 1) * LD + 12 * g);
+    const bool e0 = k0 < S, e1 = k0 + 1 < S;
+    float4 va[3], vb[3];
 #pragma unroll
-      for (int dt = 0; dt < HD / 8; ++dt) {
+    for (int c = 0; c < 3; ++c) {
+      va[c] = e0 ? __ldg(v0 + c) : zero4;
+      vb[c] = e1 ? __ldg(v1 + c) : zero4;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float xa[4] = {va[c].x, va[c].y, va[c].z, va[c].w};
+      const float xb[4] = {vb[c].x, vb[c].y, vb[c].z, vb[c].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
         uint32_t bh0, bl0, bh1, bl1;
-        split_tf32(e0 ? v0[dt * 8] : 0.f, bh0, bl0);
-        split_tf32(e1 ? v0[LD + dt * 8] : 0.f, bh1, bl1);
-        mma_tf32_1688(oacc[dt], pl, bh0, bh1);
-        mma_tf32_1688(oacc[dt], ph, bl0, bl1);
-        mma_tf32_1688(oacc[dt], ph, bh0, bh1);
+        split_tf32(xa[j], bh0, bl0);
+        split_tf32(xb[j], bh1, bl1);
+        mma_tf32_1688(oacc[4 * c + j], pl, bh0, bh1);
+        mma_tf32_1688(oacc[4 * c + j], ph, bl0, bl1);
+        mma_tf32_1688(oacc[4 * c + j], ph, bh0, bh1);
       }
     }
   }
-  __nv_bfloat16* oa = out_split + int64_t(t0 + r0 + g) * (2 * E) + h * HD + 2 * t;
-  __nv_bfloat16* ob = oa + int64_t(8) * (2 * E);
+  // D columns (2t, 2t + 1) of dim tile dt are dims 24t + dt and 24t + 12 + dt: rows g / g + 8, dims [24t, 24t + 24) contiguous
 #pragma unroll
-  for (int dt = 0; dt < HD / 8; ++dt) {
-    if (qa) {
-      const uint32_t hi = pack_bf16x2(oacc[dt][0], oacc[dt][1]);
-      *reinterpret_cast<uint32_t*>(oa + dt * 8) = hi;
-      *reinterpret_cast<uint32_t*>(oa + E + dt * 8) = pack_bf16x2(oacc[dt][0] - bf16_lo(hi), oacc[dt][1] - bf16_hi(hi));
-    }
-    if (qb) {
-      const uint32_t hi = pack_bf16x2(oacc[dt][2], oacc[dt][3]);
-      *reinterpret_cast<uint32_t*>(ob + dt * 8) = hi;
-      *reinterpret_cast<uint32_t*>(ob + E + dt * 8) = pack_bf16x2(oacc[dt][2] - bf16_lo(hi), oacc[dt][3] - bf16_hi(hi));
+  for (int rr = 0; rr < 2; ++rr) {
+    if (rr ? qb : qa) {
+      __nv_bfloat16* op = out_split + int64_t(t0 + r0 + g + 8 * rr) * (2 * E) + h * HD + 24 * t;
+      uint32_t hi[12], lo[12];
+#pragma unroll
+      for (int j = 0; j < 12; ++j) {  // dims 24t + 2j, + 1
+        const int d0 = 2 * j, d1 = 2 * j + 1;
+        const float x0 = oacc[d0 % 12][2 * rr + d0 / 12], x1 = oacc[d1 % 12][2 * rr + d1 / 12];
+        hi[j] = pack_bf16x2(x0, x1);
+        lo[j] = pack_bf16x2(x0 - bf16_lo(hi[j]), x1 - bf16_hi(hi[j]));
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        *reinterpret_cast<uint4*>(op + 8 * c) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+        *reinterpret_cast<uint4*>(op + E + 8 * c) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+      }
     }
   }
 }

@@ -13,6 +13,8 @@
 * :func:`custom_gesture_windows` / :func:`custom_gesture_indices` / :func:`gather_ragged`: the ``Custom_Gestures``
   inference sampling contract of ``main.sh:27`` (``prepare_dataset.py:1711-1726, 2642-2672``), pinned to the reference's
   own statements by the fixture ``tests/golden/custom_gesture_windows.npz``.
+* :func:`stitch_indices`: the ``VUA_EASE_Stitch`` form (``prepare_dataset.py:2279-2396``: per stitch sub-phase, stride-10 rows,
+  TTA views that shift the whole range), pinned the same way (``tests/golden/stitch_windows.npz``).
 * :class:`SaisPipeline`: frames -> ViT -> windows -> temporal head -> prototype scores, the whole path.
 * :class:`CapturedStep`: a fixed-geometry step (e.g. one clip: ViT + head + scoring) captured once as a CUDA graph and
   replayed with a single launch — for the latency-bound, one-clip-at-a-time end of the path.
@@ -362,6 +364,51 @@ def custom_gesture_indices(start_frames, end_frames, n_rgb: int, n_flow: int, tt
     return rgb, flow
 
 
+# --------------------------------------------------------------------------------------------- VUA_EASE_Stitch sampling
+STITCH_RACES = ("Needle Withdrawal", "Needle Handling", "Needle Driving")
+
+
+def stitch_indices(race: str, start_frame: int, end_frame: int, n_rgb: int, n_flow: int, jump_size: int,
+                   phase: str = "inference", tta_offsets: Sequence[int] = (0, 3, 6)):
+    """Row indices the ``VUA_EASE_Stitch`` dataset branch reads for one stitch sub-phase and its TTA views
+    (prepare_dataset.py:2279-2396; the skill-assessment inference form of ``main.sh``), quirks included:
+
+    * ``race`` selects the sub-phase; the caller passes the two frame numbers the reference takes from the data frame
+      (Withdrawal: 'Needle Withdrawal Start / End Frame', Handling: 'Needle Handling Start Frame' / 'Needle Entry Start
+      Frame', Driving: 'Needle Entry Start Frame' / 'Needle Withdrawal Start Frame', :2299-2307); both are shifted by -1;
+    * ``phase`` 'val' / 'test': Withdrawal ``[s - 40, s + 40)``, Handling ``[s, e - 20)``, Driving ``[s, e - int(0.2 (e - s)))``
+      (:2310-2320); any ``'...inference'`` phase: Withdrawal ``[s, s + 60)``, Handling and Driving ``[s, e)`` (:2329-2340);
+    * every view is ``arange(start + o, end + o, 10)`` — the END moves with the offset here (unlike ``Custom_Gestures``);
+    * flow rows: ``unique(rows // jump_size)`` with ``jump_size`` = 15 for the 30-fps 'Gronau_inference' videos and
+      ``int(fps // 2)`` otherwise (:2362-2369), with NO ``< len(flow)`` filter: an out-of-range row raises IndexError like the
+      reference's ``flow_reps[flow_indices, :]``; negative rows wrap (numpy semantics), floor division before the wrap.
+
+    Returns ``(rgb, flow)``: lists with one int64 row array per view (ragged between views)."""
+    if race not in STITCH_RACES:
+        raise ValueError(f"race must be one of {STITCH_RACES}")
+    if jump_size <= 0:
+        raise ValueError("jump_size must be positive")
+    s0, e0 = int(start_frame) - 1, int(end_frame) - 1
+    if phase in ("val", "test"):
+        if race == "Needle Withdrawal":
+            start, end = s0 - 40, s0 + 40
+        elif race == "Needle Handling":
+            start, end = s0, e0 - 20
+        else:
+            start, end = s0, e0 - int((e0 - s0) * 0.20)
+    elif "inference" in phase:
+        start, end = (s0, s0 + 60) if race == "Needle Withdrawal" else (s0, e0)
+    else:
+        raise ValueError("phase must be 'val', 'test' or an '...inference' phase")
+    rgb, flow = [], []
+    for o in tta_offsets:
+        raw = np.arange(start + o, end + o, 10, dtype=np.int64)
+        f = np.unique(raw // jump_size)
+        rgb.append(_wrap_rows(raw, n_rgb, "RGB"))
+        flow.append(_wrap_rows(f, n_flow, "flow") if f.size else f)
+    return rgb, flow
+
+
 def gather_ragged(embeddings: torch.Tensor, rows: Sequence[np.ndarray]):
     """Ragged row lists -> zero-padded ``[W,1,Lmax,384]`` + key-padding mask ``bool [W,1,Lmax+1]`` built like
     ``createPaddingMask`` (prepare_dataset.py:2798-2806: ``mask[b,:,len_b+1:] = True``) + the lengths."""
@@ -562,6 +609,30 @@ class SaisPipeline:
             out, attn = self.head(xs, fs, none, none, 'Prototypes', xp, fp, None)
         pred, probs = scoring.predict(out, self.prototypes.to(dev))
         return pred, probs, attn, ids
+
+    @torch.no_grad()
+    def score_rows(self, rgb_emb: torch.Tensor, flow_emb: torch.Tensor, rgb_rows, flow_rows):
+        """The general ragged form behind every sampler: ``rgb_rows[v][w]`` / ``flow_rows[v][w]`` are the embedding rows of
+        TTA view ``v`` of sample ``w`` (e.g. from :func:`stitch_indices`, one call per stitch sub-phase).  Views are padded to
+        the batch maximum with key-padding masks built like ``createPaddingMask`` (``pad_collate``,
+        prepare_dataset.py:2798-2871) and go through the head's TTA list form.  Returns ``(pred [W], probs [W,P] averaged
+        over the views, attn [W,S,S] of RGB view 0)``."""
+        if len(rgb_rows) != len(flow_rows) or not rgb_rows:
+            raise ValueError("rgb_rows and flow_rows need the same, non-zero number of views")
+        xs, xp, fs, fp = [], [], [], []
+        for rows, frows in zip(rgb_rows, flow_rows):
+            if len(rows) != len(frows):
+                raise ValueError("every view needs one RGB and one flow row list per sample")
+            x, m, _ = gather_ragged(rgb_emb, rows)
+            f, fm, _ = gather_ragged(flow_emb, frows)
+            xs.append(x), xp.append(m), fs.append(f), fp.append(fm)
+        if len(xs) == 1:
+            out, attn = self.head(xs[0], fs[0], None, None, 'Prototypes', xp[0], fp[0], None)
+        else:
+            none = [None] * len(xs)
+            out, attn = self.head(xs, fs, none, none, 'Prototypes', xp, fp, None)
+        pred, probs = scoring.predict(out, self.prototypes.to(rgb_emb.device))
+        return pred, probs, attn
 
     @torch.no_grad()
     def run_video(self, rgb_frames, flow_frames, precision=None):

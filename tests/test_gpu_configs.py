@@ -204,3 +204,39 @@ def test_custom_gestures_pipeline_against_oracle(dev, golden_dir, head_sd):
         _, pr, _, _ = pipe.score_windows(rgb_emb.to(dev), flow_emb.to(dev), own)
         got[torch.from_numpy(own).to(dev)] = pr
     assert float((got - probs).abs().max()) <= 1e-6
+
+
+def test_stitch_sampling_through_the_head_against_oracle(dev, golden_dir, head_sd):
+    """VUA_EASE_Stitch form end to end: rows from pipeline.stitch_indices (pinned to the reference's statements by
+    tests/golden/stitch_windows.npz) -> SaisPipeline.score_rows (ragged views of different lengths in one padded batch,
+    S up to 67) -> every sample equals the oracle head run on that stitch ALONE with the fixture's rows."""
+    from sais_b200 import pipeline
+    g = np.load(golden_dir / "stitch_windows.npz")
+    n_rgb, n_flow = int(g["n_rgb"]), int(g["n_flow"])
+    gen = torch.Generator().manual_seed(78)
+    rgb_emb, flow_emb = torch.randn(n_rgb, 384, generator=gen), torch.randn(n_flow, 384, generator=gen)
+    head = _head(head_sd, dev, "RGB-Flow")
+    protos = O.make_prototypes(2, seed=2)
+    pipe = pipeline.SaisPipeline(None, head, protos, sampling="plain")
+    cases = [ci for ci, m in enumerate(g["cases"]) if str(m).split("|")[0] in ("Gronau_inference", "HMH_inference")]
+    rgb_rows, flow_rows = [[], [], []], [[], [], []]
+    for ci in cases:
+        phase, race, s, e, fps = str(g["cases"][ci]).split("|")
+        jump = 15 if phase == "Gronau_inference" else int(int(fps) // 2)
+        r, f = pipeline.stitch_indices(pipeline.STITCH_RACES[int(race)], int(s), int(e), n_rgb, n_flow, jump, phase)
+        for v in range(3):
+            rgb_rows[v].append(r[v])
+            flow_rows[v].append(f[v])
+    pred, probs, attn = pipe.score_rows(rgb_emb.to(dev), flow_emb.to(dev), rgb_rows, flow_rows)
+    assert probs.shape == (len(cases), 2) and pred.shape == (len(cases),)
+    for k in (0, 5, 14, len(cases) - 1, len(cases) - 3):
+        ci = cases[k]
+        xs = [rgb_emb[torch.from_numpy(g[f"c{ci}_rgb{v}"])].view(1, 1, -1, 384) for v in range(3)]
+        fs = [flow_emb[torch.from_numpy(g[f"c{ci}_flow{v}"])].view(1, 1, -1, 384) for v in range(3)]
+        xp = [O.padding_mask([t.shape[2]], t.shape[2]) for t in xs]
+        fp = [O.padding_mask([t.shape[2]], t.shape[2]) for t in fs]
+        r_out, r_attn = O.full_model_forward(head_sd, xs, fs, xp, fp)
+        r_probs = torch.stack([O.prototype_probs(o, protos)[0] for o in r_out], 0).mean(0)
+        assert float((probs[k].cpu() - r_probs[0]).abs().max()) <= 1e-4, ci
+        S = xs[0].shape[2] + 1
+        assert float((attn[k, :S, :S].cpu() - r_attn[0]).abs().max()) <= 1e-4, ci

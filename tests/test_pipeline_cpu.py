@@ -216,3 +216,25 @@ def test_embedding_gatherer_single_rank_is_a_plain_buffer():
     own.fill_(3.0)
     gat.gather_async(0)
     assert gat.buffer(0).data_ptr() == own.data_ptr() and gat.buffer(0).shape == (10, 384)
+
+
+def test_stitch_sampling_matches_reference_statements(golden_dir):
+    """VUA_EASE_Stitch index arithmetic (prepare_dataset.py:2279-2396) == the fixture written by executing the reference's
+    own statements (oracle/make_golden_stitch.py): 4 phases x 3 stitch sub-phases x 5 frame ranges, three TTA views each,
+    including 24-fps videos (jump 12), rows that wrap below 0 and a 66-row view."""
+    from sais_b200 import pipeline
+
+    g = np.load(golden_dir / "stitch_windows.npz")
+    n_rgb, n_flow = int(g["n_rgb"]), int(g["n_flow"])
+    assert len(g["cases"]) == 60
+    for ci, meta in enumerate(g["cases"]):
+        phase, race, s, e, fps = str(meta).split("|")
+        jump = 15 if phase == "Gronau_inference" else int(int(fps) // 2)
+        rgb, flow = pipeline.stitch_indices(pipeline.STITCH_RACES[int(race)], int(s), int(e), n_rgb, n_flow, jump, phase)
+        for v in range(3):
+            assert np.array_equal(rgb[v], g[f"c{ci}_rgb{v}"]), (meta, v)
+            assert np.array_equal(flow[v], g[f"c{ci}_flow{v}"]), (meta, v)
+    with pytest.raises(IndexError):  # no '< len(flow)' filter in this branch: the reference's fancy index raises
+        pipeline.stitch_indices("Needle Handling", 3000, 3651, 4000, 100, 15, "Gronau_inference")
+    with pytest.raises(ValueError):
+        pipeline.stitch_indices("Needle Poking", 1, 2, 10, 10, 15)
