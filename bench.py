@@ -224,6 +224,11 @@ def main():
     ap.add_argument("--lanes", type=int, default=3,
                     help="pipeline lanes (pipeline.Lanes): consecutive steps go to consecutive CUDA streams, so one batch's kernel "
                          "tails and head are filled by the other batches' kernels (default 3)")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"],
+                    help="N > 1: how the per-step embeddings reach the other ranks.  nccl: in-place asynchronous all-gather "
+                         "(pipeline.EmbeddingGatherer); peer: no collective — the ViT's final-LayerNorm kernel stores its rows "
+                         "into every GPU's symmetric gather buffer (NVSwitch multicast / NVLink peer stores) and one barrier "
+                         "publishes them (pipeline.PeerGatherer)")
     ap.add_argument("--head-stream", type=int, default=0,
                     help="1: run the temporal head + scoring of a step on a separate high-priority stream "
                          "(pipeline.SideStream) instead of on the step's lane; with --lanes 1 --vit-sms 140 this is the "
@@ -273,7 +278,20 @@ def main():
     lanes = pipeline.Lanes(dev, args.lanes)
     depth = len(lanes) if len(lanes) > 1 else 2
     xgroup = pipeline.low_footprint_group() if world > 1 else None   # one-CTA NCCL collectives for the exchange
-    gatherer = pipeline.EmbeddingGatherer(n_global, 384, rank, world, dev, depth=depth, group=xgroup)
+    peer_x = args.exchange == "peer" and world > 1
+    if peer_x:
+        gatherer = pipeline.PeerGatherer(n_global, 384, rank, world, dev, depth=depth)
+    else:
+        gatherer = pipeline.EmbeddingGatherer(n_global, 384, rank, world, dev, depth=depth, group=xgroup)
+
+    def fan(i):
+        return {"fanout": gatherer.fanout(i)} if peer_x else {}
+
+    def exchange(i):
+        if peer_x:
+            gatherer.publish(i)       # one barrier on the gatherer's own stream: the rows are already on their way
+        else:
+            gatherer.gather_async(i)  # in place, on NCCL's stream; the head below reads own rows only
 
     def head_and_score(own):
         # this rank's clips: 8 RGB clips from the first half of its frame range, 8 flow clips from the second half
@@ -304,8 +322,8 @@ def main():
         with lanes.lane(i):
             own = claim_slot(i)                   # the final-LN kernel writes at rank * count of the gather buffer
             with vit_limit:
-                vit.forward_u8(dev_batches[i % nbuf], out=own)
-            gatherer.gather_async(i)              # in place, on NCCL's stream; the head below reads own rows only
+                vit.forward_u8(dev_batches[i % nbuf], out=own, **fan(i))
+            exchange(i)
             return own, run_head(i, own)
 
     emb_host = [torch.empty((FRAMES_PER_STEP, 384), dtype=torch.float32).pin_memory() for _ in range(depth)]
@@ -315,8 +333,8 @@ def main():
         with lanes.lane(i):
             own = claim_slot(i)
             with vit_limit:
-                pipeline.extract_features(vit, host_batches[i % nbuf], batch_size=FRAMES_PER_STEP, device=dev, out=own)
-            gatherer.gather_async(i)
+                pipeline.extract_features(vit, host_batches[i % nbuf], batch_size=FRAMES_PER_STEP, device=dev, out=own, **fan(i))
+            exchange(i)
             out, probs, pred = run_head(i, own)
             # device->host reads of the step's results: embeddings + clip probabilities, behind the head on its stream
             with torch.cuda.stream(side.stream if side is not None else torch.cuda.current_stream(dev)):
@@ -448,6 +466,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": dict(workload_config(world), lanes=len(lanes), head_stream=bool(args.head_stream),
+                           exchange=(("peer:" + gatherer.mode) if peer_x else ("nccl" if world > 1 else "none")),
                            vit_sms=args.vit_sms or "all"),
             "flop_per_frame": {"reference_forward": FLOP_PER_FRAME, "executed": FLOP_PER_FRAME_EXECUTED,
                                "note": "last block evaluated on the CLS rows only (dead rows of the reference "

@@ -231,6 +231,27 @@ int sais_vit_forward(const SaisVitWeights* w_host, const void* input, int32_t in
                      int32_t chunk_frames, int32_t precise, void* workspace, size_t workspace_bytes,
                      float* out_cls, float* out_probs, float* out_tokens, sais_stream_t stream);
 
+/* The same forward with the path's ONE exchange step fused into its last kernel (when a video is sharded by
+ * frame range, every rank needs all ranks' [n/R,384] embeddings ahead of the temporal head).  `out_cls` is this rank's
+ * slice of a gather buffer that exists at the same offset on every GPU of the group (symmetric memory); `fan` tells the
+ * final-LayerNorm kernel where that slice lives in the other GPUs' mappings, and the kernel stores every embedding row
+ * there as it produces it — over NVLink, either with ONE multimem.st per 16 bytes to the NVSwitch multicast address
+ * (`multicast`: the address of `out_cls` in the group's multicast mapping; the switch replicates the store to every GPU)
+ * or with one plain store per peer (`peers[i]`: the address of `out_cls` in peer i's mapping, self excluded).  The local
+ * slice is always written with a plain store as well, so this rank's own consumers need no cross-GPU ordering.  There
+ * is no collective and no NCCL kernel on the data path; the caller orders consumers on other ranks behind a barrier that
+ * follows this call in stream order (sais_b200.pipeline.PeerGatherer).  fan == NULL: exactly sais_vit_forward. */
+#define SAIS_MAX_PEERS 15
+typedef struct {
+  void* multicast;
+  void* peers[SAIS_MAX_PEERS];
+  int32_t n_peers;
+} SaisFanout;
+int sais_vit_forward_fanout(const SaisVitWeights* w_host, const void* input, int32_t input_kind, int32_t B,
+                            int32_t chunk_frames, int32_t precise, void* workspace, size_t workspace_bytes,
+                            float* out_cls, float* out_probs, float* out_tokens, const SaisFanout* fan,
+                            sais_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * SAIS temporal head (prepare_model.py:179-221 + README-patched nn.TransformerEncoder).
  * Sequences are PACKED: sequence i owns tokens [seq_offsets[i], seq_offsets[i+1]) with S_i = T_i+1

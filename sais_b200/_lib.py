@@ -50,6 +50,24 @@ class SaisVitWeights(C.Structure):
     ]
 
 
+MAX_PEERS = 15
+
+
+class SaisFanout(C.Structure):
+    """include/sais_b200.h SaisFanout: where this rank's output slice lives in the other GPUs' mappings."""
+    _fields_ = [("multicast", C.c_void_p), ("peers", C.c_void_p * MAX_PEERS), ("n_peers", C.c_int32)]
+
+
+def fanout_shifted(f, byte_offset):
+    """Copy of a SaisFanout with every address advanced by ``byte_offset`` (a sub-range of the output slice)."""
+    g = SaisFanout()
+    g.multicast = (f.multicast + byte_offset) if f.multicast else None
+    g.n_peers = f.n_peers
+    for i in range(f.n_peers):
+        g.peers[i] = f.peers[i] + byte_offset
+    return g
+
+
 class SaisTemporalLayerWeights(C.Structure):
     _fields_ = [(n, _p) for n in (
         "in_w", "in_b", "out_w", "out_b", "n1_w", "n1_b", "ff1_w", "ff1_b", "ff2_w", "ff2_b", "n2_w", "n2_b")]
@@ -90,6 +108,8 @@ SIGNATURES = {
     "sais_vit_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "sais_vit_forward": (C.c_int, [C.POINTER(SaisVitWeights), _p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _p,
                                    C.c_size_t, _p, _p, _p, _p]),
+    "sais_vit_forward_fanout": (C.c_int, [C.POINTER(SaisVitWeights), _p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _p,
+                                          C.c_size_t, _p, _p, _p, C.POINTER(SaisFanout), _p]),
     "sais_temporal_prep": (C.c_int, [_p, _p, C.c_int32, C.c_int32, _p, _p, C.c_int32, _p, _p, _p]),
     "sais_temporal_attention": (C.c_int, [_p, _p, _p, _p, C.c_int32, C.c_int32, _p, _p, _p]),
     "sais_temporal_workspace_bytes": (C.c_size_t, [C.c_int32]),

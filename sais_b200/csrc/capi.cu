@@ -426,6 +426,14 @@ size_t sais_vit_workspace_bytes(int32_t chunk_frames, int32_t precise) {
 int sais_vit_forward(const SaisVitWeights* w, const void* input, int32_t input_kind, int32_t B,
                      int32_t chunk_frames, int32_t precise, void* workspace, size_t workspace_bytes,
                      float* out_cls, float* out_probs, float* out_tokens, sais_stream_t stream_) {
+  return sais_vit_forward_fanout(w, input, input_kind, B, chunk_frames, precise, workspace, workspace_bytes, out_cls,
+                                 out_probs, out_tokens, nullptr, stream_);
+}
+
+int sais_vit_forward_fanout(const SaisVitWeights* w, const void* input, int32_t input_kind, int32_t B,
+                            int32_t chunk_frames, int32_t precise, void* workspace, size_t workspace_bytes,
+                            float* out_cls, float* out_probs, float* out_tokens, const SaisFanout* fan,
+                            sais_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!w || !input || !workspace || !out_cls || B < 0 || chunk_frames <= 0 ||
       (input_kind != SAIS_INPUT_F32_CHW && input_kind != SAIS_INPUT_U8_HWC)) {
@@ -545,7 +553,8 @@ int sais_vit_forward(const SaisVitWeights* w, const void* input, int32_t input_k
         g.a = hid; g.w = bw.fc2_w; g.bias = bw.fc2_b; g.residual = x_cls; g.out_f32 = x_cls;
         g.M = Bc; g.N = Dm; g.K = Hid; g.lda = Hid; g.ldw = Hid; g.ldr = Dm; g.ldo32 = Dm;
         if ((rc = gemm_bias_act(g, stream))) return rc;
-        if ((rc = layernorm(x_cls, Dm, w->norm_w, w->norm_b, 1e-6f, Bc, out_cls + size_t(b0) * Dm, nullptr, stream)))
+        if ((rc = layernorm(x_cls, Dm, w->norm_w, w->norm_b, 1e-6f, Bc, out_cls + size_t(b0) * Dm, nullptr, stream, 0,
+                            nullptr, nullptr, fan, int64_t(b0) * Dm)))
           return rc;
         cls_done = true;
         break;
@@ -605,7 +614,7 @@ int sais_vit_forward(const SaisVitWeights* w, const void* input, int32_t input_k
     }
     // final norm: only the CLS rows are consumed (vision_transformer.py:213-214)
     if (!cls_done && (rc = layernorm(x, int64_t(Tk) * Dm, w->norm_w, w->norm_b, 1e-6f, Bc, out_cls + size_t(b0) * Dm,
-                                     nullptr, stream)))
+                                     nullptr, stream, 0, nullptr, nullptr, fan, int64_t(b0) * Dm)))
       return rc;
     if (out_tokens) {
       if ((rc = layernorm(x, Dm, w->norm_w, w->norm_b, 1e-6f, tok, out_tokens + size_t(b0) * Tk * Dm, nullptr,

@@ -19,13 +19,27 @@ constexpr int D = 384;
 // ----------------------------------------------------------------------------------------------
 constexpr int kLnRows = 4;  // rows per warp per iteration: 12 independent 16-byte loads in flight per lane
 
+// Fan-out of the fp32 output rows to the other GPUs of a symmetric-memory group (SaisFanout, include/sais_b200.h): the
+// exchange step of the path fused into the kernel that produces the embeddings.  mc != nullptr: one multimem.st per 16
+// bytes to the NVSwitch multicast mapping (replicated to every GPU by the switch); else n plain stores to peer mappings.
+struct LnFan {
+  float* mc;
+  float* peer[SAIS_MAX_PEERS];
+  int n;
+};
+__device__ __forceinline__ void multimem_st_f32x4(float* addr, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+
 __global__ void __launch_bounds__(256) layernorm384_kernel(const float* __restrict__ x, int64_t in_pitch,
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, float eps, int64_t rows,
                                                            float* __restrict__ out_f32,
                                                            __nv_bfloat16* __restrict__ out_bf16, int split,
                                                            float* __restrict__ out_plus,
-                                                           const float* __restrict__ plus_vec) {
+                                                           const float* __restrict__ plus_vec, const LnFan fan) {
   pdl_wait();  // (PDL, common.cuh) no global access above this line
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -89,6 +103,11 @@ __global__ void __launch_bounds__(256) layernorm384_kernel(const float* __restri
         y.z = (v[r][i].z - mean[r]) * rs * g[i].z + b[i].z;
         y.w = (v[r][i].w - mean[r]) * rs * g[i].w + b[i].w;
         if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * D + c) = y;
+        if (fan.mc != nullptr) {
+          multimem_st_f32x4(fan.mc + row * D + c, y);
+        } else {
+          for (int pi = 0; pi < fan.n; ++pi) *reinterpret_cast<float4*>(fan.peer[pi] + row * D + c) = y;
+        }
         if (out_plus) {  // y + vector: the pre-loaded accumulator of the next residual GEMM (accumulate mode)
           const float4 pv = __ldg(reinterpret_cast<const float4*>(plus_vec + c));
           *reinterpret_cast<float4*>(out_plus + row * D + c) = make_float4(y.x + pv.x, y.y + pv.y, y.z + pv.z, y.w + pv.w);
@@ -406,11 +425,37 @@ __global__ void __launch_bounds__(128) prototype_score_kernel(const float* __res
 
 int layernorm(const float* x, int64_t in_pitch, const float* gamma, const float* beta, float eps, int64_t rows,
               float* out_f32, sais_bf16* out_bf16, cudaStream_t stream, int split, float* out_plus,
-              const float* plus_vec) {
+              const float* plus_vec, const SaisFanout* fan, int64_t fan_offset) {
   if (rows == 0) return kOk;
   if (!x || !gamma || !beta || (!out_f32 && !out_bf16) || rows < 0 || in_pitch % 4 || (out_plus && !plus_vec)) {
     set_last_error("layernorm: bad arguments");
     return kErrInvalidArg;
+  }
+  LnFan lf;
+  memset(&lf, 0, sizeof(lf));
+  if (fan != nullptr && (fan->multicast != nullptr || fan->n_peers > 0)) {
+    if (!out_f32 || fan->n_peers < 0 || fan->n_peers > SAIS_MAX_PEERS) {
+      set_last_error("layernorm: fan-out needs the fp32 output and 0..%d peers", SAIS_MAX_PEERS);
+      return kErrInvalidArg;
+    }
+    uintptr_t bits = reinterpret_cast<uintptr_t>(fan->multicast);
+    if (fan->multicast != nullptr) {
+      lf.mc = static_cast<float*>(fan->multicast) + fan_offset;
+    } else {
+      lf.n = fan->n_peers;
+      for (int i = 0; i < lf.n; ++i) {
+        if (!fan->peers[i]) {
+          set_last_error("layernorm: fan-out peer %d is NULL", i);
+          return kErrInvalidArg;
+        }
+        bits |= reinterpret_cast<uintptr_t>(fan->peers[i]);
+        lf.peer[i] = static_cast<float*>(fan->peers[i]) + fan_offset;
+      }
+    }
+    if ((bits | uintptr_t(fan_offset * 4)) & 15) {
+      set_last_error("layernorm: fan-out addresses must be 16-byte aligned");
+      return kErrInvalidArg;
+    }
   }
   int64_t blocks = (rows + 8 * kLnRows - 1) / (8 * kLnRows);
   const int64_t cap = int64_t(num_sms()) * 8;  // persistent beyond one full wave (8 blocks x 8 warps per SM)
@@ -418,7 +463,7 @@ int layernorm(const float* x, int64_t in_pitch, const float* gamma, const float*
   LaunchScope ls(kClsLayerNorm, stream, double(rows) * D * (4 + (out_f32 ? 4 : 0) + (out_bf16 ? 2 : 0)));
   return check_cuda(launch_pdl(layernorm384_kernel, dim3(unsigned(blocks)), dim3(256), size_t(0), stream, 1, x, in_pitch, gamma, beta, eps, rows, out_f32,
                                                             reinterpret_cast<__nv_bfloat16*>(out_bf16), split, out_plus,
-                                                            plus_vec),
+                                                            plus_vec, lf),
                     "layernorm launch");
 }
 

@@ -48,9 +48,11 @@ int vit_mlp_fused(const sais_bf16* xn, const sais_bf16* w1, const float* b1, con
 
 // elementwise.cu
 // out_plus (optional) = LayerNorm output + plus_vec[384]: the pre-loaded accumulator of an accumulate-mode GEMM
+// fan (optional, with out_f32): the rows are also stored to the other GPUs' mappings of out_f32 (+ fan_offset elements):
+// SaisFanout in include/sais_b200.h
 int layernorm(const float* x, int64_t in_pitch, const float* gamma, const float* beta, float eps, int64_t rows,
               float* out_f32, sais_bf16* out_bf16, cudaStream_t stream, int split = 0, float* out_plus = nullptr,
-              const float* plus_vec = nullptr);
+              const float* plus_vec = nullptr, const SaisFanout* fan = nullptr, int64_t fan_offset = 0);
 int rowstats_cast(const float* x, int64_t rows, sais_bf16* xb, float* stats, cudaStream_t stream);
 int normalize_patchify_u8(const uint8_t* frames, int B, const float* mean3, const float* std3, sais_bf16* patches,
                           cudaStream_t stream, int split = 0);

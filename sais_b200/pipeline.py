@@ -8,6 +8,8 @@
   range, one process per GPU; the only exchange on the path is an NCCL all-gather of the per-rank ``[n/R,384]``
   embeddings ahead of the temporal encoder — in place into a persistent buffer the ViT writes to, and
   asynchronous so that the head / next batch overlap it.  ``gloo`` works too (CPU tensors) for the host-logic tests.
+* :class:`PeerGatherer`: the same exchange without a collective — symmetric-memory gather buffers, the ViT's final-LayerNorm
+  kernel stores its rows straight into every GPU's buffer (NVSwitch multicast or peer stores over NVLink), one barrier.
 * :func:`sliding_windows` / :func:`gather_windows`: dense window + TTA index arithmetic (step-recognition form,
   ``prepare_dataset.py:469-473, 2324``) done with tensor ops so the gather stays on the device.
 * :func:`custom_gesture_windows` / :func:`custom_gesture_indices` / :func:`gather_ragged`: the ``Custom_Gestures``
@@ -149,6 +151,126 @@ class EmbeddingGatherer:
     def wait_all(self) -> None:
         for k in range(len(self.slots)):
             self._join(k)
+
+
+class PeerGatherer:
+    """The exchange step WITHOUT a collective: the same job as :class:`EmbeddingGatherer` (every rank ends up with all
+    ranks' ``[n/R,384]`` embeddings), but the bytes move inside the ViT's last kernel.
+
+    The gather buffers live in symmetric memory (``torch.distributed._symmetric_memory``: one allocation per rank at the same
+    offsets, every peer's copy mapped into this process, plus the NVSwitch multicast mapping where the box has one).
+    :meth:`fanout` describes this rank's slice in the other GPUs' mappings; ``forward_u8(frames, out=own_slice(i),
+    fanout=fanout(i))`` makes the final-LayerNorm kernel store each embedding row locally AND — one ``multimem.st`` per 16
+    bytes to the multicast address, replicated by the switch; or one plain NVLink store per peer — into every other GPU's
+    buffer while it computes them.  No NCCL kernel, no extra copy, no SM spinning for its peers during the data movement;
+    :meth:`publish` then enqueues one stream-ordered barrier (a one-CTA signal / wait over the symmetric signal pads) after
+    which :meth:`buffer` holds every rank's rows.
+
+    Slot protocol (why there are ``2 * depth`` slots): step ``i`` writes slot ``i % (2 * depth)`` on EVERY GPU, so the
+    peers must have finished reading that slot's previous content (step ``i - 2 * depth``).  A rank that has passed the
+    barrier of step ``i - depth`` on this channel knows every peer has *enqueued past* its own barrier of step
+    ``i - depth`` on that channel, i.e. past everything it enqueued for step ``i - 2 * depth`` — provided each rank enqueues
+    its reads of ``buffer(j)`` on the stream it called ``publish(j)`` on (or orders them before its ``publish(j + depth)``).
+    Steps ``j`` and ``j + depth`` share channel ``j % depth`` — with :class:`Lanes` that is the lane, and one barrier per step
+    is the only synchronisation.  Rows are split evenly (``ceil(n / R)`` per rank)."""
+
+    def __init__(self, n_rows: int, dim: int, rank: int, world: int, device, depth: int = 2, group=None,
+                 use_multicast: bool = True, timeout_ms: int = 20000):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        from . import _lib
+
+        if world - 1 > _lib.MAX_PEERS:
+            raise ValueError(f"at most {_lib.MAX_PEERS + 1} ranks")
+        self.n, self.dim, self.rank, self.world = int(n_rows), int(dim), int(rank), int(world)
+        self.depth, self.nslots = int(depth), 2 * int(depth)
+        self.timeout_ms = int(timeout_ms)
+        self.width = (self.n + world - 1) // world
+        self.ranges = [(min(r * self.width, self.n), min((r + 1) * self.width, self.n)) for r in range(world)]
+        self.device = torch.device(device)
+        slot_elems = world * self.width * dim
+        self.slot_bytes = slot_elems * 4
+        if self.slot_bytes % 16:
+            raise ValueError("slot size must be a multiple of 16 bytes")
+        self.mem = symm.empty((self.nslots, world * self.width, dim), dtype=torch.float32, device=self.device)
+        self.mem.zero_()
+        torch.cuda.synchronize(self.device)
+        self.handle = symm.rendezvous(self.mem, group if group is not None else dist.group.WORLD)
+        self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        mc = int(self.handle.multicast_ptr) if use_multicast else 0
+        self.multicast_ptr = mc if mc else 0
+        self.handle.barrier(channel=0, timeout_ms=self.timeout_ms)  # every rank has zeroed and mapped its buffers
+        self._fan = {}
+        self.published = [None] * self.nslots
+        self._streams = [torch.cuda.Stream(device=self.device) for _ in range(self.depth)]
+
+    @property
+    def mode(self) -> str:
+        return "multicast" if self.multicast_ptr else "peer-stores"
+
+    def _slot(self, i: int) -> int:
+        return i % self.nslots
+
+    def own_slice(self, i: int) -> torch.Tensor:
+        """This rank's rows of step ``i``'s slot.  The current stream first waits for this rank's barrier of step
+        ``i - depth`` (same channel): once that has passed, no peer still reads what step ``i`` is about to overwrite."""
+        prev = self.published[self._slot(i - self.depth)] if i >= self.depth else None
+        if prev is not None:
+            torch.cuda.current_stream(self.device).wait_event(prev)
+        lo, hi = self.ranges[self.rank]
+        return self.mem[self._slot(i)][self.rank * self.width: self.rank * self.width + (hi - lo)]
+
+    def fanout(self, i: int):
+        """``SaisFanout`` for :meth:`own_slice` ``(i)``: its address in the multicast mapping, or in every peer's mapping."""
+        from . import _lib
+
+        k = self._slot(i)
+        f = self._fan.get(k)
+        if f is None:
+            off = k * self.slot_bytes + self.rank * self.width * self.dim * 4
+            f = _lib.SaisFanout()
+            if self.multicast_ptr:
+                f.multicast, f.n_peers = self.multicast_ptr + off, 0
+            else:
+                peers = [p for r, p in enumerate(self.peer_ptrs) if r != self.rank]
+                f.multicast, f.n_peers = None, len(peers)
+                for j, p in enumerate(peers):
+                    f.peers[j] = p + off
+            self._fan[k] = f
+        return f
+
+    def publish(self, i: int) -> None:
+        """Call on the stream that ran step ``i``'s forward: one barrier over channel ``i % depth``; once it has passed,
+        every rank's rows of slot ``i`` are in this GPU's buffer (and every peer has this rank's)."""
+        cur = torch.cuda.current_stream(self.device)
+        ch = i % self.depth
+        wrote = torch.cuda.Event()
+        wrote.record(cur)
+        st = self._streams[ch]
+        st.wait_event(wrote)
+        with torch.cuda.stream(st):  # the barrier spins for the peers on its own stream, not in front of the caller's next kernel
+            if self.world > 1:
+                self.handle.barrier(channel=1 + ch, timeout_ms=self.timeout_ms)
+            done = torch.cuda.Event()
+            done.record(st)
+        self.published[self._slot(i)] = done
+
+    def buffer(self, i: int) -> torch.Tensor:
+        """All ``n`` rows of step ``i`` in frame order; the current stream waits for that step's barrier."""
+        ev = self.published[self._slot(i)]
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
+        slot = self.mem[self._slot(i)]
+        if all(hi - lo == self.width for lo, hi in self.ranges):
+            return slot[: self.n]
+        return torch.cat([slot[r * self.width: r * self.width + (hi - lo)] for r, (lo, hi) in enumerate(self.ranges)], 0)
+
+    def wait_all(self) -> None:
+        cur = torch.cuda.current_stream(self.device)
+        for ev in self.published:
+            if ev is not None:
+                cur.wait_event(ev)
 
 
 class SideStream:
@@ -501,12 +623,22 @@ def _stager_for(model, device, batch_size: int) -> HostFrameStager:
 
 @torch.no_grad()
 def extract_features(model, frames, batch_size: int = 256, device=None, precision: Optional[str] = None,
-                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     out: Optional[torch.Tensor] = None, fanout=None) -> torch.Tensor:
     """``extractFeatures`` (extract_representations.py:351-378): walk the frames in batches, ``reps = model(inputs)``.
     ``frames``: uint8 ``[n,224,224,3]`` (host, ideally pinned; or already on the device).  Returns fp32 ``[n,384]`` on
     the device.  Host batches are double-buffered through the model's :class:`HostFrameStager`: the copy of batch
-    i+1 overlaps the ViT on batch i, within a call and across calls."""
+    i+1 overlaps the ViT on batch i, within a call and across calls.  ``fanout`` (with ``out``): see
+    :meth:`PeerGatherer.fanout` — every batch's embeddings also go to the other GPUs' copies of ``out``."""
     device = torch.device(device) if device is not None else next(model.parameters()).device
+    if fanout is not None and out is None:
+        raise ValueError("fanout needs out= (this rank's slice of the symmetric gather buffer)")
+
+    def fan(lo):
+        if fanout is None:
+            return {}
+        from . import _lib
+        return {"fanout": _lib.fanout_shifted(fanout, lo * 384 * 4)}
+
     frames = _pin(frames)
     n = frames.shape[0]
     if out is None:
@@ -515,7 +647,7 @@ def extract_features(model, frames, batch_size: int = 256, device=None, precisio
         return out
     if frames.device.type == "cuda":
         for lo in range(0, n, batch_size):
-            model.forward_u8(frames[lo:lo + batch_size], precision=precision, out=out[lo:lo + batch_size])
+            model.forward_u8(frames[lo:lo + batch_size], precision=precision, out=out[lo:lo + batch_size], **fan(lo))
         return out
     with torch.cuda.device(device):
         st = _stager_for(model, device, min(batch_size, n))
@@ -529,7 +661,7 @@ def extract_features(model, frames, batch_size: int = 256, device=None, precisio
                 nlo = starts[i + 1]
                 pending = st.stage(frames[nlo:min(nlo + batch_size, n)])
             buf = st.acquire(k, hi - lo, main)
-            model.forward_u8(buf, precision=precision, out=out[lo:hi])
+            model.forward_u8(buf, precision=precision, out=out[lo:hi], **fan(lo))
             st.release(k, main)
     return out
 

@@ -184,7 +184,7 @@ class VisionTransformer(nn.Module):
         return ws, need
 
     # ------------------------------------------------------------------ forward paths
-    def _run(self, x, kind, want_probs=False, want_tokens=False, precision=None, out=None):
+    def _run(self, x, kind, want_probs=False, want_tokens=False, precision=None, out=None, fanout=None):
         if self.training:
             raise _lib.SaisError("sais_b200.VisionTransformer is inference-only; call .eval()")
         require_cuda(x, "input")
@@ -206,8 +206,13 @@ class VisionTransformer(nn.Module):
         probs = torch.empty((B, HEADS, TOKENS, TOKENS), device=x.device, dtype=torch.float32) if want_probs else None
         toks = torch.empty((B, TOKENS, DIM), device=x.device, dtype=torch.float32) if want_tokens else None
         with torch.cuda.device(x.device):
-            check(lib().sais_vit_forward(C.byref(w), ptr(x), kind, B, chunk, int(precise), ptr(ws), need, ptr(out),
-                                         ptr(probs), ptr(toks), current_stream()), "sais_vit_forward")
+            if fanout is None:
+                check(lib().sais_vit_forward(C.byref(w), ptr(x), kind, B, chunk, int(precise), ptr(ws), need, ptr(out),
+                                             ptr(probs), ptr(toks), current_stream()), "sais_vit_forward")
+            else:
+                check(lib().sais_vit_forward_fanout(C.byref(w), ptr(x), kind, B, chunk, int(precise), ptr(ws), need,
+                                                    ptr(out), ptr(probs), ptr(toks), C.byref(fanout), current_stream()),
+                      "sais_vit_forward_fanout")
         return out, probs, toks
 
     @staticmethod
@@ -223,12 +228,16 @@ class VisionTransformer(nn.Module):
         return self._run(self._check_f32(x), _lib.INPUT_F32_CHW, precision=precision)[0]
 
     @torch.no_grad()
-    def forward_u8(self, frames, precision=None, out=None):
+    def forward_u8(self, frames, precision=None, out=None, fanout=None):
         """Raw ``uint8 [B,224,224,3]`` frames; ToTensor+Normalize(ImageNet) is fused into the patch kernel.
-        ``out``: optional fp32 ``[B,384]`` device tensor the embeddings are written to (e.g. a slice of a gather buffer)."""
+        ``out``: optional fp32 ``[B,384]`` device tensor the embeddings are written to (e.g. a slice of a gather buffer).
+        ``fanout``: optional ``_lib.SaisFanout`` — the final-LayerNorm kernel then also stores the rows into the other
+        GPUs' mappings of ``out`` over NVLink (``pipeline.PeerGatherer.fanout``; the exchange step fused into the forward)."""
         if frames.dtype != torch.uint8 or tuple(frames.shape[1:]) != (IMG, IMG, 3):
             raise NotImplementedError(f"forward_u8 expects uint8 [B,224,224,3] (got {frames.dtype} {tuple(frames.shape)})")
-        return self._run(frames, _lib.INPUT_U8_HWC, precision=precision, out=out)[0]
+        if fanout is not None and out is None:
+            raise _lib.SaisError("fanout needs out= (this rank's slice of the symmetric gather buffer)")
+        return self._run(frames, _lib.INPUT_U8_HWC, precision=precision, out=out, fanout=fanout)[0]
 
     @torch.no_grad()
     def get_last_selfattention(self, x, precision="fp32"):
