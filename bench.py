@@ -199,7 +199,9 @@ def workload_config(n_gpus):
         "workload": "C2: DINO ViT-S/16 feature extraction, batch 256 u8 frames 224x224 (128 RGB + 128 flow) per GPU, "
                     "+ SAIS temporal head on 8 clips x 16 frames (RGB+flow) + 2 prototypes",
         "frames_per_gpu_per_step": FRAMES_PER_STEP, "clips_per_gpu_per_step": CLIPS_PER_STEP, "clip_frames": CLIP_T,
-        "sharding": "frame range per rank; in-place all-gather of embeddings (overlapped with the head) when n_gpus > 1",
+        "sharding": "frame range per rank; when n_gpus > 1 every rank's embeddings reach all ranks each step: stored into the "
+                    "peers' symmetric gather buffers by the ViT's last kernel (NVSwitch multicast) + one barrier, or "
+                    "(--exchange nccl) an in-place asynchronous NCCL all-gather; overlapped with the head either way",
         "l2": "inputs rotate over 4 distinct 38.5 MB frame batches and the 426 MB per-step working set exceeds "
               "the 126 MB L2",
         "parallelism": f"dp{n_gpus}",
@@ -224,7 +226,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=3,
                     help="pipeline lanes (pipeline.Lanes): consecutive steps go to consecutive CUDA streams, so one batch's kernel "
                          "tails and head are filled by the other batches' kernels (default 3)")
-    ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"],
+    ap.add_argument("--exchange", default="peer", choices=["nccl", "peer"],
                     help="N > 1: how the per-step embeddings reach the other ranks.  nccl: in-place asynchronous all-gather "
                          "(pipeline.EmbeddingGatherer); peer: no collective — the ViT's final-LayerNorm kernel stores its rows "
                          "into every GPU's symmetric gather buffer (NVSwitch multicast / NVLink peer stores) and one barrier "
@@ -279,9 +281,14 @@ def main():
     depth = len(lanes) if len(lanes) > 1 else 2
     xgroup = pipeline.low_footprint_group() if world > 1 else None   # one-CTA NCCL collectives for the exchange
     peer_x = args.exchange == "peer" and world > 1
+    exchange_note = None
     if peer_x:
-        gatherer = pipeline.PeerGatherer(n_global, 384, rank, world, dev, depth=depth)
-    else:
+        # measured at N = 8 (profiles/r02_exchange_ab.md): same device-resident rate as the NCCL all-gather, +2 % end to end
+        try:
+            gatherer = pipeline.PeerGatherer(n_global, 384, rank, world, dev, depth=depth)
+        except Exception as ex:  # no symmetric memory on this box: every rank fails alike -> the NCCL exchange
+            peer_x, exchange_note = False, f"peer exchange unavailable ({type(ex).__name__}: {str(ex)[:120]}); NCCL all-gather used"
+    if not peer_x:
         gatherer = pipeline.EmbeddingGatherer(n_global, 384, rank, world, dev, depth=depth, group=xgroup)
 
     def fan(i):
@@ -467,6 +474,7 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": dict(workload_config(world), lanes=len(lanes), head_stream=bool(args.head_stream),
                            exchange=(("peer:" + gatherer.mode) if peer_x else ("nccl" if world > 1 else "none")),
+                           **({"exchange_note": exchange_note} if exchange_note else {}),
                            vit_sms=args.vit_sms or "all"),
             "flop_per_frame": {"reference_forward": FLOP_PER_FRAME, "executed": FLOP_PER_FRAME_EXECUTED,
                                "note": "last block evaluated on the CLS rows only (dead rows of the reference "
