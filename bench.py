@@ -560,6 +560,14 @@ def run_extra_configs(torch, dist, dev, rank, world, vit, head, pipeline, postpr
         graphed = pipeline.CapturedStep(c1_step, c1_frames)
         ms_g = time_passes(lambda: graphed(c1_frames), 3, 20)
         out["C1_clip_10+10_frames"].update({"ms_per_clip_cuda_graph": ms_g, "frames_per_s_cuda_graph": 20 / (ms_g * 1e-3)})
+        # ... and with the small-batch MLP policy (fc1 / fc2 GEMM pair below 48 frames: lower latency, but a frame's
+        # embedding then depends on the batch size in the last bits, so it is opt-in: _lib.mlp_policy / sais_set_mlp_policy)
+        from sais_b200 import _lib as _l
+        with _l.mlp_policy(1):
+            graphed_lat = pipeline.CapturedStep(c1_step, c1_frames)
+        ms_l = time_passes(lambda: graphed_lat(c1_frames), 3, 20)
+        out["C1_clip_10+10_frames"].update({"ms_per_clip_cuda_graph_latency_policy": ms_l,
+                                            "frames_per_s_cuda_graph_latency_policy": 20 / (ms_l * 1e-3)})
     except Exception as ex:  # reported, never fatal for the headline
         out["C1_clip_10+10_frames"]["cuda_graph_error"] = f"{type(ex).__name__}: {str(ex)[:160]}"
 

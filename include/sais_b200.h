@@ -49,6 +49,13 @@ const char* sais_last_error(void);
 /* number of kernels this library has launched since load (for bench.py's gpu_launches) */
 int64_t sais_launch_count(void);
 
+/* Which kernels run the MLP of a ViT block on the bf16 path.  0 (default): the fused MLP kernel for every batch size —
+ * a frame's embedding is then independent of the batch it arrives in, bit for bit.  1: the fc1 / fc2 GEMM pair below 48
+ * frames per chunk (lower latency for single clips: 10 + 10 frames 1.11 -> 0.97 ms; rounding points differ from the fused
+ * kernel's, tolerances unchanged).  2: the GEMM pair always.  Returns the previous policy (>= 0) or a negative error code.
+ * Process-wide; SAIS_MLP_FOLD=auto / 0 set the initial value. */
+int sais_set_mlp_policy(int32_t policy);
+
 /* Spatial partitioning of the GPU between two streams of this library's kernels.  Every persistent kernel sizes its grid
  * from the SM count; with a limit set (an even number below the device's count, 0 = no limit) the kernels LAUNCHED while it is
  * in force occupy at most that many SMs and leave the rest to kernels launched on another stream without it.  Used to run

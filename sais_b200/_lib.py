@@ -108,6 +108,7 @@ SIGNATURES = {
     "sais_vit_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "sais_vit_forward": (C.c_int, [C.POINTER(SaisVitWeights), _p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _p,
                                    C.c_size_t, _p, _p, _p, _p]),
+    "sais_set_mlp_policy": (C.c_int, [C.c_int32]),
     "sais_vit_forward_fanout": (C.c_int, [C.POINTER(SaisVitWeights), _p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _p,
                                           C.c_size_t, _p, _p, _p, C.POINTER(SaisFanout), _p]),
     "sais_temporal_prep": (C.c_int, [_p, _p, C.c_int32, C.c_int32, _p, _p, C.c_int32, _p, _p, _p]),
@@ -173,6 +174,25 @@ class sm_limit:
 
     def __exit__(self, *exc):
         lib().sais_set_sm_limit(self.prev)
+        return False
+
+
+class mlp_policy:
+    """``with mlp_policy(1): ...`` — ``sais_set_mlp_policy`` for the forwards launched inside: 0 = fused MLP kernel always
+    (default: embeddings independent of the batch size, bit for bit), 1 = fc1 / fc2 GEMM pair below 48 frames (single-clip
+    latency), 2 = GEMM pair always."""
+
+    def __init__(self, policy: int):
+        self.p, self.prev = int(policy), 0
+
+    def __enter__(self):
+        self.prev = lib().sais_set_mlp_policy(self.p)
+        if self.prev < 0:
+            check(self.prev, "sais_set_mlp_policy")
+        return self
+
+    def __exit__(self, *exc):
+        lib().sais_set_mlp_policy(self.prev)
         return False
 
 

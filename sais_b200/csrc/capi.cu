@@ -75,6 +75,25 @@ bool pdl_enabled() {
 }
 
 namespace {
+int mlp_policy_from_env() {
+  const char* e = getenv("SAIS_MLP_FOLD");
+  if (!e) return 0;
+  if (!strcmp(e, "auto")) return 1;
+  return atoi(e) == 0 ? 2 : 0;
+}
+std::atomic<int> g_mlp_policy{mlp_policy_from_env()};  // 0 fused MLP always, 1 by batch size, 2 fc1 / fc2 GEMM pair always
+}  // namespace
+
+int balanced_ctas(int64_t units, int max_ctas) {
+  static const bool on = !(getenv("SAIS_BALANCED_GRID") && atoi(getenv("SAIS_BALANCED_GRID")) == 0);
+  if (max_ctas < 1) max_ctas = 1;
+  if (units <= max_ctas) return int(units < 1 ? 1 : units);
+  if (!on) return max_ctas;
+  const int64_t rounds = (units + max_ctas - 1) / max_ctas;
+  return int((units + rounds - 1) / rounds);
+}
+
+namespace {
 constexpr int kMaxDevices = 64;
 int current_device_index() {
   int dev = 0;
@@ -317,6 +336,14 @@ int sais_clock_probe(int64_t* out4, int32_t spin_iters, sais_stream_t stream_) {
                     "clock_probe launch");
 }
 
+int sais_set_mlp_policy(int32_t policy) {
+  if (policy < 0 || policy > 2) {
+    set_last_error("set_mlp_policy: 0 (fused MLP kernel always), 1 (GEMM pair below 48 frames) or 2 (GEMM pair always)");
+    return kErrInvalidArg;
+  }
+  return g_mlp_policy.exchange(policy, std::memory_order_relaxed);
+}
+
 int sais_set_sm_limit(int32_t n_sms) {
   if (n_sms < 0 || (n_sms & 1)) {
     set_last_error("set_sm_limit: need 0 (all SMs) or an even count (CTA pairs)");
@@ -508,7 +535,15 @@ int sais_vit_forward_fanout(const SaisVitWeights* w, const void* input, int32_t 
     // other path walk forward).
     static const bool env_nosnake = getenv("SAIS_SNAKE") != nullptr && atoi(getenv("SAIS_SNAKE")) == 0;
     const bool snake = fold && !env_nosnake;
-    static const bool mlp_fold = !(getenv("SAIS_MLP_FOLD") != nullptr && atoi(getenv("SAIS_MLP_FOLD")) == 0);
+    // The fused MLP kernel walks 256-row units, one CTA pair each, through all 24 hidden chunks (~33 us per unit whatever
+    // the batch); below ~48 frames it cannot fill the chip and the fc1 / fc2 GEMM pair, whose tiles spread over N as well,
+    // has the lower latency (measured: 8 frames 598 vs 780 us per forward, 20 frames 678 vs 830, 32 frames 787 vs 901,
+    // 64 frames 1,142 vs 1,081 — tools/c1_bench.py).  SAIS_MLP_FOLD=0 / 1 forces either.
+    // DEFAULT = always fused: a frame's embedding then does not depend on the size of the batch it arrives in, bit for bit
+    // (shards of any size reassemble to the single-rank result; pinned by tests).  sais_set_mlp_policy(1) — or
+    // SAIS_MLP_FOLD=auto — trades that invariance for the small-batch latency (different rounding points, same tolerances).
+    const int policy = g_mlp_policy.load(std::memory_order_relaxed);
+    const bool mlp_fold = policy == 0 ? true : (policy == 2 ? false : Bc >= 48);
     static const bool mlp_cast = !(getenv("SAIS_MLP_CAST") != nullptr && atoi(getenv("SAIS_MLP_CAST")) == 0);
     int dir = 1;  // rowstats_cast (like the patch GEMM before it) walks forward, so block 0's qkv starts from the end
     struct DirGuard { ~DirGuard() { g_tile_reverse = 0; } } dir_guard;  // never leaks into later calls on this thread

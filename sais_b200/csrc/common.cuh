@@ -547,6 +547,12 @@ int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t 
                       uint64_t ld2, uint32_t box0, uint32_t box1);
 
 int num_sms();  // of the CURRENT device (cached per device)
+// Grid of a persistent kernel that walks `units` equal work units round-robin: the SMALLEST number of CTAs (or CTA pairs)
+// that still finishes in the same number of rounds as `max_ctas` would (197 MLP row tiles: 66 pairs instead of 74, three
+// rounds either way; 1,536 attention items: 140 CTAs instead of 148, eleven rounds either way).  The kernel is no slower,
+// and the SMs it does not occupy are free for the other pipeline lanes for its WHOLE run time instead of only during its
+// partially filled last round.  SAIS_BALANCED_GRID=0 restores min(units, max_ctas).
+int balanced_ctas(int64_t units, int max_ctas);
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE function attribute: set it once per (device, kernel)
 int ensure_dynamic_smem(const void* kernel, int bytes, const char* what);
 

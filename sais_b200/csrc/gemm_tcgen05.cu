@@ -1065,8 +1065,7 @@ int launch_gemm(const SaisGemmArgs& a, cudaStream_t stream) {
   p.reverse = g_tile_reverse;
   p.remap_tma = remap_tma ? 1 : 0;
   const int units = ((m_tiles + cluster - 1) / cluster) * (p.N / BLOCK_N) * p.k_slices;
-  int grid = units * cluster < num_sms() ? units * cluster : num_sms();
-  grid -= grid % cluster;
+  int grid = balanced_ctas(units, num_sms() / cluster) * cluster;
   const int cls = a.split3 ? kClsGemmSplit
                   : (a.M >= 4096 && a.N == 1152 && a.K == 384 && a.out_bf16) ? kClsGemmQkv
                   : (a.M >= 4096 && a.N == 384 && a.K == 384 && a.out_f32) ? kClsGemmProj

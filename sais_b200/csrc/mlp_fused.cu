@@ -566,8 +566,7 @@ int vit_mlp_fused(const sais_bf16* xn, const sais_bf16* w1, const float* b1, con
   p.x = x;
   p.xb_out = reinterpret_cast<__nv_bfloat16*>(xb_out);
   p.stats_out = stats_out;
-  const int pairs_max = num_sms() / 2;
-  const int pairs = p.num_tiles < pairs_max ? p.num_tiles : pairs_max;
+  const int pairs = balanced_ctas(p.num_tiles, num_sms() / 2);  // 197 row tiles at batch 256: 66 pairs, three rounds
 
   static const char* timeline = getenv("SAIS_MLP_TIMELINE");
   p.dbg = nullptr;

@@ -369,7 +369,7 @@ int launch_attn(const CUtensorMap& tm, const CUtensorMap& tm_out, float* probs, 
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(vit_attention_tc_kernel<kEmitProbs>), kSmemBytes,
                                    "vit_attention_tc"))
     return rc;
-  const int grid = items < num_sms() ? items : num_sms();
+  const int grid = balanced_ctas(items, num_sms());  // 1,536 items at batch 256: 140 CTAs, eleven rounds
   return check_cuda(launch_pdl(vit_attention_tc_kernel<kEmitProbs>, dim3(grid), dim3(kThreads), size_t(kSmemBytes), stream, 1,
                                tm, tm_out, probs, items, g_tile_reverse ? 1 : 0, dbg),
                     "vit_attention_tc launch");

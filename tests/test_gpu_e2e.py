@@ -129,3 +129,24 @@ def test_captured_step_replays_the_eager_clip_path(dev, vit):
         assert torch.equal(got[3], want[3]) and torch.allclose(got[4], want[4], atol=1e-4)
     assert step.replays == 3
     torch.cuda.synchronize()
+
+
+def test_mlp_policy_small_batch_path_within_tolerance(dev, vit):
+    """sais_set_mlp_policy(1): batches below 48 frames take the fc1 / fc2 GEMM pair (single-clip latency).  Same tolerances
+    against the oracle; the default policy keeps a frame's embedding independent of the batch size bit for bit."""
+    from sais_b200 import _lib
+
+    fr = _host_frames(20, 600).to(dev)
+    base = vit.forward_u8(fr)
+    with _lib.mlp_policy(1):
+        lat = vit.forward_u8(fr)
+        big = vit.forward_u8(_host_frames(64, 601).to(dev))
+    assert torch.equal(vit.forward_u8(fr), base)                       # policy restored
+    assert torch.equal(big, vit.forward_u8(_host_frames(64, 601).to(dev)))  # >= 48 frames: fused kernel either way
+    ref = O.vit_forward(O.make_vit_weights(0, "stress"), O.normalize_frames(fr[:4].cpu()))
+    cos, rel = O.embedding_errors(lat[:4].cpu(), ref)
+    assert cos >= COS_MIN and rel <= REL_MAX, (cos, rel)
+    assert float((lat - base).abs().max()) <= 2e-2 * float(base.abs().max())
+    with pytest.raises(_lib.SaisError):
+        with _lib.mlp_policy(7):
+            pass
