@@ -231,6 +231,9 @@ def main():
                          "(pipeline.EmbeddingGatherer); peer: no collective — the ViT's final-LayerNorm kernel stores its rows "
                          "into every GPU's symmetric gather buffer (NVSwitch multicast / NVLink peer stores) and one barrier "
                          "publishes them (pipeline.PeerGatherer)")
+    ap.add_argument("--numa-bind", type=int, default=1,
+                    help="N > 1: pin every rank to the CPU cores local to its GPU before the pinned host buffers are allocated "
+                         "(pipeline.bind_to_gpu_numa); matters for the end-to-end number only")
     ap.add_argument("--head-stream", type=int, default=0,
                     help="1: run the temporal head + scoring of a step on a separate high-priority stream "
                          "(pipeline.SideStream) instead of on the step's lane; with --lanes 1 --vit-sms 140 this is the "
@@ -259,6 +262,7 @@ def main():
     from sais_b200 import _lib, pipeline, postprocess, scoring
     from sais_b200.prepare_model import fullModel
 
+    numa_cpus = pipeline.bind_to_gpu_numa(local_rank) if (world > 1 and args.numa_bind) else None
     lib = _lib.lib()
     # random-init weights of the named architectures (the modules' own init = the reference's distributions)
     torch.manual_seed(0)
@@ -475,6 +479,7 @@ def main():
             "config": dict(workload_config(world), lanes=len(lanes), head_stream=bool(args.head_stream),
                            exchange=(("peer:" + gatherer.mode) if peer_x else ("nccl" if world > 1 else "none")),
                            **({"exchange_note": exchange_note} if exchange_note else {}),
+                           **({"numa_bound_cpus": len(numa_cpus)} if numa_cpus else {}),
                            vit_sms=args.vit_sms or "all"),
             "flop_per_frame": {"reference_forward": FLOP_PER_FRAME, "executed": FLOP_PER_FRAME_EXECUTED,
                                "note": "last block evaluated on the CLS rows only (dead rows of the reference "

@@ -238,6 +238,12 @@ int sais_vit_forward(const SaisVitWeights* w_host, const void* input, int32_t in
                      int32_t chunk_frames, int32_t precise, void* workspace, size_t workspace_bytes,
                      float* out_cls, float* out_probs, float* out_tokens, sais_stream_t stream);
 
+/* get_intermediate_layers(x, n) (vision_transformer.py:225-233; eval_linear.py calls it with n = 4): the final-LayerNorm'd
+ * tokens after each of the last n_last blocks, earliest first, fp32 [n_last,B,197,384]; out_cls as in sais_vit_forward. */
+int sais_vit_forward_layers(const SaisVitWeights* w_host, const void* input, int32_t input_kind, int32_t B,
+                            int32_t chunk_frames, int32_t precise, void* workspace, size_t workspace_bytes,
+                            float* out_cls, int32_t n_last, float* out_tokens_stack, sais_stream_t stream);
+
 /* The same forward with the path's ONE exchange step fused into its last kernel (when a video is sharded by
  * frame range, every rank needs all ranks' [n/R,384] embeddings ahead of the temporal head).  `out_cls` is this rank's
  * slice of a gather buffer that exists at the same offset on every GPU of the group (symmetric memory); `fan` tells the

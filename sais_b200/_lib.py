@@ -109,6 +109,8 @@ SIGNATURES = {
     "sais_vit_forward": (C.c_int, [C.POINTER(SaisVitWeights), _p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _p,
                                    C.c_size_t, _p, _p, _p, _p]),
     "sais_set_mlp_policy": (C.c_int, [C.c_int32]),
+    "sais_vit_forward_layers": (C.c_int, [C.POINTER(SaisVitWeights), _p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _p,
+                                          C.c_size_t, _p, C.c_int32, _p, _p]),
     "sais_vit_forward_fanout": (C.c_int, [C.POINTER(SaisVitWeights), _p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _p,
                                           C.c_size_t, _p, _p, _p, C.POINTER(SaisFanout), _p]),
     "sais_temporal_prep": (C.c_int, [_p, _p, C.c_int32, C.c_int32, _p, _p, C.c_int32, _p, _p, _p]),

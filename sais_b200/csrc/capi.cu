@@ -450,6 +450,13 @@ size_t sais_vit_workspace_bytes(int32_t chunk_frames, int32_t precise) {
          + a256(tok * 8 * 4);                              // LayerNorm row-statistics partials (folded path)
 }
 
+}  // extern "C"
+static int vit_forward_impl(const SaisVitWeights* w, const void* input, int32_t input_kind, int32_t B,
+                            int32_t chunk_frames, int32_t precise, void* workspace, size_t workspace_bytes,
+                            float* out_cls, float* out_probs, float* out_tokens, int n_last, const SaisFanout* fan,
+                            sais_stream_t stream_);
+extern "C" {
+
 int sais_vit_forward(const SaisVitWeights* w, const void* input, int32_t input_kind, int32_t B,
                      int32_t chunk_frames, int32_t precise, void* workspace, size_t workspace_bytes,
                      float* out_cls, float* out_probs, float* out_tokens, sais_stream_t stream_) {
@@ -460,6 +467,29 @@ int sais_vit_forward(const SaisVitWeights* w, const void* input, int32_t input_k
 int sais_vit_forward_fanout(const SaisVitWeights* w, const void* input, int32_t input_kind, int32_t B,
                             int32_t chunk_frames, int32_t precise, void* workspace, size_t workspace_bytes,
                             float* out_cls, float* out_probs, float* out_tokens, const SaisFanout* fan,
+                            sais_stream_t stream_) {
+  return vit_forward_impl(w, input, input_kind, B, chunk_frames, precise, workspace, workspace_bytes, out_cls, out_probs,
+                          out_tokens, out_tokens ? 1 : 0, fan, stream_);
+}
+
+int sais_vit_forward_layers(const SaisVitWeights* w, const void* input, int32_t input_kind, int32_t B,
+                            int32_t chunk_frames, int32_t precise, void* workspace, size_t workspace_bytes,
+                            float* out_cls, int32_t n_last, float* out_tokens_stack, sais_stream_t stream_) {
+  if (n_last < 1 || n_last > SAIS_VIT_DEPTH || !out_tokens_stack) {
+    set_last_error("vit_forward_layers: n_last must be 1..%d with a [n_last,B,197,384] output", SAIS_VIT_DEPTH);
+    return kErrInvalidArg;
+  }
+  return vit_forward_impl(w, input, input_kind, B, chunk_frames, precise, workspace, workspace_bytes, out_cls, nullptr,
+                          out_tokens_stack, n_last, nullptr, stream_);
+}
+
+}  // extern "C"
+
+// out_tokens: [n_last][B][197][384] — the final-norm'd tokens after each of the last n_last blocks, earliest first
+// (n_last = 1: the plain out_tokens of sais_vit_forward)
+static int vit_forward_impl(const SaisVitWeights* w, const void* input, int32_t input_kind, int32_t B,
+                            int32_t chunk_frames, int32_t precise, void* workspace, size_t workspace_bytes,
+                            float* out_cls, float* out_probs, float* out_tokens, int n_last, const SaisFanout* fan,
                             sais_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!w || !input || !workspace || !out_cls || B < 0 || chunk_frames <= 0 ||
@@ -551,6 +581,13 @@ int sais_vit_forward_fanout(const SaisVitWeights* w, const void* input, int32_t 
       g_tile_reverse = snake ? dir : 0;
       dir ^= 1;
     };
+    // get_intermediate_layers(n > 1): the final norm of the stream after block l, for the n_last - 1 blocks before the last
+    auto tap = [&](int l) -> int {
+      const int j = l - (SAIS_VIT_DEPTH - n_last);
+      if (out_tokens == nullptr || j < 0 || l == SAIS_VIT_DEPTH - 1) return kOk;
+      return layernorm(x, Dm, w->norm_w, w->norm_b, 1e-6f, tok, out_tokens + (size_t(j) * B + size_t(b0)) * Tk * Dm, nullptr,
+                       stream);
+    };
     for (int l = 0; l < SAIS_VIT_DEPTH; ++l) {
       const SaisVitBlockWeights& bw = w->blocks[l];
       const bool last = (l == SAIS_VIT_DEPTH - 1);
@@ -628,6 +665,7 @@ int sais_vit_forward_fanout(const SaisVitWeights* w, const void* input, int32_t 
           }
           xn_ready = true;
         }
+        if ((rc = tap(l))) return rc;
         continue;
       }
       // fc1 + GELU
@@ -646,19 +684,22 @@ int sais_vit_forward_fanout(const SaisVitWeights* w, const void* input, int32_t 
       if (fold && !last) { g.ln_stats_out = stats; g.out2_bf16 = xn; g.ldo2 = Dm; xn_ready = true; }
       next_dir();
       if ((rc = gemm_bias_act(g, stream))) return rc;
+      if ((rc = tap(l))) return rc;
     }
     // final norm: only the CLS rows are consumed (vision_transformer.py:213-214)
     if (!cls_done && (rc = layernorm(x, int64_t(Tk) * Dm, w->norm_w, w->norm_b, 1e-6f, Bc, out_cls + size_t(b0) * Dm,
                                      nullptr, stream, 0, nullptr, nullptr, fan, int64_t(b0) * Dm)))
       return rc;
     if (out_tokens) {
-      if ((rc = layernorm(x, Dm, w->norm_w, w->norm_b, 1e-6f, tok, out_tokens + size_t(b0) * Tk * Dm, nullptr,
-                          stream)))
+      if ((rc = layernorm(x, Dm, w->norm_w, w->norm_b, 1e-6f, tok,
+                          out_tokens + (size_t(n_last - 1) * B + size_t(b0)) * Tk * Dm, nullptr, stream)))
         return rc;
     }
   }
   return kOk;
 }
+
+extern "C" {
 
 int sais_temporal_prep(const float* x_frames, const int32_t* seq_offsets, int32_t nseq, int32_t total_tokens,
                        const float* frame_cls, const float* frame_pos, int32_t n_pos, float* tok_f32,

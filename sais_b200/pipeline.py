@@ -46,6 +46,35 @@ def shard_items(n_items: int, rank: int, world: int) -> np.ndarray:
     return np.arange(rank, n_items, world, dtype=np.int64)
 
 
+def bind_to_gpu_numa(device_index: int) -> Optional[List[int]]:
+    """Pin this process (one process per GPU) to the CPU cores NVML reports as local to ``device_index`` — so that the
+    pinned host staging buffers allocated afterwards are first-touched on the GPU's own NUMA node and the host->device
+    copies of eight ranks do not cross the socket interconnect.  Returns the CPU list, or ``None`` when NVML is not
+    available, reports nothing usable inside this process's cpuset, or the platform has no ``sched_setaffinity``."""
+    import os
+
+    if not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        try:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+            words = (os.cpu_count() + 63) // 64
+            mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        finally:
+            pynvml.nvmlShutdown()
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
+
+
 def gather_embeddings(local: torch.Tensor, n_frames: int, group=None) -> torch.Tensor:
     """All-gather per-rank embeddings ``[hi-lo, D]`` (ranges from :func:`frame_range`) into ``[n_frames, D]`` on every
     rank.  Uneven ranges are padded to the largest one for the collective and trimmed afterwards."""

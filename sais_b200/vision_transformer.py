@@ -253,10 +253,31 @@ class VisionTransformer(nn.Module):
 
     @torch.no_grad()
     def get_intermediate_layers(self, x, n=1, precision=None):
-        """Final-norm'd tokens of the last block (reference :225-233); only ``n == 1`` is on the hot path."""
-        if n != 1:
-            raise NotImplementedError("get_intermediate_layers is implemented for n=1 only")
-        return [self._run(self._check_f32(x), _lib.INPUT_F32_CHW, want_tokens=True, precision=precision)[2]]
+        """Final-norm'd tokens after each of the last ``n`` blocks, earliest first (reference :225-233; ``eval_linear.py``
+        calls it with ``n = 4``): a list of ``n`` fp32 ``[B,197,384]`` tensors."""
+        n = int(n)
+        if not 1 <= n <= DEPTH:
+            raise ValueError(f"n must be 1..{DEPTH}")
+        if n == 1:
+            return [self._run(self._check_f32(x), _lib.INPUT_F32_CHW, want_tokens=True, precision=precision)[2]]
+        if self.training:
+            raise _lib.SaisError("sais_b200.VisionTransformer is inference-only; call .eval()")
+        x = self._check_f32(x)
+        require_cuda(x, "input")
+        x = x.contiguous()
+        B = x.shape[0]
+        if B == 0:
+            return [torch.empty((0, TOKENS, DIM), device=x.device) for _ in range(n)]
+        precise = (precision or self.precision) == "fp32"
+        w, _ = self.pack_weights(precise)
+        chunk = max(1, min(self.chunk_frames, B))
+        ws, need = self._workspace(chunk, x.device, precise)
+        cls = torch.empty((B, DIM), device=x.device, dtype=torch.float32)
+        stack = torch.empty((n, B, TOKENS, DIM), device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            check(lib().sais_vit_forward_layers(C.byref(w), ptr(x), _lib.INPUT_F32_CHW, B, chunk, int(precise), ptr(ws), need,
+                                                ptr(cls), n, ptr(stack), current_stream()), "sais_vit_forward_layers")
+        return list(stack.unbind(0))
 
     def train(self, mode=True):
         if mode:

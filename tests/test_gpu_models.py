@@ -95,6 +95,29 @@ def test_vit_fp32_mode_matches_oracle_and_golden(dev, golden_dir, name, style, w
     assert rel <= 2 * REL_MAX_FP32, (name, "tokens", cos, rel)
 
 
+def test_vit_intermediate_layers_n4(dev, golden_dir):
+    """get_intermediate_layers(x, 4) — eval_linear.py's call (vision_transformer.py:225-233): four final-norm'd token tensors,
+    earliest first, against the executed reference (tests/golden/vit_inter4.npz) and the oracle; chunked through the
+    workspace (2 frames per chunk), bf16 and fp32-equivalent mode; the last entry equals the n = 1 call bit for bit."""
+    g = np.load(golden_dir / "vit_inter4.npz")["layers_first8"]
+    sd = O.make_vit_weights(0, "stress")
+    x = O.normalize_frames(O.make_frames_u8(3, 1))
+    ref = O.vit_intermediate_layers(sd, x, 4)
+    for precision, tol in (("bf16", 2 * REL_MAX), ("fp32", 2 * REL_MAX_FP32)):
+        model = _vit(sd, dev, precision=precision, chunk_frames=2)
+        outs = model.get_intermediate_layers(x.to(dev), 4)
+        assert len(outs) == 4 and all(tuple(t.shape) == (3, 197, 384) for t in outs)
+        for j, t in enumerate(outs):
+            cos, rel = O.embedding_errors(t[:, :8].cpu(), torch.from_numpy(g[j]))
+            assert cos >= COS_MIN and rel <= tol, (precision, j, cos, rel)
+            cos, rel = O.embedding_errors(t.cpu().reshape(-1, 384), ref[j].reshape(-1, 384))
+            assert cos >= COS_MIN and rel <= tol, (precision, j, "all tokens", cos, rel)
+        assert torch.equal(outs[-1], model.get_intermediate_layers(x.to(dev), 1)[0])
+        assert torch.equal(model.get_intermediate_layers(x.to(dev), 12)[-4], outs[0])
+    with pytest.raises(ValueError):
+        model.get_intermediate_layers(x.to(dev), 13)
+
+
 @pytest.mark.parametrize("B,chunk", [(1, 96), (5, 2), (9, 4), (33, 96)])
 def test_vit_chunking_is_invisible(dev, B, chunk):
     """results must not depend on how the batch is chunked through the workspace (ragged last chunk included)."""

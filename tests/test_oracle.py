@@ -29,6 +29,17 @@ def test_vit_oracle_matches_reference(golden_dir, name, style, wseed, n, iseed):
     np.testing.assert_allclose(toks[:, :8].numpy(), g["tokens_first8"], atol=5e-5, rtol=1e-4)
 
 
+def test_vit_intermediate_layers_oracle_matches_reference(golden_dir):
+    """get_intermediate_layers(x, 4) (vision_transformer.py:225-233, eval_linear.py's call) vs the executed reference."""
+    g = _load(golden_dir, "vit_inter4")
+    outs = O.vit_intermediate_layers(O.make_vit_weights(0, "stress"), O.normalize_frames(O.make_frames_u8(3, 1)), 4)
+    assert len(outs) == 4
+    for j, t in enumerate(outs):
+        np.testing.assert_allclose(t[:, :8].numpy(), g["layers_first8"][j], atol=5e-5, rtol=1e-4)
+    assert torch.equal(outs[-1], O.vit_forward(O.make_vit_weights(0, "stress"), O.normalize_frames(O.make_frames_u8(3, 1)),
+                                               return_tokens=True))
+
+
 @pytest.mark.parametrize("name,style,seed,mods,B,t_rgb,t_flow,ragged", MG.HEAD_CASES)
 def test_head_oracle_matches_reference(golden_dir, name, style, seed, mods, B, t_rgb, t_flow, ragged):
     g = _load(golden_dir, name)
