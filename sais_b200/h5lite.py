@@ -292,7 +292,7 @@ def write(path: str, datasets: Dict[str, np.ndarray]) -> None:
     # ---- addresses
     SB = 96  # superblock v0 with 8-byte offsets: 24 + 4*8 + 40
     root_ohdr_addr = SB
-    root_ohdr_len = 16 + 8 + 16
+    root_ohdr_len = 16 + (8 + 16) + 8  # symbol-table message + a zero-size NIL message: libhdf5 never writes < 32 bytes of messages
     heap_addr = _pad8(root_ohdr_addr + root_ohdr_len)
     heap_data_addr = heap_addr + 32
     btree_addr = _pad8(heap_data_addr + len(heap_data))
@@ -324,7 +324,8 @@ def write(path: str, datasets: Dict[str, np.ndarray]) -> None:
     out[0:SB] = (SIGNATURE + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0, leaf_k, int_k, 0)
                  + struct.pack("<QQQQ", 0, UNDEF, eof, UNDEF) + root_entry)
     # ---- root group
-    hdr = _ohdr([_msg(0x11, struct.pack("<QQ", btree_addr, heap_addr))])
+    hdr = _ohdr([_msg(0x11, struct.pack("<QQ", btree_addr, heap_addr)), _msg(0x0, b"")])
+    assert len(hdr) == root_ohdr_len
     out[root_ohdr_addr:root_ohdr_addr + len(hdr)] = hdr
     out[heap_addr:heap_addr + 32] = b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap_data), free_off, heap_data_addr)
     out[heap_data_addr:heap_data_addr + len(heap_data)] = heap_data
