@@ -222,21 +222,25 @@ class PeerGatherer:
         self.slot_bytes = slot_elems * 4
         if self.slot_bytes % 16:
             raise ValueError("slot size must be a multiple of 16 bytes")
-        self.mem = symm.empty((self.nslots, world * self.width, dim), dtype=torch.float32, device=self.device)
-        self.mem.zero_()
-        torch.cuda.synchronize(self.device)
-        self.handle = symm.rendezvous(self.mem, group if group is not None else dist.group.WORLD)
-        self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
-        mc = int(self.handle.multicast_ptr) if use_multicast else 0
-        self.multicast_ptr = mc if mc else 0
-        self.handle.barrier(channel=0, timeout_ms=self.timeout_ms)  # every rank has zeroed and mapped its buffers
+        if world == 1:  # nothing to exchange: a plain buffer, no fan-out, publish() only records an event
+            self.mem = torch.zeros((self.nslots, self.width, dim), dtype=torch.float32, device=self.device)
+            self.handle, self.peer_ptrs, self.multicast_ptr = None, [], 0
+        else:
+            self.mem = symm.empty((self.nslots, world * self.width, dim), dtype=torch.float32, device=self.device)
+            self.mem.zero_()
+            torch.cuda.synchronize(self.device)
+            self.handle = symm.rendezvous(self.mem, group if group is not None else dist.group.WORLD)
+            self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+            mc = int(self.handle.multicast_ptr) if use_multicast else 0
+            self.multicast_ptr = mc if mc else 0
+            self.handle.barrier(channel=0, timeout_ms=self.timeout_ms)  # every rank has zeroed and mapped its buffers
         self._fan = {}
         self.published = [None] * self.nslots
         self._streams = [torch.cuda.Stream(device=self.device) for _ in range(self.depth)]
 
     @property
     def mode(self) -> str:
-        return "multicast" if self.multicast_ptr else "peer-stores"
+        return "single-rank" if self.world == 1 else ("multicast" if self.multicast_ptr else "peer-stores")
 
     def _slot(self, i: int) -> int:
         return i % self.nslots
@@ -251,8 +255,12 @@ class PeerGatherer:
         return self.mem[self._slot(i)][self.rank * self.width: self.rank * self.width + (hi - lo)]
 
     def fanout(self, i: int):
-        """``SaisFanout`` for :meth:`own_slice` ``(i)``: its address in the multicast mapping, or in every peer's mapping."""
+        """``SaisFanout`` for :meth:`own_slice` ``(i)``: its address in the multicast mapping, or in every peer's mapping
+        (``None`` for a single rank: ``forward_u8(..., fanout=None)`` is the plain forward)."""
         from . import _lib
+
+        if self.world == 1:
+            return None
 
         k = self._slot(i)
         f = self._fan.get(k)

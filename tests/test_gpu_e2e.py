@@ -150,3 +150,18 @@ def test_mlp_policy_small_batch_path_within_tolerance(dev, vit):
     with pytest.raises(_lib.SaisError):
         with _lib.mlp_policy(7):
             pass
+
+
+def test_peer_gatherer_single_rank_is_a_plain_buffer(dev, vit):
+    """world == 1: no symmetric memory, no fan-out, same interface (the N = 1 case of code written for N ranks)."""
+    from sais_b200 import pipeline
+
+    gat = pipeline.PeerGatherer(10, 384, 0, 1, dev, depth=2)
+    assert gat.mode == "single-rank" and gat.fanout(0) is None
+    for i in range(5):
+        fr = _host_frames(10, 700 + i).to(dev)
+        own = gat.own_slice(i)
+        vit.forward_u8(fr, out=own, fanout=gat.fanout(i))
+        gat.publish(i)
+        assert torch.equal(gat.buffer(i), vit.forward_u8(fr))
+    gat.wait_all()
