@@ -510,7 +510,7 @@ def main():
             "kernel_classes": shares,
             "extra_configs": extra,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # the CPU leg is timed at N = 1 only (bench contract)
             v, cores, sample = cpu_reference_rate()
             line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(line))
