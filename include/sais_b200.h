@@ -165,6 +165,10 @@ int sais_rowstats_cast(const float* x, int64_t rows, sais_bf16* xb, float* stats
 int sais_jpeg_info(const uint8_t* data, size_t len, int32_t* hw2_host);
 int sais_jpeg_decode_batch(const uint8_t* const* data_host, const size_t* lengths_host, int32_t n, int32_t H, int32_t W,
                            uint8_t* out_device, sais_stream_t stream);
+/* Which nvJPEG decoder served the last sais_jpeg_decode_batch call on the current device: 1 = the GPU's fixed-function JPEG
+ * engines (NVJPEG_BACKEND_HARDWARE), 2 = the batched CUDA decoder (NVJPEG_BACKEND_GPU_HYBRID / HYBRID), 3 = the threaded decoder (default: the frames of a call dealt
+ * to T host threads, one nvJPEG state + CUDA stream each), 0 = none yet. */
+int sais_jpeg_last_backend(void);
 
 /* Frame front-end: centre crop + Pillow-exact antialiased bilinear resize to 224 x 224.
  * Replaces, for decoded uint8 frames, `transforms.CenterCrop((height_frac*height, width_frac*width))`

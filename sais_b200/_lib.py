@@ -95,6 +95,7 @@ SIGNATURES = {
     "sais_rowstats_cast": (C.c_int, [_p, C.c_int64, _p, _p, _p]),
     "sais_layernorm": (C.c_int, [_p, C.c_int64, _p, _p, C.c_float, C.c_int64, C.c_int32, _p, _p, C.c_int32, _p]),
     "sais_jpeg_info": (C.c_int, [_p, C.c_size_t, C.POINTER(C.c_int32)]),
+    "sais_jpeg_last_backend": (C.c_int, []),
     "sais_jpeg_decode_batch": (C.c_int, [_p, _p, C.c_int32, C.c_int32, C.c_int32, _p, _p]),
     "sais_center_crop_box": (C.c_int, [C.c_int32, C.c_int32, C.c_double, C.c_double, C.POINTER(C.c_int32)]),
     "sais_resize_table_ints": (C.c_int64, [C.c_int32]),

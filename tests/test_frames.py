@@ -206,9 +206,17 @@ def test_jpeg_decode_batch_against_pillow(dev, h, w, kw):
     print(f"[jpeg decode vs Pillow] {h}x{w} {kw}: mean {d.mean():.3f} max {d.max()} p99.9 {np.percentile(d, 99.9):.1f}")
     sub = kw.get("subsampling", 2) != 0
     assert d.mean() <= (1.5 if sub else 0.75) and np.percentile(d, 99.9) <= (6 if sub else 3)
-    # a second call with another batch size re-initialises the batched state; a mismatching frame size is refused
+    # the default decoder deals the frames of a call to several host threads / CUDA streams (csrc/jpeg.cu): the result must
+    # be ordered on the caller's stream (read right away above) and must not depend on the batch size or on what the
+    # caller's stream did to the output buffer just before (the worker streams wait for it)
+    from sais_b200 import _lib
+    assert _lib.lib().sais_jpeg_last_backend() == 3
     again = F.decode_jpegs(streams[:2], dev)
     assert torch.equal(again, got[:2])
+    buf = torch.empty_like(got)
+    for _ in range(3):
+        buf.fill_(7)  # enqueued on the caller's stream immediately before the decode into the same buffer
+        assert torch.equal(F.decode_jpegs(streams, dev, out=buf), got)
     from sais_b200 import SaisError
     with pytest.raises(SaisError):
         F.decode_jpegs([streams[0], _encode(_smooth_frame(h // 2, w, 3))], dev)
