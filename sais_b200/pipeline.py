@@ -591,10 +591,9 @@ def gather_ragged(embeddings: torch.Tensor, rows: Sequence[np.ndarray]):
 
 # --------------------------------------------------------------------------------------------- feature extraction
 def _pin(frames):
-    t = torch.from_numpy(frames) if isinstance(frames, np.ndarray) else frames
-    if t.device.type == "cpu" and not t.is_pinned() and torch.cuda.is_available():
-        t = t.pin_memory()
-    return t
+    """numpy -> tensor view.  Pageable memory is NOT pinned wholesale here: :class:`HostFrameStager` bounces it through
+    two persistent pinned buffers batch by batch, overlapping the host copies with the GPU work."""
+    return torch.from_numpy(frames) if isinstance(frames, np.ndarray) else frames
 
 
 class HostFrameStager:
@@ -616,16 +615,38 @@ class HostFrameStager:
         self.freed = [torch.cuda.Event(), torch.cuda.Event()]
         self.used = [False, False]  # freed[k] has been recorded at least once
         self.turn = 0               # buffer the next batch goes to (persists across calls)
+        # pageable sources go through two persistent pinned bounce buffers, one batch at a time (allocated on first use)
+        self.pinned = [None, None]
+        self.h2d_done = [None, None]
+
+    def _bounce(self, k: int, src: torch.Tensor) -> torch.Tensor:
+        """Pageable ``src`` -> pinned bounce buffer ``k`` (host memcpy of ONE batch; the previous device copy out of that
+        buffer must have finished).  Pinning the caller's whole array per call instead — what round 1 did — allocates and
+        fills a pinned copy of every frame before the first kernel can start: 92.8 ms per 1,024 frames against 12.0 ms from
+        pinned memory (tools/e2e_host_bench.py)."""
+        if self.pinned[k] is None:
+            self.pinned[k] = torch.empty((self.batch_size, 224, 224, 3), dtype=torch.uint8).pin_memory()
+            self.h2d_done[k] = torch.cuda.Event()
+        else:
+            self.h2d_done[k].synchronize()
+        dst = self.pinned[k][: src.shape[0]]
+        dst.copy_(src)
+        return dst
 
     def stage(self, src: torch.Tensor) -> int:
         """Enqueue the copy of ``src`` (host, <= batch_size frames) into the next buffer; returns the buffer index."""
         k = self.turn
         self.turn ^= 1
+        bounced = not src.is_pinned()
+        if bounced:
+            src = self._bounce(k, src)
         with torch.cuda.stream(self.copy_stream):
             if self.used[k]:
                 self.copy_stream.wait_event(self.freed[k])
             self.bufs[k][: src.shape[0]].copy_(src, non_blocking=True)
             self.ready[k].record(self.copy_stream)
+            if bounced:
+                self.h2d_done[k].record(self.copy_stream)
         return k
 
     def acquire(self, k: int, n: int, stream) -> torch.Tensor:
@@ -662,7 +683,8 @@ def _stager_for(model, device, batch_size: int) -> HostFrameStager:
 def extract_features(model, frames, batch_size: int = 256, device=None, precision: Optional[str] = None,
                      out: Optional[torch.Tensor] = None, fanout=None) -> torch.Tensor:
     """``extractFeatures`` (extract_representations.py:351-378): walk the frames in batches, ``reps = model(inputs)``.
-    ``frames``: uint8 ``[n,224,224,3]`` (host, ideally pinned; or already on the device).  Returns fp32 ``[n,384]`` on
+    ``frames``: uint8 ``[n,224,224,3]`` (host — pinned memory is copied from directly, pageable memory / numpy arrays go through
+    the stager's pinned bounce buffers one batch at a time — or already on the device).  Returns fp32 ``[n,384]`` on
     the device.  Host batches are double-buffered through the model's :class:`HostFrameStager`: the copy of batch
     i+1 overlaps the ViT on batch i, within a call and across calls.  ``fanout`` (with ``out``): see
     :meth:`PeerGatherer.fanout` — every batch's embeddings also go to the other GPUs' copies of ``out``."""
