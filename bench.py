@@ -628,7 +628,7 @@ def run_extra_configs(torch, dist, dev, rank, world, vit, head, pipeline, postpr
                              "scaling": "strong", "frames": 2 * n, "windows": 359, "tta_views": 3}
 
     # ---- C5: 1,000 clips of 8-64 RGB frames (+ ceil(len/2) flow frames), sharded by clip id mod world: ViT over the
-    # shard's frames, padded batches of 32 clips through the head, all-gather of the [n_own,256] clip vectors
+    # shard's frames, length-bucketed padded batches of 128 clips through the head, all-gather of the [n_own,256] clip vectors
     import numpy as np
     rng = np.random.default_rng(3)
     lens = rng.integers(8, 65, 1000)
@@ -643,6 +643,8 @@ def run_extra_configs(torch, dist, dev, rank, world, vit, head, pipeline, postpr
     vec_own = torch.zeros((width, 256), dtype=torch.float32, device=dev)
     vec_all = torch.empty((world * width, 256), dtype=torch.float32, device=dev)
 
+    pipe5 = pipeline.SaisPipeline(vit, head, protos2)
+
     def c5():
         lanes.fork()
         k = 0
@@ -652,12 +654,8 @@ def run_extra_configs(torch, dist, dev, rank, world, vit, head, pipeline, postpr
                 vit.forward_u8(shard_frames(k)[:nb], out=emb[b0:b0 + nb])
             k += 1
         lanes.join()
-        for b0 in range(0, len(own_ids), 32):
-            ids = range(b0, min(b0 + 32, len(own_ids)))
-            xs, xp, _ = postprocess.pad_collate([emb[r_off[i]:r_off[i + 1]].unsqueeze(0) for i in ids])
-            fs, fp, _ = postprocess.pad_collate([emb[f_off[i]:f_off[i + 1]].unsqueeze(0) for i in ids])
-            o, _ = head(xs, fs, None, None, 'Prototypes', xp, fp, None)
-            vec_own[b0:b0 + len(ids)] = o
+        # length-bucketed padded batches of 128 clips through the head (pipeline.SaisPipeline.clip_vectors)
+        vec_own[:len(own_ids)] = pipe5.clip_vectors(emb, r_off, f_off, batch=128)
         if world > 1:
             dist.all_gather_into_tensor(vec_all, vec_own)
             return scoring.predict(vec_all, protos2)

@@ -575,18 +575,21 @@ def gather_ragged(embeddings: torch.Tensor, rows: Sequence[np.ndarray]):
     lens = np.asarray([len(r) for r in rows], dtype=np.int64)
     L = int(lens.max()) if W else 0
     D = embeddings.shape[1]
-    out = torch.zeros((W, 1, L, D), dtype=embeddings.dtype, device=embeddings.device)
-    mask = torch.zeros((W, 1, L + 1), dtype=torch.bool)
-    if W and L:
-        idx = np.zeros((W, L), dtype=np.int64)
-        valid = np.zeros((W, L), dtype=bool)
-        for w, r in enumerate(rows):
-            idx[w, :len(r)] = r
-            valid[w, :len(r)] = True
-            mask[w, :, len(r) + 1:] = True
-        g = embeddings[torch.from_numpy(idx.reshape(-1)).to(embeddings.device)].view(W, L, D)
-        out[:, 0] = g * torch.from_numpy(valid).to(embeddings.device).unsqueeze(-1)
-    return out, mask.to(embeddings.device), lens
+    dev = embeddings.device
+    if not (W and L):
+        return (torch.zeros((W, 1, L, D), dtype=embeddings.dtype, device=dev),
+                torch.zeros((W, 1, L + 1), dtype=torch.bool, device=dev), lens)
+    # vectorised on the host (no per-clip Python work: a 1,000-clip sweep spent more time here than in the head's kernels),
+    # one index + one mask transfer per call
+    valid = np.arange(L, dtype=np.int64)[None, :] < lens[:, None]
+    idx = np.zeros((W, L), dtype=np.int64)
+    idx[valid] = np.concatenate([np.asarray(r, dtype=np.int64).reshape(-1) for r in rows])  # row-major fill = clip order
+    keypad = np.concatenate([np.zeros((W, 1), dtype=bool), ~valid], axis=1)                   # token 0 (CLS) is never padded
+    valid_d = torch.from_numpy(valid).to(dev, non_blocking=True)
+    g = embeddings[torch.from_numpy(idx.reshape(-1)).to(dev, non_blocking=True)].view(W, L, D)
+    out = (g * valid_d.unsqueeze(-1)).view(W, 1, L, D)
+    mask = torch.from_numpy(keypad).to(dev, non_blocking=True).view(W, 1, L + 1)
+    return out, mask, lens
 
 
 # --------------------------------------------------------------------------------------------- feature extraction
@@ -824,6 +827,30 @@ class SaisPipeline:
             out, attn = self.head(xs, fs, none, none, 'Prototypes', xp, fp, None)
         pred, probs = scoring.predict(out, self.prototypes.to(rgb_emb.device))
         return pred, probs, attn
+
+    @torch.no_grad()
+    def clip_vectors(self, emb: torch.Tensor, rgb_offsets, flow_offsets, batch: int = 128) -> torch.Tensor:
+        """Clip vectors ``[n,256]`` of ``n`` ragged clips (the skill-assessment sweep, BASELINE config C5): clip ``i`` owns the
+        RGB rows ``[rgb_offsets[i], rgb_offsets[i+1])`` and the flow rows ``[flow_offsets[i], flow_offsets[i+1])`` of ``emb``.
+        Clips are **bucketed by length** before they are padded into batches of ``batch`` (``pad_collate`` /
+        ``createPaddingMask`` semantics, prepare_dataset.py:2798-2871): a clip's vector does not depend on what it is batched
+        with (padded frames are masked keys and only the CLS row is consumed — pinned by the padding-invariance tests), so
+        the order is free, and sorted batches carry a fraction of the padding of arrival-order batches of 8..64-frame clips
+        while 4x larger batches need a quarter of the launches.  Results are returned in the original clip order."""
+        r_off = np.asarray(rgb_offsets, dtype=np.int64)
+        f_off = np.asarray(flow_offsets, dtype=np.int64)
+        n = len(r_off) - 1
+        out = torch.empty((n, 256), dtype=torch.float32, device=emb.device)
+        if n == 0:
+            return out
+        order = np.argsort(r_off[1:] - r_off[:-1], kind="stable")
+        for b0 in range(0, n, batch):
+            ids = order[b0:b0 + batch]
+            xs, xp, _ = gather_ragged(emb, [np.arange(r_off[i], r_off[i + 1]) for i in ids])
+            fs, fp, _ = gather_ragged(emb, [np.arange(f_off[i], f_off[i + 1]) for i in ids])
+            o, _ = self.head(xs, fs, None, None, 'Prototypes', xp, fp, None)
+            out[torch.from_numpy(ids).to(emb.device)] = o
+        return out
 
     @torch.no_grad()
     def run_video(self, rgb_frames, flow_frames, precision=None):

@@ -240,3 +240,28 @@ def test_stitch_sampling_through_the_head_against_oracle(dev, golden_dir, head_s
         assert float((probs[k].cpu() - r_probs[0]).abs().max()) <= 1e-4, ci
         S = xs[0].shape[2] + 1
         assert float((attn[k, :S, :S].cpu() - r_attn[0]).abs().max()) <= 1e-4, ci
+
+
+def test_clip_vectors_bucketed_batches_equal_arrival_order_batches(dev, head_sd):
+    """SaisPipeline.clip_vectors (length-bucketed batches of 128) vs arrival-order pad_collate batches of 32 on 300 ragged clips:
+    a clip's vector does not depend on its batch (same bound as the padding-invariance check of the C5 test), results come
+    back in the original order."""
+    from sais_b200 import pipeline, postprocess
+    head = _head(head_sd, dev, "RGB-Flow")
+    rng = np.random.default_rng(4)
+    lens = rng.integers(8, 65, 300)
+    fl = (lens + 1) // 2
+    r_off = np.concatenate([[0], np.cumsum(lens)])
+    f_off = int(lens.sum()) + np.concatenate([[0], np.cumsum(fl)])
+    emb = torch.randn(int(lens.sum() + fl.sum()), 384, generator=torch.Generator().manual_seed(56)).to(dev)
+    pipe = pipeline.SaisPipeline(None, head, O.make_prototypes(2, seed=2))
+    got = pipe.clip_vectors(emb, r_off, f_off, batch=128)
+    want = torch.empty_like(got)
+    for b0 in range(0, 300, 32):
+        ids = range(b0, min(b0 + 32, 300))
+        xs, xp, _ = postprocess.pad_collate([emb[r_off[i]:r_off[i + 1]].unsqueeze(0) for i in ids])
+        fs, fp, _ = postprocess.pad_collate([emb[f_off[i]:f_off[i + 1]].unsqueeze(0) for i in ids])
+        o, _ = head(xs, fs, None, None, 'Prototypes', xp.to(dev), fp.to(dev), None)
+        want[b0:b0 + len(ids)] = o
+    assert float((got - want).abs().max()) <= 2e-5 * float(want.abs().max()) + 1e-6
+    assert pipe.clip_vectors(emb[:0], [0], [0]).shape == (0, 256)
