@@ -502,6 +502,10 @@ def custom_gesture_indices(start_frames, end_frames, n_rgb: int, n_flow: int, tt
     Returns ``(rgb, flow)``: ``rgb[v]`` is an int64 matrix ``[W, L_v]``; ``flow[v]`` a list of W int64 arrays (ragged)."""
     starts = np.asarray(start_frames, dtype=np.int64)
     ends = np.asarray(end_frames, dtype=np.int64)
+    if starts.size and bool(np.all(ends - starts == ends[0] - starts[0])):
+        # every window has the same duration (what custom_gesture_windows produces): all windows of a view at once — the
+        # per-window loop below costs 0.54 s for a 60-minute 30-fps video (7,200 windows), more than the head's kernels
+        return _custom_gesture_indices_uniform(starts, ends, n_rgb, n_flow, tta_offsets, flow_stride)
     rgb, flow = [], []
     for o in tta_offsets:
         rows, frows = [], []
@@ -565,6 +569,27 @@ def stitch_indices(race: str, start_frame: int, end_frame: int, n_rgb: int, n_fl
         f = np.unique(raw // jump_size)
         rgb.append(_wrap_rows(raw, n_rgb, "RGB"))
         flow.append(_wrap_rows(f, n_flow, "flow") if f.size else f)
+    return rgb, flow
+
+
+def _custom_gesture_indices_uniform(starts, ends, n_rgb, n_flow, tta_offsets, flow_stride):
+    """:func:`custom_gesture_indices` for windows of one common duration, vectorised over the windows (same rows, same
+    errors; pinned to the loop form and to the reference fixture by tests/test_pipeline_cpu.py)."""
+    s0, e0 = starts - 1, ends - 1
+    d = int(e0[0] - s0[0])
+    jump = d // 10
+    if jump <= 0:
+        raise ValueError("windows shorter than 10 frames have no valid stride (reference: arange step 0)")
+    rgb, flow = [], []
+    for o in tta_offsets:
+        raw = (s0[:, None] + o) + np.arange(0, d - o, jump, dtype=np.int64)[None, :]   # arange(s0 + o, e0, jump) per window
+        q = raw // flow_stride                                                           # floor division BEFORE the wrap
+        first = np.ones(q.shape, dtype=bool)
+        first[:, 1:] = q[:, 1:] != q[:, :-1]                                             # unique() of an ascending row
+        keep = first & (q < n_flow)
+        vals = _wrap_rows(q[keep], n_flow, "flow")                                       # row-major = window order
+        rgb.append(_wrap_rows(raw, n_rgb, "RGB"))
+        flow.append(np.split(vals, np.cumsum(keep.sum(1))[:-1]))
     return rgb, flow
 
 

@@ -238,3 +238,49 @@ def test_stitch_sampling_matches_reference_statements(golden_dir):
         pipeline.stitch_indices("Needle Handling", 3000, 3651, 4000, 100, 15, "Gronau_inference")
     with pytest.raises(ValueError):
         pipeline.stitch_indices("Needle Poking", 1, 2, 10, 10, 15)
+
+
+def _loop_form(pipeline, s, e, n_rgb, n_flow, stride):
+    """The reference arithmetic for ONE window, statement by statement (prepare_dataset.py:2642-2672)."""
+    s0, e0 = int(s) - 1, int(e) - 1
+    jump = (e0 - s0) // 10
+    rgb, flow = [], []
+    for o in (0, 3, 6):
+        raw = np.arange(s0 + o, e0, jump, dtype=np.int64)
+        q = np.unique(raw // stride)
+        q = q[q < n_flow]
+        rgb.append([np.where(raw < 0, raw + n_rgb, raw)])
+        flow.append([np.where(q < 0, q + n_flow, q)])
+    return rgb, flow
+
+
+def test_custom_gesture_indices_vectorised_form_equals_the_loop_form():
+    """Windows of one duration take the vectorised path; windows of mixed durations the per-window loop: same rows, same
+    errors (the reference fixture above pins the loop's arithmetic)."""
+    from sais_b200 import pipeline
+
+    rng = np.random.default_rng(7)
+    for n_rgb, n_flow, dur, stride in [(450, 30, 15, 15), (2000, 40, 30, 12), (100, 3, 15, 15), (64, 64, 20, 1)]:
+        starts = np.sort(rng.integers(0, n_rgb - dur, 37)).astype(np.int64)
+        starts[0] = 0  # the row -1 wrap
+        ends = starts + dur
+        fast = pipeline.custom_gesture_indices(starts, ends, n_rgb, n_flow, (0, 3, 6), stride)
+        slow_rgb, slow_flow = [], []
+        for s, e in zip(starts, ends):  # the per-window reference form: the loop body of custom_gesture_indices, one window at a time
+            r, f = _loop_form(pipeline, s, e, n_rgb, n_flow, stride)
+            slow_rgb.append([v[0] for v in r]), slow_flow.append([v[0] for v in f])
+        for v in range(3):
+            assert np.array_equal(fast[0][v], np.stack([w[v] for w in slow_rgb]))
+            for w in range(len(starts)):
+                assert np.array_equal(fast[1][v][w], slow_flow[w][v]), (n_rgb, v, w)
+                assert fast[1][v][w].dtype == np.int64
+    # windows of two durations with equal row counts (20 and 30 frames -> 10 rows each) go through the per-window loop
+    # (only view 0: the later views of the two durations differ in length, which one call refuses like the reference's collate)
+    mixed = pipeline.custom_gesture_indices([40, 100], [60, 130], 450, 30, (0,), 15)
+    for w, (s, e) in enumerate([(40, 60), (100, 130)]):
+        r, f = _loop_form(pipeline, s, e, 450, 30, 15)
+        assert np.array_equal(mixed[0][0][w], r[0][0]) and np.array_equal(mixed[1][0][w], f[0][0])
+    with pytest.raises(IndexError):
+        pipeline.custom_gesture_indices([90, 95], [105, 110], 100, 7)
+    with pytest.raises(ValueError):
+        pipeline.custom_gesture_indices([0, 20], [9, 29], 100, 7)
