@@ -108,9 +108,10 @@ def decode_jpegs(streams: Sequence[bytes], device, out: torch.Tensor = None) -> 
         out = torch.empty((n, h, w, 3), dtype=torch.uint8, device=device)
     elif tuple(out.shape) != (n, h, w, 3) or out.dtype != torch.uint8 or not out.is_contiguous() or out.device != device:
         raise ValueError(f"out must be a contiguous uint8 [{n},{h},{w},3] tensor on {device}")
-    bufs = [(C.c_uint8 * len(d)).from_buffer_copy(d) for d in streams]
-    ptrs = (C.c_void_p * n)(*[C.cast(b, C.c_void_p) for b in bufs])
-    lens = (C.c_size_t * n)(*[len(d) for d in streams])
+    # pointers into the bytes objects themselves (no copy of the bit streams; `streams` keeps them alive past the sync below)
+    bufs = [d if isinstance(d, bytes) else bytes(d) for d in streams]
+    ptrs = (C.c_void_p * n)(*[C.cast(C.c_char_p(b), C.c_void_p) for b in bufs])
+    lens = (C.c_size_t * n)(*[len(b) for b in bufs])
     with torch.cuda.device(device):
         check(lib().sais_jpeg_decode_batch(C.cast(ptrs, C.c_void_p), C.cast(lens, C.c_void_p), n, h, w, ptr(out),
                                            current_stream()), "sais_jpeg_decode_batch")
