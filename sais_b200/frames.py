@@ -115,8 +115,11 @@ def decode_jpegs(streams: Sequence[bytes], device, out: torch.Tensor = None) -> 
     with torch.cuda.device(device):
         check(lib().sais_jpeg_decode_batch(C.cast(ptrs, C.c_void_p), C.cast(lens, C.c_void_p), n, h, w, ptr(out),
                                            current_stream()), "sais_jpeg_decode_batch")
-        # nvJPEG reads the host bit streams while the decode is in flight: keep them alive until the stream has passed it
-        torch.cuda.current_stream(device).synchronize()
+        if lib().sais_jpeg_last_backend() != 3:
+            # the batched API may read the host bit streams while the decode is in flight: keep them alive until the stream
+            # has passed it.  (The threaded decoder entropy-decodes every stream on the host before its call returns; only
+            # the IDCT / colour kernels are still in flight then, ordered before anything the caller enqueues next.)
+            torch.cuda.current_stream(device).synchronize()
     return out
 
 
